@@ -1,0 +1,122 @@
+"""
+Model recipes used as benchmark / parity inputs.
+
+These are *inputs* to the engine, rebuilt from the notebooks' recipes -- the reference's pickled
+models are missing blobs (.MISSING_LARGE_BLOBS) -- not part of the hot path:
+
+* `tiger_model`            Cassandra's tiger.95 (S2 A3 O2 R2), the reference's CPU-runnable config.
+* `olfactory_wrap_model`   the 61x361 = 22021-state toroidal olfactory-navigation POMDP of
+                           `Experiments/Olfactory Navigation/Olfactory_Alternation_Paper_Wrap.ipynb[3-15]`
+                           (6 actions, 3 observations, deterministic moves => R=1).
+* `synthetic_sparse_model` the random sparse POMDP recipe of BASELINE.json configs[4].
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .model import Model
+
+_GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def tiger_model() -> Model:
+    """tiger.95: listen / open-left / open-right; hearing accuracy 0.85; +10 / -100 / -1."""
+    T = np.empty((2, 3, 2))
+    T[:, 0, :] = np.eye(2)
+    T[:, 1:, :] = 0.5
+    Obs = np.full((2, 3, 2), 0.5)
+    Obs[0, 0] = [0.85, 0.15]
+    Obs[1, 0] = [0.15, 0.85]
+    rew_sa = np.array([[-1.0, -100.0, 10.0], [-1.0, 10.0, -100.0]])
+    Rw = np.broadcast_to(rew_sa[:, :, None, None], (2, 3, 2, 2)).copy()
+    return Model(states=['tiger-left', 'tiger-right'], actions=['listen', 'open-left', 'open-right'],
+                 observations=['tiger-left', 'tiger-right'], transitions=T, rewards=Rw, observation_table=Obs,
+                 start_probabilities=[0.5, 0.5])
+
+
+def load_olfactory_maps(path: str | None = None):
+    """
+    The two plume detection-probability maps (ground, nose/air), each 31x121, as produced by the notebook's
+    `cv2.resize(data.T, dsize=(121, 31))` of `Data/statistics_abs_{ground,nose}_3e6.dat` (cell [4]).
+    Stored as a derived fixture (`tests/golden/olfactory_maps.npz`, written by tests/golden/make_golden.py)
+    because neither the raw data nor the reference travel to the GPU box.
+    """
+    path = path or os.path.join(_GOLDEN_DIR, 'olfactory_maps.npz')
+    z = np.load(path)
+    return z['ground'], z['nose']
+
+
+def olfactory_wrap_model(ground_map: np.ndarray | None = None, nose_map: np.ndarray | None = None,
+                         points_per_unit: int = 30, wrap: bool = True) -> Model:
+    """
+    Olfactory navigation POMDP (notebook cells [3]-[15]).  Grid (2*ppu+1) x (12*ppu+1); actions N,E,S,W,
+    sniff-ground, sniff-air; observations nothing / something / goal; the plume maps are placed at
+    rows [ppu/2, ppu/2 + ppu], cols [2*ppu, 6*ppu]; source (goal) at (ppu, 2*ppu); reward 1 on landing on
+    the goal; start belief uniform over rows [ppu/2, 1.5*ppu], cols [2*ppu, 10.5*ppu].
+    `wrap=False` gives the non-toroidal variant of `Olfactory_Alternation_Paper.ipynb` (moves off the grid stay put).
+    With ppu != 30 the maps are resampled by nearest neighbour (used for reduced-size test models only).
+    """
+    if ground_map is None or nose_map is None:
+        ground_map, nose_map = load_olfactory_maps()
+    ppu = points_per_unit
+    H, W = 2 * ppu + 1, 12 * ppu + 1
+    S = H * W
+    r0, c0 = ppu // 2, 2 * ppu
+    mh, mw = ppu + 1, 4 * ppu + 1
+    if ground_map.shape != (mh, mw):
+        ri = np.round(np.linspace(0, ground_map.shape[0] - 1, mh)).astype(int)
+        ci = np.round(np.linspace(0, ground_map.shape[1] - 1, mw)).astype(int)
+        ground_map = ground_map[np.ix_(ri, ci)]
+        nose_map = nose_map[np.ix_(ri, ci)]
+    ground = np.zeros((H, W)); ground[r0:r0 + mh, c0:c0 + mw] = ground_map
+    nose = np.zeros((H, W)); nose[r0:r0 + mh, c0:c0 + mw] = nose_map
+    goal = ppu * W + 2 * ppu
+
+    obs = np.empty((S, 6, 3))
+    obs[:, :5, 0] = (1 - ground.ravel()[:, None])
+    obs[:, :5, 1] = ground.ravel()[:, None]
+    obs[:, 5, 0] = (1 - nose.ravel())
+    obs[:, 5, 1] = nose.ravel()
+    obs[:, :, 2] = 0.0
+    obs[goal, :, :] = 0.0
+    obs[goal, :, 2] = 1.0
+
+    s = np.arange(S)
+    row, col = s // W, s % W
+    reach = np.zeros((S, 6, 1), dtype=int)
+    if wrap:
+        reach[:, 0, 0] = ((row - 1) % H) * W + col
+        reach[:, 1, 0] = row * W + (col + 1) % W
+        reach[:, 2, 0] = ((row + 1) % H) * W + col
+        reach[:, 3, 0] = row * W + (col - 1) % W
+    else:
+        reach[:, 0, 0] = np.where(row > 0, s - W, s)
+        reach[:, 1, 0] = np.where(col < W - 1, s + 1, s)
+        reach[:, 2, 0] = np.where(row < H - 1, s + W, s)
+        reach[:, 3, 0] = np.where(col > 0, s - 1, s)
+    reach[:, 4, 0] = s
+    reach[:, 5, 0] = s
+
+    start = np.zeros((H, W))
+    start[r0:r0 + mh, c0:c0 + int(8.5 * ppu) + 1] = 1.0
+    start /= np.sum(start)
+
+    def reward_func(s_, a_, sn_, o_):
+        return np.where(sn_ == goal, 1.0, 0.0)
+
+    grid_labels = [[f's_{i}_{j}' for j in range(W)] for i in range(H)]
+    return Model(states=grid_labels, actions=['N', 'E', 'S', 'W', 'O_Ground', 'O_Air'],
+                 observations=['nothing', 'something', 'goal'], reachable_states=reach, rewards=reward_func,
+                 observation_table=obs, end_states=[goal], start_probabilities=start.ravel())
+
+
+def synthetic_sparse_model(S: int, A: int, O: int, R: int, seed: int = 0) -> Model:
+    """Random sparse POMDP (BASELINE.json configs[4]): uniform 1/R transitions to
+    `rng.integers(0,S,(S,A,R))`, Dirichlet-free normalised random observation table, reward 1 on reaching S//2."""
+    rng = np.random.default_rng(seed)
+    reach = rng.integers(0, S, (S, A, R))
+    obs = rng.random((S, A, O))
+    obs /= obs.sum(2, keepdims=True)
+    return Model(states=S, actions=A, observations=O, reachable_states=reach, observation_table=obs, end_states=[S // 2])
