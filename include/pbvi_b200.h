@@ -1,0 +1,146 @@
+/*
+ * pbvi_b200.h -- C ABI of the B200-native PBVI backup engine (libpbvi_b200.so).
+ *
+ * The reference (PimLb/POMDP_PBVI_Exploration) is pure Python and has no FFI of its own; its "device
+ * boundary" is CuPy (`xp = cp.get_array_module(...)`, src/pomdp.py:1482).  The entry points below are
+ * what a binding for the hot path would bind: each one replaces the body of one reference method and
+ * cites it.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative pbvi_status; the message of the last failure on
+ *     the calling thread is returned by pbvi_last_error().  No C++ exception crosses the boundary.
+ *   - pointers named d_* are DEVICE pointers on the handle's device, h_* are HOST pointers.  All arrays are
+ *     C-contiguous.  Floating data is IEEE binary64, indices int32 unless stated (host model tables use the
+ *     reference's int64 `reachable_states`).
+ *   - the library BORROWS every pointer for the duration of the call; the only object that outlives a call
+ *     is the opaque model handle, which owns the device copy of the model tables and a grow-only scratch arena.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls enqueue work on it and
+ *     return without synchronising unless stated otherwise.
+ *   - a handle is not re-entrant: one host thread per handle (one process per GPU under torchrun).
+ */
+#ifndef PBVI_B200_H
+#define PBVI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PBVI_API __attribute__((visibility("default")))
+#else
+#define PBVI_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbvi_model pbvi_model;
+
+typedef enum pbvi_status {
+    PBVI_OK = 0,
+    PBVI_ERR_BAD_ARG = -1,
+    PBVI_ERR_CUDA = -2,
+    PBVI_ERR_OOM = -3,
+    PBVI_ERR_UNSUPPORTED = -4
+} pbvi_status;
+
+/* library version (major*100 + minor) and the message of the calling thread's last error */
+PBVI_API int pbvi_version(void);
+PBVI_API const char* pbvi_last_error(void);
+
+/* ---- model tables --------------------------------------------------------------------------------
+ * Replaces Model.gpu_model (src/mdp.py:533-560): uploads the tables the kernels consume, re-laid out
+ * action-major.  Host inputs are in the reference's layouts:
+ *   h_reach [S][A][R] int64  reachable_states                           (src/mdp.py:296-353)
+ *   h_probs [S][A][R] f64    reachable_probabilities (may be NULL: VI sweep then unavailable)
+ *   h_rto   [S][A][O][R] f64 reachable_transitional_observation_table   (src/pomdp.py:197-205)
+ *   h_rbar  [S][A] f64       expected_rewards_table                     (src/pomdp.py:231-254)
+ */
+PBVI_API int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_reach, const double* h_probs,
+                      const double* h_rto, const double* h_rbar, int device, pbvi_model** out);
+PBVI_API int pbvi_model_destroy(pbvi_model* m);
+PBVI_API int pbvi_model_dims(const pbvi_model* m, int* S, int* A, int* O, int* R);
+
+/* ---- point-based backup (PBVI_Solver.backup, src/pomdp.py:1447-1524) -------------------------------
+ * pbvi_backup_select: steps 1-3 without materialising Gamma.  For every belief b:
+ *   v_star[b][a][o] = first index of max_v  belief_b . Gamma[a,o,v]                      (:1489-1495)
+ *   value[b][a]     = belief_b . (Rbar[:,a] + sum_o Gamma[a,o,v_star[b][a][o]])          (:1502-1505)
+ *   a_star[b]       = first index of max_a value[b][a]                                   (:1505)
+ * d_beliefs [nB][S], d_alphas [nV][S]; outputs d_vstar [nB][A][O] int32, d_value [nB][A] (nullable),
+ * d_astar [nB] int32.
+ */
+PBVI_API int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV,
+                       double gamma, int32_t* d_vstar, double* d_value, int32_t* d_astar, void* stream);
+
+/* pbvi_backup_assemble: alpha_a rows for n (action, v_star[O]) tuples                    (:1497-1506)
+ *   out[i][s] = Rbar[s,a_i] + ((G_0 + G_1) + ...),  G_o = gamma * sum_r RTO[s,a_i,o,r] * alpha[v_i[o]][reach[s,a_i,r]]
+ * with the reference's operation order and no FMA contraction (bit-identical rows when R == 1).
+ * d_actions [n] int32, d_vsel [n][O] int32, d_out [n][S].
+ */
+PBVI_API int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int nV, double gamma, const int32_t* d_actions,
+                         const int32_t* d_vsel, int n, double* d_out, void* stream);
+
+/* pbvi_backup: select + assemble for every belief (no dedup): d_out_alpha [nB][S], d_out_action [nB];
+ * d_out_vstar [nB][A][O] and d_out_value [nB][A] may be NULL. */
+PBVI_API int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                double* d_out_alpha, int32_t* d_out_action, int32_t* d_out_vstar, double* d_out_value, void* stream);
+
+/* Same with HOST buffers: copies inputs to the device, runs pbvi_backup, copies alpha rows and actions back and
+ * synchronises.  This is the end-to-end entry point a CPU-resident caller (the reference's NumPy path) would use. */
+PBVI_API int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
+                     double* h_out_alpha, int32_t* h_out_action, void* stream);
+
+/* ---- maxima over a value function (src/pomdp.py:2165-2167 compute_change, :1639 SSGA, :1735 GER, :1393) ----
+ * d_max[b] = max_v belief_b . alpha_v, d_arg[b] = its first index.  Either output may be NULL. */
+PBVI_API int pbvi_max_values(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV,
+                    double* d_max, int32_t* d_arg, void* stream);
+
+/* ---- belief update (Belief.update, src/pomdp.py:382-421; batched twin :1415-1419) ----------------
+ * out[i][s'] = sum_{(s,r): reach[s,a_i,r]=s'} RTO[s,a_i,o_i,r] * belief_i[s], accumulated in ascending (s,r) order like
+ * bincount, then divided by its NumPy-pairwise sum when `normalise` != 0 (0/0 = NaN for impossible observations, as
+ * in the reference).  d_norm[i] (nullable) receives the un-normalised mass P(o_i | b_i, a_i).
+ */
+PBVI_API int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const int32_t* d_actions, const int32_t* d_observations,
+                       int n, int normalise, double* d_out, double* d_norm, void* stream);
+
+/* Every successor of every belief (Belief.generate_successors, src/pomdp.py:424-438; the B*A*O loop of SSEA :1679 and
+ * GER :1732): d_out [n][A][O][S], d_norm [n][A][O] (nullable).  Rows of impossible observations are NaN when normalised. */
+PBVI_API int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, void* stream);
+
+/* P(o | b, a) for every (a,o): d_out [n][A][O]  (einsum 'sor,s->o', src/pomdp.py:1814, 2046; 'bs,saor->bao' :1751) */
+PBVI_API int pbvi_observation_probabilities(pbvi_model* m, const double* d_beliefs, int n, double* d_out, void* stream);
+
+/* ---- raw-byte set semantics (src/mdp.py:668-669, 773-774; src/pomdp.py:581,600) --------------------
+ * pbvi_row_hash: 128-bit hash of the raw bytes of each row, d_hash [n][2] uint64.
+ * pbvi_rows_equal: flags[i] = 1 iff rows_a[ia[i]] and rows_b[ib[i]] are bytewise identical (used to confirm hash matches,
+ * so the dedup is exact, not probabilistic). */
+PBVI_API int pbvi_row_hash(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, void* stream);
+PBVI_API int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int32_t* d_ia, const double* d_rows_b, const int32_t* d_ib,
+                    int n, int row_len, int32_t* d_flags, void* stream);
+
+/* ---- MDP value iteration sweep (src/mdp.py:1507) ---------------------------------------------------
+ * d_alpha_out[a][s] = Rbar[s,a] + gamma * sum_r P[s,a,r] * d_vopt[reach[s,a,r]];  d_vopt_out[s] = max_a (nullable) */
+PBVI_API int pbvi_vi_sweep(pbvi_model* m, const double* d_vopt, double gamma, double* d_alpha_out, double* d_vopt_out, void* stream);
+
+/* ---- pointwise-domination prune (ValueFunction.prune level 2, src/mdp.py:857-866) -------------------
+ * d_keep[i] = 1 iff alpha_i is >= everywhere by no vector other than itself. */
+PBVI_API int pbvi_prune_dominated(pbvi_model* m, const double* d_alphas, int nV, int32_t* d_keep, void* stream);
+
+/* ---- HSVI sawtooth upper bound (BeliefValueMapping.evaluate, src/pomdp.py:887-895) -----------------
+ * d_out[q] = min(v0_q, min_i v0_q + (ub_value_i - ub_belief_i . corner) * min_{s: ub_belief_i[s] > 0} query_q[s]/ub_belief_i[s]) */
+PBVI_API int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double* d_ub_beliefs, const double* d_ub_values, int n_ub,
+                  const double* d_queries, int n_q, double* d_out, void* stream);
+
+/* ---- SSEA novelty score (src/pomdp.py:1682-1686) --------------------------------------------------
+ * d_out[j] = min_i || d_beliefs[i] - d_candidates[j] ||_2 */
+PBVI_API int pbvi_min_l2_distance(pbvi_model* m, const double* d_beliefs, int nB, const double* d_candidates, int nC, double* d_out,
+                         void* stream);
+
+/* ---- instrumentation: flops actually issued by the last pbvi_backup_select / pbvi_max_values score launch, its grid size
+ * and kernel launch count of the last call (for bench.py's roofline / gpu_launches accounting) */
+PBVI_API int pbvi_last_stats(const pbvi_model* m, double* executed_flops, double* dense_flops, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBVI_B200_H */

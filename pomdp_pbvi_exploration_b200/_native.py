@@ -1,0 +1,283 @@
+"""
+ctypes binding of libpbvi_b200.so (C ABI in include/pbvi_b200.h) -- the only compute path of the package.
+
+PyTorch is used for device memory, streams and (in `parallel.py`) torch.distributed; every kernel is the
+library's.  There is no CPU fallback: importing this module without the built library, or creating a
+`DeviceModel` without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpbvi_b200.so')
+
+PBVI_OK, PBVI_ERR_BAD_ARG, PBVI_ERR_CUDA, PBVI_ERR_OOM, PBVI_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+
+# name -> argtypes; every function returns int except pbvi_last_error.  Kept in one table so that the CPU test-suite can
+# check the library exports exactly what include/pbvi_b200.h declares.
+_P = c_void_p
+SIGNATURES = {
+    'pbvi_version': [],
+    'pbvi_model_create': [c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, POINTER(c_void_p)],
+    'pbvi_model_destroy': [_P],
+    'pbvi_model_dims': [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)],
+    'pbvi_backup_select': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P],
+    'pbvi_backup_assemble': [_P, _P, c_int, c_double, _P, _P, c_int, _P, _P],
+    'pbvi_backup': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P, _P],
+    'pbvi_backup_host': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P],
+    'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
+    'pbvi_belief_update': [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    'pbvi_belief_successors': [_P, _P, c_int, c_int, _P, _P, _P],
+    'pbvi_observation_probabilities': [_P, _P, c_int, _P, _P],
+    'pbvi_row_hash': [_P, _P, c_int, c_int, _P, _P],
+    'pbvi_rows_equal': [_P, _P, _P, _P, _P, c_int, c_int, _P, _P],
+    'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
+    'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
+    'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
+    'pbvi_min_l2_distance': [_P, _P, c_int, _P, c_int, _P, _P],
+    'pbvi_last_stats': [_P, POINTER(c_double), POINTER(c_double), POINTER(c_int)],
+}
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads the engine.  Raises (never falls back) when it has not been built: run `python -m pomdp_pbvi_exploration_b200.build`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m pomdp_pbvi_exploration_b200.build` '
+                           '(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.pbvi_last_error.argtypes = []
+    lib.pbvi_last_error.restype = c_char_p
+    _lib = lib
+    return lib
+
+
+class PBVIError(RuntimeError):
+    pass
+
+
+def _check(rc: int) -> None:
+    if rc == PBVI_OK:
+        return
+    msg = load_library().pbvi_last_error().decode(errors='replace')
+    if rc == PBVI_ERR_OOM:
+        raise MemoryError(msg)          # the solve loop's `except MemoryError` keeps working (reference src/pomdp.py:2399)
+    if rc == PBVI_ERR_BAD_ARG:
+        raise ValueError(msg)
+    raise PBVIError(f'libpbvi_b200 error {rc}: {msg}')
+
+
+def _ptr(t) -> int:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _f64(t: torch.Tensor, device) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64))
+    return t.to(device=device, dtype=torch.float64).contiguous()
+
+
+def _i32(t, device) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.ascontiguousarray(t))
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class DeviceModel:
+    """
+    Device-resident model tables + scratch (one `pbvi_model` handle).  Inputs are the reference's host tensors:
+    reachable_states [S,A,R] int, reachable_probabilities [S,A,R], RTO [S,A,O,R], expected_rewards_table [S,A]
+    (reference Model.gpu_model, src/mdp.py:533-560).  All methods take / return CUDA float64 / int32 torch tensors on
+    `self.device` and enqueue on the current torch stream.
+    """
+
+    def __init__(self, reach: np.ndarray, probs: np.ndarray | None, rto: np.ndarray, rbar: np.ndarray, device: int | None = None):
+        self._h = None
+        self._lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device: the PBVI B200 engine has no CPU path')
+        if device is None:
+            device = torch.cuda.current_device()
+        S, A, R = reach.shape
+        O = rto.shape[2]
+        assert rto.shape == (S, A, O, R) and rbar.shape == (S, A)
+        reach64 = np.ascontiguousarray(reach, dtype=np.int64)
+        rto64 = np.ascontiguousarray(rto, dtype=np.float64)
+        rbar64 = np.ascontiguousarray(rbar, dtype=np.float64)
+        probs64 = None if probs is None else np.ascontiguousarray(probs, dtype=np.float64)
+        h = c_void_p()
+        _check(self._lib.pbvi_model_create(S, A, O, R, reach64.ctypes.data, None if probs64 is None else probs64.ctypes.data,
+                                           rto64.ctypes.data, rbar64.ctypes.data, int(device), byref(h)))
+        self._h = h
+        self.S, self.A, self.O, self.R = S, A, O, R
+        self.device = torch.device('cuda', int(device))
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.pbvi_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _beliefs(self, beliefs) -> torch.Tensor:
+        b = _f64(beliefs, self.device)
+        if b.dim() == 1:
+            b = b[None, :]
+        assert b.dim() == 2 and b.shape[1] == self.S, f'beliefs must be [n, {self.S}], got {tuple(b.shape)}'
+        return b
+
+    def backup_select(self, beliefs, alphas, gamma: float, want_value: bool = True):
+        """v*[b,a,o], value[b,a], a*[b] (reference src/pomdp.py:1485-1505)."""
+        b, al = self._beliefs(beliefs), self._beliefs(alphas)
+        nB, nV = b.shape[0], al.shape[0]
+        vstar = torch.empty((nB, self.A, self.O), dtype=torch.int32, device=self.device)
+        value = torch.empty((nB, self.A), dtype=torch.float64, device=self.device) if want_value else None
+        astar = torch.empty((nB,), dtype=torch.int32, device=self.device)
+        _check(self._lib.pbvi_backup_select(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(vstar), _ptr(value), _ptr(astar),
+                                            self._stream))
+        return vstar, value, astar
+
+    def backup_assemble(self, alphas, gamma: float, actions, vsel) -> torch.Tensor:
+        """alpha_a rows for (action, v*[O]) tuples (reference src/pomdp.py:1497-1506)."""
+        al = self._beliefs(alphas)
+        act, vs = _i32(actions, self.device), _i32(vsel, self.device)
+        n = act.shape[0]
+        assert vs.shape == (n, self.O)
+        out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_backup_assemble(self._h, _ptr(al), al.shape[0], float(gamma), _ptr(act), _ptr(vs), n, _ptr(out), self._stream))
+        return out
+
+    def backup(self, beliefs, alphas, gamma: float):
+        """select + assemble for every belief, no dedup: (alpha [nB,S], action [nB], v* [nB,A,O], value [nB,A])."""
+        b, al = self._beliefs(beliefs), self._beliefs(alphas)
+        nB, nV = b.shape[0], al.shape[0]
+        out = torch.empty((nB, self.S), dtype=torch.float64, device=self.device)
+        act = torch.empty((nB,), dtype=torch.int32, device=self.device)
+        vstar = torch.empty((nB, self.A, self.O), dtype=torch.int32, device=self.device)
+        value = torch.empty((nB, self.A), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_backup(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(out), _ptr(act), _ptr(vstar), _ptr(value),
+                                     self._stream))
+        return out, act, vstar, value
+
+    def backup_host(self, beliefs: np.ndarray, alphas: np.ndarray, gamma: float, out_alpha: np.ndarray | None = None,
+                    out_action: np.ndarray | None = None):
+        """Host-buffer entry point (copies inside): returns (alpha [nB,S] float64, action [nB] int32) NumPy arrays."""
+        b = np.ascontiguousarray(beliefs, dtype=np.float64)
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        nB, nV = b.shape[0], al.shape[0]
+        if out_alpha is None:
+            out_alpha = np.empty((nB, self.S), dtype=np.float64)
+        if out_action is None:
+            out_action = np.empty((nB,), dtype=np.int32)
+        _check(self._lib.pbvi_backup_host(self._h, b.ctypes.data, nB, al.ctypes.data, nV, float(gamma), out_alpha.ctypes.data,
+                                          out_action.ctypes.data, self._stream))
+        return out_alpha, out_action
+
+    def max_values(self, beliefs, alphas):
+        """(max_v b.alpha_v, first argmax) -- reference src/pomdp.py:2165, 1639, 1735."""
+        b, al = self._beliefs(beliefs), self._beliefs(alphas)
+        nB = b.shape[0]
+        mx = torch.empty((nB,), dtype=torch.float64, device=self.device)
+        arg = torch.empty((nB,), dtype=torch.int32, device=self.device)
+        _check(self._lib.pbvi_max_values(self._h, _ptr(b), nB, _ptr(al), al.shape[0], _ptr(mx), _ptr(arg), self._stream))
+        return mx, arg
+
+    def belief_update(self, beliefs, actions, observations, normalise: bool = True):
+        """Row-wise Belief.update (reference src/pomdp.py:382-421): returns (b' [n,S], mass [n])."""
+        b = self._beliefs(beliefs)
+        a, o = _i32(actions, self.device), _i32(observations, self.device)
+        n = b.shape[0]
+        assert a.shape == (n,) and o.shape == (n,)
+        out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
+        norm = torch.empty((n,), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_belief_update(self._h, _ptr(b), _ptr(a), _ptr(o), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
+        return out, norm
+
+    def belief_successors(self, beliefs, normalise: bool = True):
+        """All (a,o) successors: (succ [n,A,O,S], mass [n,A,O]); NaN rows for impossible observations when normalised."""
+        b = self._beliefs(beliefs)
+        n = b.shape[0]
+        out = torch.empty((n, self.A, self.O, self.S), dtype=torch.float64, device=self.device)
+        norm = torch.empty((n, self.A, self.O), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_belief_successors(self._h, _ptr(b), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
+        return out, norm
+
+    def observation_probabilities(self, beliefs) -> torch.Tensor:
+        b = self._beliefs(beliefs)
+        out = torch.empty((b.shape[0], self.A, self.O), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_observation_probabilities(self._h, _ptr(b), b.shape[0], _ptr(out), self._stream))
+        return out
+
+    def row_hash(self, rows: torch.Tensor) -> torch.Tensor:
+        """128-bit hash of the raw bytes of each float64 row, as int64 [n,2]."""
+        r = _f64(rows, self.device)
+        out = torch.empty((r.shape[0], 2), dtype=torch.int64, device=self.device)
+        _check(self._lib.pbvi_row_hash(self._h, _ptr(r), r.shape[0], r.shape[1], _ptr(out), self._stream))
+        return out
+
+    def rows_equal(self, rows_a, ia, rows_b, ib) -> torch.Tensor:
+        ra, rb = _f64(rows_a, self.device), _f64(rows_b, self.device)
+        ia, ib = _i32(ia, self.device), _i32(ib, self.device)
+        assert ra.shape[1] == rb.shape[1] and ia.shape == ib.shape
+        flags = torch.empty((ia.shape[0],), dtype=torch.int32, device=self.device)
+        _check(self._lib.pbvi_rows_equal(self._h, _ptr(ra), _ptr(ia), _ptr(rb), _ptr(ib), ia.shape[0], ra.shape[1], _ptr(flags), self._stream))
+        return flags
+
+    def vi_sweep(self, vopt, gamma: float):
+        v = _f64(vopt, self.device)
+        assert v.shape == (self.S,)
+        alpha = torch.empty((self.A, self.S), dtype=torch.float64, device=self.device)
+        vnew = torch.empty((self.S,), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_vi_sweep(self._h, _ptr(v), float(gamma), _ptr(alpha), _ptr(vnew), self._stream))
+        return alpha, vnew
+
+    def prune_dominated(self, alphas) -> torch.Tensor:
+        al = self._beliefs(alphas)
+        keep = torch.empty((al.shape[0],), dtype=torch.int32, device=self.device)
+        _check(self._lib.pbvi_prune_dominated(self._h, _ptr(al), al.shape[0], _ptr(keep), self._stream))
+        return keep
+
+    def sawtooth(self, corner, ub_beliefs, ub_values, queries) -> torch.Tensor:
+        c, q = _f64(corner, self.device), self._beliefs(queries)
+        ubb = _f64(ub_beliefs, self.device).reshape(-1, self.S)
+        ubv = _f64(ub_values, self.device).reshape(-1)
+        out = torch.empty((q.shape[0],), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_sawtooth(self._h, _ptr(c), _ptr(ubb) if ubb.shape[0] else None, _ptr(ubv) if ubb.shape[0] else None,
+                                       ubb.shape[0], _ptr(q), q.shape[0], _ptr(out), self._stream))
+        return out
+
+    def min_l2_distance(self, beliefs, candidates) -> torch.Tensor:
+        b, c = self._beliefs(beliefs), self._beliefs(candidates)
+        out = torch.empty((c.shape[0],), dtype=torch.float64, device=self.device)
+        _check(self._lib.pbvi_min_l2_distance(self._h, _ptr(b), b.shape[0], _ptr(c), c.shape[0], _ptr(out), self._stream))
+        return out
+
+    def last_stats(self) -> dict:
+        e, d, n = c_double(), c_double(), c_int()
+        _check(self._lib.pbvi_last_stats(self._h, byref(e), byref(d), byref(n)))
+        return dict(executed_flops=e.value, dense_flops=d.value, launches=n.value)

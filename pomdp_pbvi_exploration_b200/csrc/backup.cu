@@ -1,0 +1,428 @@
+// Point-based backup (reference PBVI_Solver.backup, src/pomdp.py:1447-1524) and max_v b.alpha_v
+// (compute_change src/pomdp.py:2165-2167) on sm_100a.  Gamma[a,o,v,s] is never materialised for
+// reachable_state_count == 1 models; see score_kernel.cuh for the dominant kernel.
+//
+// Pipeline of pbvi_backup_select:
+//   transpose_kernel          alphas [V][S] -> alphaT [S][Vp]          (so a gathered successor row is one coalesced line)
+//   belief_mask_kernel        4-bit row-group occupancy of every (belief tile, K chunk)
+//   build_chunk_lists_kernel  per (tile, a, o): ordered list of chunks live in both the beliefs and RTO[a][o]
+//   (R > 1) gamma_project_kernel  GammaT[a,o][s][v] = sum_r RTO * alphaT[reach]   (HBM-bound gather)
+//   score_kernel              block-sparse DMMA + fused first-index argmax over v
+//   combine_tiles_kernel      argmax across the alpha tiles (ascending, strict >)
+//   backup_value_kernel       value[b][a] = b . (Rbar[:,a] + sum_o Gamma[a,o,v*]) in the reference's operation order
+//   first_argmax_kernel       a*[b]
+// pbvi_backup_assemble:
+//   assemble_kernel           alpha_a rows for (action, v*[O]) tuples, reference operation order, no FMA contraction
+#include <algorithm>
+
+#include "score_kernel.cuh"
+
+namespace pbvi {
+
+static_assert(KC == 16 && RG == 32 && BM == 128, "belief_mask_kernel assumes 16-state chunks and 4 row groups of 32");
+
+// ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int v0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int v = v0 + ty + j * 8, s = s0 + tx;
+        tile[ty + j * 8][tx] = (v < V && s < S) ? in[(size_t)v * S + s] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int s = s0 + ty + j * 8, v = v0 + tx;
+        if (s < S && v < Vp) out[(size_t)s * Vp + v] = tile[tx][ty + j * 8];
+    }
+}
+
+int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st) {
+    dim3 grid(ceil_div(Vp, 32), ceil_div(m->S, 32));
+    transpose_kernel<<<grid, 256, 0, st>>>(d_alphas, nV, m->S, Vp, d_alphaT);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+// ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c ---------------------
+__global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
+                                                          uint8_t* __restrict__ bits) {
+    __shared__ unsigned smask[NRG];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int cb = blockIdx.x, mt = blockIdx.y;
+    if (tid < NRG) smask[tid] = 0u;
+    __syncthreads();
+    unsigned mask = 0u;
+    for (int rr = 0; rr < 16; rr++) {
+        const int row = mt * BM + w * 16 + rr;
+        if (row >= nB) break;
+        const double* brow = beliefs + (size_t)row * S;
+#pragma unroll 4
+        for (int j = 0; j < 16; j++) {
+            const int s = cb * 512 + j * 32 + lane;
+            const bool nz = (s < S) && (brow[s] != 0.0);
+            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            if (bal & 0xFFFFu) mask |= 1u << (2 * j);
+            if (bal >> 16) mask |= 1u << (2 * j + 1);
+        }
+    }
+    if (lane == 0 && mask) atomicOr(&smask[w >> 1], mask);
+    __syncthreads();
+    if (tid < 32) {
+        const int c = cb * 32 + tid;
+        if (c < nChunks) {
+            unsigned b = 0u;
+#pragma unroll
+            for (int g = 0; g < NRG; g++) b |= ((smask[g] >> tid) & 1u) << g;
+            bits[(size_t)mt * nChunks + c] = (uint8_t)b;
+        }
+    }
+}
+
+// ---- ordered live-chunk list of every (tile, z); one warp per list ------------------------------------------------
+__global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ zMask,
+                                                               int nChunks, int nZ, uint32_t* __restrict__ lists,
+                                                               int32_t* __restrict__ counts) {
+    const int z = blockIdx.x, mt = blockIdx.y, lane = threadIdx.x;
+    uint32_t* list = lists + ((size_t)mt * nZ + z) * nChunks;
+    int base = 0;
+    for (int c0 = 0; c0 < nChunks; c0 += 32) {
+        const int c = c0 + lane;
+        unsigned b = 0u;
+        if (c < nChunks) {
+            b = bits[(size_t)mt * nChunks + c];
+            if (zMask && !zMask[(size_t)z * nChunks + c]) b = 0u;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, b != 0u);
+        if (b) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c | (b << 24);
+        base += __popc(bal);
+    }
+    if (lane == 0) counts[mt * nZ + z] = base;
+}
+
+// ---- argmax across alpha tiles: ascending tile order, strict > keeps the lowest index on ties ----------------------
+__global__ void __launch_bounds__(256) combine_tiles_kernel(const double* __restrict__ pval, const int32_t* __restrict__ pidx, int nNt,
+                                                            size_t n, double* __restrict__ outVal, int32_t* __restrict__ outIdx) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double best = pval[i];
+    int idx = pidx[i];
+    for (int t = 1; t < nNt; t++) {
+        const double v = pval[(size_t)t * n + i];
+        if (v > best) { best = v; idx = pidx[(size_t)t * n + i]; }
+    }
+    if (outVal) outVal[i] = best;
+    if (outIdx) outIdx[i] = idx;
+}
+
+// ---- R > 1: GammaT[j][s][v] = sum_r RTO[z][s*R+r] * alphaT[reach[a][s*R+r]][v] for z = zOrder[zBegin + j] ----------
+__global__ void __launch_bounds__(256) gamma_project_kernel(const double* __restrict__ alphaT, const int32_t* __restrict__ reachK,
+                                                            const double* __restrict__ rtoK, const int32_t* __restrict__ zOrder,
+                                                            int zBegin, int S, int R, int O, int Vp, double* __restrict__ out) {
+    const int j = blockIdx.y, z = zOrder[zBegin + j], a = z / O;
+    const int s0 = blockIdx.x * 8;
+    const int32_t* reach = reachK + (size_t)a * S * R;
+    const double* rto = rtoK + (size_t)z * S * R;
+    for (int idx = threadIdx.x; idx < 8 * Vp; idx += 256) {
+        const int sl = idx / Vp, v = idx - sl * Vp, s = s0 + sl;
+        if (s >= S) break;
+        double acc = 0.0;
+        for (int r = 0; r < R; r++) {
+            const size_t k = (size_t)s * R + r;
+            const double w = rto[k];
+            if (w != 0.0) acc += w * alphaT[(size_t)reach[k] * Vp + v];
+        }
+        out[((size_t)j * S + s) * Vp + v] = acc;
+    }
+}
+
+// fixed-shape block sum (256 threads): shuffle tree inside each warp, then warp 0 lane 0 adds the 8 partials in order
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += sh[w];
+    }
+    return tot;   // valid on thread 0
+}
+
+// alpha_a[s] of the reference for one (action, v*[O]) tuple: Rbar[s,a] + ((G_0 + G_1) + ...),
+// G_o = gamma * sum_r RTO[s,a,o,r] * alpha[v_o][reach[s,a,r]]  (src/pomdp.py:1489-1502), no FMA contraction.
+__device__ __forceinline__ double alpha_a_entry(const double* __restrict__ alphas, int S, int R, int O, const int* vsel,
+                                                const int32_t* __restrict__ reach, const double* __restrict__ rtoA,
+                                                const double* __restrict__ rbarA, double gamma, int s) {
+    double tot = 0.0;
+    for (int o = 0; o < O; o++) {
+        const double* arow = alphas + (size_t)vsel[o] * S;
+        const double* rto = rtoA + (size_t)o * S * R;
+        double inner = 0.0;
+        for (int r = 0; r < R; r++) {
+            const size_t k = (size_t)s * R + r;
+            const double prod = __dmul_rn(rto[k], arow[reach[k]]);
+            inner = (r == 0) ? prod : __dadd_rn(inner, prod);
+        }
+        const double term = __dmul_rn(gamma, inner);
+        tot = (o == 0) ? term : __dadd_rn(tot, term);
+    }
+    return __dadd_rn(rbarA[s], tot);
+}
+
+// ---- value[b][a] = sum_s b[s] * alpha_a[b,a,s]; block per (a, b); only the support of b is visited ----------------
+__global__ void __launch_bounds__(256) backup_value_kernel(const double* __restrict__ beliefs, const double* __restrict__ alphas,
+                                                           const int32_t* __restrict__ vstar, const int32_t* __restrict__ reachK,
+                                                           const double* __restrict__ rtoK, const double* __restrict__ rbarT,
+                                                           double gamma, int S, int R, int A, int O, double* __restrict__ value) {
+    extern __shared__ int s_vsel[];
+    __shared__ double sh[8];
+    const int a = blockIdx.x, b = blockIdx.y;
+    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vstar[((size_t)b * A + a) * O + o];
+    __syncthreads();
+    const double* brow = beliefs + (size_t)b * S;
+    const int32_t* reach = reachK + (size_t)a * S * R;
+    const double* rtoA = rtoK + (size_t)a * O * S * R;
+    const double* rbarA = rbarT + (size_t)a * S;
+    double part = 0.0;
+    for (int s = threadIdx.x; s < S; s += 256) {
+        const double bs = brow[s];
+        if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s), part);
+    }
+    const double tot = block_sum_256(part, sh);
+    if (threadIdx.x == 0) value[(size_t)b * A + a] = tot;
+}
+
+// ---- first index of the maximum along the last axis (np.argmax: a NaN counts as the maximum) ----------------------
+__global__ void __launch_bounds__(256) first_argmax_kernel(const double* __restrict__ value, int n, int A, int32_t* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    double best = value[(size_t)b * A];
+    int idx = 0;
+    bool isn = best != best;
+    for (int a = 1; a < A && !isn; a++) {
+        const double v = value[(size_t)b * A + a];
+        if (v != v) { idx = a; isn = true; }
+        else if (v > best) { best = v; idx = a; }
+    }
+    out[b] = idx;
+}
+
+// ---- out[i][s] = alpha_a entry of tuple i; vsel_i = vsel + i*vselStride + (perAction ? action_i*O : 0) ---------------
+__global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict__ alphas, const int32_t* __restrict__ actions,
+                                                       const int32_t* __restrict__ vsel, size_t vselStride, int perAction,
+                                                       const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
+                                                       const double* __restrict__ rbarT, double gamma, int S, int R, int O,
+                                                       double* __restrict__ out) {
+    extern __shared__ int s_vsel[];
+    const int i = blockIdx.y, a = actions[i];
+    const int32_t* vs = vsel + (size_t)i * vselStride + (perAction ? (size_t)a * O : 0);
+    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vs[o];
+    __syncthreads();
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= S) return;
+    out[(size_t)i * S + s] = alpha_a_entry(alphas, S, R, O, s_vsel, reachK + (size_t)a * S * R, rtoK + (size_t)a * O * S * R,
+                                           rbarT + (size_t)a * S, gamma, s);
+}
+
+// =====================================================================================================================
+static int launch_score(pbvi_model* m, bool gather, const ScoreParams& p, int nNt, int nMt, int nZ, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        PBVI_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
+        PBVI_CUDA(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
+        configured = true;
+    }
+    dim3 grid(nNt, nMt, nZ);
+    if (gather) score_kernel<true><<<grid, SCORE_THREADS, SCORE_SMEM, st>>>(p);
+    else score_kernel<false><<<grid, SCORE_THREADS, SCORE_SMEM, st>>>(p);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+// beliefs x (alphaT or Gamma) with fused argmax.  nZ == 0: plain max_v b.alpha_v (one z, no RTO mask).
+// outVal/outIdx [nB][max(nZ,1)].
+static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, bool backup,
+                        double* outVal, int32_t* outIdx, cudaStream_t st) {
+    const int S = m->S, R = m->R, nC = m->nChunks;
+    const int nZ = backup ? m->nZ : 1;
+    const int Vp = ceil_div(nV, BN) * BN, nNt = Vp / BN, nMt = ceil_div(nB, BM);
+    PBVI_REQUIRE(nMt <= 65535, "too many beliefs in one call (limit 65535 * 128)");
+    PBVI_REQUIRE(nZ <= 65535, "too many (action, observation) pairs");
+
+    PBVI_TAKE(alphaT, double, (size_t)S * Vp);
+    PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
+
+    PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
+    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits);
+    m->last_launches++;
+    PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nC);
+    PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ);
+    build_chunk_lists_kernel<<<dim3(nZ, nMt), 32, 0, st>>>(bits, backup ? m->zMask : nullptr, nC, nZ, lists, counts);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+
+    PBVI_TAKE(pval, double, (size_t)nNt * nB * nZ);
+    PBVI_TAKE(pidx, int32_t, (size_t)nNt * nB * nZ);
+    PBVI_CUDA(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), st));
+    m->last_exec_scale = 2.0 * RG * BN * KC;
+    m->last_dense_flops = 2.0 * nB * (double)nV * nZ * S;
+
+    ScoreParams p{};
+    p.beliefs = d_beliefs; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
+    p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nZ = nZ; p.O = m->O;
+    if (!backup) {
+        p.bmat = alphaT; p.zStrideB = 0; p.zOrder = nullptr;
+        PBVI_TRY(launch_score(m, false, p, nNt, nMt, 1, st));
+    } else if (R == 1) {
+        p.bmat = alphaT; p.zStrideB = 0; p.zOrder = m->zOrder; p.reachP = m->reachP; p.rtoP = m->rtoP;
+        PBVI_TRY(launch_score(m, true, p, nNt, nMt, nZ, st));
+    } else {
+        // Gamma projection in groups of z bounded by ~8 GB of scratch
+        const size_t perZ = (size_t)S * Vp * sizeof(double);
+        const int zGroup = (int)std::max<size_t>(1, std::min<size_t>(nZ, (size_t(8) << 30) / perZ));
+        PBVI_TAKE(gammaT, double, (size_t)zGroup * S * Vp);
+        for (int z0 = 0; z0 < nZ; z0 += zGroup) {
+            const int nz = std::min(zGroup, nZ - z0);
+            gamma_project_kernel<<<dim3(ceil_div(S, 8), nz), 256, 0, st>>>(alphaT, m->reachK, m->rtoK, m->zOrder, z0, S, R, m->O, Vp, gammaT);
+            m->last_launches++;
+            p.bmat = gammaT; p.zStrideB = (size_t)S * Vp; p.zOrder = m->zOrder + z0;
+            PBVI_TRY(launch_score(m, false, p, nNt, nMt, nz, st));
+        }
+    }
+    const size_t n = (size_t)nB * nZ;
+    combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt, n, outVal, outIdx);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+static int check_backup_args(const pbvi_model* m, const void* beliefs, int nB, const void* alphas, int nV, double gamma) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(nB >= 0 && nV > 0, "need nB >= 0 beliefs and nV > 0 alpha vectors");
+    PBVI_REQUIRE(nB == 0 || beliefs != nullptr, "beliefs pointer is NULL");
+    PBVI_REQUIRE(alphas != nullptr, "alphas pointer is NULL");
+    PBVI_REQUIRE(gamma > 0.0, "gamma must be positive (the score kernel drops it as an argmax-invariant scale)");
+    return PBVI_OK;
+}
+
+static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                       int32_t* d_vstar, double* d_value, int32_t* d_astar, cudaStream_t st) {
+    if (nB == 0) return PBVI_OK;
+    PBVI_TRY(score_argmax(m, d_beliefs, nB, d_alphas, nV, true, nullptr, d_vstar, st));
+    if (!d_value && !d_astar) return PBVI_OK;
+    if (!d_value) {
+        d_value = m->arena.take<double>((size_t)nB * m->A);
+        if (!d_value) return PBVI_ERR_OOM;
+    }
+    PBVI_REQUIRE(nB <= 65535 * 128, "too many beliefs in one call");
+    // grid.y is limited to 65535: walk the beliefs in slabs
+    for (int b0 = 0; b0 < nB; b0 += 65535) {
+        const int nb = std::min(65535, nB - b0);
+        backup_value_kernel<<<dim3(m->A, nb), 256, m->O * sizeof(int), st>>>(
+            d_beliefs + (size_t)b0 * m->S, d_alphas, d_vstar + (size_t)b0 * m->nZ, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->R,
+            m->A, m->O, d_value + (size_t)b0 * m->A);
+        m->last_launches++;
+    }
+    if (d_astar) {
+        first_argmax_kernel<<<ceil_div(nB, 256), 256, 0, st>>>(d_value, nB, m->A, d_astar);
+        m->last_launches++;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+static int assemble_impl(pbvi_model* m, const double* d_alphas, double gamma, const int32_t* d_actions, const int32_t* d_vsel,
+                         size_t vselStride, int perAction, int n, double* d_out, cudaStream_t st) {
+    for (int i0 = 0; i0 < n; i0 += 65535) {
+        const int ni = std::min(65535, n - i0);
+        assemble_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, m->O * sizeof(int), st>>>(
+            d_alphas, d_actions + i0, d_vsel + (size_t)i0 * vselStride, vselStride, perAction, m->reachK, m->rtoK, m->rbarT, gamma,
+            m->S, m->R, m->O, d_out + (size_t)i0 * m->S);
+        m->last_launches++;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+}  // namespace pbvi
+
+using namespace pbvi;
+
+extern "C" int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                                  int32_t* d_vstar, double* d_value, int32_t* d_astar, void* stream) {
+    PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, gamma));
+    PBVI_REQUIRE(nB == 0 || d_vstar != nullptr, "v_star output is required");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    return select_impl(m, d_beliefs, nB, d_alphas, nV, gamma, d_vstar, d_value, d_astar, (cudaStream_t)stream);
+}
+
+extern "C" int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int nV, double gamma, const int32_t* d_actions,
+                                    const int32_t* d_vsel, int n, double* d_out, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0 && nV > 0, "need n >= 0 tuples and nV > 0 alpha vectors");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_alphas && d_actions && d_vsel && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    return assemble_impl(m, d_alphas, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                           double* d_out_alpha, int32_t* d_out_action, int32_t* d_out_vstar, double* d_out_value, void* stream) {
+    PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, gamma));
+    if (nB == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_out_alpha && d_out_action, "alpha / action outputs are required");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_out_vstar) {
+        d_out_vstar = m->arena.take<int32_t>((size_t)nB * m->nZ);
+        if (!d_out_vstar) return PBVI_ERR_OOM;
+    }
+    PBVI_TRY(select_impl(m, d_beliefs, nB, d_alphas, nV, gamma, d_out_vstar, d_out_value, d_out_action, st));
+    return assemble_impl(m, d_alphas, gamma, d_out_action, d_out_vstar, (size_t)m->nZ, 1, nB, d_out_alpha, st);
+}
+
+extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
+                                double* h_out_alpha, int32_t* h_out_action, void* stream) {
+    PBVI_TRY(check_backup_args(m, h_beliefs, nB, h_alphas, nV, gamma));
+    if (nB == 0) return PBVI_OK;
+    PBVI_REQUIRE(h_out_alpha && h_out_action, "alpha / action outputs are required");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t S = m->S;
+    PBVI_TAKE(d_b, double, (size_t)nB * S);
+    PBVI_TAKE(d_a, double, (size_t)nV * S);
+    PBVI_TAKE(d_out, double, (size_t)nB * S);
+    PBVI_TAKE(d_act, int32_t, (size_t)nB);
+    PBVI_TAKE(d_vs, int32_t, (size_t)nB * m->nZ);
+    PBVI_CUDA(cudaMemcpyAsync(d_b, h_beliefs, (size_t)nB * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    PBVI_CUDA(cudaMemcpyAsync(d_a, h_alphas, (size_t)nV * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    PBVI_TRY(select_impl(m, d_b, nB, d_a, nV, gamma, d_vs, nullptr, d_act, st));
+    PBVI_TRY(assemble_impl(m, d_a, gamma, d_act, d_vs, (size_t)m->nZ, 1, nB, d_out, st));
+    PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, d_out, (size_t)nB * S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaMemcpyAsync(h_out_action, d_act, (size_t)nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_max_values(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max,
+                               int32_t* d_arg, void* stream) {
+    PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, 1.0));
+    if (nB == 0) return PBVI_OK;
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    return score_argmax(m, d_beliefs, nB, d_alphas, nV, false, d_max, d_arg, (cudaStream_t)stream);
+}

@@ -1,0 +1,193 @@
+// Belief update and observation likelihoods (reference Belief.update, src/pomdp.py:382-421; batched twin :1415-1419;
+// P(o|b,a) einsum at :1814 / :2046 / :1751).  HBM-bound gather kernels.
+//
+// Bit-parity with the reference: np.bincount accumulates the weights of one bin in ascending flattened (s,r) order, so
+// a CSR over landing states with ascending sources reproduces it exactly; the normaliser is np.sum's float64 pairwise
+// summation, reproduced from the precomputed combine tree of the model handle.
+#include "pbvi_common.cuh"
+
+namespace pbvi {
+
+// out[i][s'] = sum over predecessors k of s' under action a_i (ascending k) of RTO[a_i][o_i][k] * belief_i[k / R]
+__global__ void __launch_bounds__(256) belief_project_kernel(const double* __restrict__ beliefs, const int32_t* __restrict__ actions,
+                                                             const int32_t* __restrict__ observations, size_t beliefStride,
+                                                             const int32_t* __restrict__ predPtr, const int32_t* __restrict__ predK,
+                                                             const double* __restrict__ rtoK, int S, int R, int O,
+                                                             double* __restrict__ out) {
+    const int i = blockIdx.y;
+    const int sp = blockIdx.x * 256 + threadIdx.x;
+    if (sp >= S) return;
+    const int a = actions[i], o = observations[i];
+    const size_t K = (size_t)S * R;
+    const int32_t* ptr = predPtr + (size_t)a * (S + 1);
+    const int32_t* pk = predK + (size_t)a * K;
+    const double* rto = rtoK + ((size_t)a * O + o) * K;
+    const double* b = beliefs + (size_t)i * beliefStride;
+    double acc = 0.0;   // bincount starts every bin at +0.0 and adds in order
+    const int end = ptr[sp + 1];
+    for (int j = ptr[sp]; j < end; j++) {
+        const int k = pk[j];
+        acc = __dadd_rn(acc, __dmul_rn(rto[k], b[R == 1 ? k : k / R]));
+    }
+    out[(size_t)i * S + sp] = acc;
+}
+
+// NumPy pairwise sum of each row (block per row), then optional in-place division by it
+__global__ void __launch_bounds__(256) pairwise_normalise_kernel(double* __restrict__ rows, int S, const int2* __restrict__ leaves,
+                                                                 int nLeaves, const int2* __restrict__ nodes, int nNodes,
+                                                                 int normalise, double* __restrict__ norm) {
+    extern __shared__ double s_sum[];   // [nLeaves] leaf sums, then [nNodes] node sums
+    __shared__ double s_total;
+    double* row = rows + (size_t)blockIdx.x * S;
+    for (int l = threadIdx.x; l < nLeaves; l += 256) {
+        const int off = leaves[l].x, n = leaves[l].y;
+        const double* a = row + off;
+        double res;
+        if (n < 8) {
+            res = 0.0;
+            for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+        } else {
+            double r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = a[j];
+            int i = 8;
+            for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+            }
+            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            for (; i < n; i++) res = __dadd_rn(res, a[i]);
+        }
+        s_sum[l] = res;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* nsum = s_sum + nLeaves;
+        for (int j = 0; j < nNodes; j++) {
+            const int l = nodes[j].x, r = nodes[j].y;
+            const double lv = l < 0 ? s_sum[~l] : nsum[l];
+            const double rv = r < 0 ? s_sum[~r] : nsum[r];
+            nsum[j] = __dadd_rn(lv, rv);
+        }
+        s_total = nNodes ? nsum[nNodes - 1] : s_sum[0];
+        if (norm) norm[blockIdx.x] = s_total;
+    }
+    __syncthreads();
+    if (normalise) {
+        const double tot = s_total;
+        for (int s = threadIdx.x; s < S; s += 256) row[s] = row[s] / tot;   // 0/0 = NaN for impossible observations, as in the reference
+    }
+}
+
+// out[i][a][o] = sum_k RTO[a][o][k] * belief_i[k / R]; block per (z, i)
+__global__ void __launch_bounds__(256) observation_probability_kernel(const double* __restrict__ beliefs, const double* __restrict__ rtoK,
+                                                                      int S, int R, int nZ, double* __restrict__ out) {
+    __shared__ double sh[8];
+    const int z = blockIdx.x, i = blockIdx.y;
+    const size_t K = (size_t)S * R;
+    const double* rto = rtoK + (size_t)z * K;
+    const double* b = beliefs + (size_t)i * S;
+    double part = 0.0;
+    for (int s = threadIdx.x; s < S; s += 256) {
+        const double bs = b[s];
+        if (bs != 0.0)
+            for (int r = 0; r < R; r++) part = fma(rto[(size_t)s * R + r], bs, part);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += sh[w];
+        out[(size_t)i * nZ + z] = tot;
+    }
+}
+
+}  // namespace pbvi
+
+using namespace pbvi;
+
+// belief_stride: doubles between consecutive source beliefs (S for one belief per (a,o) pair, 0 to update one belief n ways)
+static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t beliefStride, const int32_t* d_actions,
+                              const int32_t* d_observations, int n, int normalise, double* d_out, double* d_norm, cudaStream_t st) {
+    const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        PBVI_REQUIRE(smem <= 200 * 1024, "state space too large for the pairwise-sum kernel");
+        if (!configured) {
+            PBVI_CUDA(cudaFuncSetAttribute(pairwise_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+    }
+    for (int i0 = 0; i0 < n; i0 += 65535) {
+        const int ni = std::min(65535, n - i0);
+        double* out = d_out + (size_t)i0 * m->S;
+        belief_project_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, 0, st>>>(d_beliefs + (size_t)i0 * beliefStride, d_actions + i0,
+                                                                            d_observations + i0, beliefStride, m->predPtr, m->predK,
+                                                                            m->rtoK, m->S, m->R, m->O, out);
+        m->last_launches++;
+        if (normalise || d_norm) {
+            pairwise_normalise_kernel<<<ni, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
+                                                            d_norm ? d_norm + i0 : nullptr);
+            m->last_launches++;
+        }
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const int32_t* d_actions, const int32_t* d_observations,
+                                  int n, int normalise, double* d_out, double* d_norm, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_actions && d_observations && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    return belief_update_impl(m, d_beliefs, (size_t)m->S, d_actions, d_observations, n, normalise, d_out, d_norm, (cudaStream_t)stream);
+}
+
+extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm,
+                                      void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nZ = m->nZ;
+    // (a, o) index vectors for one belief, reused for every belief (stride-0 source)
+    std::vector<int32_t> ha(nZ), ho(nZ);
+    for (int z = 0; z < nZ; z++) { ha[z] = z / m->O; ho[z] = z % m->O; }
+    PBVI_TAKE(d_a, int32_t, (size_t)nZ);
+    PBVI_TAKE(d_o, int32_t, (size_t)nZ);
+    PBVI_CUDA(cudaMemcpyAsync(d_a, ha.data(), nZ * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PBVI_CUDA(cudaMemcpyAsync(d_o, ho.data(), nZ * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));   // ha / ho are stack-owned
+    for (int i = 0; i < n; i++)
+        PBVI_TRY(belief_update_impl(m, d_beliefs + (size_t)i * m->S, 0, d_a, d_o, nZ, normalise, d_out + (size_t)i * nZ * m->S,
+                                    d_norm ? d_norm + (size_t)i * nZ : nullptr, st));
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_observation_probabilities(pbvi_model* m, const double* d_beliefs, int n, double* d_out, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i0 = 0; i0 < n; i0 += 65535) {
+        const int ni = std::min(65535, n - i0);
+        observation_probability_kernel<<<dim3(m->nZ, ni), 256, 0, (cudaStream_t)stream>>>(d_beliefs + (size_t)i0 * m->S, m->rtoK, m->S, m->R,
+                                                                                        m->nZ, d_out + (size_t)i0 * m->nZ);
+        m->last_launches++;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}

@@ -1,0 +1,254 @@
+// Set semantics on raw bytes (reference src/mdp.py:668-669, 773-774; src/pomdp.py:581, 600), the MDP value-iteration
+// sweep (src/mdp.py:1507), pointwise-domination pruning (src/mdp.py:857-866), HSVI's sawtooth upper bound
+// (src/pomdp.py:887-895) and SSEA's novelty distance (src/pomdp.py:1682-1686).  All HBM-bound streaming kernels.
+#include <algorithm>
+
+#include "pbvi_common.cuh"
+
+namespace pbvi {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+// 128-bit hash of the raw 8-byte words of each row: position-salted mixes combined by wrapping addition (associative,
+// so any reduction shape gives the same value).  Block per row.
+__global__ void __launch_bounds__(256) row_hash_kernel(const uint64_t* __restrict__ rows, int rowLen, uint64_t* __restrict__ out) {
+    __shared__ uint64_t sh[2][8];
+    const uint64_t* row = rows + (size_t)blockIdx.x * rowLen;
+    uint64_t h0 = 0, h1 = 0;
+    for (int i = threadIdx.x; i < rowLen; i += 256) {
+        const uint64_t w = row[i];
+        h0 += mix64(w ^ (0x9e3779b97f4a7c15ull * (uint64_t)(i + 1)));
+        h1 += mix64((w + 0xd6e8feb86659fd93ull) ^ (0xc2b2ae3d27d4eb4full * (uint64_t)(i + 1)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        h0 += __shfl_down_sync(0xffffffffu, h0, off);
+        h1 += __shfl_down_sync(0xffffffffu, h1, off);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = h0; sh[1][threadIdx.x >> 5] = h1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += sh[0][w]; b += sh[1][w]; }
+        out[(size_t)blockIdx.x * 2] = mix64(a + (uint64_t)rowLen);
+        out[(size_t)blockIdx.x * 2 + 1] = mix64(b ^ (uint64_t)rowLen);
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_equal_kernel(const uint64_t* __restrict__ ra, const int32_t* __restrict__ ia,
+                                                         const uint64_t* __restrict__ rb, const int32_t* __restrict__ ib, int rowLen,
+                                                         int32_t* __restrict__ flags) {
+    const uint64_t* a = ra + (size_t)ia[blockIdx.x] * rowLen;
+    const uint64_t* b = rb + (size_t)ib[blockIdx.x] * rowLen;
+    int diff = 0;
+    for (int i = threadIdx.x; i < rowLen; i += 256) diff |= (a[i] != b[i]);
+    const int any = __syncthreads_or(diff);
+    if (threadIdx.x == 0) flags[blockIdx.x] = any ? 0 : 1;
+}
+
+// alpha[a][s] = Rbar[s,a] + gamma * sum_r P[s,a,r] * V*[reach[s,a,r]]; vopt_out[s] = max_a
+__global__ void __launch_bounds__(256) vi_sweep_kernel(const double* __restrict__ vopt, const int32_t* __restrict__ reachK,
+                                                       const double* __restrict__ probK, const double* __restrict__ rbarT, double gamma,
+                                                       int S, int R, int A, double* __restrict__ alphaOut, double* __restrict__ voptOut) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= S) return;
+    double best = -INFINITY;
+    for (int a = 0; a < A; a++) {
+        const size_t base = ((size_t)a * S + s) * R;
+        double inner = 0.0;
+        for (int r = 0; r < R; r++) {
+            const double prod = __dmul_rn(probK[base + r], vopt[reachK[base + r]]);
+            inner = (r == 0) ? prod : __dadd_rn(inner, prod);
+        }
+        const double v = __dadd_rn(rbarT[(size_t)a * S + s], __dmul_rn(gamma, inner));
+        if (alphaOut) alphaOut[(size_t)a * S + s] = v;
+        best = fmax(best, v);
+    }
+    if (voptOut) voptOut[s] = best;
+}
+
+// keep[i] = 1 iff exactly one vector (alpha_i itself, or none when it holds a NaN... the reference counts rows with
+// all(alpha_j >= alpha_i)) dominates alpha_i everywhere.  Block per i, early exit per j on the first losing coordinate block.
+__global__ void __launch_bounds__(256) prune_dominated_kernel(const double* __restrict__ alphas, int nV, int S, int32_t* __restrict__ keep) {
+    const int i = blockIdx.x;
+    const double* ai = alphas + (size_t)i * S;
+    int count = 0;
+    for (int j = 0; j < nV; j++) {
+        const double* aj = alphas + (size_t)j * S;
+        int dominated = 1;
+        for (int s0 = 0; s0 < S && dominated; s0 += 256 * 8) {
+            int ok = 1;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * 256 + threadIdx.x;
+                if (s < S && !(aj[s] >= ai[s])) ok = 0;
+            }
+            dominated = __syncthreads_and(ok);
+        }
+        count += dominated;
+    }
+    if (threadIdx.x == 0) keep[i] = (count == 1) ? 1 : 0;
+}
+
+// Sawtooth upper bound.  Block per query q:
+//   v0 = q . corner;  out = min(v0, min_i v0 + (ub_value_i - ub_belief_i . corner) * min_{s: ub_belief_i[s] > 0} q[s] / ub_belief_i[s])
+__global__ void __launch_bounds__(256) sawtooth_kernel(const double* __restrict__ corner, const double* __restrict__ ubB,
+                                                       const double* __restrict__ ubV, int nUb, const double* __restrict__ queries, int S,
+                                                       double* __restrict__ out) {
+    __shared__ double sh[8];
+    __shared__ double s_bc;
+    const double* q = queries + (size_t)blockIdx.x * S;
+    auto block_reduce = [&](double v, bool isMin) -> double {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double o = __shfl_down_sync(0xffffffffu, v, off);
+            v = isMin ? fmin(v, o) : v + o;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = sh[0];
+            for (int w = 1; w < 8; w++) t = isMin ? fmin(t, sh[w]) : t + sh[w];
+            s_bc = t;
+        }
+        __syncthreads();
+        return s_bc;
+    };
+    double part = 0.0;
+    for (int s = threadIdx.x; s < S; s += 256) part = fma(q[s], corner[s], part);
+    const double v0 = block_reduce(part, false);
+    double best = v0;
+    for (int i = 0; i < nUb; i++) {
+        const double* bi = ubB + (size_t)i * S;
+        double dotp = 0.0, ratio = INFINITY;
+        for (int s = threadIdx.x; s < S; s += 256) {
+            const double b = bi[s];
+            dotp = fma(b, corner[s], dotp);
+            if (b > 0.0) ratio = fmin(ratio, q[s] / b);
+        }
+        const double bc = block_reduce(dotp, false);
+        const double rmin = block_reduce(ratio, true);
+        best = fmin(best, v0 + (ubV[i] - bc) * rmin);
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = best;
+}
+
+// out[j] = min_i || beliefs[i] - candidates[j] ||_2; block per candidate
+__global__ void __launch_bounds__(256) min_l2_kernel(const double* __restrict__ beliefs, int nB, const double* __restrict__ cands, int S,
+                                                     double* __restrict__ out) {
+    __shared__ double sh[8];
+    __shared__ double s_bc;
+    const double* c = cands + (size_t)blockIdx.x * S;
+    double best = INFINITY;
+    bool sawNan = false;
+    for (int i = 0; i < nB; i++) {
+        const double* b = beliefs + (size_t)i * S;
+        double part = 0.0;
+        for (int s = threadIdx.x; s < S; s += 256) { const double d = b[s] - c[s]; part = fma(d, d, part); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; w++) t += sh[w];
+            s_bc = t;
+        }
+        __syncthreads();
+        const double d2 = s_bc;
+        if (d2 != d2) sawNan = true;       // np.min propagates NaN
+        best = fmin(best, d2);
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sawNan ? NAN : sqrt(best);
+}
+
+}  // namespace pbvi
+
+using namespace pbvi;
+
+extern "C" int pbvi_row_hash(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0 && row_len > 0, "need n >= 0 rows of positive length");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_rows && d_hash, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    row_hash_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_hash);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int32_t* d_ia, const double* d_rows_b, const int32_t* d_ib,
+                               int n, int row_len, int32_t* d_flags, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0 && row_len > 0, "need n >= 0 pairs of positive length");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_rows_a && d_rows_b && d_ia && d_ib && d_flags, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    rows_equal_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint64_t*>(d_rows_a), d_ia,
+                                                          reinterpret_cast<const uint64_t*>(d_rows_b), d_ib, row_len, d_flags);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_vi_sweep(pbvi_model* m, const double* d_vopt, double gamma, double* d_alpha_out, double* d_vopt_out, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(d_vopt != nullptr, "vopt pointer is NULL");
+    if (!m->has_probs) {
+        set_error("the model was created without reachable_probabilities; the VI sweep is unavailable");
+        return PBVI_ERR_UNSUPPORTED;
+    }
+    PBVI_CUDA(cudaSetDevice(m->device));
+    vi_sweep_kernel<<<ceil_div(m->S, 256), 256, 0, (cudaStream_t)stream>>>(d_vopt, m->reachK, m->probK, m->rbarT, gamma, m->S, m->R, m->A,
+                                                                          d_alpha_out, d_vopt_out);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_prune_dominated(pbvi_model* m, const double* d_alphas, int nV, int32_t* d_keep, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(nV >= 0, "nV must be non-negative");
+    if (nV == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_alphas && d_keep, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    prune_dominated_kernel<<<nV, 256, 0, (cudaStream_t)stream>>>(d_alphas, nV, m->S, d_keep);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double* d_ub_beliefs, const double* d_ub_values, int n_ub,
+                             const double* d_queries, int n_q, double* d_out, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n_ub >= 0 && n_q >= 0, "counts must be non-negative");
+    if (n_q == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_corner && d_queries && d_out && (n_ub == 0 || (d_ub_beliefs && d_ub_values)), "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    sawtooth_kernel<<<n_q, 256, 0, (cudaStream_t)stream>>>(d_corner, d_ub_beliefs, d_ub_values, n_ub, d_queries, m->S, d_out);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_min_l2_distance(pbvi_model* m, const double* d_beliefs, int nB, const double* d_candidates, int nC, double* d_out,
+                                    void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(nB > 0 && nC >= 0, "need nB > 0 beliefs and nC >= 0 candidates");
+    if (nC == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_candidates && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    min_l2_kernel<<<nC, 256, 0, (cudaStream_t)stream>>>(d_beliefs, nB, d_candidates, m->S, d_out);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}

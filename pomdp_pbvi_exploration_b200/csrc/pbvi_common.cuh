@@ -1,0 +1,108 @@
+// Shared declarations for the PBVI B200 engine: model handle, scratch arena, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pbvi_b200.h"
+
+namespace pbvi {
+
+// ---- tiling constants of the score kernel (see score_kernel.cuh) --------------------------------
+constexpr int KC = 16;         // source states per K chunk -- the sparsity-skipping granule along K
+constexpr int BM = 128;        // beliefs per block tile
+constexpr int BN = 128;        // alpha vectors per block tile
+constexpr int RG = 32;         // beliefs per row group (one warp's rows) -- the skipping granule along M
+constexpr int NRG = BM / RG;   // 4 row groups per tile
+constexpr int SCORE_THREADS = 256;
+
+void set_error(const char* fmt, ...);
+
+#define PBVI_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            pbvi::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (_e == cudaErrorMemoryAllocation) ? PBVI_ERR_OOM : PBVI_ERR_CUDA;                 \
+        }                                                                                            \
+    } while (0)
+
+#define PBVI_REQUIRE(cond, msg)                                          \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            pbvi::set_error("bad argument: %s (%s)", msg, #cond);        \
+            return PBVI_ERR_BAD_ARG;                                     \
+        }                                                                \
+    } while (0)
+
+#define PBVI_TRY(expr)                \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != PBVI_OK) return _rc; \
+    } while (0)
+
+// Grow-only device scratch owned by the model handle.  Allocation is a bump pointer over a list of chunks; a call that
+// outgrows the current chunk adds one (pointers handed out earlier stay valid), and the next `reset()` -- the start of
+// the next API call -- consolidates them, so steady-state calls never allocate.
+struct Arena {
+    struct Chunk { char* base; size_t cap, off; };
+    std::vector<Chunk> chunks;
+    void* take_bytes(size_t bytes);     // nullptr (and the error string set) when the device is out of memory
+    void reset();
+    void release();
+    template <typename T> T* take(size_t n) { return reinterpret_cast<T*>(take_bytes(n * sizeof(T))); }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+#define PBVI_TAKE(var, T, n)                         \
+    T* var = m->arena.take<T>(n);                    \
+    if (!var) return PBVI_ERR_OOM
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace pbvi
+
+struct pbvi_model {
+    int S = 0, A = 0, O = 0, R = 0;
+    int K = 0;        // S*R
+    int Sp = 0;       // S padded to a multiple of KC
+    int nChunks = 0;  // Sp / KC
+    int nZ = 0;       // A*O
+    int device = 0;
+    int sm_count = 148;
+    bool has_probs = false;
+
+    // action-major device tables
+    int32_t* reachK = nullptr;   // [A][S*R]      landing state of k = s*R + r
+    double* rtoK = nullptr;      // [A][O][S*R]   RTO
+    double* probK = nullptr;     // [A][S*R]      transition probabilities (nullptr when not supplied)
+    double* rbarT = nullptr;     // [A][S]
+    // R == 1 fast path of the score kernel: chunk-padded copies (pad: landing state 0, RTO 0)
+    int32_t* reachP = nullptr;   // [A][Sp]
+    double* rtoP = nullptr;      // [A][O][Sp]
+    uint8_t* zMask = nullptr;    // [nZ][nChunks]  1 iff some RTO[s,a,o,:] != 0 for a source state s of the chunk
+    int32_t* zOrder = nullptr;   // [nZ] (a*O+o) sorted by decreasing number of live chunks (heavy blocks first)
+    // CSR over landing states (bincount order of Belief.update)
+    int32_t* predPtr = nullptr;  // [A][S+1]
+    int32_t* predK = nullptr;    // [A][K]       source k's in ascending order
+    // NumPy pairwise-sum tree over a length-S row
+    int2* pwLeaves = nullptr;    // [nLeaves] (offset, length)
+    int2* pwNodes = nullptr;     // [nNodes]  (left, right); child >= 0: node id, < 0: leaf ~id; root is the last node
+    int nLeaves = 0, nNodes = 0;
+
+    pbvi::Arena arena;
+    // instrumentation of the last select / max_values call
+    unsigned long long* d_stats = nullptr;   // [1] live (tile, z, chunk, row group) quadruples visited by the score launch
+    double last_dense_flops = 0.0;
+    double last_exec_scale = 0.0;            // flops per visited quadruple
+    int last_launches = 0;
+};
+
+namespace pbvi {
+// implemented in backup.cu, used by other translation units
+int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st);
+}

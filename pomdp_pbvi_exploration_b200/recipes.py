@@ -120,3 +120,28 @@ def synthetic_sparse_model(S: int, A: int, O: int, R: int, seed: int = 0) -> Mod
     obs = rng.random((S, A, O))
     obs /= obs.sum(2, keepdims=True)
     return Model(states=S, actions=A, observations=O, reachable_states=reach, observation_table=obs, end_states=[S // 2])
+
+
+def perseus_walk_beliefs(model: Model, n: int, seed: int = 0, restart: int = 100) -> np.ndarray:
+    """
+    Synthetic belief points for benchmarks / tests: the random walk in belief space of the reference's `expand_perseus`
+    (src/pomdp.py:2010-2056: a uniform, o ~ P(o|b,a), b <- update(b,a,o)), restarted from the start belief every
+    `restart` steps.  Host NumPy input synthesis with its own RNG stream (`default_rng(seed)`); not part of the solver.
+    """
+    rng = np.random.default_rng(seed)
+    S, A, O = model.state_count, model.action_count, model.observation_count
+    reach = model.reachable_states
+    rto = model.reachable_transitional_observation_table
+    out = np.empty((n, S))
+    b = model.start_probabilities
+    for i in range(n):
+        if i % restart == 0:
+            b = model.start_probabilities
+        a = int(rng.integers(A))
+        w = rto[:, a, :, :] * b[:, None, None]                    # [S,O,R]
+        po = w.sum(axis=(0, 2))
+        o = int(rng.choice(O, p=po / po.sum()))
+        nb = np.bincount(reach[:, a, :].ravel(), weights=w[:, o, :].ravel(), minlength=S)
+        b = nb / nb.sum()
+        out[i] = b
+    return out

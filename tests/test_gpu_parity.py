@@ -1,0 +1,297 @@
+"""
+GPU parity tests: the CUDA engine, called through the C ABI (pomdp_pbvi_exploration_b200._native -> libpbvi_b200.so),
+against the CPU oracle (oracle/pbvi_oracle.py) and the golden fixtures produced by the unmodified reference.
+
+Contract (BASELINE.json north_star): bit-exact alpha-argmax and action indices wherever the value gap exceeds the
+tolerance; alpha entries within 1e-9 relative (bit-exact for reachable_state_count == 1 models, whose rows are sums of
+single products in the reference's own operation order).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pbvi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GAP_TOL = 1e-9
+MODELS = ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid', 'hallway', 'synth300', 'olfactory_wrap']
+
+
+@pytest.fixture(scope='module')
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), 'these tests need a CUDA device'
+    return torch
+
+
+_dev_cache = {}
+
+
+def device_model(tag):
+    from pomdp_pbvi_exploration_b200._native import DeviceModel
+    if tag not in _dev_cache:
+        m = load_golden('model_' + tag)
+        reach = m['reach'].astype(np.int64)
+        probs = m['probs'] if 'probs' in m else np.full(reach.shape, 1.0 / reach.shape[2])
+        _dev_cache[tag] = (DeviceModel(reach, probs, m['rto'], m['rbar']), m, reach, probs)
+    return _dev_cache[tag]
+
+
+def check_backup_against_oracle(dev, reach, rto, rbar, gamma, B, V, exact_rows):
+    """Runs the engine and the oracle on the same inputs and applies the parity contract.  Returns the engine outputs."""
+    alpha, act, vstar, value = [t.cpu().numpy() for t in dev.backup(B, V, gamma)]
+    ref = orc.backup_chunked(reach, rto, rbar, gamma, B, V, chunk=64) if B.shape[0] > 64 else orc.backup(reach, rto, rbar, gamma, B, V)
+    sc = np.concatenate([orc.backup(reach, rto, rbar, gamma, B[i:i + 64], V, return_scores=True)['scores'] for i in range(0, B.shape[0], 64)])
+    # ---- v*: identical wherever the oracle's top-2 gap exceeds the tolerance; otherwise a near-maximal column
+    top = np.sort(sc, axis=3)
+    best = top[..., -1]
+    gap = best - top[..., -2] if sc.shape[3] > 1 else np.full(best.shape, np.inf)
+    scale = np.maximum(1.0, np.abs(best))
+    decided = gap > GAP_TOL * scale
+    assert np.array_equal(vstar[decided], ref['v_star'][decided])
+    picked = np.take_along_axis(sc, vstar[..., None].astype(np.int64), axis=3)[..., 0]
+    assert np.all(picked >= best - GAP_TOL * scale)
+    # exact ties of a whole row (the all-zero (b,a,o) rows of sparse models): lowest index wins, as np.argmax
+    flat = np.all(sc == sc[..., :1], axis=3)
+    assert np.all(vstar[flat] == 0)
+    # ---- values and a*
+    np.testing.assert_allclose(value, ref['values'], rtol=1e-9, atol=1e-12)
+    vs = np.sort(ref['values'], axis=1)
+    agap = vs[:, -1] - vs[:, -2] if vs.shape[1] > 1 else np.full(vs.shape[0], np.inf)
+    adecided = agap > GAP_TOL * np.maximum(1.0, np.abs(vs[:, -1]))
+    assert np.array_equal(act[adecided], ref['a_star'][adecided])
+    # a* must be the FIRST maximiser of the engine's own values (np.argmax semantics)
+    assert np.array_equal(act, np.argmax(value, axis=1))
+    # ---- alpha rows: compare where both engines selected the same (a*, v*[a*]) tuple
+    same = (act == ref['a_star'])
+    ours_sel = np.take_along_axis(vstar, act[:, None, None].astype(np.int64), axis=1)[:, 0, :]
+    ref_sel = np.take_along_axis(ref['v_star'], ref['a_star'][:, None, None], axis=1)[:, 0, :]
+    same &= np.all(ours_sel == ref_sel, axis=1)
+    assert same.mean() > 0.5
+    if exact_rows:
+        assert np.array_equal(alpha[same], ref['alpha'][same])
+    else:
+        np.testing.assert_allclose(alpha[same], ref['alpha'][same], rtol=1e-9, atol=1e-12)
+    return alpha, act, vstar, value, ref
+
+
+@pytest.mark.parametrize('tag', MODELS)
+def test_backup_golden(torch_cuda, tag):
+    dev, m, reach, _ = device_model(tag)
+    g = load_golden('backup_' + tag)
+    gamma = float(m['gamma'])
+    exact = reach.shape[2] == 1
+    alpha, act, vstar, value, ref = check_backup_against_oracle(dev, reach, m['rto'], m['rbar'], gamma, g['beliefs'], g['alphas'], exact)
+    # against the reference's own per-belief outputs
+    vals = np.sort(ref['values'], axis=1)
+    gap = vals[:, -1] - vals[:, -2]
+    decided = gap > GAP_TOL * np.maximum(1.0, np.abs(vals[:, -1]))
+    assert np.array_equal(act[decided], g['ref_row_action'][decided])
+    same = act == g['ref_row_action']
+    if exact:
+        assert same.all() and np.array_equal(alpha, g['ref_row_alpha'])
+    else:
+        np.testing.assert_allclose(alpha[same], g['ref_row_alpha'][same], rtol=1e-9, atol=1e-12)
+    # host-buffer entry point gives the same bytes as the device entry point
+    ha, hact = dev.backup_host(g['beliefs'], g['alphas'], gamma)
+    assert np.array_equal(ha, alpha) and np.array_equal(hact, act)
+    # select + assemble of the selected tuples == fused call
+    sel = np.take_along_axis(vstar, act[:, None, None].astype(np.int64), axis=1)[:, 0, :]
+    rows = dev.backup_assemble(g['alphas'], gamma, act, sel).cpu().numpy()
+    assert np.array_equal(rows, alpha)
+
+
+def _sparse_beliefs(rng, n, S, ks):
+    B = np.zeros((n, S))
+    for i in range(n):
+        k = min(S, ks[i % len(ks)])
+        idx = rng.choice(S, k, replace=False)
+        B[i, idx] = rng.dirichlet(np.ones(k))
+    return B
+
+
+@pytest.mark.parametrize('S,A,O,R,nB,nV', [
+    (37, 2, 2, 1, 1, 1), (100, 3, 2, 1, 127, 5), (300, 4, 3, 1, 129, 129), (515, 3, 4, 1, 300, 257),
+    (64, 3, 3, 2, 40, 17), (200, 4, 2, 5, 131, 130), (1000, 2, 2, 3, 64, 260),
+])
+def test_backup_synthetic_shapes(torch_cuda, S, A, O, R, nB, nV):
+    """Tile-boundary coverage (ragged M / N / K tiles, one belief, one alpha) on the configs[4] recipe."""
+    from pomdp_pbvi_exploration_b200._native import DeviceModel
+    rng = np.random.default_rng(S * 7 + R)
+    reach = rng.integers(0, S, (S, A, R))
+    probs = np.full(reach.shape, 1.0 / R)
+    obs = rng.random((S, A, O)); obs /= obs.sum(2, keepdims=True)
+    obs[rng.random((S, A, O)) < 0.3] = 0.0            # impossible observations -> exact-zero score rows
+    rto = orc.build_rto(reach, probs, obs)
+    rbar = orc.expected_rewards(rto, orc.end_state_reachable_rewards(reach, O, [S // 2]))
+    B = _sparse_beliefs(rng, nB, S, [S, 40, 5, 1])
+    V = rng.random((nV, S))
+    dev = DeviceModel(reach, probs, rto, rbar)
+    check_backup_against_oracle(dev, reach, rto, rbar, 0.95, B, V, exact_rows=(R == 1))
+    dev.close()
+
+
+def test_backup_all_zero_and_duplicate_rows(torch_cuda):
+    """Empty support intersections: beliefs that only see impossible observations give all-zero score rows -> v* = 0."""
+    from pomdp_pbvi_exploration_b200._native import DeviceModel
+    S, A, O = 50, 2, 3
+    reach = ((np.arange(S)[:, None, None] + np.arange(1, A + 1)[None, :, None]) % S).astype(np.int64)
+    obs = np.zeros((S, A, O)); obs[:, :, 0] = 1.0                                  # only o = 0 ever happens
+    rto = orc.build_rto(reach, np.ones(reach.shape), obs)
+    rbar = np.zeros((S, A)); rbar[:, 1] = 0.0
+    dev = DeviceModel(reach, None, rto, rbar)
+    rng = np.random.default_rng(3)
+    B = _sparse_beliefs(rng, 10, S, [3])
+    V = rng.random((9, S))
+    alpha, act, vstar, value = [t.cpu().numpy() for t in dev.backup(B, V, 0.9)]
+    assert np.all(vstar[:, :, 1:] == 0)
+    ref = orc.backup(reach, rto, rbar, 0.9, B, V)
+    assert np.array_equal(vstar, ref['v_star']) and np.array_equal(act, ref['a_star']) and np.array_equal(alpha, ref['alpha'])
+    dev.close()
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'hallway', 'olfactory_wrap'])
+def test_max_values_and_change(torch_cuda, tag):
+    dev, m, reach, _ = device_model(tag)
+    g = load_golden('misc_' + tag)
+    B = g['change_beliefs']
+    for V in (g['change_alphas_a'], g['change_alphas_b']):
+        mx, arg = [t.cpu().numpy() for t in dev.max_values(B, V)]
+        rmx, rarg = orc.max_values(B, V)
+        np.testing.assert_allclose(mx, rmx, rtol=1e-12, atol=1e-14)
+        prod = B @ V.T
+        top = np.sort(prod, axis=1)
+        decided = (top[:, -1] - top[:, -2] > GAP_TOL * np.maximum(1, np.abs(top[:, -1]))) if V.shape[0] > 1 else np.ones(len(B), bool)
+        assert np.array_equal(arg[decided], rarg[decided])
+    va = dev.max_values(B, g['change_alphas_a'])[0]
+    vb = dev.max_values(B, g['change_alphas_b'])[0]
+    change = float((vb - va).abs().max())
+    assert change == pytest.approx(float(g['ref_change']), rel=1e-9, abs=1e-12)
+
+
+@pytest.mark.parametrize('tag', [t for t in MODELS if t != 'synth300'])
+def test_belief_update_bit_exact(torch_cuda, tag):
+    """Belief.update: bincount accumulation order + NumPy pairwise normaliser reproduced bit for bit (NaN rows included)."""
+    dev, m, reach, _ = device_model(tag)
+    g = load_golden('misc_' + tag)
+    B = g['beliefs']
+    if 'pairs' in g:
+        pairs = g['pairs']
+        bb = np.repeat(B, len(pairs), axis=0)
+        aa = np.tile(pairs[:, 0], len(B)); oo = np.tile(pairs[:, 1], len(B))
+        out, mass = dev.belief_update(bb, aa, oo)
+        got = out.cpu().numpy().reshape(len(B), len(pairs), -1)
+        assert np.array_equal(got, g['ref_updates'], equal_nan=True)
+    else:
+        succ, mass = dev.belief_successors(B)
+        assert np.array_equal(succ.cpu().numpy(), g['ref_updates'], equal_nan=True)
+        probs = dev.observation_probabilities(B).cpu().numpy()
+        want = np.einsum('bs,saor->bao', B, m['rto'])
+        np.testing.assert_allclose(probs, want, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(mass.cpu().numpy(), want, rtol=1e-12, atol=1e-15)
+    # un-normalised projection is the bincount itself
+    a0 = np.zeros(len(B), dtype=np.int32); o0 = np.zeros(len(B), dtype=np.int32)
+    raw, _ = dev.belief_update(B, a0, o0, normalise=False)
+    want = orc.belief_update_batch(reach, m['rto'], B, a0, o0, normalise=False)
+    assert np.array_equal(raw.cpu().numpy(), want)
+
+
+def test_row_hash_and_equality(torch_cuda):
+    dev, m, reach, _ = device_model('hallway')
+    rng = np.random.default_rng(1)
+    S = dev.S
+    rows = rng.random((40, S))
+    rows[7] = rows[3]; rows[21] = rows[3]
+    rows[9, 5] = 0.0; rows[10] = rows[9]; rows[10, 5] = -0.0          # -0.0 and 0.0 differ bytewise
+    h = dev.row_hash(rows).cpu().numpy()
+    assert np.array_equal(h[7], h[3]) and np.array_equal(h[21], h[3])
+    assert not np.array_equal(h[9], h[10])
+    keys = {tuple(x) for x in h.tolist()}
+    assert len(keys) == 38
+    swapped = rows[0].copy(); swapped[[1, 2]] = swapped[[2, 1]]         # position dependence
+    assert not np.array_equal(dev.row_hash(swapped[None]).cpu().numpy()[0], h[0])
+    flags = dev.rows_equal(rows, [3, 3, 9, 0], rows, [7, 21, 10, 1]).cpu().numpy()
+    assert flags.tolist() == [1, 1, 0, 0]
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'grid4x4', 'tigergrid', 'hallway'])
+def test_vi_sweep_and_solve(torch_cuda, tag):
+    dev, m, reach, probs = device_model(tag)
+    g = load_golden('misc_' + tag)
+    gamma = float(m['gamma'])
+    v = np.max(m['rbar'], axis=1)
+    alpha, vnew = dev.vi_sweep(v, gamma)
+    want = orc.vi_sweep(reach, probs, m['rbar'], gamma, v)
+    np.testing.assert_allclose(alpha.cpu().numpy(), want, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(vnew.cpu().numpy(), want.max(0), rtol=1e-13, atol=1e-13)
+
+
+def test_prune_sawtooth_distance(torch_cuda):
+    dev, m, reach, _ = device_model('tiger')
+    g = load_golden('tiger_extras')
+    got = dev.sawtooth(g['ub_corner'], g['ub_beliefs'], g['ub_values'], g['ub_queries']).cpu().numpy()
+    np.testing.assert_allclose(got, g['ref_ub_eval'], rtol=1e-12)
+    assert dev.sawtooth(g['ub_corner'], np.zeros((0, 2)), np.zeros(0), g['ub_queries'][:1]).item() == pytest.approx(
+        float(g['ub_queries'][0] @ g['ub_corner']))
+    dev2, m2, reach2, _ = device_model('hallway')
+    rng = np.random.default_rng(2)
+    al = rng.random((30, dev2.S))
+    al[4] = al[2] - 0.1; al[11] = al[7]; al[20] = np.minimum(al[1], al[3]) - 1e-3
+    keep = dev2.prune_dominated(al).cpu().numpy().astype(bool)
+    assert np.array_equal(np.flatnonzero(keep), orc.prune_pointwise_dominated(al))
+    B = _sparse_beliefs(rng, 12, dev2.S, [dev2.S, 7])
+    succ = orc.all_successors(reach2, m2['rto'], B[:3])
+    with np.errstate(all='ignore'):
+        want = orc.ssea_min_distances(B, succ)
+    got = dev2.min_l2_distance(B, succ.reshape(-1, dev2.S)).cpu().numpy().reshape(want.shape)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+def test_error_convention(torch_cuda):
+    from pomdp_pbvi_exploration_b200 import _native
+    dev, m, reach, _ = device_model('tiger')
+    with pytest.raises(ValueError):
+        dev.backup(np.array([[0.5, 0.5]]), np.zeros((1, 2)), -1.0)
+    with pytest.raises(ValueError):
+        _native.DeviceModel(np.full((2, 1, 1), 5), None, np.ones((2, 1, 1, 1)), np.zeros((2, 1)))   # landing state out of range
+    assert b'reachable_states' in _native.load_library().pbvi_last_error()
+
+
+def test_olfactory_full_size_properties(torch_cuda):
+    """
+    BASELINE-size model (S = 22021): properties that do not need the CPU oracle on the whole input --
+    determinism, tile independence (a row's result does not depend on its tile mates), alpha-order equivariance --
+    plus the oracle on a sample of rows.
+    """
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs
+    torch = torch_cuda
+    model = olfactory_wrap_model()
+    dev = model.device
+    rng = np.random.default_rng(0)
+    B = perseus_walk_beliefs(model, 700, seed=0)
+    g = load_golden('backup_olfactory_wrap')
+    V = np.concatenate([g['alphas'], rng.random((300 - g['alphas'].shape[0], dev.S)) * 0.05])
+    alpha, act, vstar, value = dev.backup(B, V, 0.99)
+    alpha2, act2, vstar2, value2 = dev.backup(B, V, 0.99)
+    assert torch.equal(alpha, alpha2) and torch.equal(vstar, vstar2) and torch.equal(value, value2)
+    idx = np.sort(rng.choice(700, 150, replace=False))
+    a3, act3, vs3, val3 = dev.backup(B[idx], V, 0.99)
+    tidx = torch.as_tensor(idx, device=alpha.device)
+    assert torch.equal(vs3, vstar[tidx]) and torch.equal(act3, act[tidx]) and torch.equal(a3, alpha[tidx])
+    # reversing the alpha order maps decided v* to V-1-v*
+    a4, act4, vs4, val4 = dev.backup(B[idx], V[::-1].copy(), 0.99)
+    torch.testing.assert_close(val4, val3, rtol=1e-12, atol=1e-14)
+    # oracle on a sample of rows (full parity contract), and the sample's rows equal the full run's rows
+    samp = idx[:24]
+    tsamp = torch.as_tensor(samp, device=alpha.device)
+    a5, act5, vs5, val5, ref = check_backup_against_oracle(dev, model.reachable_states, model.reachable_transitional_observation_table,
+                                                           model.expected_rewards_table, 0.99, B[samp], V, exact_rows=True)
+    assert np.array_equal(vs5, vstar[tsamp].cpu().numpy()) and np.array_equal(a5, alpha[tsamp].cpu().numpy())
+    # reversing the alpha order maps every decided v* to V-1-v*
+    sc = orc.backup(model.reachable_states, model.reachable_transitional_observation_table, model.expected_rewards_table, 0.99, B[samp], V,
+                    return_scores=True)['scores']
+    top = np.sort(sc, axis=3)
+    decided = (top[..., -1] - top[..., -2]) > GAP_TOL * np.maximum(1.0, np.abs(top[..., -1]))
+    rev = vs4[:24].cpu().numpy()
+    assert np.array_equal((V.shape[0] - 1 - rev)[decided], ref['v_star'][decided])
