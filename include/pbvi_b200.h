@@ -136,9 +136,24 @@ PBVI_API int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double* 
 PBVI_API int pbvi_min_l2_distance(pbvi_model* m, const double* d_beliefs, int nB, const double* d_candidates, int nC, double* d_out,
                          void* stream);
 
+/* ---- GER error terms (src/pomdp.py:1738-1748) ----------------------------------------------------
+ * d_eps[i][a][o] = sum_s (alpha'[s] - d_alpha_b[i][s]) * (d_succ[i][a][o][s] - d_beliefs[i][s]),  alpha'[s] = r_max where the
+ * successor gained mass and r_min elsewhere; 0 for the NaN successor of an impossible observation. */
+PBVI_API int pbvi_ger_scores(pbvi_model* m, const double* d_beliefs, const double* d_alpha_b, const double* d_succ, int n,
+                             double r_min, double r_max, double* d_eps, void* stream);
+
 /* ---- instrumentation: flops actually issued by the last pbvi_backup_select / pbvi_max_values score launch, its grid size
  * and kernel launch count of the last call (for bench.py's roofline / gpu_launches accounting) */
 PBVI_API int pbvi_last_stats(const pbvi_model* m, double* executed_flops, double* dense_flops, int* launches);
+
+/* kernels launched by the last API call on this handle (host-side counter, no synchronisation) */
+PBVI_API int pbvi_last_launches(const pbvi_model* m);
+
+/* pbvi_set_profiling(m, 1): bracket the score kernel launch(es) of every following pbvi_backup* / pbvi_max_values call with CUDA
+ * events on the caller's stream; pbvi_last_score_ms waits for the closing event and returns the device time between them
+ * (the GEMM-with-argmax launch, plus the Gamma projection for reachable_state_count > 1 models). */
+PBVI_API int pbvi_set_profiling(pbvi_model* m, int enable);
+PBVI_API int pbvi_last_score_ms(pbvi_model* m, float* ms);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,11 @@ SIGNATURES = {
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_min_l2_distance': [_P, _P, c_int, _P, c_int, _P, _P],
+    'pbvi_ger_scores': [_P, _P, _P, _P, c_int, c_double, c_double, _P, _P],
     'pbvi_last_stats': [_P, POINTER(c_double), POINTER(c_double), POINTER(c_int)],
+    'pbvi_last_launches': [_P],
+    'pbvi_set_profiling': [_P, c_int],
+    'pbvi_last_score_ms': [_P, POINTER(ctypes.c_float)],
 }
 
 _lib = None
@@ -109,6 +113,7 @@ class DeviceModel:
 
     def __init__(self, reach: np.ndarray, probs: np.ndarray | None, rto: np.ndarray, rbar: np.ndarray, device: int | None = None):
         self._h = None
+        self.launch_count = 0           # kernels launched through this handle since creation (bench.py: gpu_launches)
         self._lib = load_library()
         if not torch.cuda.is_available():
             raise RuntimeError('no CUDA device: the PBVI B200 engine has no CPU path')
@@ -127,6 +132,10 @@ class DeviceModel:
         self._h = h
         self.S, self.A, self.O, self.R = S, A, O, R
         self.device = torch.device('cuda', int(device))
+
+    def _call(self, rc: int) -> None:
+        _check(rc)
+        self.launch_count += self._lib.pbvi_last_launches(self._h)
 
     def close(self) -> None:
         if self._h is not None:
@@ -158,7 +167,7 @@ class DeviceModel:
         vstar = torch.empty((nB, self.A, self.O), dtype=torch.int32, device=self.device)
         value = torch.empty((nB, self.A), dtype=torch.float64, device=self.device) if want_value else None
         astar = torch.empty((nB,), dtype=torch.int32, device=self.device)
-        _check(self._lib.pbvi_backup_select(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(vstar), _ptr(value), _ptr(astar),
+        self._call(self._lib.pbvi_backup_select(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(vstar), _ptr(value), _ptr(astar),
                                             self._stream))
         return vstar, value, astar
 
@@ -169,7 +178,7 @@ class DeviceModel:
         n = act.shape[0]
         assert vs.shape == (n, self.O)
         out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_backup_assemble(self._h, _ptr(al), al.shape[0], float(gamma), _ptr(act), _ptr(vs), n, _ptr(out), self._stream))
+        self._call(self._lib.pbvi_backup_assemble(self._h, _ptr(al), al.shape[0], float(gamma), _ptr(act), _ptr(vs), n, _ptr(out), self._stream))
         return out
 
     def backup(self, beliefs, alphas, gamma: float):
@@ -180,7 +189,7 @@ class DeviceModel:
         act = torch.empty((nB,), dtype=torch.int32, device=self.device)
         vstar = torch.empty((nB, self.A, self.O), dtype=torch.int32, device=self.device)
         value = torch.empty((nB, self.A), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_backup(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(out), _ptr(act), _ptr(vstar), _ptr(value),
+        self._call(self._lib.pbvi_backup(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(out), _ptr(act), _ptr(vstar), _ptr(value),
                                      self._stream))
         return out, act, vstar, value
 
@@ -194,7 +203,7 @@ class DeviceModel:
             out_alpha = np.empty((nB, self.S), dtype=np.float64)
         if out_action is None:
             out_action = np.empty((nB,), dtype=np.int32)
-        _check(self._lib.pbvi_backup_host(self._h, b.ctypes.data, nB, al.ctypes.data, nV, float(gamma), out_alpha.ctypes.data,
+        self._call(self._lib.pbvi_backup_host(self._h, b.ctypes.data, nB, al.ctypes.data, nV, float(gamma), out_alpha.ctypes.data,
                                           out_action.ctypes.data, self._stream))
         return out_alpha, out_action
 
@@ -204,7 +213,7 @@ class DeviceModel:
         nB = b.shape[0]
         mx = torch.empty((nB,), dtype=torch.float64, device=self.device)
         arg = torch.empty((nB,), dtype=torch.int32, device=self.device)
-        _check(self._lib.pbvi_max_values(self._h, _ptr(b), nB, _ptr(al), al.shape[0], _ptr(mx), _ptr(arg), self._stream))
+        self._call(self._lib.pbvi_max_values(self._h, _ptr(b), nB, _ptr(al), al.shape[0], _ptr(mx), _ptr(arg), self._stream))
         return mx, arg
 
     def belief_update(self, beliefs, actions, observations, normalise: bool = True):
@@ -215,7 +224,7 @@ class DeviceModel:
         assert a.shape == (n,) and o.shape == (n,)
         out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
         norm = torch.empty((n,), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_belief_update(self._h, _ptr(b), _ptr(a), _ptr(o), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
+        self._call(self._lib.pbvi_belief_update(self._h, _ptr(b), _ptr(a), _ptr(o), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
         return out, norm
 
     def belief_successors(self, beliefs, normalise: bool = True):
@@ -224,20 +233,20 @@ class DeviceModel:
         n = b.shape[0]
         out = torch.empty((n, self.A, self.O, self.S), dtype=torch.float64, device=self.device)
         norm = torch.empty((n, self.A, self.O), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_belief_successors(self._h, _ptr(b), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
+        self._call(self._lib.pbvi_belief_successors(self._h, _ptr(b), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
         return out, norm
 
     def observation_probabilities(self, beliefs) -> torch.Tensor:
         b = self._beliefs(beliefs)
         out = torch.empty((b.shape[0], self.A, self.O), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_observation_probabilities(self._h, _ptr(b), b.shape[0], _ptr(out), self._stream))
+        self._call(self._lib.pbvi_observation_probabilities(self._h, _ptr(b), b.shape[0], _ptr(out), self._stream))
         return out
 
     def row_hash(self, rows: torch.Tensor) -> torch.Tensor:
         """128-bit hash of the raw bytes of each float64 row, as int64 [n,2]."""
         r = _f64(rows, self.device)
         out = torch.empty((r.shape[0], 2), dtype=torch.int64, device=self.device)
-        _check(self._lib.pbvi_row_hash(self._h, _ptr(r), r.shape[0], r.shape[1], _ptr(out), self._stream))
+        self._call(self._lib.pbvi_row_hash(self._h, _ptr(r), r.shape[0], r.shape[1], _ptr(out), self._stream))
         return out
 
     def rows_equal(self, rows_a, ia, rows_b, ib) -> torch.Tensor:
@@ -245,7 +254,7 @@ class DeviceModel:
         ia, ib = _i32(ia, self.device), _i32(ib, self.device)
         assert ra.shape[1] == rb.shape[1] and ia.shape == ib.shape
         flags = torch.empty((ia.shape[0],), dtype=torch.int32, device=self.device)
-        _check(self._lib.pbvi_rows_equal(self._h, _ptr(ra), _ptr(ia), _ptr(rb), _ptr(ib), ia.shape[0], ra.shape[1], _ptr(flags), self._stream))
+        self._call(self._lib.pbvi_rows_equal(self._h, _ptr(ra), _ptr(ia), _ptr(rb), _ptr(ib), ia.shape[0], ra.shape[1], _ptr(flags), self._stream))
         return flags
 
     def vi_sweep(self, vopt, gamma: float):
@@ -253,13 +262,13 @@ class DeviceModel:
         assert v.shape == (self.S,)
         alpha = torch.empty((self.A, self.S), dtype=torch.float64, device=self.device)
         vnew = torch.empty((self.S,), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_vi_sweep(self._h, _ptr(v), float(gamma), _ptr(alpha), _ptr(vnew), self._stream))
+        self._call(self._lib.pbvi_vi_sweep(self._h, _ptr(v), float(gamma), _ptr(alpha), _ptr(vnew), self._stream))
         return alpha, vnew
 
     def prune_dominated(self, alphas) -> torch.Tensor:
         al = self._beliefs(alphas)
         keep = torch.empty((al.shape[0],), dtype=torch.int32, device=self.device)
-        _check(self._lib.pbvi_prune_dominated(self._h, _ptr(al), al.shape[0], _ptr(keep), self._stream))
+        self._call(self._lib.pbvi_prune_dominated(self._h, _ptr(al), al.shape[0], _ptr(keep), self._stream))
         return keep
 
     def sawtooth(self, corner, ub_beliefs, ub_values, queries) -> torch.Tensor:
@@ -267,15 +276,33 @@ class DeviceModel:
         ubb = _f64(ub_beliefs, self.device).reshape(-1, self.S)
         ubv = _f64(ub_values, self.device).reshape(-1)
         out = torch.empty((q.shape[0],), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_sawtooth(self._h, _ptr(c), _ptr(ubb) if ubb.shape[0] else None, _ptr(ubv) if ubb.shape[0] else None,
+        self._call(self._lib.pbvi_sawtooth(self._h, _ptr(c), _ptr(ubb) if ubb.shape[0] else None, _ptr(ubv) if ubb.shape[0] else None,
                                        ubb.shape[0], _ptr(q), q.shape[0], _ptr(out), self._stream))
         return out
 
     def min_l2_distance(self, beliefs, candidates) -> torch.Tensor:
         b, c = self._beliefs(beliefs), self._beliefs(candidates)
         out = torch.empty((c.shape[0],), dtype=torch.float64, device=self.device)
-        _check(self._lib.pbvi_min_l2_distance(self._h, _ptr(b), b.shape[0], _ptr(c), c.shape[0], _ptr(out), self._stream))
+        self._call(self._lib.pbvi_min_l2_distance(self._h, _ptr(b), b.shape[0], _ptr(c), c.shape[0], _ptr(out), self._stream))
         return out
+
+    def ger_scores(self, beliefs, alpha_b, successors, r_min: float, r_max: float) -> torch.Tensor:
+        """GER error terms eps[n,A,O] (reference src/pomdp.py:1738-1748)."""
+        b, al = self._beliefs(beliefs), self._beliefs(alpha_b)
+        sc = _f64(successors, self.device)
+        n = b.shape[0]
+        assert al.shape == b.shape and sc.shape == (n, self.A, self.O, self.S)
+        eps = torch.empty((n, self.A, self.O), dtype=torch.float64, device=self.device)
+        self._call(self._lib.pbvi_ger_scores(self._h, _ptr(b), _ptr(al), _ptr(sc), n, float(r_min), float(r_max), _ptr(eps), self._stream))
+        return eps
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(self._lib.pbvi_set_profiling(self._h, int(enable)))
+
+    def last_score_ms(self) -> float:
+        ms = ctypes.c_float()
+        _check(self._lib.pbvi_last_score_ms(self._h, byref(ms)))
+        return float(ms.value)
 
     def last_stats(self) -> dict:
         e, d, n = c_double(), c_double(), c_int()

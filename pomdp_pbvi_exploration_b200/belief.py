@@ -1,0 +1,185 @@
+"""
+Belief / BeliefSet with the reference's interface (src/pomdp.py:311-783) on device-resident storage.
+
+`Belief.values` is a CUDA float64 tensor [S]; `Belief.update(a, o)` runs the engine's belief-update kernel, whose result
+is bit-identical to the reference's bincount + np.sum normalisation (so byte-identity of beliefs, which `BeliefSet.union`
+and the solver rely on, means the same thing in both engines).  `BeliefSet.belief_array` is a CUDA tensor [N,S].
+"""
+from __future__ import annotations
+
+from typing import Union
+
+import numpy as np
+import torch
+
+from .model import Model
+from .sets import dedup_rows
+
+
+def _to_device(model: Model, values) -> torch.Tensor:
+    dev = model.device.device
+    if isinstance(values, torch.Tensor):
+        return values.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+
+
+class Belief:
+    """
+    A probability distribution over the states of `model` (reference src/pomdp.py:311-486).
+
+    Parameters
+    ----------
+    model : Model
+    values : np.ndarray | torch.Tensor, optional
+        Defaults to the model's start probabilities.  Must sum to 1 (rounded to 3 decimals), as in the reference.
+    """
+
+    def __new__(cls, *args, **kwargs):
+        instance = super().__new__(cls)
+        instance._bytes_repr = None
+        instance._successors = {}
+        instance._host = None
+        return instance
+
+    def __init__(self, model: Model, values=None):
+        assert model is not None
+        self.model = model
+        if values is not None:
+            assert values.shape[0] == model.state_count, "Belief must contain be of dimension |S|"
+            self._values = _to_device(model, values)
+            prob_sum = float(self._values.sum())
+            rounded_sum = round(prob_sum, 3)
+            assert rounded_sum == 1.0, f"States probabilities in belief must sum to 1 (found: {prob_sum}; rounded {rounded_sum})"
+        else:
+            self._values = model.start_belief_device
+
+    @classmethod
+    def _from_device(cls, model: Model, values: torch.Tensor) -> 'Belief':
+        """No sum check, like the reference's `update` (which builds the successor through __new__, src/pomdp.py:414-416)."""
+        b = cls.__new__(cls)
+        b.model = model
+        b._values = values
+        return b
+
+    @property
+    def values(self) -> torch.Tensor:
+        return self._values
+
+    @property
+    def values_host(self) -> np.ndarray:
+        if self._host is None:
+            self._host = self._values.cpu().numpy()
+        return self._host
+
+    @property
+    def bytes_repr(self) -> bytes:
+        if self._bytes_repr is None:
+            self._bytes_repr = self.values_host.tobytes()
+        return self._bytes_repr
+
+    def __eq__(self, other: object) -> bool:
+        return self.bytes_repr == other.bytes_repr
+
+    def __hash__(self):
+        return hash(self.bytes_repr)
+
+    def update(self, a: int, o: int) -> 'Belief':
+        """b'(s') proportional to sum_s RTO[s,a,o,.] b(s) (reference src/pomdp.py:382-421); successors are memoised."""
+        succ_id = f'{a}_{o}'
+        succ = self._successors.get(succ_id)
+        if succ is not None:
+            return succ
+        out, _ = self.model.device.belief_update(self._values[None, :], [int(a)], [int(o)])
+        new_belief = Belief._from_device(self.model, out[0])
+        self._successors[succ_id] = new_belief
+        return new_belief
+
+    def generate_successors(self) -> list:
+        """All (a,o) successors in action-major order (reference src/pomdp.py:424-438), one kernel launch pair."""
+        succ, _ = self.model.device.belief_successors(self._values[None, :])
+        out = []
+        for a in self.model.actions:
+            for o in self.model.observations:
+                key = f'{a}_{o}'
+                if key not in self._successors:
+                    self._successors[key] = Belief._from_device(self.model, succ[0, a, o])
+                out.append(self._successors[key])
+        return out
+
+    def random_state(self) -> int:
+        """A state drawn from the belief with the host NumPy RNG, like the reference's CPU path (src/pomdp.py:441-452)."""
+        return int(np.random.choice(a=self.model.states, size=1, p=self.values_host)[0])
+
+
+class BeliefSet:
+    """
+    An ordered set of beliefs (reference src/pomdp.py:489-783).
+
+    Parameters
+    ----------
+    model : Model
+    beliefs : list[Belief] | np.ndarray | torch.Tensor
+    """
+
+    def __init__(self, model: Model, beliefs: Union[list, np.ndarray, torch.Tensor], *, _hashes: np.ndarray | None = None):
+        self.model = model
+        self.is_on_gpu = True
+        self._belief_list = None
+        self._hashes = _hashes
+        S = model.state_count
+        if isinstance(beliefs, list):
+            assert all(b.values.shape[0] == S for b in beliefs), f"Beliefs in belief list provided dont all have shape ({S},)"
+            self._belief_list = beliefs
+            self._array = torch.stack([b.values for b in beliefs]) if len(beliefs) else \
+                torch.empty((0, S), dtype=torch.float64, device=model.device.device)
+        else:
+            assert beliefs.shape[1] == S, f"Belief array provided doesnt have the right shape (expected (-,{S}), received {tuple(beliefs.shape)})"
+            self._array = _to_device(model, beliefs)
+            if not isinstance(beliefs, torch.Tensor):
+                # the reference builds Belief objects here, which asserts every row sums to 1 (src/pomdp.py:531-533, 345-347)
+                sums = np.round(np.asarray(beliefs, dtype=np.float64).sum(axis=1), 3)
+                bad = np.flatnonzero(~(sums == 1.0))
+                assert bad.size == 0, f"States probabilities in belief must sum to 1 (found: {float(np.asarray(beliefs)[bad[0]].sum())})"
+
+    @property
+    def belief_array(self) -> torch.Tensor:
+        """[N,S] CUDA float64 tensor."""
+        return self._array
+
+    @property
+    def belief_list(self) -> list:
+        if self._belief_list is None:
+            self._belief_list = [Belief._from_device(self.model, row) for row in self._array]
+        return self._belief_list
+
+    @property
+    def row_hashes(self) -> np.ndarray:
+        if self._hashes is None:
+            self._hashes = self.model.device.row_hash(self._array).cpu().numpy() if len(self) else np.zeros((0, 2), dtype=np.int64)
+        return self._hashes
+
+    def __len__(self) -> int:
+        return int(self._array.shape[0])
+
+    def numpy(self) -> np.ndarray:
+        return self._array.cpu().numpy()
+
+    def generate_all_successors(self) -> 'BeliefSet':
+        succ, _ = self.model.device.belief_successors(self._array)
+        return BeliefSet(self.model, succ.reshape(-1, self.model.state_count))
+
+    def union(self, other_belief_set: 'BeliefSet') -> 'BeliefSet':
+        """Own unique beliefs in order, then the unseen beliefs of the other set (reference src/pomdp.py:585-606)."""
+        rows = torch.cat([self._array, other_belief_set._array], dim=0)
+        hashes = np.concatenate([self.row_hashes, other_belief_set.row_hashes], axis=0)
+        first, _, _, _ = dedup_rows(self.model.device, rows, hashes)
+        if first.shape[0] != rows.shape[0]:
+            rows = rows[torch.as_tensor(first, device=rows.device)]
+            hashes = hashes[first]
+        return BeliefSet(self.model, rows, _hashes=hashes)
+
+    def to_gpu(self) -> 'BeliefSet':
+        return self
+
+    def to_cpu(self) -> 'BeliefSet':
+        return self

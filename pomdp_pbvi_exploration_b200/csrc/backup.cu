@@ -273,6 +273,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     m->last_exec_scale = 2.0 * RG * BN * KC;
     m->last_dense_flops = 2.0 * nB * (double)nV * nZ * S;
 
+    if (m->profile) PBVI_CUDA(cudaEventRecord(m->evScore0, st));
     ScoreParams p{};
     p.beliefs = d_beliefs; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
     p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nZ = nZ; p.O = m->O;
@@ -295,6 +296,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
             PBVI_TRY(launch_score(m, false, p, nNt, nMt, nz, st));
         }
     }
+    if (m->profile) { PBVI_CUDA(cudaEventRecord(m->evScore1, st)); m->score_timed = true; }
     const size_t n = (size_t)nB * nZ;
     combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt, n, outVal, outIdx);
     m->last_launches++;

@@ -170,9 +170,54 @@ __global__ void __launch_bounds__(256) min_l2_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) out[blockIdx.x] = sawNan ? NAN : sqrt(best);
 }
 
+// GER error term of one successor (block per (b, z)): sum_s (alpha'[s] - alpha_b[s]) * (succ[s] - b[s]),
+// alpha'[s] = r_max where the successor gained mass, r_min elsewhere (src/pomdp.py:1738-1748).
+// A NaN successor (impossible observation) yields 0: its weight P(o|b,a) is 0.
+__global__ void __launch_bounds__(256) ger_eps_kernel(const double* __restrict__ beliefs, const double* __restrict__ alphaB,
+                                                      const double* __restrict__ succ, int S, int nZ, double rMin, double rMax,
+                                                      double* __restrict__ eps) {
+    __shared__ double sh[8];
+    const int z = blockIdx.x, b = blockIdx.y;
+    const double* bel = beliefs + (size_t)b * S;
+    const double* al = alphaB + (size_t)b * S;
+    const double* sc = succ + ((size_t)b * nZ + z) * S;
+    double part = 0.0;
+    for (int s = threadIdx.x; s < S; s += 256) {
+        const double d = sc[s] - bel[s];
+        part = fma((d >= 0.0 ? rMax : rMin) - al[s], d, part);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        eps[(size_t)b * nZ + z] = (t != t) ? 0.0 : t;
+    }
+}
+
 }  // namespace pbvi
 
 using namespace pbvi;
+
+extern "C" int pbvi_ger_scores(pbvi_model* m, const double* d_beliefs, const double* d_alpha_b, const double* d_succ, int n,
+                               double r_min, double r_max, double* d_eps, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_alpha_b && d_succ && d_eps, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    for (int i0 = 0; i0 < n; i0 += 65535) {
+        const int ni = std::min(65535, n - i0);
+        ger_eps_kernel<<<dim3(m->nZ, ni), 256, 0, (cudaStream_t)stream>>>(d_beliefs + (size_t)i0 * m->S, d_alpha_b + (size_t)i0 * m->S,
+                                                                         d_succ + (size_t)i0 * m->nZ * m->S, m->S, m->nZ, r_min, r_max,
+                                                                         d_eps + (size_t)i0 * m->nZ);
+    }
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
 
 extern "C" int pbvi_row_hash(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, void* stream) {
     PBVI_REQUIRE(m != nullptr, "model handle is NULL");

@@ -210,6 +210,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->reachP); cudaFree(m->rtoP); cudaFree(m->zMask); cudaFree(m->zOrder);
     cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes);
     cudaFree(m->d_stats);
+    if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
     m->arena.release();
     delete m;
     return PBVI_OK;
@@ -221,6 +222,28 @@ extern "C" int pbvi_model_dims(const pbvi_model* m, int* S, int* A, int* O, int*
     if (A) *A = m->A;
     if (O) *O = m->O;
     if (R) *R = m->R;
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_last_launches(const pbvi_model* m) { return m ? m->last_launches : 0; }
+
+extern "C" int pbvi_set_profiling(pbvi_model* m, int enable) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    if (enable && !m->evScore0) {
+        PBVI_CUDA(cudaEventCreate(&m->evScore0));
+        PBVI_CUDA(cudaEventCreate(&m->evScore1));
+    }
+    m->profile = enable != 0;
+    m->score_timed = false;
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_last_score_ms(pbvi_model* m, float* ms) {
+    PBVI_REQUIRE(m != nullptr && ms != nullptr, "NULL argument");
+    PBVI_REQUIRE(m->profile && m->score_timed, "profiling is off or no score kernel has run since it was enabled");
+    PBVI_CUDA(cudaEventSynchronize(m->evScore1));
+    PBVI_CUDA(cudaEventElapsedTime(ms, m->evScore0, m->evScore1));
     return PBVI_OK;
 }
 

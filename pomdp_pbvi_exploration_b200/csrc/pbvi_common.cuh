@@ -100,6 +100,10 @@ struct pbvi_model {
     double last_dense_flops = 0.0;
     double last_exec_scale = 0.0;            // flops per visited quadruple
     int last_launches = 0;
+    // optional timing of the dominant (score) kernel with CUDA events on the caller's stream
+    bool profile = false;
+    bool score_timed = false;
+    cudaEvent_t evScore0 = nullptr, evScore1 = nullptr;
 };
 
 namespace pbvi {

@@ -267,6 +267,7 @@ class Model:
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_device_handle'] = None
+        d['_start_device'] = None
         return d
 
     def save(self, file_name: str, path: str = './Models') -> None:
@@ -289,6 +290,14 @@ class Model:
     @property
     def cpu_model(self) -> 'Model':
         return self
+
+    @property
+    def start_belief_device(self):
+        """start_probabilities as a cached CUDA tensor (the initial belief b0)."""
+        if getattr(self, '_start_device', None) is None:
+            import torch
+            self._start_device = torch.as_tensor(self.start_probabilities, dtype=torch.float64).to(self.device.device)
+        return self._start_device
 
     @property
     def device(self):

@@ -1,0 +1,73 @@
+"""
+Raw-byte set semantics of the reference's containers, on device-resident rows.
+
+The reference keys Python dicts by `values.tobytes()` (ValueFunction ctor src/mdp.py:668-669, `extend` :773-774,
+BeliefSet.union src/pomdp.py:585-606) -- on its GPU path that is one D2H copy per row.  Here rows stay on the
+device: `pbvi_row_hash` gives a 128-bit key per row, the grouping runs on the host over 16 bytes per row, and every
+key match is confirmed bytewise on the device (`pbvi_rows_equal`), so the result is exact, not probabilistic.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+_KEY = np.dtype([('a', '<i8'), ('b', '<i8')])
+
+
+def group_by_key(hashes: np.ndarray):
+    """
+    hashes [n,2] int64 -> (first [g], last [g], inverse [n]) with groups numbered in order of first occurrence --
+    the insertion order of a Python dict keyed by the row bytes.
+    """
+    n = hashes.shape[0]
+    if n == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    keys = np.ascontiguousarray(hashes, dtype=np.int64).view(_KEY).reshape(n)
+    _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind='stable')                 # unique() sorts by key; renumber by first occurrence
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.shape[0])
+    inverse = rank[inverse.reshape(n)]
+    first = first[order]
+    last = np.zeros_like(first)
+    np.maximum.at(last, inverse, np.arange(n))
+    return first.astype(np.int64), last.astype(np.int64), inverse.astype(np.int64)
+
+
+def dedup_rows(dev, rows: torch.Tensor, hashes: np.ndarray | None = None):
+    """
+    Dict-insertion dedup of device rows [n,S]: returns (first, last, hashes, inverse) where `first[g]` is the position of the
+    first occurrence of group g (groups in first-occurrence order) and `last[g]` of its last occurrence
+    (the reference keeps the first POSITION and the last VALUE, i.e. the last action: src/mdp.py:668-669);
+    `inverse[i]` is the group of row i.
+    """
+    n = rows.shape[0]
+    if hashes is None:
+        hashes = dev.row_hash(rows).cpu().numpy() if n else np.zeros((0, 2), dtype=np.int64)
+    first, last, inverse = group_by_key(hashes)
+    if first.shape[0] == n:
+        return first, last, hashes, inverse
+    # confirm every key match bytewise against the group's first row
+    dup = np.flatnonzero(first[inverse] != np.arange(n))
+    flags = dev.rows_equal(rows, first[inverse[dup]].astype(np.int32), rows, dup.astype(np.int32)).cpu().numpy()
+    if not flags.all():
+        return _dedup_exact_host(rows, hashes)
+    return first, last, hashes, inverse
+
+
+def _dedup_exact_host(rows: torch.Tensor, hashes: np.ndarray):
+    """128-bit key collision between different rows (never observed): redo the grouping on the actual bytes."""
+    host = rows.cpu().numpy()
+    table = {}
+    inverse = np.empty(host.shape[0], dtype=np.int64)
+    for i in range(host.shape[0]):
+        k = host[i].tobytes()
+        if k in table:
+            table[k][1] = i
+        else:
+            table[k] = [i, i, len(table)]
+        inverse[i] = table[k][2]
+    first = np.array([v[0] for v in table.values()], dtype=np.int64)
+    last = np.array([v[1] for v in table.values()], dtype=np.int64)
+    return first, last, hashes, inverse

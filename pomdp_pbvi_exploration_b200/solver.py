@@ -1,0 +1,734 @@
+"""
+Point-Based Value Iteration solver with the reference's interface (src/pomdp.py:1299-2578, src/mdp.py:1414-1525),
+running on the B200 engine (libpbvi_b200.so through `_native.DeviceModel`).
+
+Host Python keeps what the reference keeps in Python -- the expand/backup loop, set bookkeeping on 16-byte row keys,
+host RNG draws (same generators, same draw order as the reference's CPU path, so seeded runs pick the same states /
+actions / observations) -- and every array operation of the hot path is a kernel of the library:
+
+    backup            pbvi_backup_select + pbvi_backup_assemble (+ pbvi_row_hash / pbvi_rows_equal for the byte-dedup)
+    compute_change    pbvi_max_values
+    Belief.update     pbvi_belief_update (bit-identical to the reference, NaN rows included)
+    SSEA / GER / HSVI pbvi_belief_successors, pbvi_min_l2_distance, pbvi_ger_scores, pbvi_sawtooth,
+                      pbvi_observation_probabilities
+    VI_Solver         pbvi_vi_sweep
+
+There is no CPU path: `use_gpu` is accepted for signature compatibility and ignored.
+"""
+from __future__ import annotations
+
+import random
+from datetime import datetime
+from typing import Union
+
+import numpy as np
+import torch
+
+from .belief import Belief, BeliefSet
+from .model import Model, log
+from .sets import dedup_rows, group_by_key
+from .value_function import AlphaVector, ValueFunction  # noqa: F401
+
+
+def _now_synced(model: Model) -> datetime:
+    """Wall clock after the device drained, so the recorded stage times are device-complete (the reference's CuPy path
+    reads the clock without synchronising)."""
+    torch.cuda.synchronize(model.device.device)
+    return datetime.now()
+
+
+def unique_rows_first(keys: np.ndarray):
+    """Unique rows of an int array in order of first occurrence: (first [u], last [u], inverse [n])."""
+    n = keys.shape[0]
+    if n == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    span = keys.max(axis=0) + 1
+    bits = np.ceil(np.log2(np.maximum(span, 2))).astype(np.int64)
+    if int(bits.sum()) <= 62 and keys.min() >= 0:          # pack a row into one int64 (the common case)
+        packed = np.zeros(n, dtype=np.int64)
+        for j in range(keys.shape[1]):
+            packed = (packed << int(bits[j])) | keys[:, j]
+        _, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
+    else:
+        _, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+    inverse = inverse.reshape(n)
+    order = np.argsort(first, kind='stable')
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.shape[0])
+    inverse = rank[inverse]
+    first = first[order]
+    last = np.zeros_like(first)
+    np.maximum.at(last, inverse, np.arange(n))
+    return first, last, inverse
+
+
+# =====================================================================================================================
+class MDPSolverHistory:
+    """History of a value-iteration run (reference src/mdp.py:1281-1400, data fields and summary; plots out of scope)."""
+
+    def __init__(self, tracking_level: int, model: Model, gamma: float, eps: float, initial_value_function=None):
+        self.tracking_level = tracking_level
+        self.model = model
+        self.gamma = gamma
+        self.eps = eps
+        self.run_ts = datetime.now()
+        self.iteration_times = []
+        self.value_function_changes = []
+        self.value_functions = []
+        if self.tracking_level >= 2:
+            self.value_functions.append(initial_value_function)
+
+    @property
+    def solution(self) -> ValueFunction:
+        assert self.tracking_level >= 2, "Tracking level is set too low, increase it to 2 if you want to have value function tracking as well."
+        return self.value_functions[-1]
+
+    def add(self, iteration_time: float, value_function_change: float, value_function) -> None:
+        if self.tracking_level >= 1:
+            self.iteration_times.append(float(iteration_time))
+            self.value_function_changes.append(float(value_function_change))
+        if self.tracking_level >= 2:
+            self.value_functions.append(value_function)
+
+    @property
+    def summary(self) -> str:
+        s = 'Summary of Value Iteration run'
+        s += f'\n  - Model: {self.model.state_count}-state, {self.model.action_count}-action'
+        s += f'\n  - Converged in {len(self.iteration_times)} iterations and {sum(self.iteration_times):.4f} seconds'
+        if self.tracking_level >= 1:
+            s += f'\n  - Took on average {sum(self.iteration_times) / len(self.iteration_times):.4f}s per iteration'
+        return s
+
+
+class VI_Solver:
+    """
+    MDP value iteration (reference src/mdp.py:1414-1525): alpha[a,s] = Rbar[s,a] + gamma * sum_r P[s,a,r] V*[reach[s,a,r]],
+    until max |V* - V*_old| < eps * gamma / (1 - gamma).  One `pbvi_vi_sweep` launch per iteration.
+    """
+
+    def __init__(self, horizon: int = 10000, gamma: float = 0.99, eps: float = 0.001):
+        self.horizon = horizon
+        self.gamma = gamma
+        self.eps = eps
+
+    def solve(self, model: Model, initial_value_function: Union[ValueFunction, None] = None, use_gpu: bool = False,
+              history_tracking_level: int = 1, print_progress: bool = True):
+        dev = model.device
+        if initial_value_function is None:
+            V = ValueFunction(model, model.expected_rewards_table.T, model.actions)
+        else:
+            V = initial_value_function
+        v_opt = torch.max(V.alpha_vector_array, dim=0).values
+        history = MDPSolverHistory(history_tracking_level, model, self.gamma, self.eps, V)
+        max_allowed_change = self.eps * (self.gamma / (1 - self.gamma))
+        alpha = V.alpha_vector_array
+        swept = False
+        for _ in range(self.horizon):
+            start = datetime.now()
+            alpha, v_new = dev.vi_sweep(v_opt, self.gamma)
+            swept = True
+            max_change = float(torch.max(torch.abs(v_new - v_opt)))          # one scalar D2H per sweep = the convergence test
+            v_opt = v_new
+            if history_tracking_level >= 2:
+                history.add((datetime.now() - start).total_seconds(), max_change, ValueFunction(model, alpha.clone(), model.actions))
+            else:
+                history.add((datetime.now() - start).total_seconds(), max_change, None)
+            if max_change < max_allowed_change:
+                break
+        if swept:
+            V = ValueFunction(model, alpha, model.actions)       # byte-dedup of identical action rows, last action wins
+        return V, history
+
+
+# =====================================================================================================================
+class BeliefValueMapping:
+    """
+    HSVI's upper bound: (belief, value) pairs interpolated with the sawtooth rule over the corner values of an MDP
+    solution (reference src/pomdp.py:786-895).  The stored arrays are refreshed by `update()` only, as in the
+    reference.  Divergence (documented): the ratio min_s b(s)/b_i(s) runs over the support of b_i
+    -- the reference's formula takes 0/0 = NaN on sparse beliefs, which disables its own HSVI outside tiger-class models;
+    on strictly positive beliefs the two agree.
+    """
+
+    def __init__(self, model: Model, corner_belief_values: ValueFunction) -> None:
+        self.model = model
+        self.corner_belief_values = corner_belief_values
+        self.corner_values = torch.max(corner_belief_values.alpha_vector_array, dim=0).values
+        self.beliefs = []
+        self.belief_value_mapping = {}
+        self._belief_array = None
+        self._value_array = None
+
+    def add(self, b: Belief, v: float) -> None:
+        if b.bytes_repr not in self.belief_value_mapping:
+            self.beliefs.append(b)
+            self.belief_value_mapping[b.bytes_repr] = v
+
+    @property
+    def belief_array(self) -> torch.Tensor:
+        if self._belief_array is None:
+            self._belief_array = torch.stack([b.values for b in self.beliefs])
+        return self._belief_array
+
+    @property
+    def value_array(self) -> torch.Tensor:
+        if self._value_array is None:
+            self._value_array = torch.as_tensor(list(self.belief_value_mapping.values()), dtype=torch.float64,
+                                                device=self.model.device.device)
+        return self._value_array
+
+    def update(self) -> None:
+        if len(self.beliefs) == 0:
+            return
+        self._belief_array = torch.stack([b.values for b in self.beliefs])
+        self._value_array = torch.as_tensor(list(self.belief_value_mapping.values()), dtype=torch.float64,
+                                            device=self.model.device.device)
+
+    def evaluate(self, belief: Belief) -> float:
+        hit = self.belief_value_mapping.get(belief.bytes_repr)
+        if hit is not None:
+            return hit
+        dev = self.model.device
+        if len(self.beliefs) == 0:
+            return float(dev.sawtooth(self.corner_values, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device),
+                                      torch.empty((0,), dtype=torch.float64, device=dev.device), belief.values)[0])
+        return float(dev.sawtooth(self.corner_values, self.belief_array, self.value_array, belief.values)[0])
+
+
+# =====================================================================================================================
+class SolverHistory:
+    """History of a PBVI run (reference src/pomdp.py:898-1117: data fields and `summary`; plots / videos out of scope)."""
+
+    def __init__(self, tracking_level: int, model: Model, gamma: float, eps: float, expand_function: str, expand_append: bool,
+                 initial_value_function: ValueFunction, initial_belief_set: BeliefSet):
+        self.tracking_level = tracking_level
+        self.model = model
+        self.gamma = gamma
+        self.eps = eps
+        self.run_ts = datetime.now()
+        self.expand_function = expand_function
+        self.expand_append = expand_append
+        self.expansion_times = []
+        self.backup_times = []
+        self.pruning_times = []
+        self.alpha_vector_counts = []
+        self.beliefs_counts = []
+        self.prune_counts = []
+        if self.tracking_level >= 1:
+            self.alpha_vector_counts.append(len(initial_value_function))
+            self.beliefs_counts.append(len(initial_belief_set))
+        self.belief_sets = []
+        self.value_functions = []
+        self.value_function_changes = []
+        if self.tracking_level >= 2:
+            self.belief_sets.append(initial_belief_set)
+            self.value_functions.append(initial_value_function)
+
+    @property
+    def solution(self) -> ValueFunction:
+        assert self.tracking_level >= 2, "Tracking level is set too low, increase it to 2 if you want to have value function tracking as well."
+        return self.value_functions[-1]
+
+    @property
+    def explored_beliefs(self) -> BeliefSet:
+        assert self.tracking_level >= 2, "Tracking level is set too low, increase it to 2 if you want to have belief sets tracking as well."
+        return self.belief_sets[-1]
+
+    def add_expand_step(self, expansion_time: float, belief_set: BeliefSet) -> None:
+        if self.tracking_level >= 1:
+            self.expansion_times.append(float(expansion_time))
+            self.beliefs_counts.append(len(belief_set))
+        if self.tracking_level >= 2:
+            self.belief_sets.append(belief_set)
+
+    def add_backup_step(self, backup_time: float, value_function_change: float, value_function: ValueFunction) -> None:
+        if self.tracking_level >= 1:
+            self.backup_times.append(float(backup_time))
+            self.alpha_vector_counts.append(len(value_function))
+            self.value_function_changes.append(float(value_function_change))
+        if self.tracking_level >= 2:
+            self.value_functions.append(value_function)
+
+    def add_prune_step(self, prune_time: float, alpha_vectors_pruned: int) -> None:
+        if self.tracking_level >= 1:
+            self.pruning_times.append(prune_time)
+            self.prune_counts.append(alpha_vectors_pruned)
+
+    @property
+    def summary(self) -> str:
+        s = 'Summary of Value Iteration run'
+        s += f'\n  - Model: {self.model.state_count} state, {self.model.action_count} action, {self.model.observation_count} observations'
+        s += f'\n  - Converged or stopped after {len(self.expansion_times)} expansion steps and {len(self.backup_times)} backup steps.'
+        if self.tracking_level >= 1:
+            s += f'\n  - Resulting value function has {self.alpha_vector_counts[-1]} alpha vectors.'
+            s += f'\n  - Converged in {(sum(self.expansion_times) + sum(self.backup_times)):.4f}s'
+            s += '\n'
+            s += f'\n  - Expand function took on average {sum(self.expansion_times) / len(self.expansion_times):.4f}s '
+            if self.expand_append:
+                s += f'and yielded on average {sum(np.diff(self.beliefs_counts)) / len(self.beliefs_counts[1:]):.2f} beliefs per iteration.'
+            else:
+                s += f'and yielded on average {sum(self.beliefs_counts[1:]) / len(self.beliefs_counts[1:]):.2f} beliefs per iteration.'
+            s += f' ({np.sum(np.divide(self.expansion_times, self.beliefs_counts[1:])) / len(self.expansion_times):.4f}s/it/belief)'
+            s += f'\n  - Backup function took on average {sum(self.backup_times) / len(self.backup_times):.4f}s '
+            s += f'and yielded on average {np.average(np.diff(self.alpha_vector_counts)):.2f} alpha vectors per iteration.'
+            s += f' ({np.sum(np.divide(self.backup_times, self.alpha_vector_counts[1:])) / len(self.backup_times):.4f}s/it/alpha)'
+            s += f'\n  - Pruning function took on average {sum(self.pruning_times) / len(self.pruning_times):.4f}s '
+            s += f'and yielded on average prunings of {sum(self.prune_counts) / len(self.prune_counts):.2f} alpha vectors per iteration.'
+        return s
+
+
+# =====================================================================================================================
+class PBVI_Solver:
+    """
+    Point-Based Value Iteration (reference src/pomdp.py:1299-2413).
+
+    Parameters
+    ----------
+    gamma : float, default=0.99
+    eps : float, default=0.001
+    expand_function : str, default='ssea'
+        One of ra, ssra, ssga, ssea, ger, hsvi, fsvi, fsvi_eg, perseus (matched by substring like the reference).
+    expand_function_params
+        Extra parameters of the expand function (epsilon, mdp_policy, eps_greedy).
+    """
+
+    def __init__(self, gamma: float = 0.99, eps: float = 0.001, expand_function: str = 'ssea', **expand_function_params):
+        self.gamma = gamma
+        self.eps = eps
+        self.expand_function = expand_function
+        self.expand_function_params = expand_function_params
+
+    # ------------------------------------------------------------------------------------------------------------
+    def backup(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, append: bool = False,
+               belief_dominance_prune: bool = True) -> ValueFunction:
+        """
+        Point-based backup (reference src/pomdp.py:1447-1524).  For every belief: v*[a,o] = argmax_v b.Gamma[a,o,v],
+        a* = argmax_a b.(Rbar[:,a] + sum_o Gamma[a,o,v*]), alpha_b = that vector; then the byte-dedup of the
+        ValueFunction constructor and, with `append`, the union with the old value function.
+
+        Two beliefs that select the same (a*, v*[a*,:]) tuple produce the same bytes, so only the distinct tuples are
+        assembled; the byte-dedup then runs over those rows (different tuples can still give identical rows).
+        """
+        dev = model.device
+        B, V = belief_set.belief_array, value_function.alpha_vector_array
+        nB = B.shape[0]
+        if nB == 0:
+            new_vf = ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
+            if append:
+                new_vf.extend(value_function)
+            return new_vf
+        vstar, value, astar = dev.backup_select(B, V, self.gamma)
+        ar = torch.arange(nB, device=dev.device)
+        sel = vstar[ar, astar.long()]                                                    # [nB, O]
+        keys = torch.cat([astar[:, None], sel], dim=1)
+        keep_idx = None
+        if belief_dominance_prune:
+            # keep b iff b.alpha_b > max_v b.alpha_v, strict (reference :1509-1515)
+            best_old, _ = dev.max_values(B, V)
+            keep = value[ar, astar.long()] > best_old
+            keep_idx = torch.nonzero(keep)[:, 0]
+            keys = keys[keep_idx]
+        keys_h = keys.cpu().numpy()
+        first, last, inverse = unique_rows_first(keys_h)
+        tuples = keys_h[first]
+        if tuples.shape[0] == 0:
+            new_vf = ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
+        else:
+            rows = dev.backup_assemble(V, self.gamma, tuples[:, 0], tuples[:, 1:])
+            gfirst, _, hashes, ginv = dedup_rows(dev, rows)
+            # the surviving action of a byte group is the action of the LAST belief that produced those bytes
+            glast_belief = np.zeros(gfirst.shape[0], dtype=np.int64)
+            owner = np.zeros(gfirst.shape[0], dtype=np.int64)
+            for t in range(tuples.shape[0]):                         # tuples are few (distinct alpha rows of this backup)
+                g = ginv[t]
+                if last[t] >= glast_belief[g]:
+                    glast_belief[g] = last[t]
+                    owner[g] = t
+            actions = tuples[owner, 0].astype(np.int64)
+            if gfirst.shape[0] != rows.shape[0]:
+                rows = rows[torch.as_tensor(gfirst, device=rows.device)]
+            new_vf = ValueFunction(model, rows, actions, _trusted=True, _hashes=hashes[gfirst])
+        if append:
+            new_vf.extend(value_function)
+        return new_vf
+
+    # ------------------------------------------------------------------------------------------------------------
+    def compute_change(self, value_function: ValueFunction, new_value_function: ValueFunction, belief_set: BeliefSet) -> float:
+        """max_b | max_v b.alpha_v - max_v' b.alpha'_v' | (reference src/pomdp.py:2141-2169)."""
+        dev = belief_set.model.device
+        if len(belief_set) == 0:
+            return 0.0
+        a, _ = dev.max_values(belief_set.belief_array, value_function.alpha_vector_array)
+        b, _ = dev.max_values(belief_set.belief_array, new_value_function.alpha_vector_array)
+        return float(torch.max(torch.abs(b - a)))
+
+    # ---- expansions ------------------------------------------------------------------------------------------------
+    def expand_ra(self, model: Model, belief_set: BeliefSet, max_generation: int = 10) -> BeliefSet:
+        """Random beliefs (reference src/pomdp.py:1527-1548); host NumPy RNG."""
+        generation_count = min(len(belief_set), max_generation)
+        new_beliefs = np.random.random((generation_count, model.state_count))
+        new_beliefs /= np.sum(new_beliefs, axis=1)[:, None]
+        return BeliefSet(model, new_beliefs)
+
+    def _stochastic_step(self, model: Model, belief_set: BeliefSet, max_generation: int, choose_action) -> BeliefSet:
+        """Shared body of SSRA / SSGA: the host draws (s, a, s', o) per selected belief in the reference's order, then
+        ONE batched belief-update launch replaces the per-belief `b.update(a, o)`."""
+        n_old = len(belief_set)
+        to_generate = min(max_generation, n_old)
+        rand_ind = np.random.choice(np.arange(n_old), to_generate, replace=False)
+        src = belief_set.belief_array[torch.as_tensor(rand_ind, device=belief_set.belief_array.device)]
+        host = src.cpu().numpy()
+        acts, obs = np.zeros(to_generate, dtype=np.int32), np.zeros(to_generate, dtype=np.int32)
+        for i in range(to_generate):
+            s = int(np.random.choice(a=model.states, size=1, p=host[i])[0])
+            a = int(choose_action(int(rand_ind[i])))
+            s_p = model.transition(s, a)
+            o = model.observe(s_p, a)
+            acts[i], obs[i] = a, o
+        new_rows, _ = model.device.belief_update(src, acts, obs)
+        return BeliefSet(model, new_rows)
+
+    def expand_ssra(self, model: Model, belief_set: BeliefSet, max_generation: int = 10) -> BeliefSet:
+        """Stochastic Simulation with Random Action (reference src/pomdp.py:1551-1592)."""
+        return self._stochastic_step(model, belief_set, max_generation, lambda belief_index: random.choice(model.actions))
+
+    def expand_ssga(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, epsilon: float = 0.1,
+                    max_generation: int = 10) -> BeliefSet:
+        """Stochastic Simulation with Greedy Action (reference src/pomdp.py:1595-1648): greedy a = action of argmax_v alpha_v.b."""
+        _, best = model.device.max_values(belief_set.belief_array, value_function.alpha_vector_array)
+        greedy = value_function.actions[best.cpu().numpy()]
+
+        def choose(belief_index):
+            if random.random() < epsilon:
+                return random.choice(model.actions)
+            return greedy[belief_index]
+        return self._stochastic_step(model, belief_set, max_generation, choose)
+
+    def _successors_chunked(self, model: Model, belief_set: BeliefSet, chunk: int = 256):
+        B = belief_set.belief_array
+        for i0 in range(0, B.shape[0], chunk):
+            succ, mass = model.device.belief_successors(B[i0:i0 + chunk])
+            yield i0, succ, mass
+
+    def expand_ssea(self, model: Model, belief_set: BeliefSet, max_generation: int = 10) -> BeliefSet:
+        """
+        Stochastic Simulation with Exploratory Action (reference src/pomdp.py:1651-1694): of all B*A*O successors keep the
+        `max_generation` farthest (L2) from the current belief set.  Successors of impossible observations are NaN rows
+        in the reference, which then crashes on every model that has one; here they are never selected.
+        """
+        dev = model.device
+        to_generate = min(max_generation, len(belief_set))
+        dists = []
+        for i0, succ, mass in self._successors_chunked(model, belief_set):
+            d = dev.min_l2_distance(belief_set.belief_array, succ.reshape(-1, dev.S)).reshape(succ.shape[:3])
+            dists.append(d.cpu().numpy())
+        dist = np.concatenate(dists, axis=0)
+        dist = np.where(np.isnan(dist), -np.inf, dist)
+        pick = np.argsort(dist, axis=None)[::-1][:to_generate]
+        pick = pick[np.isfinite(dist.reshape(-1)[pick])]
+        b_star, a_star, o_star = np.unravel_index(pick, dist.shape)
+        src = belief_set.belief_array[torch.as_tensor(b_star, device=dev.device)]
+        rows, _ = dev.belief_update(src, a_star.astype(np.int32), o_star.astype(np.int32))
+        return BeliefSet(model, rows)
+
+    def expand_ger(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, max_generation: int = 10) -> BeliefSet:
+        """Greedy Error Reduction (reference src/pomdp.py:1697-1765); impossible-observation successors weigh 0."""
+        dev = model.device
+        to_generate = min(max_generation, len(belief_set))
+        r_min = model._min_reward / (1 - self.gamma)
+        r_max = model._max_reward / (1 - self.gamma)
+        B, V = belief_set.belief_array, value_function.alpha_vector_array
+        _, best = dev.max_values(B, V)
+        b_alphas = V[best.long()]
+        eps_l, prob_l = [], []
+        for i0, succ, mass in self._successors_chunked(model, belief_set):
+            eps_l.append(dev.ger_scores(B[i0:i0 + succ.shape[0]], b_alphas[i0:i0 + succ.shape[0]], succ, r_min, r_max).cpu().numpy())
+            prob_l.append(dev.observation_probabilities(B[i0:i0 + succ.shape[0]]).cpu().numpy())
+        eps, bao_probs = np.concatenate(eps_l), np.concatenate(prob_l)
+        res = np.einsum('bao,bao->ba', bao_probs, eps)
+        b_stars, a_stars = np.unravel_index(np.argsort(res, axis=None)[::-1][:to_generate], res.shape)
+        o_star = np.argmax(bao_probs[b_stars, a_stars] * eps[b_stars, a_stars], axis=1)
+        src = B[torch.as_tensor(b_stars, device=dev.device)]
+        rows, _ = dev.belief_update(src, a_stars.astype(np.int32), o_star.astype(np.int32))
+        return BeliefSet(model, rows)
+
+    def expand_hsvi(self, model: Model, b: Belief, value_function: ValueFunction, upper_bound_belief_value_map: BeliefValueMapping,
+                    conv_term: Union[float, None] = None, max_generation: int = 10) -> BeliefSet:
+        """
+        HSVI exploration (reference src/pomdp.py:1768-1868): a = argmax of the upper-bound Q, o = argmax P(o|b,a) * (upper - lower),
+        recursing until the gap closes or `max_generation` is reached.  Observations with P(o|b,a) = 0 are skipped
+        (their successor is 0/0 in the reference).
+        """
+        dev = model.device
+        if conv_term is None:
+            conv_term = self.eps
+        conv_term /= self.gamma
+        probs = dev.observation_probabilities(b.values[None, :])[0].cpu().numpy()          # [A,O]
+        rb = (torch.as_tensor(model.expected_rewards_table, device=dev.device).T @ b.values).cpu().numpy()
+        max_qv, best_a = -np.inf, -1
+        for a in model.actions:
+            b_prob_val = 0
+            for o in model.observations:
+                if probs[a, o] > 0:
+                    b_prob_val += probs[a, o] * upper_bound_belief_value_map.evaluate(b.update(a, o))
+            qva = float(rb[a] + self.gamma * b_prob_val)
+            if qva > max_qv:
+                max_qv, best_a = qva, a
+        max_o_val, best_v_diff, next_b = -np.inf, -np.inf, b
+        for o in model.observations:
+            if not probs[best_a, o] > 0:
+                continue
+            bao = b.update(best_a, o)
+            upper_v = upper_bound_belief_value_map.evaluate(bao)
+            lower_v = float(dev.max_values(bao.values[None, :], value_function.alpha_vector_array)[0][0])
+            v_diff = upper_v - lower_v
+            o_val = probs[best_a, o] * v_diff
+            if o_val > max_o_val:
+                max_o_val, best_v_diff, next_b = o_val, v_diff, bao
+        if best_v_diff < conv_term or max_generation <= 1:
+            return BeliefSet(model, [next_b])
+        upper_bound_belief_value_map.add(b, max_qv)
+        b_set = self.expand_hsvi(model=model, b=next_b, value_function=value_function,
+                                 upper_bound_belief_value_map=upper_bound_belief_value_map, conv_term=conv_term,
+                                 max_generation=max_generation - 1)
+        new_belief_list = list(b_set.belief_list)
+        new_belief_list.append(next_b)
+        return BeliefSet(model, new_belief_list)
+
+    def _trajectory(self, model: Model, b0: Belief, mdp_policy: ValueFunction, max_generation: int, eps_greedy=None) -> BeliefSet:
+        """
+        FSVI / FSVI_EG trajectory (reference src/pomdp.py:1871-2007).  The state walk only needs host draws, so the whole
+        (a, o) sequence is drawn first -- same generators, same order as the reference -- and the belief chain is then
+        advanced on the device with no host round trip.  `a_star` is the ROW index of the best MDP alpha vector at s, used
+        as the action, exactly as the reference does (`xp.argmax(mdp_policy.alpha_vector_array[:, s])`).
+        """
+        dev = model.device
+        policy_rows = torch.argmax(mdp_policy.alpha_vector_array, dim=0).cpu().numpy()
+        b0_host = b0.values_host
+        s = int(np.random.choice(a=model.states, size=1, p=b0_host)[0])
+        steps = []
+        for i in range(max_generation - 1):
+            if eps_greedy is not None and random.random() < eps_greedy(i):
+                a_star = int(random.choice(model.actions))
+            else:
+                a_star = int(policy_rows[s])
+            s_p = model.transition(s, a_star)
+            o = model.observe(s_p, a_star)
+            reset = s_p in model.end_states
+            steps.append((a_star, o, reset))
+            s = s_p
+            if reset:
+                s = int(np.random.choice(a=model.states, size=1, p=b0_host)[0])
+        rows = [b0.values]
+        b = b0.values
+        for a_star, o, reset in steps:
+            out, _ = dev.belief_update(b[None, :], [a_star], [o])
+            rows.append(out[0])
+            b = b0.values if reset else out[0]
+        return BeliefSet(model, torch.stack(rows))
+
+    def expand_fsvi(self, model: Model, b0: Belief, mdp_policy: ValueFunction, max_generation: int = 10) -> BeliefSet:
+        """Forward Search Value Iteration exploration (reference src/pomdp.py:1871-1935)."""
+        return self._trajectory(model, b0, mdp_policy, max_generation)
+
+    def expand_fsvi_eg(self, model: Model, b0: Belief, mdp_policy: ValueFunction, eps_greedy=None, max_generation: int = 10) -> BeliefSet:
+        """FSVI with epsilon-greedy actions (reference src/pomdp.py:1938-2007)."""
+        if eps_greedy is None:
+            eps_greedy = (lambda t: 0.2)
+        return self._trajectory(model, b0, mdp_policy, max_generation, eps_greedy)
+
+    def expand_perseus(self, model: Model, b: Belief, max_generation: int = 10) -> BeliefSet:
+        """Random walk in belief space (reference src/pomdp.py:2010-2056): a uniform, o ~ P(o|b,a), b <- update(b,a,o)."""
+        dev = model.device
+        rows = []
+        cur = b.values
+        for _ in range(max_generation):
+            a = int(np.random.choice(model.actions, size=1)[0])
+            obs_prob = dev.observation_probabilities(cur[None, :])[0, a].cpu().numpy()
+            o = int(np.random.choice(model.observations, size=1, p=obs_prob)[0])
+            out, _ = dev.belief_update(cur[None, :], [a], [o])
+            cur = out[0]
+            rows.append(cur)
+        return BeliefSet(model, torch.stack(rows))
+
+    def expand(self, model: Model, belief_set: BeliefSet, max_generation: int, **function_specific_parameters) -> BeliefSet:
+        """Dispatcher (reference src/pomdp.py:2059-2138): the strategy is matched by substring, e.g. 'ra', 'ssra', 'expand_ssra'."""
+        p = function_specific_parameters
+        if self.expand_function in 'expand_ra':
+            return self.expand_ra(model=model, belief_set=belief_set, max_generation=max_generation)
+        elif self.expand_function in 'expand_ssra':
+            return self.expand_ssra(model=model, belief_set=belief_set, max_generation=max_generation)
+        elif self.expand_function in 'expand_ssga':
+            args = {arg: p[arg] for arg in ['value_function', 'epsilon'] if arg in p}
+            return self.expand_ssga(model=model, belief_set=belief_set, max_generation=max_generation, **args)
+        elif self.expand_function in 'expand_ssea':
+            return self.expand_ssea(model=model, belief_set=belief_set, max_generation=max_generation)
+        elif self.expand_function in 'expand_ger':
+            args = {arg: p[arg] for arg in ['value_function'] if arg in p}
+            return self.expand_ger(model=model, belief_set=belief_set, max_generation=max_generation, **args)
+        elif self.expand_function in 'expand_hsvi':
+            args = {arg: p[arg] for arg in ['value_function', 'mdp_policy'] if arg in p}
+            if not hasattr(self, '_upper_bound'):
+                self._upper_bound = BeliefValueMapping(model, args['mdp_policy'])
+            else:
+                self._upper_bound.update()
+            return self.expand_hsvi(model=model, b=belief_set.belief_list[0], value_function=args['value_function'],
+                                    upper_bound_belief_value_map=self._upper_bound, max_generation=max_generation)
+        elif self.expand_function in 'expand_fsvi':
+            return self.expand_fsvi(model=model, b0=belief_set.belief_list[0], mdp_policy=p['mdp_policy'], max_generation=max_generation)
+        elif self.expand_function in 'expand_fsvi_eg':
+            return self.expand_fsvi_eg(model=model, b0=belief_set.belief_list[0], mdp_policy=p['mdp_policy'],
+                                       eps_greedy=p.get('eps_greedy'), max_generation=max_generation)
+        elif self.expand_function in 'expand_perseus':
+            return self.expand_perseus(model=model, b=belief_set.belief_list[0], max_generation=max_generation)
+        raise Exception('Not implemented')
+
+    # ------------------------------------------------------------------------------------------------------------
+    def solve(self, model: Model, expansions: int, full_backup: Union[bool, None] = None, update_passes: int = 1,
+              max_belief_growth: int = 10, initial_belief: Union[BeliefSet, Belief, None] = None,
+              initial_value_function: Union[ValueFunction, None] = None, prune_level: int = 1, prune_interval: int = 10,
+              limit_value_function_size: int = -1, use_gpu: bool = True, history_tracking_level: int = 1,
+              print_progress: bool = True):
+        """
+        Expand / backup loop (reference src/pomdp.py:2172-2413), same arguments, same control flow.  Always runs on the device.
+        Returns (ValueFunction, SolverHistory).
+        """
+        if initial_belief is None:
+            belief_set = BeliefSet(model, [Belief(model)])
+        elif isinstance(initial_belief, BeliefSet):
+            belief_set = initial_belief
+        else:
+            belief_set = BeliefSet(model, [Belief(model, initial_belief.values)])
+        if initial_value_function is None:
+            value_function = ValueFunction(model, model.expected_rewards_table.T, model.actions)
+        else:
+            value_function = initial_value_function
+        if full_backup is None:
+            full_backup = any([self.expand_function in func for func in ['expand_ra', 'expand_ssra', 'expand_ssga', 'expand_ssea', 'expand_ger']])
+        if (('fsvi' in self.expand_function or 'hsvi' in self.expand_function) and
+                (('mdp_policy' not in self.expand_function_params) or (self.expand_function_params['mdp_policy'] is None))):
+            log('[Warning] MDP solution not provided, running value iteration on the problem to retrieve it...')
+            vi_solver = VI_Solver(gamma=self.gamma, eps=self.eps)
+            log('    > Starting MDP Value Iteration...')
+            mdp_solution, hist = vi_solver.solve(model, use_gpu=use_gpu, print_progress=False)
+            log(f'    > Value Iteration stopped or converged in {sum(hist.iteration_times):.3f}s, and after {len(hist.iteration_times)} iteration.\n')
+            self.expand_function_params['mdp_policy'] = mdp_solution
+
+        max_allowed_change = self.eps * (self.gamma / (1 - self.gamma))
+        solver_history = SolverHistory(tracking_level=history_tracking_level, model=model, gamma=self.gamma, eps=self.eps,
+                                       expand_function=self.expand_function, expand_append=full_backup,
+                                       initial_value_function=value_function, initial_belief_set=belief_set)
+        iteration = 0
+        expand_value_function = value_function
+        old_value_function = value_function
+        try:
+            if print_progress:
+                from tqdm.auto import trange
+                iterator = trange(expansions, desc='Expansions')
+            else:
+                iterator = range(expansions)
+            iterator_postfix = {}
+            for expansion_i in iterator:
+                # 1: expand the belief set
+                start_ts = _now_synced(model)
+                new_belief_set = self.expand(model=model, belief_set=belief_set, value_function=value_function,
+                                             max_generation=max_belief_growth, **self.expand_function_params)
+                belief_set = belief_set.union(new_belief_set)
+                solver_history.add_expand_step(expansion_time=(_now_synced(model) - start_ts).total_seconds(), belief_set=belief_set)
+
+                # 2: backup
+                for _ in range(update_passes):
+                    start_ts = _now_synced(model)
+                    value_function = self.backup(model, belief_set if full_backup else new_belief_set, value_function,
+                                                 append=(not full_backup), belief_dominance_prune=False)
+                    backup_time = (_now_synced(model) - start_ts).total_seconds()
+
+                    if (iteration % prune_interval) == 0 and iteration > 0:
+                        start_ts = _now_synced(model)
+                        vf_len = len(value_function)
+                        value_function.prune(prune_level)
+                        solver_history.add_prune_step((_now_synced(model) - start_ts).total_seconds(), len(value_function) - vf_len)
+
+                    if limit_value_function_size >= 0 and len(value_function) > limit_value_function_size:
+                        value_function, n_useful = self._limit_value_function(model, value_function, belief_set, max_belief_growth)
+                        iterator_postfix['|useful|'] = n_useful
+
+                    max_change = self.compute_change(value_function, old_value_function, belief_set)
+                    solver_history.add_backup_step(backup_time, max_change, value_function)
+                    if max_change < max_allowed_change:
+                        break
+                    old_value_function = value_function
+                    iteration += 1
+
+                expand_max_change = self.compute_change(expand_value_function, value_function, belief_set)
+                if expand_max_change < max_allowed_change:
+                    print('Converged!')
+                    break
+                expand_value_function = value_function
+                iterator_postfix['|V|'] = len(value_function)
+                iterator_postfix['|B|'] = len(belief_set)
+                if print_progress:
+                    iterator.set_postfix(iterator_postfix)
+        except MemoryError as e:
+            print(f'Memory full: {e}')
+            print('Returning value function and history as is...\n')
+
+        start_ts = _now_synced(model)
+        vf_len = len(value_function)
+        value_function.prune(prune_level)
+        solver_history.add_prune_step((_now_synced(model) - start_ts).total_seconds(), len(value_function) - vf_len)
+        return value_function, solver_history
+
+    def _limit_value_function(self, model: Model, value_function: ValueFunction, belief_set: BeliefSet, max_belief_growth: int):
+        """Drops `max_belief_growth` randomly chosen alpha vectors that are best at no belief (reference src/pomdp.py:2347-2367;
+        sampled WITH replacement and a linearly decaying weight, like the reference)."""
+        _, best = model.device.max_values(belief_set.belief_array, value_function.alpha_vector_array)
+        useful = np.unique(best.cpu().numpy())
+        unuseful = np.delete(np.arange(len(value_function)), useful)
+        weights = np.arange(len(unuseful))[::-1] / np.sum(np.arange(len(unuseful)))
+        to_delete = np.random.choice(unuseful, size=max_belief_growth, p=weights)
+        keep = np.delete(np.arange(len(value_function)), to_delete)
+        rows = value_function.alpha_vector_array[torch.as_tensor(keep, device=model.device.device)]
+        return ValueFunction(model, rows, value_function.actions[keep], _trusted=True, _hashes=value_function.row_hashes[keep]), useful.shape[0]
+
+
+class HSVI_Solver(PBVI_Solver):
+    """Heuristic Search Value Iteration preset (reference src/pomdp.py:2416-2479): new-points backup, one pass."""
+
+    def __init__(self, gamma: float = 0.99, eps: float = 0.001, mdp_solution: Union[ValueFunction, None] = None):
+        super().__init__(gamma=gamma, eps=eps, expand_function='hsvi', mdp_policy=mdp_solution)
+
+    def solve(self, model: Model, expansions: int, max_belief_growth: int = 10, initial_belief=None, initial_value_function=None,
+              prune_level: int = 1, prune_interval: int = 10, limit_value_function_size: int = -1, use_gpu: bool = True,
+              history_tracking_level: int = 1, print_progress: bool = True):
+        return super().solve(model=model, expansions=expansions, full_backup=False, update_passes=1, max_belief_growth=max_belief_growth,
+                             initial_belief=initial_belief, initial_value_function=initial_value_function, prune_level=prune_level,
+                             prune_interval=prune_interval, limit_value_function_size=limit_value_function_size, use_gpu=use_gpu,
+                             history_tracking_level=history_tracking_level, print_progress=print_progress)
+
+
+class FSVI_Solver(PBVI_Solver):
+    """Forward Search Value Iteration preset (reference src/pomdp.py:2482-2545); note the default gamma of 0.9."""
+
+    def __init__(self, gamma: float = 0.9, eps: float = 0.001, mdp_policy: Union[ValueFunction, None] = None):
+        super().__init__(gamma=gamma, eps=eps, expand_function='fsvi', mdp_policy=mdp_policy)
+
+    def solve(self, model: Model, expansions: int, max_belief_growth: int = 10, initial_belief=None, initial_value_function=None,
+              prune_level: int = 1, prune_interval: int = 10, limit_value_function_size: int = -1, use_gpu: bool = True,
+              history_tracking_level: int = 1, print_progress: bool = True):
+        return PBVI_Solver.solve(self, model=model, expansions=expansions, full_backup=False, update_passes=1,
+                                 max_belief_growth=max_belief_growth, initial_belief=initial_belief,
+                                 initial_value_function=initial_value_function, prune_level=prune_level, prune_interval=prune_interval,
+                                 limit_value_function_size=limit_value_function_size, use_gpu=use_gpu,
+                                 history_tracking_level=history_tracking_level, print_progress=print_progress)
+
+
+class FSVI_EG_Solver(FSVI_Solver):
+    """FSVI with epsilon-greedy exploration (reference src/pomdp.py:2548-2578)."""
+
+    def __init__(self, gamma: float = 0.9, eps: float = 0.001, mdp_policy: Union[ValueFunction, None] = None, eps_greedy=None):
+        super().__init__(gamma, eps, mdp_policy)
+        self.expand_function = 'fsvi_eg'
+        self.expand_function_params['eps_greedy'] = eps_greedy if eps_greedy is not None else (lambda t: 0.2)
