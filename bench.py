@@ -233,12 +233,12 @@ def run_b200(args):
         blob = torch.load(args.load_workload)
         solver = PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus')
         beliefs = blob['beliefs'].to(dev.device)
-        vf = ValueFunction(model, blob['alphas'].to(dev.device), blob['actions'])
+        vf = ValueFunction(model, blob['alphas'].to(dev.device), blob['actions'].numpy())
         grow_iters = int(blob['grow_iters'])
     else:
         solver, beliefs, vf, grow_iters = build_workload(model, args.beliefs, args.alphas, seed=rank)
     if args.save_workload and rank == 0:
-        torch.save({'beliefs': beliefs.cpu(), 'alphas': vf.alpha_vector_array.cpu(), 'actions': vf.actions, 'grow_iters': grow_iters},
+        torch.save({'beliefs': beliefs.cpu(), 'alphas': vf.alpha_vector_array.cpu(), 'actions': torch.as_tensor(vf.actions), 'grow_iters': grow_iters},
                    args.save_workload)
     B, V = beliefs.shape[0], len(vf)
     A, O, S = model.action_count, model.observation_count, model.state_count
