@@ -4,7 +4,7 @@
 //
 // Pipeline of pbvi_backup_select:
 //   transpose_kernel          alphas [V][S] -> alphaT [S][Vp]          (so a gathered successor row is one coalesced line)
-//   belief_mask_kernel        4-bit row-group occupancy of every (belief tile, K chunk)
+//   belief_mask_kernel        row-group occupancy bits of every (belief tile, K chunk)
 //   build_chunk_lists_kernel  per (tile, a, o): ordered list of chunks live in both the beliefs and RTO[a][o]
 //   (R > 1) gamma_project_kernel  GammaT[a,o][s][v] = sum_r RTO * alphaT[reach]   (HBM-bound gather)
 //   score_kernel              block-sparse DMMA + fused first-index argmax over v
@@ -19,7 +19,8 @@
 
 namespace pbvi {
 
-static_assert(KC == 16 && RG == 32 && BM == 128, "belief_mask_kernel assumes 16-state chunks and 4 row groups of 32");
+static_assert(KC == 16 && RG == 32 && BM % RG == 0 && BM <= 256, "belief_mask_kernel assumes 16-state chunks and 32-row groups");
+constexpr int MASK_ROWS_PER_WARP = BM / 8;   // 8 warps cover the tile; a warp's rows lie inside one row group
 
 // ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out) {
@@ -47,29 +48,33 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
     return PBVI_OK;
 }
 
-// ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c ---------------------
-__global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
-                                                          uint8_t* __restrict__ bits) {
+// ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c; the same pass writes the
+//      chunk-padded copy beliefsP [nMt*BM][Sp] (zero beyond nB rows / S columns) that the score kernel's bulk copies read
+//      (every 16-state segment of it starts on a 128-byte boundary, which a row of odd length S cannot offer).
+__global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int Sp, int nChunks,
+                                                          uint8_t* __restrict__ bits, double* __restrict__ beliefsP) {
     __shared__ unsigned smask[NRG];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cb = blockIdx.x, mt = blockIdx.y;
     if (tid < NRG) smask[tid] = 0u;
     __syncthreads();
     unsigned mask = 0u;
-    for (int rr = 0; rr < 16; rr++) {
-        const int row = mt * BM + w * 16 + rr;
-        if (row >= nB) break;
-        const double* brow = beliefs + (size_t)row * S;
+    for (int rr = 0; rr < MASK_ROWS_PER_WARP; rr++) {
+        const int row = mt * BM + w * MASK_ROWS_PER_WARP + rr;
+        const bool live = row < nB;
+        const double* brow = beliefs + (size_t)(live ? row : 0) * S;
+        double* prow = beliefsP + (size_t)row * Sp;
 #pragma unroll 4
         for (int j = 0; j < 16; j++) {
             const int s = cb * 512 + j * 32 + lane;
-            const bool nz = (s < S) && (brow[s] != 0.0);
-            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            const double v = (live && s < S) ? brow[s] : 0.0;
+            if (s < Sp) prow[s] = v;
+            const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
             if (bal & 0xFFFFu) mask |= 1u << (2 * j);
             if (bal >> 16) mask |= 1u << (2 * j + 1);
         }
     }
-    if (lane == 0 && mask) atomicOr(&smask[w >> 1], mask);
+    if (lane == 0 && mask) atomicOr(&smask[(w * MASK_ROWS_PER_WARP) / RG], mask);
     __syncthreads();
     if (tid < 32) {
         const int c = cb * 32 + tid;
@@ -238,8 +243,8 @@ static int launch_score(pbvi_model* m, bool gather, const ScoreParams& p, int nN
         configured = true;
     }
     dim3 grid(nNt, nMt, nZ);
-    if (gather) score_kernel<true><<<grid, SCORE_THREADS, SCORE_SMEM, st>>>(p);
-    else score_kernel<false><<<grid, SCORE_THREADS, SCORE_SMEM, st>>>(p);
+    if (gather) score_kernel<true><<<grid, SCORE_THREADS_TOTAL, SCORE_SMEM, st>>>(p);
+    else score_kernel<false><<<grid, SCORE_THREADS_TOTAL, SCORE_SMEM, st>>>(p);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
@@ -252,14 +257,15 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     const int S = m->S, R = m->R, nC = m->nChunks;
     const int nZ = backup ? m->nZ : 1;
     const int Vp = ceil_div(nV, BN) * BN, nNt = Vp / BN, nMt = ceil_div(nB, BM);
-    PBVI_REQUIRE(nMt <= 65535, "too many beliefs in one call (limit 65535 * 128)");
+    PBVI_REQUIRE(nMt <= 65535, "too many beliefs in one call (limit 65535 * 64)");
     PBVI_REQUIRE(nZ <= 65535, "too many (action, observation) pairs");
 
     PBVI_TAKE(alphaT, double, (size_t)S * Vp);
     PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
 
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
-    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits);
+    PBVI_TAKE(beliefsP, double, (size_t)nMt * BM * m->Sp);
+    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, m->Sp, nC, bits, beliefsP);
     m->last_launches++;
     PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nC);
     PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ);
@@ -275,7 +281,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
 
     if (m->profile) PBVI_CUDA(cudaEventRecord(m->evScore0, st));
     ScoreParams p{};
-    p.beliefs = d_beliefs; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
+    p.beliefsP = beliefsP; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
     p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nZ = nZ; p.O = m->O;
     if (!backup) {
         p.bmat = alphaT; p.zStrideB = 0; p.zOrder = nullptr;
@@ -322,7 +328,7 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
         d_value = m->arena.take<double>((size_t)nB * m->A);
         if (!d_value) return PBVI_ERR_OOM;
     }
-    PBVI_REQUIRE(nB <= 65535 * 128, "too many beliefs in one call");
+    PBVI_REQUIRE(nB <= 65535 * BM, "too many beliefs in one call");
     // grid.y is limited to 65535: walk the beliefs in slabs
     for (int b0 = 0; b0 < nB; b0 += 65535) {
         const int nb = std::min(65535, nB - b0);

@@ -13,10 +13,10 @@ namespace pbvi {
 
 // ---- tiling constants of the score kernel (see score_kernel.cuh) --------------------------------
 constexpr int KC = 16;         // source states per K chunk -- the sparsity-skipping granule along K
-constexpr int BM = 128;        // beliefs per block tile
-constexpr int BN = 128;        // alpha vectors per block tile
+constexpr int BM = 64;         // beliefs per block tile
+constexpr int BN = 256;        // alpha vectors per block tile
 constexpr int RG = 32;         // beliefs per row group (one warp's rows) -- the skipping granule along M
-constexpr int NRG = BM / RG;   // 4 row groups per tile
+constexpr int NRG = BM / RG;   // 2 row groups per tile
 constexpr int SCORE_THREADS = 256;
 
 void set_error(const char* fmt, ...);

@@ -10,10 +10,22 @@
 //   bmat is alphaT (z stride 0: max_v b.alpha_v of compute_change / SSGA / GER) or the transposed Gamma projection
 //   GammaT[a,o] built by gamma_project_kernel for models with reachable_state_count > 1.
 //
-// One block owns a BM x BN tile of one z = (a,o) and walks only the K chunks (KC source states) in which some belief
-// of the tile is non-zero AND some RTO entry of (a,o) is non-zero (list built by build_chunk_lists_kernel); inside a
-// chunk a warp whose RG beliefs are all zero is skipped.  gamma > 0 scales every score equally and is left out
-// (argmax invariant; exact-zero rows stay exactly zero, so "first index of the maximum" is preserved).
+// One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 16 source states) in which
+// some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero (list built by build_chunk_lists_kernel).
+//
+// Warp specialisation (9 warps):
+//   warp 8      producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
+//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (16), one 128 B
+//               copy per belief row of every live row group (beliefs come from the chunk-padded copy written by
+//               belief_mask_kernel, so every source is 128 B aligned) and the RTO chunk.  List entries and gathered row
+//               indices are prefetched one chunk ahead, so the producer never waits on a dependent global load.
+//   warps 0-7   consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
+//               Warp w owns row group w / 4 (RG = 32 beliefs) and column quarter w % 4, so each SM sub-partition
+//               (warp id mod 4) holds one warp of EACH row group: a row group that is all-zero on the chunk is skipped
+//               and the saving is spread over all four FP64 pipes (the first, 128 x 128 layout stalled on the barrier
+//               instead: profiles/r01_score_kernel_v1_ncu_summary.txt).
+// gamma > 0 scales every score equally and is left out (argmax invariant; exact-zero rows stay exactly zero, so "first
+// index of the maximum" is preserved).
 // Bound: the FP64 pipe (DMMA.8x8x4 runs at the FP64 peak on sm_100a, see profiles/r01_fp64_pipe_microbench.txt).
 #pragma once
 #include "pbvi_common.cuh"
@@ -22,19 +34,25 @@ namespace pbvi {
 
 constexpr int STAGES = 5;
 constexpr int LDA = KC + 4;   // 20: row stride 4 mod 16 doubles -> conflict-free 8-byte fragment loads
-constexpr int LDB = BN + 4;   // 132
+constexpr int LDB = BN + 4;   // 260
+constexpr int NCW = BN / 64;  // 4 column warps, 64 columns each
+constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 8
+constexpr int SCORE_THREADS_TOTAL = (N_CONSUMER_WARPS + 1) * 32;   // + the producer warp
 
-struct __align__(16) ScoreStage {
+struct __align__(128) ScoreStage {
     double Bs[KC * LDB];
     double As[BM * LDA];
     double Rs[KC];
 };
 constexpr size_t SCORE_SMEM = sizeof(ScoreStage) * STAGES;
-static_assert(sizeof(ScoreStage) % 16 == 0, "stage alignment");
-static_assert(SCORE_SMEM <= 227 * 1024, "score pipeline exceeds shared memory");
+static_assert(sizeof(ScoreStage) % 128 == 0, "stage alignment");
+static_assert(SCORE_SMEM <= 226 * 1024, "score pipeline exceeds shared memory");
+static_assert(BM == NRG * RG && N_CONSUMER_WARPS * 32 == SCORE_THREADS, "warp layout: NRG row groups x NCW column warps");
+static_assert(2 * sizeof(double) * NCW * BM <= sizeof(ScoreStage), "argmax staging reuses the first stage");
+static_assert(KC <= 32 && BM <= 64, "producer lane mapping: one B row and two A rows per lane");
 
 struct ScoreParams {
-    const double* beliefs;     // [nB][S]
+    const double* beliefsP;    // [nMt*BM][Sp]  chunk-padded beliefs (zero rows / columns beyond nB / S)
     const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [gridDim.z][S][Vp], matrix of block z at blockIdx.z * zStrideB
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
@@ -48,18 +66,38 @@ struct ScoreParams {
     int nB, S, Sp, V, Vp, nChunks, nZ, O;
 };
 
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -73,150 +111,147 @@ __device__ __forceinline__ void argmax_combine(double& v, int& i, double ov, int
 }
 
 template <bool GATHER>
-__global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const ScoreParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     ScoreStage* stages = reinterpret_cast<ScoreStage*>(smem_raw);
+    __shared__ __align__(8) uint64_t s_full[STAGES];
+    __shared__ __align__(8) uint64_t s_empty[STAGES];
     __shared__ uint32_t s_meta[STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int warp_m = warp & 3, warp_n = warp >> 2;
     const int nt = blockIdx.x, mt = blockIdx.y;
     const int z = p.zOrder ? p.zOrder[blockIdx.z] : (int)blockIdx.z;
-    const int a = GATHER ? z / p.O : 0;
     const int m0 = mt * BM, n0 = nt * BN;
     const uint32_t* __restrict__ list = p.lists + ((size_t)mt * p.nZ + z) * p.nChunks;
     const int nAct = p.listCount[mt * p.nZ + z];
-    const double* __restrict__ bsrc = (GATHER ? p.bmat : p.bmat + (size_t)blockIdx.z * p.zStrideB) + n0;
-    const int32_t* __restrict__ reach = GATHER ? p.reachP + (size_t)a * p.Sp : nullptr;
-    const double* __restrict__ rto = GATHER ? p.rtoP + (size_t)z * p.Sp : nullptr;
 
-    double acc[4][8][2];
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int n = 0; n < 8; n++) { acc[i][n][0] = 0.0; acc[i][n][1] = 0.0; }
-
-    // ---- producer state, software-pipelined so that no thread waits on a dependent global load:
-    //      e0/rows0 describe the chunk issued by the NEXT call of issue(); e1 the one after it.
-    const int bkk = tid >> 6;            // B tile: this thread copies piece (tid & 63) of rows bkk + 4*i
-    const int bpiece = (tid & 63) * 2;
-    uint32_t e0 = 0, e1 = 0;
-    int rows0[4] = {0, 0, 0, 0};
-    int fetched = 0;                     // list position whose entry sits in e1
-    auto load_rows = [&](uint32_t e, int (&rows)[4]) {
-        const int k0 = (int)(e & 0xFFFFFFu) * KC;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int k = k0 + bkk + 4 * i;
-            rows[i] = GATHER ? reach[k] : min(k, p.S - 1);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], N_CONSUMER_WARPS);
         }
-    };
-    if (nAct > 0) {
-        e0 = list[0];
-        e1 = list[min(1, nAct - 1)];
-        fetched = 1;
-        load_rows(e0, rows0);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    __syncthreads();
 
-    auto issue = [&](int slot) {
-        ScoreStage& st = stages[slot];
-        const uint32_t e = e0;
-        const int k0 = (int)(e & 0xFFFFFFu) * KC;
-        const uint32_t rg = e >> 24;
-        if (tid == 0) s_meta[slot] = e;
-#pragma unroll
-        for (int i = 0; i < BM * KC / SCORE_THREADS; i++) {
-            const int idx = tid + i * SCORE_THREADS;
-            const int m = idx >> 4, kk = idx & 15;
-            if (!((rg >> (m >> 5)) & 1u)) continue;          // rows of an all-zero row group are never read
-            const int k = k0 + kk, row = m0 + m;
-            const bool valid = (row < p.nB) && (k < p.S);
-            const double* src = valid ? p.beliefs + (size_t)row * p.S + k : p.beliefs;
-            cp_async8(&st.As[m * LDA + kk], src, valid);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int kk = bkk + 4 * i;
-            const bool valid = (k0 + kk) < p.S;
-            cp_async16(&st.Bs[kk * LDB + bpiece], bsrc + (size_t)rows0[i] * p.Vp + bpiece, valid);
-        }
-        if (GATHER && tid < KC) cp_async8(&st.Rs[tid], rto + k0 + tid, true);
-        // advance the prefetch registers (consumed by the next issue, one full chunk of math from now)
-        e0 = e1;
-        load_rows(e0, rows0);
-        fetched = min(fetched + 1, nAct - 1);
-        e1 = list[fetched];
-    };
-
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nAct) issue(s);
-        cp_async_commit();
-    }
-
-    unsigned long long visited = 0;
-    for (int it = 0; it < nAct; it++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (it + STAGES - 1 < nAct) issue((it + STAGES - 1) % STAGES);
-        cp_async_commit();
-
-        const ScoreStage& st = stages[it % STAGES];
-        const uint32_t rg = s_meta[it % STAGES] >> 24;
-        if (tid == 0) visited += __popc(rg);
-        if ((rg >> warp_m) & 1u) {
-            const double* Ab = st.As + (warp_m * RG + g) * LDA + t;
-            const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
-#pragma unroll
-            for (int ks = 0; ks < KC / 4; ks++) {
-                double af[4], bf[8];
-#pragma unroll
-                for (int i = 0; i < 4; i++) af[i] = Ab[i * 8 * LDA + ks * 4];
-                if (GATHER) {
-                    const double r = st.Rs[ks * 4 + t];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) af[i] *= r;
-                }
-#pragma unroll
-                for (int n = 0; n < 8; n++) bf[n] = Bb[ks * 4 * LDB + n * 8];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int n = 0; n < 8; n++) dmma884(acc[i][n], af[i], bf[n]);
-            }
-        }
-    }
-    cp_async_wait<0>();
-    if (tid == 0 && p.stats && visited) atomicAdd(p.stats, visited);
-
-    // ---- fused argmax: ascending columns per thread, then the quad (disjoint columns of the same rows), then the
-    //      two column-warps through shared memory.  An empty list leaves acc == 0: every score is 0, first column wins.
     double best[4];
     int bidx[4];
-    const int cbase = n0 + warp_n * 64 + 2 * t;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        best[i] = -INFINITY;
-        bidx[i] = 0x7fffffff;
-#pragma unroll
-        for (int n = 0; n < 8; n++)
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int col = cbase + n * 8 + j;
-                const double v = acc[i][n][j];
-                if (col < p.V && v > best[i]) { best[i] = v; bidx[i] = col; }
+    const int g = lane >> 2, t = lane & 3;
+    const int warp_m = warp / NCW, warp_n = warp % NCW;     // meaningful for consumer warps only
+
+    if (warp == N_CONSUMER_WARPS) {
+        // =============================== producer warp ===============================
+        const int a = GATHER ? z / p.O : 0;
+        const double* __restrict__ bsrc = (GATHER ? p.bmat : p.bmat + (size_t)blockIdx.z * p.zStrideB) + n0;
+        const int32_t* __restrict__ reach = GATHER ? p.reachP + (size_t)a * p.Sp : nullptr;
+        const double* __restrict__ rto = GATHER ? p.rtoP + (size_t)z * p.Sp : nullptr;
+        const double* __restrict__ arow0 = p.beliefsP + (size_t)(m0 + lane) * p.Sp;            // tile row `lane`   (row group 0)
+        const double* __restrict__ arow1 = p.beliefsP + (size_t)(m0 + 32 + lane) * p.Sp;       // tile row 32+lane (row group 1)
+        auto gathered_row = [&](uint32_t e) -> int {
+            const int k = (int)(e & 0xFFFFFFu) * KC + (lane & (KC - 1));
+            return GATHER ? reach[k] : min(k, p.S - 1);
+        };
+        uint32_t e0 = 0, e1 = 0;
+        int row0 = 0;
+        if (nAct > 0) {
+            e0 = list[0];
+            e1 = list[min(1, nAct - 1)];
+            row0 = gathered_row(e0);
+        }
+        unsigned long long visited = 0;
+        for (int q = 0; q < nAct; q++) {
+            const int slot = q % STAGES;
+            const unsigned use = (unsigned)(q / STAGES);
+            mbar_wait(&s_empty[slot], (use & 1u) ^ 1u);          // first use of a slot passes immediately
+            ScoreStage& st = stages[slot];
+            const uint32_t e = e0;
+            const int k0 = (int)(e & 0xFFFFFFu) * KC;
+            const uint32_t rg = e >> 24;
+            if (lane == 0) {
+                s_meta[slot] = e;
+                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & 3u) * RG * KC * 8;
+                mbar_arrive_expect_tx(&s_full[slot], bytes);
+                visited += __popc(rg & 3u);
             }
+            __syncwarp();
+            if (lane < KC) bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
+            if (rg & 1u) bulk_g2s(&st.As[lane * LDA], arow0 + k0, KC * 8, &s_full[slot]);
+            if (rg & 2u) bulk_g2s(&st.As[(32 + lane) * LDA], arow1 + k0, KC * 8, &s_full[slot]);
+            if (GATHER && lane == KC) bulk_g2s(&st.Rs[0], rto + k0, KC * 8, &s_full[slot]);
+            // prefetch for the next chunk (consumed one iteration from now)
+            e0 = e1;
+            row0 = gathered_row(e0);
+            e1 = list[min(q + 2, nAct - 1)];
+        }
+        if (lane == 0 && p.stats && visited) atomicAdd(p.stats, visited);
+    } else {
+        // =============================== consumer warps ===============================
+        double acc[4][8][2];
 #pragma unroll
-        for (int off = 1; off <= 2; off <<= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best[i], off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], off);
-            argmax_combine(best[i], bidx[i], ov, oi);
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int n = 0; n < 8; n++) { acc[i][n][0] = 0.0; acc[i][n][1] = 0.0; }
+
+        for (int it = 0; it < nAct; it++) {
+            const int slot = it % STAGES;
+            mbar_wait(&s_full[slot], (unsigned)(it / STAGES) & 1u);
+            const ScoreStage& st = stages[slot];
+            const uint32_t rg = s_meta[slot] >> 24;
+            if ((rg >> warp_m) & 1u) {
+                const double* Ab = st.As + (warp_m * RG + g) * LDA + t;
+                const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ks++) {
+                    double af[4], bf[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) af[i] = Ab[i * 8 * LDA + ks * 4];
+                    if (GATHER) {
+                        const double r = st.Rs[ks * 4 + t];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) af[i] *= r;
+                    }
+#pragma unroll
+                    for (int n = 0; n < 8; n++) bf[n] = Bb[ks * 4 * LDB + n * 8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int n = 0; n < 8; n++) dmma884(acc[i][n], af[i], bf[n]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[slot]);
+        }
+
+        // ---- fused argmax, part 1: ascending columns per thread, then the quad (disjoint columns of the same rows).
+        //      An empty list leaves acc == 0: every score is 0, first column wins.
+        const int cbase = n0 + warp_n * 64 + 2 * t;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            best[i] = -INFINITY;
+            bidx[i] = 0x7fffffff;
+#pragma unroll
+            for (int n = 0; n < 8; n++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int col = cbase + n * 8 + j;
+                    const double v = acc[i][n][j];
+                    if (col < p.V && v > best[i]) { best[i] = v; bidx[i] = col; }
+                }
+#pragma unroll
+            for (int off = 1; off <= 2; off <<= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best[i], off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], off);
+                argmax_combine(best[i], bidx[i], ov, oi);
+            }
         }
     }
-    __syncthreads();   // all warps are done with the stage buffers
-    double* sval = reinterpret_cast<double*>(smem_raw);                         // [2][BM]
-    int* sidx = reinterpret_cast<int*>(smem_raw + sizeof(double) * 2 * BM);     // [2][BM]
-    if (t == 0) {
+
+    // ---- fused argmax, part 2: the column warps through shared memory (every stage has been consumed by now)
+    __syncthreads();
+    double* sval = reinterpret_cast<double*>(smem_raw);                           // [NCW][BM]
+    int* sidx = reinterpret_cast<int*>(smem_raw + sizeof(double) * NCW * BM);     // [NCW][BM]
+    if (warp < N_CONSUMER_WARPS && t == 0) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int row = warp_m * RG + i * 8 + g;
@@ -228,7 +263,8 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
     if (tid < BM && m0 + tid < p.nB) {
         double v = sval[tid];
         int i = sidx[tid];
-        argmax_combine(v, i, sval[BM + tid], sidx[BM + tid]);
+#pragma unroll
+        for (int w = 1; w < NCW; w++) argmax_combine(v, i, sval[w * BM + tid], sidx[w * BM + tid]);
         const size_t out = ((size_t)nt * p.nB + (m0 + tid)) * p.nZ + z;
         p.pval[out] = v;
         p.pidx[out] = i;
