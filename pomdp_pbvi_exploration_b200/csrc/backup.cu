@@ -48,10 +48,12 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
     return PBVI_OK;
 }
 
-// ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c; the same pass writes the
-//      chunk-padded copy beliefsP [nMt*BM][Sp] (zero beyond nB rows / S columns) that the score kernel's bulk copies read
-//      (every 16-state segment of it starts on a 128-byte boundary, which a row of odd length S cannot offer).
-__global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int Sp, int nChunks,
+// ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c.  The same pass writes
+//      beliefsP, the belief tiles re-laid out as the shared-memory image the score kernel wants:
+//          beliefsP[mt][chunk][row group][RG rows][LDA]      (LDA = KC + 4 padded row stride, zero beyond nB rows / S columns)
+//      so that the A operand of one (tile, chunk, row group) is ONE contiguous, 128-byte aligned block of RG*LDA doubles that a
+//      single bulk async copy drops into shared memory already in its bank-conflict-free layout.
+__global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
                                                           uint8_t* __restrict__ bits, double* __restrict__ beliefsP) {
     __shared__ unsigned smask[NRG];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -60,15 +62,17 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
     __syncthreads();
     unsigned mask = 0u;
     for (int rr = 0; rr < MASK_ROWS_PER_WARP; rr++) {
-        const int row = mt * BM + w * MASK_ROWS_PER_WARP + rr;
+        const int m = w * MASK_ROWS_PER_WARP + rr;           // row inside the tile
+        const int row = mt * BM + m;
         const bool live = row < nB;
         const double* brow = beliefs + (size_t)(live ? row : 0) * S;
-        double* prow = beliefsP + (size_t)row * Sp;
 #pragma unroll 4
         for (int j = 0; j < 16; j++) {
             const int s = cb * 512 + j * 32 + lane;
+            const int c = s / KC;
             const double v = (live && s < S) ? brow[s] : 0.0;
-            if (s < Sp) prow[s] = v;
+            if (c < nChunks)
+                beliefsP[(((size_t)mt * nChunks + c) * NRG + m / RG) * A_GROUP_DOUBLES + (m % RG) * LDA + (s % KC)] = v;
             const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
             if (bal & 0xFFFFu) mask |= 1u << (2 * j);
             if (bal >> 16) mask |= 1u << (2 * j + 1);
@@ -264,8 +268,8 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
 
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
-    PBVI_TAKE(beliefsP, double, (size_t)nMt * BM * m->Sp);
-    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, m->Sp, nC, bits, beliefsP);
+    PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
+    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP);
     m->last_launches++;
     PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nC);
     PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ);

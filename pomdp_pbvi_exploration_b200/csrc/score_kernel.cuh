@@ -15,9 +15,9 @@
 //
 // Warp specialisation (9 warps):
 //   warp 8      producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
-//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (16), one 128 B
-//               copy per belief row of every live row group (beliefs come from the chunk-padded copy written by
-//               belief_mask_kernel, so every source is 128 B aligned) and the RTO chunk.  List entries and gathered row
+//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (16), ONE 5 KB
+//               copy per live row group (belief_mask_kernel stores the belief tiles as ready-made shared-memory images,
+//               padded row stride included) and the RTO chunk: 19 copies per chunk.  List entries and gathered row
 //               indices are prefetched one chunk ahead, so the producer never waits on a dependent global load.
 //   warps 0-7   consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
 //               Warp w owns row group w / 4 (RG = 32 beliefs) and column quarter w % 4, so each SM sub-partition
@@ -36,6 +36,7 @@ constexpr int STAGES = 5;
 constexpr int LDA = KC + 4;   // 20: row stride 4 mod 16 doubles -> conflict-free 8-byte fragment loads
 constexpr int LDB = BN + 4;   // 260
 constexpr int NCW = BN / 64;  // 4 column warps, 64 columns each
+constexpr int A_GROUP_DOUBLES = RG * LDA;   // one row group of one chunk in beliefsP == its shared-memory image (640 doubles, 5 KB)
 constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 8
 constexpr int SCORE_THREADS_TOTAL = (N_CONSUMER_WARPS + 1) * 32;   // + the producer warp
 
@@ -49,10 +50,10 @@ static_assert(sizeof(ScoreStage) % 128 == 0, "stage alignment");
 static_assert(SCORE_SMEM <= 226 * 1024, "score pipeline exceeds shared memory");
 static_assert(BM == NRG * RG && N_CONSUMER_WARPS * 32 == SCORE_THREADS, "warp layout: NRG row groups x NCW column warps");
 static_assert(2 * sizeof(double) * NCW * BM <= sizeof(ScoreStage), "argmax staging reuses the first stage");
-static_assert(KC <= 32 && BM <= 64, "producer lane mapping: one B row and two A rows per lane");
+static_assert(KC + NRG + 1 <= 32, "producer lane mapping: lanes [0,KC) B rows, [KC,KC+NRG) A row groups, KC+NRG the RTO chunk");
 
 struct ScoreParams {
-    const double* beliefsP;    // [nMt*BM][Sp]  chunk-padded beliefs (zero rows / columns beyond nB / S)
+    const double* beliefsP;    // [nMt][nChunks][NRG][RG][LDA]  belief tiles as shared-memory images (written by belief_mask_kernel)
     const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [gridDim.z][S][Vp], matrix of block z at blockIdx.z * zStrideB
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
@@ -146,8 +147,7 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
         const double* __restrict__ bsrc = (GATHER ? p.bmat : p.bmat + (size_t)blockIdx.z * p.zStrideB) + n0;
         const int32_t* __restrict__ reach = GATHER ? p.reachP + (size_t)a * p.Sp : nullptr;
         const double* __restrict__ rto = GATHER ? p.rtoP + (size_t)z * p.Sp : nullptr;
-        const double* __restrict__ arow0 = p.beliefsP + (size_t)(m0 + lane) * p.Sp;            // tile row `lane`   (row group 0)
-        const double* __restrict__ arow1 = p.beliefsP + (size_t)(m0 + 32 + lane) * p.Sp;       // tile row 32+lane (row group 1)
+        const double* __restrict__ atile = p.beliefsP + (size_t)mt * p.nChunks * NRG * A_GROUP_DOUBLES;
         auto gathered_row = [&](uint32_t e) -> int {
             const int k = (int)(e & 0xFFFFFFu) * KC + (lane & (KC - 1));
             return GATHER ? reach[k] : min(k, p.S - 1);
@@ -170,15 +170,16 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             const uint32_t rg = e >> 24;
             if (lane == 0) {
                 s_meta[slot] = e;
-                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & 3u) * RG * KC * 8;
+                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & 3u) * A_GROUP_DOUBLES * 8;
                 mbar_arrive_expect_tx(&s_full[slot], bytes);
                 visited += __popc(rg & 3u);
             }
             __syncwarp();
             if (lane < KC) bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
-            if (rg & 1u) bulk_g2s(&st.As[lane * LDA], arow0 + k0, KC * 8, &s_full[slot]);
-            if (rg & 2u) bulk_g2s(&st.As[(32 + lane) * LDA], arow1 + k0, KC * 8, &s_full[slot]);
-            if (GATHER && lane == KC) bulk_g2s(&st.Rs[0], rto + k0, KC * 8, &s_full[slot]);
+            if (lane >= KC && lane < KC + NRG && ((rg >> (lane - KC)) & 1u))
+                bulk_g2s(&st.As[(lane - KC) * A_GROUP_DOUBLES], atile + ((size_t)(k0 / KC) * NRG + (lane - KC)) * A_GROUP_DOUBLES,
+                         A_GROUP_DOUBLES * 8, &s_full[slot]);
+            if (GATHER && lane == KC + NRG) bulk_g2s(&st.Rs[0], rto + k0, KC * 8, &s_full[slot]);
             // prefetch for the next chunk (consumed one iteration from now)
             e0 = e1;
             row0 = gathered_row(e0);
