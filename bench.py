@@ -289,7 +289,7 @@ def run_b200(args):
             res = sharded.backup(bs, v_in, append=False)
         else:
             res = solver.backup(model, bs, v_in, append=False, belief_dominance_prune=False)
-        rows, acts = res.numpy()                                     # D2H
+        rows, acts = res.numpy(staged=True)                          # D2H into the pinned staging buffer
         return rows, acts
 
     e2e_steps = 0 if args.no_e2e else args.steps

@@ -296,6 +296,16 @@ class DeviceModel:
         self._call(self._lib.pbvi_ger_scores(self._h, _ptr(b), _ptr(al), _ptr(sc), n, float(r_min), float(r_max), _ptr(eps), self._stream))
         return eps
 
+    def to_host_staged(self, t: torch.Tensor) -> np.ndarray:
+        """Device -> host through a grow-only pinned staging buffer; returns a NumPy view valid until the next call."""
+        n = t.numel()
+        buf = getattr(self, '_staging', None)
+        if buf is None or buf.numel() < n:
+            buf = self._staging = torch.empty((max(n, 1 << 20),), dtype=torch.float64).pin_memory()
+        view = buf[:n].view(t.shape)
+        view.copy_(t)
+        return view.numpy()
+
     def set_profiling(self, enable: bool) -> None:
         _check(self._lib.pbvi_set_profiling(self._h, int(enable)))
 

@@ -126,15 +126,22 @@ class BeliefSet:
         self.is_on_gpu = True
         self._belief_list = None
         self._hashes = _hashes
+        self._device = None
+        self._host = None
         S = model.state_count
         if isinstance(beliefs, list):
             assert all(b.values.shape[0] == S for b in beliefs), f"Beliefs in belief list provided dont all have shape ({S},)"
             self._belief_list = beliefs
-            self._array = torch.stack([b.values for b in beliefs]) if len(beliefs) else \
+            self._device = torch.stack([b.values for b in beliefs]) if len(beliefs) else \
                 torch.empty((0, S), dtype=torch.float64, device=model.device.device)
         else:
             assert beliefs.shape[1] == S, f"Belief array provided doesnt have the right shape (expected (-,{S}), received {tuple(beliefs.shape)})"
-            self._array = _to_device(model, beliefs)
+            if isinstance(beliefs, torch.Tensor) and beliefs.device.type == 'cpu':
+                # host tensor: kept on the host and uploaded on first device use, or streamed chunk by chunk behind the score
+                # kernel by PBVI_Solver.backup (pin it -- `tensor.pin_memory()` -- for the copies to overlap the compute)
+                self._host = beliefs.to(torch.float64).contiguous()
+            else:
+                self._device = _to_device(model, beliefs)
             if not isinstance(beliefs, torch.Tensor):
                 # the reference builds Belief objects here, which asserts every row sums to 1 (src/pomdp.py:531-533, 345-347)
                 sums = np.round(np.asarray(beliefs, dtype=np.float64).sum(axis=1), 3)
@@ -144,33 +151,35 @@ class BeliefSet:
     @property
     def belief_array(self) -> torch.Tensor:
         """[N,S] CUDA float64 tensor."""
-        return self._array
+        if self._device is None:
+            self._device = _to_device(self.model, self._host)
+        return self._device
 
     @property
     def belief_list(self) -> list:
         if self._belief_list is None:
-            self._belief_list = [Belief._from_device(self.model, row) for row in self._array]
+            self._belief_list = [Belief._from_device(self.model, row) for row in self.belief_array]
         return self._belief_list
 
     @property
     def row_hashes(self) -> np.ndarray:
         if self._hashes is None:
-            self._hashes = self.model.device.row_hash(self._array).cpu().numpy() if len(self) else np.zeros((0, 2), dtype=np.int64)
+            self._hashes = self.model.device.row_hash(self.belief_array).cpu().numpy() if len(self) else np.zeros((0, 2), dtype=np.int64)
         return self._hashes
 
     def __len__(self) -> int:
-        return int(self._array.shape[0])
+        return int((self._device if self._device is not None else self._host).shape[0])
 
     def numpy(self) -> np.ndarray:
-        return self._array.cpu().numpy()
+        return self.belief_array.cpu().numpy()
 
     def generate_all_successors(self) -> 'BeliefSet':
-        succ, _ = self.model.device.belief_successors(self._array)
+        succ, _ = self.model.device.belief_successors(self.belief_array)
         return BeliefSet(self.model, succ.reshape(-1, self.model.state_count))
 
     def union(self, other_belief_set: 'BeliefSet') -> 'BeliefSet':
         """Own unique beliefs in order, then the unseen beliefs of the other set (reference src/pomdp.py:585-606)."""
-        rows = torch.cat([self._array, other_belief_set._array], dim=0)
+        rows = torch.cat([self.belief_array, other_belief_set.belief_array], dim=0)
         hashes = np.concatenate([self.row_hashes, other_belief_set.row_hashes], axis=0)
         first, _, _, _ = dedup_rows(self.model.device, rows, hashes)
         if first.shape[0] != rows.shape[0]:

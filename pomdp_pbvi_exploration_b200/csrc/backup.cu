@@ -183,14 +183,49 @@ __device__ __forceinline__ double alpha_a_entry(const double* __restrict__ alpha
     return __dadd_rn(rbarA[s], tot);
 }
 
-// ---- value[b][a] = sum_s b[s] * alpha_a[b,a,s]; block per (a, b); only the support of b is visited ----------------
+// ---- approx[b][a] = b . Rbar[:,a] + gamma * sum_o max_v score[b,a,o,v]: the same quantity as value[b][a] below, but summed
+//      in the score kernel's order.  Warp per (b, a); only the non-zero rewards are touched.
+__global__ void __launch_bounds__(256) approx_value_kernel(const double* __restrict__ beliefs, const double* __restrict__ maxscore,
+                                                           const int32_t* __restrict__ nzPtr, const int32_t* __restrict__ nzIdx,
+                                                           const double* __restrict__ nzVal, double gamma, int S, int A, int O, int nB,
+                                                           double* __restrict__ approx) {
+    const size_t gw = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (gw >= (size_t)nB * A) return;
+    const int lane = threadIdx.x & 31;
+    const int b = (int)(gw / A), a = (int)(gw % A);
+    const double* brow = beliefs + (size_t)b * S;
+    double part = 0.0;
+    for (int j = nzPtr[a] + lane; j < nzPtr[a + 1]; j += 32) part = fma(brow[nzIdx[j]], nzVal[j], part);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+    if (lane == 0) {
+        double so = 0.0;
+        for (int o = 0; o < O; o++) so += maxscore[gw * O + o];
+        approx[gw] = part + gamma * so;
+    }
+}
+
+// ---- value[b][a] = sum_s b[s] * alpha_a[b,a,s] in the reference's operation order; block per (a, b); only the support of b
+//      is visited.  Screening: an action whose approximate value is more than 1e-9 (relative to max(1, |best|)) below the
+//      best approximate value of its belief cannot be the argmax -- the two sums differ by rounding only -- so it keeps the
+//      approximate value and the block exits; every action that could win or tie is evaluated exactly.
 __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restrict__ beliefs, const double* __restrict__ alphas,
                                                            const int32_t* __restrict__ vstar, const int32_t* __restrict__ reachK,
                                                            const double* __restrict__ rtoK, const double* __restrict__ rbarT,
-                                                           double gamma, int S, int R, int A, int O, double* __restrict__ value) {
+                                                           const double* __restrict__ approx, double gamma, int S, int R, int A, int O,
+                                                           double* __restrict__ value) {
     extern __shared__ int s_vsel[];
     __shared__ double sh[8];
     const int a = blockIdx.x, b = blockIdx.y;
+    {
+        const double mine = approx[(size_t)b * A + a];
+        double best = -INFINITY;
+        for (int aa = 0; aa < A; aa++) best = fmax(best, approx[(size_t)b * A + aa]);
+        if (!(mine >= best - 1e-9 * fmax(1.0, fabs(best)))) {
+            if (threadIdx.x == 0) value[(size_t)b * A + a] = mine;
+            return;
+        }
+    }
     for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vstar[((size_t)b * A + a) * O + o];
     __syncthreads();
     const double* brow = beliefs + (size_t)b * S;
@@ -326,19 +361,28 @@ static int check_backup_args(const pbvi_model* m, const void* beliefs, int nB, c
 static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
                        int32_t* d_vstar, double* d_value, int32_t* d_astar, cudaStream_t st) {
     if (nB == 0) return PBVI_OK;
-    PBVI_TRY(score_argmax(m, d_beliefs, nB, d_alphas, nV, true, nullptr, d_vstar, st));
+    double* maxscore = nullptr;
+    if (d_value || d_astar) {
+        maxscore = m->arena.take<double>((size_t)nB * m->nZ);
+        if (!maxscore) return PBVI_ERR_OOM;
+    }
+    PBVI_TRY(score_argmax(m, d_beliefs, nB, d_alphas, nV, true, maxscore, d_vstar, st));
     if (!d_value && !d_astar) return PBVI_OK;
     if (!d_value) {
         d_value = m->arena.take<double>((size_t)nB * m->A);
         if (!d_value) return PBVI_ERR_OOM;
     }
     PBVI_REQUIRE(nB <= 65535 * BM, "too many beliefs in one call");
+    PBVI_TAKE(approx, double, (size_t)nB * m->A);
+    approx_value_kernel<<<(unsigned)ceil_div_sz((size_t)nB * m->A * 32, 256), 256, 0, st>>>(d_beliefs, maxscore, m->rbarNzPtr, m->rbarNzIdx,
+                                                                                          m->rbarNzVal, gamma, m->S, m->A, m->O, nB, approx);
+    m->last_launches++;
     // grid.y is limited to 65535: walk the beliefs in slabs
     for (int b0 = 0; b0 < nB; b0 += 65535) {
         const int nb = std::min(65535, nB - b0);
         backup_value_kernel<<<dim3(m->A, nb), 256, m->O * sizeof(int), st>>>(
-            d_beliefs + (size_t)b0 * m->S, d_alphas, d_vstar + (size_t)b0 * m->nZ, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->R,
-            m->A, m->O, d_value + (size_t)b0 * m->A);
+            d_beliefs + (size_t)b0 * m->S, d_alphas, d_vstar + (size_t)b0 * m->nZ, m->reachK, m->rtoK, m->rbarT, approx + (size_t)b0 * m->A,
+            gamma, m->S, m->R, m->A, m->O, d_value + (size_t)b0 * m->A);
         m->last_launches++;
     }
     if (d_astar) {

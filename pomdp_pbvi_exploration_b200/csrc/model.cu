@@ -147,6 +147,17 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
             }
         }
 
+    // ---- CSR of the non-zero expected rewards
+    std::vector<int32_t> rbarNzPtr(A + 1, 0), rbarNzIdx;
+    std::vector<double> rbarNzVal;
+    for (int a = 0; a < A; a++) {
+        for (int s = 0; s < S; s++) {
+            const double v = rbarT[(size_t)a * S + s];
+            if (v != 0.0) { rbarNzIdx.push_back(s); rbarNzVal.push_back(v); }
+        }
+        rbarNzPtr[a + 1] = (int32_t)rbarNzIdx.size();
+    }
+
     // ---- live-chunk masks per z = (a,o) and the heavy-first order
     std::vector<uint8_t> zMask((size_t)nZ * nC, 0);
     std::vector<long long> live(nZ, 0);
@@ -188,6 +199,7 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     int rc = PBVI_OK;
     auto up = [&](auto** dst, const auto& v) { if (rc == PBVI_OK) rc = upload(dst, v); };
     up(&m->reachK, reachK); up(&m->rtoK, rtoK); up(&m->rbarT, rbarT);
+    up(&m->rbarNzPtr, rbarNzPtr); up(&m->rbarNzIdx, rbarNzIdx); up(&m->rbarNzVal, rbarNzVal);
     if (h_probs) up(&m->probK, probK);
     if (R == 1) { up(&m->reachP, reachP); up(&m->rtoP, rtoP); }
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
@@ -207,6 +219,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     cudaFree(m->reachK); cudaFree(m->rtoK); cudaFree(m->probK); cudaFree(m->rbarT);
+    cudaFree(m->rbarNzPtr); cudaFree(m->rbarNzIdx); cudaFree(m->rbarNzVal);
     cudaFree(m->reachP); cudaFree(m->rtoP); cudaFree(m->zMask); cudaFree(m->zOrder);
     cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes);
     cudaFree(m->d_stats);

@@ -81,6 +81,10 @@ struct pbvi_model {
     double* rtoK = nullptr;      // [A][O][S*R]   RTO
     double* probK = nullptr;     // [A][S*R]      transition probabilities (nullptr when not supplied)
     double* rbarT = nullptr;     // [A][S]
+    // CSR of the non-zero expected rewards per action (b . Rbar[:,a] touches only these)
+    int32_t* rbarNzPtr = nullptr;  // [A+1]
+    int32_t* rbarNzIdx = nullptr;  // [nnz] state
+    double* rbarNzVal = nullptr;   // [nnz]
     // R == 1 fast path of the score kernel: chunk-padded copies (pad: landing state 0, RTO 0)
     int32_t* reachP = nullptr;   // [A][Sp]
     double* rtoP = nullptr;      // [A][O][Sp]

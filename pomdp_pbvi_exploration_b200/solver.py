@@ -312,14 +312,18 @@ class PBVI_Solver:
         assembled; the byte-dedup then runs over those rows (different tuples can still give identical rows).
         """
         dev = model.device
-        B, V = belief_set.belief_array, value_function.alpha_vector_array
-        nB = B.shape[0]
+        V = value_function.alpha_vector_array
+        nB = len(belief_set)
         if nB == 0:
             new_vf = ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
             if append:
                 new_vf.extend(value_function)
             return new_vf
-        vstar, value, astar = dev.backup_select(B, V, self.gamma)
+        if belief_set._device is None and nB >= 2 * self.STREAM_FIRST_CHUNK:
+            vstar, value, astar = self._select_streamed(model, belief_set, V)
+        else:
+            vstar, value, astar = dev.backup_select(belief_set.belief_array, V, self.gamma)
+        B = belief_set.belief_array
         ar = torch.arange(nB, device=dev.device)
         sel = vstar[ar, astar.long()]                                                    # [nB, O]
         keys = torch.cat([astar[:, None], sel], dim=1)
@@ -353,6 +357,48 @@ class PBVI_Solver:
         if append:
             new_vf.extend(value_function)
         return new_vf
+
+    STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
+    STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
+
+    def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor):
+        """
+        Select step for a belief set that still lives in (pinned) host memory: the rows are uploaded in chunks on a
+        copy stream while the compute stream runs `pbvi_backup_select` on the chunks that have landed (rows are
+        independent given V), so the PCIe transfer hides behind the score kernel instead of preceding it.
+        """
+        dev = model.device
+        host = belief_set._host
+        nB, S = host.shape
+        full = torch.empty((nB, S), dtype=torch.float64, device=dev.device)
+        vstar = torch.empty((nB, dev.A, dev.O), dtype=torch.int32, device=dev.device)
+        value = torch.empty((nB, dev.A), dtype=torch.float64, device=dev.device)
+        astar = torch.empty((nB,), dtype=torch.int32, device=dev.device)
+        bounds, lo = [], 0
+        while lo < nB:
+            hi = min(nB, lo + (self.STREAM_FIRST_CHUNK if lo == 0 else self.STREAM_CHUNK))
+            if nB - hi < self.STREAM_FIRST_CHUNK:
+                hi = nB
+            bounds.append((lo, hi))
+            lo = hi
+        compute = torch.cuda.current_stream(dev.device)
+        copy = getattr(self, '_copy_stream', None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(device=dev.device)
+        copy.wait_stream(compute)                       # `full` must be allocated before the copies touch it
+        events = []
+        with torch.cuda.stream(copy):
+            for lo, hi in bounds:
+                full[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                events.append(ev)
+        for (lo, hi), ev in zip(bounds, events):
+            compute.wait_event(ev)
+            v, val, a = dev.backup_select(full[lo:hi], V, self.gamma)
+            vstar[lo:hi], value[lo:hi], astar[lo:hi] = v, val, a
+        belief_set._device = full
+        return vstar, value, astar
 
     # ------------------------------------------------------------------------------------------------------------
     def compute_change(self, value_function: ValueFunction, new_value_function: ValueFunction, belief_set: BeliefSet) -> float:

@@ -101,8 +101,14 @@ class ValueFunction:
     def __len__(self) -> int:
         return int(self._array.shape[0])
 
-    def numpy(self):
-        """(alpha_vector_array, actions) as host NumPy arrays."""
+    def numpy(self, staged: bool = False):
+        """
+        (alpha_vector_array, actions) as host NumPy arrays.  `staged=True` reads the rows back through the model's
+        reusable pinned staging buffer and returns a VIEW of it (valid until the next staged read): a device->host copy at
+        PCIe speed without a fresh pageable allocation per call.
+        """
+        if staged:
+            return self.model.device.to_host_staged(self._array), self._actions.copy()
         return self._array.cpu().numpy(), self._actions.copy()
 
     # ---- set operations --------------------------------------------------------------------------

@@ -202,6 +202,26 @@ def test_solve_runs_on_grid_models(flavour):
     assert np.max(rows @ b0) >= np.max(model.expected_rewards_table.T @ b0) - 1e-12
 
 
+def test_streamed_host_beliefs_equal_device_resident():
+    """A BeliefSet built from a pinned host tensor is uploaded in chunks behind the score kernel; same value function out."""
+    import torch
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs
+    model = olfactory_wrap_model()
+    g = load_golden('backup_olfactory_wrap')
+    B = perseus_walk_beliefs(model, 2500, seed=3)
+    vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
+    solver = PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus')
+    dev_out = solver.backup(model, BeliefSet(model, B), vf, append=True, belief_dominance_prune=False)
+    host_set = BeliefSet(model, torch.as_tensor(B).pin_memory())
+    assert host_set._device is None and len(host_set) == 2500
+    host_out = solver.backup(model, host_set, vf, append=True, belief_dominance_prune=False)
+    r0, a0 = dev_out.numpy()
+    r1, a1 = host_out.numpy(staged=True)
+    assert np.array_equal(r0, r1) and np.array_equal(a0, a1)
+    assert torch.equal(host_set.belief_array.cpu(), torch.as_tensor(B))
+
+
 def test_olfactory_fsvi_solve_and_backup_parity():
     """FSVI on the 22021-state model: one expansion trajectory + backup with the engine, every step checked against the oracle."""
     from pomdp_pbvi_exploration_b200 import BeliefSet, FSVI_Solver, ValueFunction
