@@ -1,0 +1,75 @@
+"""
+World-size-2 test of the N > 1 path on CPU (gloo): the variable-count all-gather of new alpha rows and the rank-ordered
+merge must give every rank the value function a single process computes over the whole belief set
+(first position, last action).  The per-rank "backup" here is a stand-in that only exercises the exchange: rows are
+produced by the oracle, keys by a host hash, and byte-equality by torch on CPU.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pbvi_oracle as orc
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _host_hash(rows: np.ndarray) -> np.ndarray:
+    import hashlib
+    out = np.zeros((rows.shape[0], 2), dtype=np.int64)
+    for i, r in enumerate(rows):
+        out[i] = np.frombuffer(hashlib.blake2b(r.tobytes(), digest_size=16).digest(), dtype=np.int64)
+    return out
+
+
+def _rows_equal(ra, ia, rb, ib):
+    return torch.tensor([int(torch.equal(ra[int(i)], rb[int(j)])) for i, j in zip(ia, ib)], dtype=torch.int32)
+
+
+def _worker(rank, world, port, rows_all, actions_all, counts, result_queue):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pomdp_pbvi_exploration_b200.parallel import allgather_rows, merge_gathered, shard_bounds
+    lo, hi = shard_bounds(rows_all.shape[0], world, rank)
+    # local dedup (what the per-rank backup returns): first position, last action
+    local_rows, local_actions, _ = orc.dedup_rows(rows_all[lo:hi], actions_all[lo:hi])
+    local_hash = _host_hash(local_rows)
+    rows, actions, hashes, got_counts = allgather_rows(torch.as_tensor(local_rows), local_actions, local_hash)
+    merged_rows, merged_actions, merged_hashes = merge_gathered(rows, actions, hashes, _rows_equal)
+    result_queue.put((rank, merged_rows.numpy(), merged_actions, got_counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_rows,world', [(37, 2), (5, 2), (1, 2)])
+def test_sharded_merge_equals_single_process(n_rows, world):
+    rng = np.random.default_rng(n_rows)
+    S = 11
+    base = rng.random((6, S))
+    pick = rng.integers(0, 6, n_rows)
+    rows_all = base[pick]                               # many duplicates, spread over both shards
+    actions_all = rng.integers(0, 4, n_rows).astype(np.int64)
+    want_rows, want_actions, _ = orc.dedup_rows(rows_all, actions_all)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows_all, actions_all, None, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rows, actions, counts in results:
+        assert np.array_equal(rows, want_rows), rank
+        assert np.array_equal(actions, want_actions), rank
+        assert counts.sum() >= want_rows.shape[0]
