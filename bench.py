@@ -196,7 +196,7 @@ def run_reference(args):
     t_step = args.beliefs * args.alphas / value
     sample = (f'per step: Gamma projection for all {args.alphas} alphas + per-belief part on {n_sample} of {args.beliefs} beliefs, '
               f'extrapolated linearly in B; NumPy/OpenBLAS, {cores} threads')
-    print(json.dumps({
+    emit(({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, 1),
@@ -303,7 +303,7 @@ def run_b200(args):
         rows, acts = step_e2e()
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1) if e2e_steps else float('nan')   # device clock; every step ends with the blocking D2H read
+    e2e_ms = e0.elapsed_time(e1) if e2e_steps else 0.0   # device clock; every step ends with the blocking D2H read
     h2d = int(h_beliefs.numel() * 8 + h_alphas.numel() * 8)
     d2h = int(rows.size * 8 + acts.size * 8)
 
@@ -318,7 +318,7 @@ def run_b200(args):
     if rank == 0:
         units = float(B) * V * world
         value = units * args.steps / (elapsed_ms * 1e-3)
-        e2e_value = units * args.steps / (e2e_ms * 1e-3)
+        e2e_value = units * args.steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None
         algo_flops = 2.0 * A * O * S * B * V                  # per launch (per rank)
         achieved = algo_flops / (score_mean * 1e-3) / 1e12
         line = {
@@ -326,7 +326,7 @@ def run_b200(args):
             'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(args, world),
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy()'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (FP64 DMMA m8n8k4 + fused argmax)', 'achieved': achieved,
@@ -345,14 +345,32 @@ def run_b200(args):
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': f'Gamma projection for all {V} alphas + per-belief part on {n_sample} of {B} beliefs, extrapolated '
                                               f'linearly in B; NumPy/OpenBLAS with {cores} threads', **detail}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-if __name__ == '__main__':
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else printed during the run (NCCL banners, library logs) was
+    redirected to stderr by main()."""
+    os.write(_JSON_OUT, (json.dumps(line) + '\n').encode())
+
+
+def main():
+    global _JSON_OUT
     a = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for native code too (NCCL prints its version banner on stdout)
+    sys.stdout = sys.stderr
     if a.impl == 'reference':
         run_reference(a)
     else:
         run_b200(a)
+
+
+if __name__ == '__main__':
+    main()
