@@ -103,6 +103,12 @@ PBVI_API int pbvi_max_values(pbvi_model* m, const double* d_beliefs, int nB, con
 PBVI_API int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const int32_t* d_actions, const int32_t* d_observations,
                        int n, int normalise, double* d_out, double* d_norm, void* stream);
 
+/* A chain of n updates from d_b0 (the FSVI / FSVI_EG trajectory, src/pomdp.py:1905-1930): d_out[i] = update(prev_i, a_i, o_i) with
+ * prev_0 = d_b0 and prev_{i+1} = d_out[i], or d_b0 again when h_reset[i] != 0 (end state reached: restart from b0).  The (a,o)
+ * sequence comes from the host RNG walk and is passed in HOST arrays; 2n launches are enqueued, nothing is read back. */
+PBVI_API int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const int32_t* h_observations,
+                                    const uint8_t* h_reset, int n, double* d_out, void* stream);
+
 /* Every successor of every belief (Belief.generate_successors, src/pomdp.py:424-438; the B*A*O loop of SSEA :1679 and
  * GER :1732): d_out [n][A][O][S], d_norm [n][A][O] (nullable).  Rows of impossible observations are NaN when normalised. */
 PBVI_API int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, void* stream);

@@ -33,6 +33,7 @@ SIGNATURES = {
     'pbvi_backup_host': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P],
     'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
     'pbvi_belief_update': [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
+    'pbvi_belief_trajectory': [_P, _P, _P, _P, _P, c_int, _P, _P],
     'pbvi_belief_successors': [_P, _P, c_int, c_int, _P, _P, _P],
     'pbvi_observation_probabilities': [_P, _P, c_int, _P, _P],
     'pbvi_row_hash': [_P, _P, c_int, c_int, _P, _P],
@@ -226,6 +227,18 @@ class DeviceModel:
         norm = torch.empty((n,), dtype=torch.float64, device=self.device)
         self._call(self._lib.pbvi_belief_update(self._h, _ptr(b), _ptr(a), _ptr(o), n, int(normalise), _ptr(out), _ptr(norm), self._stream))
         return out, norm
+
+    def belief_trajectory(self, b0: torch.Tensor, actions, observations, resets=None) -> torch.Tensor:
+        """Chain of updates from b0 following host (a, o) sequences; restarts from b0 after steps flagged in `resets`."""
+        b = _f64(b0, self.device).reshape(-1)
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        o = np.ascontiguousarray(observations, dtype=np.int32)
+        r = None if resets is None else np.ascontiguousarray(resets, dtype=np.uint8)
+        n = a.shape[0]
+        out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
+        self._call(self._lib.pbvi_belief_trajectory(self._h, _ptr(b), a.ctypes.data, o.ctypes.data, None if r is None else r.ctypes.data, n,
+                                                    _ptr(out), self._stream))
+        return out
 
     def belief_successors(self, beliefs, normalise: bool = True):
         """All (a,o) successors: (succ [n,A,O,S], mass [n,A,O]); NaN rows for impossible observations when normalised."""

@@ -7,6 +7,7 @@ and the solver rely on, means the same thing in both engines).  `BeliefSet.belie
 """
 from __future__ import annotations
 
+import itertools
 from typing import Union
 
 import numpy as np
@@ -14,6 +15,9 @@ import torch
 
 from .model import Model
 from .sets import dedup_rows
+
+
+_LINEAGE = itertools.count(1)
 
 
 def _to_device(model: Model, values) -> torch.Tensor:
@@ -128,6 +132,7 @@ class BeliefSet:
         self._hashes = _hashes
         self._device = None
         self._host = None
+        self.lineage = next(_LINEAGE)       # sets grown from one another by union() share it (their rows are prefixes)
         S = model.state_count
         if isinstance(beliefs, list):
             assert all(b.values.shape[0] == S for b in beliefs), f"Beliefs in belief list provided dont all have shape ({S},)"
@@ -185,7 +190,11 @@ class BeliefSet:
         if first.shape[0] != rows.shape[0]:
             rows = rows[torch.as_tensor(first, device=rows.device)]
             hashes = hashes[first]
-        return BeliefSet(self.model, rows, _hashes=hashes)
+        out = BeliefSet(self.model, rows, _hashes=hashes)
+        n_self = len(self)
+        if first.shape[0] >= n_self and np.array_equal(first[:n_self], np.arange(n_self)):
+            out.lineage = self.lineage          # own rows survive as a prefix: per-row results cached for `self` stay valid
+        return out
 
     def to_gpu(self) -> 'BeliefSet':
         return self

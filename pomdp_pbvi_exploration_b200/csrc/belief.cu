@@ -13,11 +13,11 @@ __global__ void __launch_bounds__(256) belief_project_kernel(const double* __res
                                                              const int32_t* __restrict__ observations, size_t beliefStride,
                                                              const int32_t* __restrict__ predPtr, const int32_t* __restrict__ predK,
                                                              const double* __restrict__ rtoK, int S, int R, int O,
-                                                             double* __restrict__ out) {
+                                                             double* __restrict__ out, int aConst, int oConst) {
     const int i = blockIdx.y;
     const int sp = blockIdx.x * 256 + threadIdx.x;
     if (sp >= S) return;
-    const int a = actions[i], o = observations[i];
+    const int a = actions ? actions[i] : aConst, o = observations ? observations[i] : oConst;
     const size_t K = (size_t)S * R;
     const int32_t* ptr = predPtr + (size_t)a * (S + 1);
     const int32_t* pk = predK + (size_t)a * K;
@@ -127,7 +127,7 @@ static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t bel
         double* out = d_out + (size_t)i0 * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, 0, st>>>(d_beliefs + (size_t)i0 * beliefStride, d_actions + i0,
                                                                             d_observations + i0, beliefStride, m->predPtr, m->predK,
-                                                                            m->rtoK, m->S, m->R, m->O, out);
+                                                                            m->rtoK, m->S, m->R, m->O, out, 0, 0);
         m->last_launches++;
         if (normalise || d_norm) {
             pairwise_normalise_kernel<<<ni, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
@@ -148,6 +148,33 @@ extern "C" int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const 
     PBVI_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
     return belief_update_impl(m, d_beliefs, (size_t)m->S, d_actions, d_observations, n, normalise, d_out, d_norm, (cudaStream_t)stream);
+}
+
+extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const int32_t* h_observations,
+                                      const uint8_t* h_reset, int n, double* d_out, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_b0 && h_actions && h_observations && d_out, "NULL pointer argument");
+    for (int i = 0; i < n; i++)
+        PBVI_REQUIRE(h_actions[i] >= 0 && h_actions[i] < m->A && h_observations[i] >= 0 && h_observations[i] < m->O,
+                     "action / observation index out of range");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
+    PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
+    const double* src = d_b0;
+    for (int i = 0; i < n; i++) {
+        double* out = d_out + (size_t)i * m->S;
+        belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
+                                                                           m->O, out, h_actions[i], h_observations[i]);
+        pairwise_normalise_kernel<<<1, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, 1, nullptr);
+        m->last_launches += 2;
+        src = (h_reset && h_reset[i]) ? d_b0 : out;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
 }
 
 extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm,

@@ -355,7 +355,10 @@ class PBVI_Solver:
                 rows = rows[torch.as_tensor(gfirst, device=rows.device)]
             new_vf = ValueFunction(model, rows, actions, _trusted=True, _hashes=hashes[gfirst])
         if append:
+            n_new = len(new_vf)
             new_vf.extend(value_function)
+            # the union keeps the new rows first and every old row (bytewise): max over it = max(new rows, old value function)
+            new_vf.parent_uid, new_vf.n_new = value_function.uid, n_new
         return new_vf
 
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
@@ -403,12 +406,43 @@ class PBVI_Solver:
     # ------------------------------------------------------------------------------------------------------------
     def compute_change(self, value_function: ValueFunction, new_value_function: ValueFunction, belief_set: BeliefSet) -> float:
         """max_b | max_v b.alpha_v - max_v' b.alpha'_v' | (reference src/pomdp.py:2141-2169)."""
-        dev = belief_set.model.device
         if len(belief_set) == 0:
             return 0.0
-        a, _ = dev.max_values(belief_set.belief_array, value_function.alpha_vector_array)
-        b, _ = dev.max_values(belief_set.belief_array, new_value_function.alpha_vector_array)
+        a = self._max_values_cached(value_function, belief_set)
+        b = self._max_values_cached(new_value_function, belief_set)
         return float(torch.max(torch.abs(b - a)))
+
+    def _max_values_cached(self, vf: ValueFunction, belief_set: BeliefSet) -> torch.Tensor:
+        """
+        max_v b.alpha_v for every belief of the set, reusing what earlier calls already computed.  The solve loop evaluates
+        the same value functions on a belief set that only grows by appended rows (`BeliefSet.union` keeps a lineage), and a
+        new-points backup returns `new rows + all old rows` (`parent_uid`), so only two thin products are ever new:
+        (all beliefs) x (new rows) and (new beliefs) x (all rows).  Each b.alpha is produced by the same kernel whatever the
+        batch it is computed in (skipped chunks contribute exact zeros), so the result equals the full recomputation bit for bit.
+        """
+        dev = belief_set.model.device
+        cache = self.__dict__.setdefault('_max_cache', {})
+        B = belief_set.belief_array
+        nB = B.shape[0]
+        key = (vf.uid, belief_set.lineage)
+        done = cache.get(key)
+        if done is None and vf.parent_uid is not None and (vf.parent_uid, belief_set.lineage) in cache and 0 < vf.n_new:
+            parent = cache[(vf.parent_uid, belief_set.lineage)]
+            n_p = min(parent.shape[0], nB)
+            if n_p > 0:
+                fresh, _ = dev.max_values(B[:n_p], vf.alpha_vector_array[:vf.n_new])
+                done = torch.maximum(parent[:n_p], fresh)
+        if done is None:
+            done = torch.empty((0,), dtype=torch.float64, device=dev.device)
+        if done.shape[0] > nB:
+            done = done[:nB]
+        if done.shape[0] < nB:
+            rest, _ = dev.max_values(B[done.shape[0]:], vf.alpha_vector_array)
+            done = torch.cat([done, rest])
+        cache[key] = done
+        while len(cache) > 8:                       # a few value functions are alive at any time in the solve loop
+            cache.pop(next(iter(cache)))
+        return done
 
     # ---- expansions ------------------------------------------------------------------------------------------------
     def expand_ra(self, model: Model, belief_set: BeliefSet, max_generation: int = 10) -> BeliefSet:
@@ -567,13 +601,10 @@ class PBVI_Solver:
             s = s_p
             if reset:
                 s = int(np.random.choice(a=model.states, size=1, p=b0_host)[0])
-        rows = [b0.values]
-        b = b0.values
-        for a_star, o, reset in steps:
-            out, _ = dev.belief_update(b[None, :], [a_star], [o])
-            rows.append(out[0])
-            b = b0.values if reset else out[0]
-        return BeliefSet(model, torch.stack(rows))
+        if not steps:
+            return BeliefSet(model, b0.values[None, :].clone())
+        chain = dev.belief_trajectory(b0.values, [st[0] for st in steps], [st[1] for st in steps], [st[2] for st in steps])
+        return BeliefSet(model, torch.cat([b0.values[None, :], chain], dim=0))
 
     def expand_fsvi(self, model: Model, b0: Belief, mdp_policy: ValueFunction, max_generation: int = 10) -> BeliefSet:
         """Forward Search Value Iteration exploration (reference src/pomdp.py:1871-1935)."""

@@ -9,6 +9,7 @@ same dict `update` (new rows first, the other side's action wins on a collision)
 from __future__ import annotations
 
 import os
+import itertools
 from datetime import datetime
 from typing import Union
 
@@ -17,6 +18,9 @@ import torch
 
 from .model import Model, log
 from .sets import dedup_rows
+
+
+_UID = itertools.count(1)
 
 
 class AlphaVector:
@@ -51,6 +55,9 @@ class ValueFunction:
         self.model = model
         self.is_on_gpu = True
         self._pruning_level = 1
+        self.uid = next(_UID)               # identity of this row set for per-belief result caches (solver.compute_change)
+        self.parent_uid = None              # set by PBVI_Solver.backup(append=True): rows == first `n_new` rows + every parent row
+        self.n_new = 0
         S = model.state_count
         if isinstance(alpha_vectors, list):
             assert all(v.values.shape[0] == S for v in alpha_vectors), \
@@ -131,6 +138,7 @@ class ValueFunction:
         self._array, self._actions, self._hashes = self._union(other)
         self._vector_list = None
         self._pruning_level = 1
+        self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
 
     def append(self, alpha_vector: AlphaVector) -> None:
         """Adds one alpha vector without de-duplication (reference src/mdp.py:739-760)."""
@@ -141,6 +149,7 @@ class ValueFunction:
         self._actions = np.append(self._actions, alpha_vector.action)
         self._hashes = None
         self._vector_list = None
+        self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
 
     def to_gpu(self) -> 'ValueFunction':
         return self
@@ -168,6 +177,7 @@ class ValueFunction:
             self._actions = self._actions[idx]
             self._hashes = None if self._hashes is None else self._hashes[idx]
             self._vector_list = None
+            self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
         self._pruning_level = level
 
     # ---- persistence (reference src/mdp.py:909-1036): column 0 `action`, then one column per state label ----------

@@ -231,6 +231,13 @@ def test_olfactory_fsvi_solve_and_backup_parity():
     solver = FSVI_Solver(gamma=0.99, eps=1e-6)
     vf, hist = solver.solve(model, expansions=4, max_belief_growth=30, history_tracking_level=2, print_progress=False)
     assert hist.beliefs_counts[0] == 1 and len(hist.backup_times) == 4
+    # the solve loop's incremental compute_change (cached per value function / belief lineage) == a from-scratch evaluation
+    dev = model.device
+    for i in range(1, len(hist.value_functions)):
+        B = hist.belief_sets[i].belief_array
+        new_max, _ = dev.max_values(B, hist.value_functions[i].alpha_vector_array)
+        old_max, _ = dev.max_values(B, hist.value_functions[i - 1].alpha_vector_array)
+        assert float((new_max - old_max).abs().max()) == hist.value_function_changes[i - 1]
     # a new-points backup of everything explored against the second-to-last value function, replayed through the oracle:
     # same value function (R = 1 => bit-identical rows, same order, same actions)
     prev = hist.value_functions[-2]
