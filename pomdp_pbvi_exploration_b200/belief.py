@@ -166,6 +166,12 @@ class BeliefSet:
             self._belief_list = [Belief._from_device(self.model, row) for row in self.belief_array]
         return self._belief_list
 
+    def belief_at(self, i: int) -> Belief:
+        """The i-th belief without materialising `belief_list` (the solve loop only ever needs `belief_list[0]`)."""
+        if self._belief_list is not None:
+            return self._belief_list[i]
+        return Belief._from_device(self.model, self.belief_array[i])
+
     @property
     def row_hashes(self) -> np.ndarray:
         if self._hashes is None:

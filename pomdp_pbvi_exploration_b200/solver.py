@@ -651,15 +651,15 @@ class PBVI_Solver:
                 self._upper_bound = BeliefValueMapping(model, args['mdp_policy'])
             else:
                 self._upper_bound.update()
-            return self.expand_hsvi(model=model, b=belief_set.belief_list[0], value_function=args['value_function'],
+            return self.expand_hsvi(model=model, b=belief_set.belief_at(0), value_function=args['value_function'],
                                     upper_bound_belief_value_map=self._upper_bound, max_generation=max_generation)
         elif self.expand_function in 'expand_fsvi':
-            return self.expand_fsvi(model=model, b0=belief_set.belief_list[0], mdp_policy=p['mdp_policy'], max_generation=max_generation)
+            return self.expand_fsvi(model=model, b0=belief_set.belief_at(0), mdp_policy=p['mdp_policy'], max_generation=max_generation)
         elif self.expand_function in 'expand_fsvi_eg':
-            return self.expand_fsvi_eg(model=model, b0=belief_set.belief_list[0], mdp_policy=p['mdp_policy'],
+            return self.expand_fsvi_eg(model=model, b0=belief_set.belief_at(0), mdp_policy=p['mdp_policy'],
                                        eps_greedy=p.get('eps_greedy'), max_generation=max_generation)
         elif self.expand_function in 'expand_perseus':
-            return self.expand_perseus(model=model, b=belief_set.belief_list[0], max_generation=max_generation)
+            return self.expand_perseus(model=model, b=belief_set.belief_at(0), max_generation=max_generation)
         raise Exception('Not implemented')
 
     # ------------------------------------------------------------------------------------------------------------
