@@ -188,8 +188,86 @@ class BeliefSet:
         succ, _ = self.model.device.belief_successors(self.belief_array)
         return BeliefSet(self.model, succ.reshape(-1, self.model.state_count))
 
+    def _key_index(self):
+        """
+        {128-bit row key: row index} of this set, or None when the set holds duplicate rows.  The dict and the row store are
+        shared along a union() chain (append-only): a set may extend them only while it is the longest set using them.
+        """
+        idx = self.__dict__.get('_keys')
+        if idx is not None and len(idx) == len(self):
+            return idx
+        h = self.row_hashes
+        idx = {}
+        for i, k in enumerate(map(tuple, h.tolist())):
+            if k in idx:
+                return None
+            idx[k] = i
+        self._keys = idx
+        return idx
+
     def union(self, other_belief_set: 'BeliefSet') -> 'BeliefSet':
         """Own unique beliefs in order, then the unseen beliefs of the other set (reference src/pomdp.py:585-606)."""
+        fast = self._union_append(other_belief_set)
+        if fast is not None:
+            return fast
+        return self._union_general(other_belief_set)
+
+    def _union_append(self, other: 'BeliefSet'):
+        """
+        The solve loop's case -- a large duplicate-free set absorbs a small one -- in O(new rows): key lookups against the
+        shared index, bytewise confirmation of every hit on the device, and an append into a capacity-doubling row store
+        that the resulting set shares with this one (rows are never mutated, so the prefix stays valid for `self`).
+        """
+        n_self, n_other = len(self), len(other)
+        if n_self == 0 or n_other == 0 or n_other > n_self:
+            return None
+        index = self._key_index()
+        if index is None:
+            return None
+        dev = self.model.device
+        other_rows = other.belief_array
+        other_keys = list(map(tuple, other.row_hashes.tolist()))
+        hit_other, hit_self, fresh = [], [], []
+        seen = {}
+        for j, k in enumerate(other_keys):
+            if k in index:
+                hit_other.append(j); hit_self.append(index[k])
+            elif k in seen:
+                hit_other.append(j); hit_self.append(-1 - seen[k])       # duplicate inside `other`: compare with its first copy
+            else:
+                seen[k] = j
+                fresh.append(j)
+        if hit_other:
+            own = [(jo, js) for jo, js in zip(hit_other, hit_self) if js >= 0]
+            twin = [(jo, -1 - js) for jo, js in zip(hit_other, hit_self) if js < 0]
+            ok = True
+            if own:
+                ok &= bool(dev.rows_equal(other_rows, [p[0] for p in own], self.belief_array, [p[1] for p in own]).all())
+            if twin:
+                ok &= bool(dev.rows_equal(other_rows, [p[0] for p in twin], other_rows, [p[1] for p in twin]).all())
+            if not ok:
+                return None                                                # 128-bit key collision: take the exact general path
+        k_new = len(fresh)
+        store = self.__dict__.get('_store')
+        if store is None or self.__dict__.get('_store_used', [0])[0] != n_self or store.shape[0] < n_self + k_new:
+            cap = max(2 * (n_self + k_new), 256)
+            store = torch.empty((cap, self.model.state_count), dtype=torch.float64, device=dev.device)
+            store[:n_self] = self.belief_array
+            used = [n_self]
+        else:
+            used = self._store_used
+        if k_new:
+            store[n_self:n_self + k_new] = other_rows[torch.as_tensor(fresh, device=dev.device)] if k_new != n_other else other_rows
+        used[0] = n_self + k_new
+        hashes = np.concatenate([self.row_hashes, other.row_hashes[fresh]], axis=0) if k_new else self.row_hashes
+        out = BeliefSet(self.model, store[:n_self + k_new], _hashes=hashes)
+        for j in fresh:
+            index[other_keys[j]] = len(index)             # == its row position: the index held exactly n_self keys on entry
+        out._keys, out._store, out._store_used = index, store, used
+        out.lineage = self.lineage
+        return out
+
+    def _union_general(self, other_belief_set: 'BeliefSet') -> 'BeliefSet':
         rows = torch.cat([self.belief_array, other_belief_set.belief_array], dim=0)
         hashes = np.concatenate([self.row_hashes, other_belief_set.row_hashes], axis=0)
         first, _, _, _ = dedup_rows(self.model.device, rows, hashes)

@@ -39,27 +39,30 @@ __global__ void __launch_bounds__(256) pairwise_normalise_kernel(double* __restr
     extern __shared__ double s_sum[];   // [nLeaves] leaf sums, then [nNodes] node sums
     __shared__ double s_total;
     double* row = rows + (size_t)blockIdx.x * S;
-    for (int l = threadIdx.x; l < nLeaves; l += 256) {
-        const int off = leaves[l].x, n = leaves[l].y;
+    // A leaf (<= 128 contiguous elements) is summed by 8 lanes: lane j owns NumPy's accumulator r[j] (every 8th element, in
+    // order), then the fixed tree ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the < 8 trailing elements -- the same additions in
+    // the same order as DOUBLE_pairwise_sum, 8 of them at a time.
+    const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
+    for (int l0 = 0; l0 < nLeaves; l0 += 32) {               // uniform trip count: the shuffles below need the whole warp
+        const int l = l0 + grp;
+        const bool valid = l < nLeaves;
+        const int off = valid ? leaves[l].x : 0, n = valid ? leaves[l].y : 0;
         const double* a = row + off;
-        double res;
-        if (n < 8) {
-            res = 0.0;
-            for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
-        } else {
-            double r[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = a[j];
-            int i = 8;
-            for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+        const int lim = n - (n % 8);
+        double r = (n >= 8) ? a[j] : 0.0;
+        for (int i = 8; i < lim; i += 8) r = __dadd_rn(r, a[i + j]);
+        const double p = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));
+        const double q = __dadd_rn(p, __shfl_down_sync(0xffffffffu, p, 2, 8));
+        double res = __dadd_rn(q, __shfl_down_sync(0xffffffffu, q, 4, 8));
+        if (valid && j == 0) {
+            if (n < 8) {
+                res = 0.0;
+                for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+            } else {
+                for (int i = lim; i < n; i++) res = __dadd_rn(res, a[i]);
             }
-            res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-            for (; i < n; i++) res = __dadd_rn(res, a[i]);
+            s_sum[l] = res;
         }
-        s_sum[l] = res;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -96,48 +96,47 @@ __global__ void __launch_bounds__(256) prune_dominated_kernel(const double* __re
     if (threadIdx.x == 0) keep[i] = (count == 1) ? 1 : 0;
 }
 
-// Sawtooth upper bound.  Block per query q:
-//   v0 = q . corner;  out = min(v0, min_i v0 + (ub_value_i - ub_belief_i . corner) * min_{s: ub_belief_i[s] > 0} q[s] / ub_belief_i[s])
-__global__ void __launch_bounds__(256) sawtooth_kernel(const double* __restrict__ corner, const double* __restrict__ ubB,
-                                                       const double* __restrict__ ubV, int nUb, const double* __restrict__ queries, int S,
-                                                       double* __restrict__ out) {
-    __shared__ double sh[8];
-    __shared__ double s_bc;
-    const double* q = queries + (size_t)blockIdx.x * S;
-    auto block_reduce = [&](double v, bool isMin) -> double {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double o = __shfl_down_sync(0xffffffffu, v, off);
-            v = isMin ? fmin(v, o) : v + o;
-        }
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = sh[0];
-            for (int w = 1; w < 8; w++) t = isMin ? fmin(t, sh[w]) : t + sh[w];
-            s_bc = t;
-        }
-        __syncthreads();
-        return s_bc;
-    };
-    double part = 0.0;
-    for (int s = threadIdx.x; s < S; s += 256) part = fma(q[s], corner[s], part);
-    const double v0 = block_reduce(part, false);
-    double best = v0;
-    for (int i = 0; i < nUb; i++) {
-        const double* bi = ubB + (size_t)i * S;
-        double dotp = 0.0, ratio = INFINITY;
-        for (int s = threadIdx.x; s < S; s += 256) {
+// Sawtooth upper bound, one block per (stored belief i, query q) -- plus one block per query for the corner term:
+//   v0_q = q . corner;  terms[q][i] = v0_q + (ub_value_i - ub_belief_i . corner) * min_{s: ub_belief_i[s] > 0} q[s] / ub_belief_i[s];
+//   terms[q][nUb] = v0_q.   row_min_kernel then takes out[q] = min_i terms[q][i].
+__global__ void __launch_bounds__(256) sawtooth_terms_kernel(const double* __restrict__ corner, const double* __restrict__ ubB,
+                                                             const double* __restrict__ ubV, int nUb, const double* __restrict__ queries,
+                                                             int S, double* __restrict__ terms) {
+    __shared__ double sh[3][8];
+    const int i = blockIdx.x, qi = blockIdx.y;
+    const double* q = queries + (size_t)qi * S;
+    const double* bi = (i < nUb) ? ubB + (size_t)i * S : nullptr;
+    double v0 = 0.0, dotp = 0.0, ratio = INFINITY;
+    for (int s = threadIdx.x; s < S; s += 256) {
+        const double c = corner[s], qs = q[s];
+        v0 = fma(qs, c, v0);
+        if (bi) {
             const double b = bi[s];
-            dotp = fma(b, corner[s], dotp);
-            if (b > 0.0) ratio = fmin(ratio, q[s] / b);
+            dotp = fma(b, c, dotp);
+            if (b > 0.0) ratio = fmin(ratio, qs / b);
         }
-        const double bc = block_reduce(dotp, false);
-        const double rmin = block_reduce(ratio, true);
-        best = fmin(best, v0 + (ubV[i] - bc) * rmin);
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = best;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        v0 += __shfl_down_sync(0xffffffffu, v0, off);
+        dotp += __shfl_down_sync(0xffffffffu, dotp, off);
+        ratio = fmin(ratio, __shfl_down_sync(0xffffffffu, ratio, off));
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = v0; sh[1][threadIdx.x >> 5] = dotp; sh[2][threadIdx.x >> 5] = ratio; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, d = 0.0, r = INFINITY;
+        for (int w = 0; w < 8; w++) { a += sh[0][w]; d += sh[1][w]; r = fmin(r, sh[2][w]); }
+        terms[(size_t)qi * (nUb + 1) + i] = bi ? a + (ubV[i] - d) * r : a;
+    }
+}
+
+__global__ void __launch_bounds__(128) row_min_kernel(const double* __restrict__ terms, int n, int width, double* __restrict__ out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n) return;
+    double best = INFINITY;
+    for (int i = 0; i < width; i++) best = fmin(best, terms[(size_t)qi * width + i]);
+    out[qi] = best;
 }
 
 // out[j] = min_i || beliefs[i] - candidates[j] ||_2; block per candidate
@@ -279,8 +278,16 @@ extern "C" int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double
     if (n_q == 0) return PBVI_OK;
     PBVI_REQUIRE(d_corner && d_queries && d_out && (n_ub == 0 || (d_ub_beliefs && d_ub_values)), "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    sawtooth_kernel<<<n_q, 256, 0, (cudaStream_t)stream>>>(d_corner, d_ub_beliefs, d_ub_values, n_ub, d_queries, m->S, d_out);
-    m->last_launches = 1;
+    m->arena.reset();
+    PBVI_TAKE(terms, double, (size_t)n_q * (n_ub + 1));
+    for (int q0 = 0; q0 < n_q; q0 += 65535) {
+        const int nq = std::min(65535, n_q - q0);
+        sawtooth_terms_kernel<<<dim3(n_ub + 1, nq), 256, 0, (cudaStream_t)stream>>>(d_corner, d_ub_beliefs, d_ub_values, n_ub,
+                                                                                   d_queries + (size_t)q0 * m->S, m->S,
+                                                                                   terms + (size_t)q0 * (n_ub + 1));
+    }
+    row_min_kernel<<<ceil_div(n_q, 128), 128, 0, (cudaStream_t)stream>>>(terms, n_q, n_ub + 1, d_out);
+    m->last_launches = 2;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
 }

@@ -161,10 +161,18 @@ class BeliefValueMapping:
         self._belief_array = None
         self._value_array = None
 
+    def _key(self, b: Belief):
+        k = b.__dict__.get('_row_key')
+        if k is None:
+            k = b._row_key = tuple(self.model.device.row_hash(b.values[None, :]).cpu().numpy()[0].tolist())
+        return k
+
     def add(self, b: Belief, v: float) -> None:
-        if b.bytes_repr not in self.belief_value_mapping:
+        """Adds (belief, value) unless the belief is already stored (reference :838-850).  Identity is the 128-bit row key."""
+        k = self._key(b)
+        if k not in self.belief_value_mapping:
             self.beliefs.append(b)
-            self.belief_value_mapping[b.bytes_repr] = v
+            self.belief_value_mapping[k] = v
 
     @property
     def belief_array(self) -> torch.Tensor:
@@ -186,15 +194,29 @@ class BeliefValueMapping:
         self._value_array = torch.as_tensor(list(self.belief_value_mapping.values()), dtype=torch.float64,
                                             device=self.model.device.device)
 
-    def evaluate(self, belief: Belief) -> float:
-        hit = self.belief_value_mapping.get(belief.bytes_repr)
-        if hit is not None:
-            return hit
+    def evaluate_rows(self, rows: torch.Tensor) -> np.ndarray:
+        """
+        Upper-bound value of every row [n,S] with two launches and one read-back: stored beliefs return their stored value
+        (the reference's shortcut, :884-885), the rest go through the sawtooth kernel against the arrays as of the last
+        `update()` (the reference refreshes them only there, :866-871).
+        """
         dev = self.model.device
+        n = rows.shape[0]
+        keys = dev.row_hash(rows).cpu().numpy().tolist()
         if len(self.beliefs) == 0:
-            return float(dev.sawtooth(self.corner_values, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device),
-                                      torch.empty((0,), dtype=torch.float64, device=dev.device), belief.values)[0])
-        return float(dev.sawtooth(self.corner_values, self.belief_array, self.value_array, belief.values)[0])
+            ub_b = torch.empty((0, dev.S), dtype=torch.float64, device=dev.device)
+            ub_v = torch.empty((0,), dtype=torch.float64, device=dev.device)
+        else:
+            ub_b, ub_v = self.belief_array, self.value_array
+        out = dev.sawtooth(self.corner_values, ub_b, ub_v, rows).cpu().numpy()
+        for i in range(n):
+            hit = self.belief_value_mapping.get(tuple(keys[i]))
+            if hit is not None:
+                out[i] = hit
+        return out
+
+    def evaluate(self, belief: Belief) -> float:
+        return float(self.evaluate_rows(belief.values[None, :])[0])
 
 
 # =====================================================================================================================
@@ -545,28 +567,37 @@ class PBVI_Solver:
         if conv_term is None:
             conv_term = self.eps
         conv_term /= self.gamma
-        probs = dev.observation_probabilities(b.values[None, :])[0].cpu().numpy()          # [A,O]
-        rb = (torch.as_tensor(model.expected_rewards_table, device=dev.device).T @ b.values).cpu().numpy()
+        A, O = model.action_count, model.observation_count
+        # one level = a handful of launches: all A*O successors with their masses P(o|b,a), their upper bounds, b . Rbar
+        succ, mass = dev.belief_successors(b.values[None, :])
+        succ, probs = succ[0], mass[0].cpu().numpy()                                          # [A,O,S], [A,O]
+        possible = probs > 0
+        upper = np.zeros((A, O))
+        if possible.any():
+            idx = np.flatnonzero(possible.reshape(-1))
+            upper.reshape(-1)[idx] = upper_bound_belief_value_map.evaluate_rows(succ.reshape(A * O, -1)[torch.as_tensor(idx, device=dev.device)])
+        if getattr(model, '_rbar_device', None) is None:
+            model._rbar_device = torch.as_tensor(np.ascontiguousarray(model.expected_rewards_table.T), dtype=torch.float64).to(dev.device)
+        rb = torch.mv(model._rbar_device, b.values).cpu().numpy()
         max_qv, best_a = -np.inf, -1
         for a in model.actions:
             b_prob_val = 0
             for o in model.observations:
-                if probs[a, o] > 0:
-                    b_prob_val += probs[a, o] * upper_bound_belief_value_map.evaluate(b.update(a, o))
+                if possible[a, o]:
+                    b_prob_val += probs[a, o] * upper[a, o]
             qva = float(rb[a] + self.gamma * b_prob_val)
             if qva > max_qv:
                 max_qv, best_a = qva, a
+        lower = dev.max_values(succ[best_a], value_function.alpha_vector_array)[0].cpu().numpy()
         max_o_val, best_v_diff, next_b = -np.inf, -np.inf, b
         for o in model.observations:
-            if not probs[best_a, o] > 0:
+            if not possible[best_a, o]:
                 continue
-            bao = b.update(best_a, o)
-            upper_v = upper_bound_belief_value_map.evaluate(bao)
-            lower_v = float(dev.max_values(bao.values[None, :], value_function.alpha_vector_array)[0][0])
-            v_diff = upper_v - lower_v
+            v_diff = upper[best_a, o] - lower[o]
             o_val = probs[best_a, o] * v_diff
             if o_val > max_o_val:
-                max_o_val, best_v_diff, next_b = o_val, v_diff, bao
+                max_o_val, best_v_diff = o_val, v_diff
+                next_b = Belief._from_device(model, succ[best_a, o])
         if best_v_diff < conv_term or max_generation <= 1:
             return BeliefSet(model, [next_b])
         upper_bound_belief_value_map.add(b, max_qv)
