@@ -29,7 +29,11 @@ void* Arena::take_bytes(size_t bytes) {
             return p;
         }
     }
-    size_t cap = std::max(bytes, chunks.empty() ? size_t(64) << 20 : chunks.back().cap);
+    // geometric growth: a new chunk at least doubles the arena, so a solve whose value function grows every iteration
+    // (alphaT, partial argmax buffers) re-allocates O(log) times instead of at every size step
+    size_t total = 0;
+    for (auto& c : chunks) total += c.cap;
+    size_t cap = std::max(bytes, std::max(total, size_t(64) << 20));
     char* p = nullptr;
     if (cudaMalloc(&p, cap) != cudaSuccess) {
         cudaGetLastError();

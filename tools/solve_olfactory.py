@@ -54,6 +54,8 @@ def main():
     out = dict(flavour=flavour, expansions=len(hist.expansion_times), growth=growth, wall_s=wall, expand_s=sum(hist.expansion_times),
                backup_s=sum(hist.backup_times), change_s=change_s[0], final_alphas=len(vf), final_beliefs=hist.beliefs_counts[-1],
                backup_pairs=float(pairs), backup_pairs_per_s=float(pairs) / max(sum(hist.backup_times), 1e-9),
+               backup_ms_at=[round(1e3 * hist.backup_times[i], 2) for i in range(0, len(hist.backup_times), max(1, len(hist.backup_times) // 10))],
+               expand_ms_at=[round(1e3 * hist.expansion_times[i], 2) for i in range(0, len(hist.expansion_times), max(1, len(hist.expansion_times) // 10))],
                reference_published={'cpu_s': 2983.5, 'cupy_gpu_s': 204.9, 'source': 'Olfactory_Alternation_Paper_Wrap.ipynb[43],[30]'})
     print(json.dumps(out))
 
