@@ -23,8 +23,16 @@ def group_by_key(hashes: np.ndarray):
     if n == 0:
         z = np.zeros(0, dtype=np.int64)
         return z, z, z
-    keys = np.ascontiguousarray(hashes, dtype=np.int64).view(_KEY).reshape(n)
-    _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+    h = np.ascontiguousarray(hashes, dtype=np.int64)
+    srt = np.lexsort((np.arange(n), h[:, 1], h[:, 0]))      # by key, ties in original order (plain int64 sorts, no structured dtype)
+    hs = h[srt]
+    boundary = np.empty(n, dtype=bool)
+    boundary[0] = True
+    boundary[1:] = np.any(hs[1:] != hs[:-1], axis=1)
+    group_sorted = np.cumsum(boundary) - 1                   # group id in key order
+    first = srt[boundary]                                    # first occurrence of each group (ties were kept in original order)
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[srt] = group_sorted
     order = np.argsort(first, kind='stable')                 # unique() sorts by key; renumber by first occurrence
     rank = np.empty_like(order)
     rank[order] = np.arange(order.shape[0])

@@ -120,22 +120,57 @@ class ValueFunction:
 
     # ---- set operations --------------------------------------------------------------------------
     def _union(self, other: 'ValueFunction') -> tuple:
+        fast = self._union_prepend(other)
+        if fast is not None:
+            return fast
         rows = torch.cat([self._array, other._array], dim=0)
         actions = np.concatenate([self._actions, other._actions])
         hashes = np.concatenate([self.row_hashes, other.row_hashes], axis=0)
         first, last, _, _ = dedup_rows(self.model.device, rows, hashes)
         if first.shape[0] != rows.shape[0]:
             rows = rows[torch.as_tensor(first, device=rows.device)]
-        return rows, actions[last], hashes[first]
+        return rows, actions[last], hashes[first], None
+
+    def _union_prepend(self, other: 'ValueFunction'):
+        """
+        The solve loop's case -- a few new rows in front of a large, disjoint old set -- without copying the old rows: they
+        live at the END of a front-growing buffer and the new rows are written just before them, so the union is the view
+        [new rows | old rows] and the old value function keeps viewing its own suffix (rows are never mutated).
+        Returns None (general path) when any key occurs twice or the buffer is shared with another descendant.
+        """
+        n_self, n_other = len(self), len(other)
+        if n_self == 0 or n_other == 0:
+            return None
+        hashes = np.concatenate([self.row_hashes, other.row_hashes], axis=0)
+        keys = set(map(tuple, hashes.tolist()))
+        if len(keys) != n_self + n_other:
+            return None
+        S = self.model.state_count
+        buf, start = other.__dict__.get('_buf'), other.__dict__.get('_buf_start')
+        shared = other.__dict__.get('_buf_front')          # [smallest start handed out so far] shared by every view of the buffer
+        if buf is None or shared[0] != start or start < n_self:
+            cap = 2 * (n_self + n_other) + 64
+            buf = torch.empty((cap, S), dtype=torch.float64, device=self._array.device)
+            start = cap - n_other
+            buf[start:] = other._array
+            shared = [start]
+        buf[start - n_self:start] = self._array
+        shared[0] = start - n_self
+        rows = buf[start - n_self:start + n_other]
+        return rows, np.concatenate([self._actions, other._actions]), hashes, (buf, start - n_self, shared)
 
     def __add__(self, other: 'ValueFunction') -> 'ValueFunction':
-        rows, actions, hashes = self._union(other)
-        return ValueFunction(self.model, rows, actions, _trusted=True, _hashes=hashes)
+        rows, actions, hashes, buf = self._union(other)
+        out = ValueFunction(self.model, rows, actions, _trusted=True, _hashes=hashes)
+        if buf is not None:
+            out._buf, out._buf_start, out._buf_front = buf
+        return out
 
     def extend(self, other: 'ValueFunction') -> None:
         """In-place union (reference src/mdp.py:763-779): own rows first, then the unseen rows of `other`; on a byte
         collision the other side's action replaces ours."""
-        self._array, self._actions, self._hashes = self._union(other)
+        self._array, self._actions, self._hashes, buf = self._union(other)
+        self._buf, self._buf_start, self._buf_front = buf if buf is not None else (None, None, None)
         self._vector_list = None
         self._pruning_level = 1
         self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
@@ -150,6 +185,7 @@ class ValueFunction:
         self._hashes = None
         self._vector_list = None
         self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
+        self._buf = None
 
     def to_gpu(self) -> 'ValueFunction':
         return self
@@ -178,6 +214,7 @@ class ValueFunction:
             self._hashes = None if self._hashes is None else self._hashes[idx]
             self._vector_list = None
             self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
+            self._buf = None
         self._pruning_level = level
 
     # ---- persistence (reference src/mdp.py:909-1036): column 0 `action`, then one column per state label ----------
