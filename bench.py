@@ -42,6 +42,9 @@ METRIC = 'belief x alpha backups/sec (olfactory POMDP S=22021, PBVI backup)'
 UNIT = 'belief*alpha pairs/s'
 GAMMA = 0.99
 FP64_PEAK_TFLOPS = 37.1        # DMMA m8n8k4 / m16n8k16 on this pool's B200, profiles/r01_fp64_pipe_microbench.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch on the default workload (B=10000, V=1000), from
+# `ncu --set full` (profiles/r01_score_kernel_v6_ncu_summary.txt); compulsory bytes are 8*S*(B+V) = 1.94e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 28.09e9
 
 
 def parse_args():
@@ -330,7 +333,8 @@ def run_b200(args):
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy()'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (FP64 DMMA m8n8k4 + fused argmax)', 'achieved': achieved,
-                         'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS, 'traffic': None,
+                         'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,
+                         'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH if (B == 10000 and V == 1000) else None,
                          'peak_source': 'own FP64 DMMA microbenchmark on this pool (profiles/r01_fp64_pipe_microbench.txt); '
                                         'MEASURED_PEAKS.json has no FP64 entry',
                          'algorithmic_flops_per_launch': algo_flops, 'executed_flops_per_launch': stats['executed_flops'],
