@@ -19,7 +19,7 @@
 
 namespace pbvi {
 
-static_assert(KC == 16 && RG == 32 && BM % RG == 0 && BM <= 256, "belief_mask_kernel assumes 16-state chunks and 32-row groups");
+static_assert(KC == 16 && BM % RG == 0 && (BM / 8) <= RG && RG % (BM / 8) == 0, "belief_mask_kernel: 16-state chunks, a warp's rows inside one row group");
 constexpr int MASK_ROWS_PER_WARP = BM / 8;   // 8 warps cover the tile; a warp's rows lie inside one row group
 
 // ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------

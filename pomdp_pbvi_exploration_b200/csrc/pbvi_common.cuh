@@ -15,9 +15,9 @@ namespace pbvi {
 constexpr int KC = 16;         // source states per K chunk -- the sparsity-skipping granule along K
 constexpr int BM = 64;         // beliefs per block tile
 constexpr int BN = 256;        // alpha vectors per block tile
-constexpr int RG = 32;         // beliefs per row group (one warp's rows) -- the skipping granule along M
-constexpr int NRG = BM / RG;   // 2 row groups per tile
-constexpr int SCORE_THREADS = 256;
+constexpr int RG = 16;         // beliefs per row group (one warp's rows) -- the skipping granule along M
+constexpr int NRG = BM / RG;   // 4 row groups per tile
+constexpr int SCORE_THREADS = NRG * (BN / 64) * 32;   // consumer threads of the score kernel (+ one producer warp)
 
 void set_error(const char* fmt, ...);
 

@@ -13,14 +13,14 @@
 // One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 16 source states) in which
 // some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero (list built by build_chunk_lists_kernel).
 //
-// Warp specialisation (9 warps):
+// Warp specialisation (N_CONSUMER_WARPS + 1 warps):
 //   warp 8      producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
 //               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (16), ONE 5 KB
 //               copy per live row group (belief_mask_kernel stores the belief tiles as ready-made shared-memory images,
 //               padded row stride included) and the RTO chunk: 19 copies per chunk.  List entries and gathered row
 //               indices are prefetched one chunk ahead, so the producer never waits on a dependent global load.
-//   warps 0-7   consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
-//               Warp w owns row group w / 4 (RG = 32 beliefs) and column quarter w % 4, so each SM sub-partition
+//   the rest    consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
+//               Warp w owns row group w / 4 (RG beliefs) and column quarter w % 4, so each SM sub-partition
 //               (warp id mod 4) holds one warp of EACH row group: a row group that is all-zero on the chunk is skipped
 //               and the saving is spread over all four FP64 pipes (the first, 128 x 128 layout stalled on the barrier
 //               instead: profiles/r01_score_kernel_v1_ncu_summary.txt).
@@ -36,6 +36,7 @@ constexpr int STAGES = 5;
 constexpr int LDA = KC + 4;   // 20: row stride 4 mod 16 doubles -> conflict-free 8-byte fragment loads
 constexpr int LDB = BN + 4;   // 260
 constexpr int NCW = BN / 64;  // 4 column warps, 64 columns each
+constexpr int MT = RG / 8;    // m8 row tiles per consumer warp
 constexpr int A_GROUP_DOUBLES = RG * LDA;   // one row group of one chunk in beliefsP == its shared-memory image (640 doubles, 5 KB)
 constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 8
 constexpr int SCORE_THREADS_TOTAL = (N_CONSUMER_WARPS + 1) * 32;   // + the producer warp
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
     }
     __syncthreads();
 
-    double best[4];
-    int bidx[4];
+    double best[MT];
+    int bidx[MT];
     const int g = lane >> 2, t = lane & 3;
     const int warp_m = warp / NCW, warp_n = warp % NCW;     // meaningful for consumer warps only
 
@@ -170,9 +171,9 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             const uint32_t rg = e >> 24;
             if (lane == 0) {
                 s_meta[slot] = e;
-                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & 3u) * A_GROUP_DOUBLES * 8;
+                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & ((1u << NRG) - 1u)) * A_GROUP_DOUBLES * 8;
                 mbar_arrive_expect_tx(&s_full[slot], bytes);
-                visited += __popc(rg & 3u);
+                visited += __popc(rg & ((1u << NRG) - 1u));
             }
             __syncwarp();
             if (lane < KC) bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
@@ -188,9 +189,9 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
         if (lane == 0 && p.stats && visited) atomicAdd(p.stats, visited);
     } else {
         // =============================== consumer warps ===============================
-        double acc[4][8][2];
+        double acc[MT][8][2];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < MT; i++)
 #pragma unroll
             for (int n = 0; n < 8; n++) { acc[i][n][0] = 0.0; acc[i][n][1] = 0.0; }
 
@@ -204,18 +205,18 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
                 const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
 #pragma unroll
                 for (int ks = 0; ks < KC / 4; ks++) {
-                    double af[4], bf[8];
+                    double af[MT], bf[8];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) af[i] = Ab[i * 8 * LDA + ks * 4];
+                    for (int i = 0; i < MT; i++) af[i] = Ab[i * 8 * LDA + ks * 4];
                     if (GATHER) {
                         const double r = st.Rs[ks * 4 + t];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) af[i] *= r;
+                        for (int i = 0; i < MT; i++) af[i] *= r;
                     }
 #pragma unroll
                     for (int n = 0; n < 8; n++) bf[n] = Bb[ks * 4 * LDB + n * 8];
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int i = 0; i < MT; i++)
 #pragma unroll
                         for (int n = 0; n < 8; n++) dmma884(acc[i][n], af[i], bf[n]);
                 }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
         //      An empty list leaves acc == 0: every score is 0, first column wins.
         const int cbase = n0 + warp_n * 64 + 2 * t;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < MT; i++) {
             best[i] = -INFINITY;
             bidx[i] = 0x7fffffff;
 #pragma unroll
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
     int* sidx = reinterpret_cast<int*>(smem_raw + sizeof(double) * NCW * BM);     // [NCW][BM]
     if (warp < N_CONSUMER_WARPS && t == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < MT; i++) {
             const int row = warp_m * RG + i * 8 + g;
             sval[warp_n * BM + row] = best[i];
             sidx[warp_n * BM + row] = bidx[i];
