@@ -323,6 +323,38 @@ class PBVI_Solver:
         self.expand_function_params = expand_function_params
 
     # ------------------------------------------------------------------------------------------------------------
+    def test_n_simulations(self, model: Model, value_function: ValueFunction, n: int = 1000, horizon: int = 300, print_progress: bool = False):
+        """
+        Evaluates a value function with n simultaneous simulations (reference src/pomdp.py:1338-1444): returns the start states,
+        the step at which each simulation reached an end state (-1: never), and the per-step rewards / discounted rewards.
+        Same host RNG draws as the reference's CPU path; argmax(B.V^T) and the belief update run on the device.
+        """
+        from .simulation import SimulationSet
+        dev = model.device
+        beliefs = Belief(model).values[None, :].repeat(n, 1)
+        sims = SimulationSet(model)
+        start_states = sims.initialize_simulations(n, None)
+        sim_is_done = np.zeros(n, dtype=bool)
+        done_at_step = np.full(n, -1)
+        discount = self.gamma
+        rewards, discounted_rewards = [], []
+        for i in range(horizon):
+            _, best = dev.max_values(beliefs, value_function.alpha_vector_array)
+            best_actions = value_function.actions[best.cpu().numpy()]
+            sims.is_done = np.zeros(n, dtype=bool)          # the reference keeps stepping finished simulations and masks their rewards
+            step_rewards, observations = sims.run_actions(best_actions)
+            beliefs, _ = dev.belief_update(beliefs, best_actions.astype(np.int32), observations.astype(np.int32))
+            rewards.append(np.where(~sim_is_done, step_rewards, 0))
+            discounted_rewards.append(np.where(~sim_is_done, step_rewards * discount, 0))
+            are_done = np.isin(sims.agent_states, np.array(model.end_states))
+            done_at_step[sim_is_done ^ are_done] = i + 1
+            sim_is_done |= are_done
+            discount *= self.gamma
+            if np.all(sim_is_done):
+                break
+        return start_states, done_at_step, rewards, discounted_rewards
+
+    # ------------------------------------------------------------------------------------------------------------
     def backup(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, append: bool = False,
                belief_dominance_prune: bool = True) -> ValueFunction:
         """

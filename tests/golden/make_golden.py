@@ -283,6 +283,87 @@ def gen_synthetic():
     backup_fixture('backup_synth300', m, gamma, B, vf)
 
 
+def gen_simulations():
+    """Agent roll-outs (src/pomdp.py:2953-3380): seeded single simulations and the vectorised n-parallel simulation on an
+    R = 1 model (the reference's vectorised next-state gather is only well defined there), plus test_n_simulations."""
+    print('[simulations]')
+    out = {}
+    for fname, tag in [('4x4.95-no_loop.POMDP', 'grid4x4_noloop'), ('tiger.95.POMDP', 'tiger')]:
+        with quiet():
+            m, s0 = ref.load_POMDP_file(os.path.join(EXAMPLES, fname))
+        g = dict(np.load(os.path.join(HERE, f'backup_{tag}.npz')))
+        with quiet():
+            vf = ref.ValueFunction(m, g['alphas'], g['alpha_actions'])
+        agent = ref.Agent(m, vf)
+        seed_all(11)
+        with quiet():
+            h = agent.simulate(max_steps=25, print_progress=False, print_stats=False)
+        out[f'{tag}_sim_states'] = np.array(h.states)
+        out[f'{tag}_sim_actions'] = np.array(h.actions)
+        out[f'{tag}_sim_observations'] = np.array(h.observations)
+        out[f'{tag}_sim_rewards'] = np.array(h.rewards, dtype=float)
+        out[f'{tag}_sim_last_belief'] = h.beliefs[-1].values
+        seed_all(12)
+        with quiet():
+            rs, hs = agent.run_n_simulations(n=4, max_steps=15, print_progress=False, print_stats=False)
+        out[f'{tag}_nsim_totals'] = np.array(rs, dtype=float)
+        out[f'{tag}_nsim_lengths'] = np.array([len(x) for x in hs])
+    # vectorised simulation: needs a reward FUNCTION (SimulationSet.run_actions calls model.immediate_reward_function, :2935) and R = 1
+    H, W = 5, 7
+    S = H * W
+    s_idx = np.arange(S)
+    row, col = s_idx // W, s_idx % W
+    reach = np.zeros((S, 5, 1), dtype=int)
+    reach[:, 0, 0] = ((row - 1) % H) * W + col
+    reach[:, 1, 0] = row * W + (col + 1) % W
+    reach[:, 2, 0] = ((row + 1) % H) * W + col
+    reach[:, 3, 0] = row * W + (col - 1) % W
+    reach[:, 4, 0] = s_idx
+    goal = 2 * W + 1
+    rng = np.random.default_rng(3)
+    p_detect = rng.random(S) * 0.6
+    obs = np.zeros((S, 5, 3))
+    obs[:, :, 0] = 1 - p_detect[:, None]
+    obs[:, :, 1] = p_detect[:, None]
+    obs[goal, :, :] = [0.0, 0.0, 1.0]
+    start = np.ones(S); start[goal] = 0; start /= start.sum()
+
+    def reward_func(s, a, sn, o):
+        return np.where(sn == goal, 1.0, 0.0)
+    with quiet():
+        m = ref.Model(states=[[f's_{i}_{j}' for j in range(W)] for i in range(H)], actions=5, observations=3, reachable_states=reach,
+                      rewards=reward_func, observation_table=obs, end_states=[goal], start_probabilities=start)
+    seed_all(5)
+    solver = ref.FSVI_Solver(gamma=0.95, eps=1e-6)
+    with quiet():
+        vf, _ = solver.solve(m, expansions=12, max_belief_growth=15, print_progress=False)
+    out.update(grid_reach=reach, grid_obs=obs, grid_start=start, grid_goal=np.int64(goal), grid_shape=np.array([H, W]),
+               grid_alphas=vf.alpha_vector_array, grid_alpha_actions=np.array(vf.actions))
+    agent = ref.Agent(m, vf)
+    seed_all(13)
+    with quiet():
+        rs, hs = agent.run_n_simulations_parallel(n=24, max_steps=30, print_progress=False, print_stats=False)
+    out['grid_par_totals'] = np.array(rs, dtype=float)
+    out['grid_par_lengths'] = np.array([len(x) for x in hs])
+    out['grid_par_states0'] = np.array(hs[0].states)
+    out['grid_par_actions_last'] = np.array(hs[-1].actions)
+    out['grid_par_observations_last'] = np.array(hs[-1].observations)
+    seed_all(14)
+    with quiet():
+        starts, done_at, rew, drew = solver.test_n_simulations(m, vf, n=16, horizon=20)
+    out['grid_test_starts'] = np.array(starts)
+    out['grid_test_done_at'] = np.array(done_at)
+    out['grid_test_rewards'] = np.array(rew, dtype=float)
+    out['grid_test_discounted'] = np.array(drew, dtype=float)
+    seed_all(15)
+    with quiet():
+        h = agent.simulate(max_steps=25, print_progress=False, print_stats=False)
+    out['grid_sim_states'] = np.array(h.states)
+    out['grid_sim_actions'] = np.array(h.actions)
+    out['grid_sim_observations'] = np.array(h.observations)
+    save('simulations', **out)
+
+
 if __name__ == '__main__':
     want = sys.argv[1:] or ['']
     def on(tag):
@@ -301,3 +382,5 @@ if __name__ == '__main__':
         gen_synthetic()
     if on('olfactory'):
         gen_olfactory()
+    if on('simulations'):
+        gen_simulations()

@@ -54,6 +54,9 @@ def fixture_model(tag):
     model._min_reward = float(m['min_reward']) if 'min_reward' in m else 0.0
     model._max_reward = float(m['max_reward']) if 'max_reward' in m else 1.0
     model.transition_table = m.get('transition_table')
+    model.immediate_reward_table = m.get('reward_table')
+    model.immediate_reward_function = None
+    model.rewards_are_probabilistic = False
     model.state_grid = np.arange(S).reshape(1, S)
     _models[tag] = (model, float(m['gamma']))
     return _models[tag]
