@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument('--beliefs', type=int, default=10000)
     ap.add_argument('--alphas', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--trace-phases', action='store_true', help='N > 1: print the phase times of the last sharded step to stderr')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (used for short ncu passes)')
     ap.add_argument('--save-workload', default=None, help='write the synthetic beliefs / alphas to this .pt file')
     ap.add_argument('--load-workload', default=None, help='read them back instead of regenerating (ncu passes: no setup kernels)')
@@ -275,6 +276,11 @@ def run_b200(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()
+    if args.trace_phases and sharded is not None:
+        sharded.trace = True
+        step_device()
+        sharded.trace = False
+        print(f'[rank {rank}] phases (ms): ' + json.dumps({k: round(v, 3) for k, v in sharded.last_phases.items()}), file=sys.stderr)
     launches = dev.launch_count - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     stats = dev.last_stats()

@@ -75,6 +75,20 @@ def merge_gathered(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarray, 
     return rows, actions[last], hashes[first]
 
 
+class _PhaseTimer:
+    def __init__(self, device):
+        import time
+        self.time, self.device, self.phases = time, device, {}
+        torch.cuda.synchronize(device)
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        torch.cuda.synchronize(self.device)
+        now = self.time.perf_counter()
+        self.phases[name] = (now - self.t) * 1e3
+        self.t = now
+
+
 class ShardedBackup:
     """
     `PBVI_Solver.backup` over a belief set sharded across the ranks of `group`.
@@ -91,20 +105,29 @@ class ShardedBackup:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.last_payload_bytes = 0
+        self.trace = False              # set True to record per-phase wall times (device-synchronised) in `last_phases`
+        self.last_phases = {}
 
     def bounds(self, n_rows: int) -> tuple:
         return shard_bounds(n_rows, self.world, self.rank)
 
     def backup(self, local_belief_set, value_function, append: bool = False, belief_dominance_prune: bool = False):
         from .value_function import ValueFunction
+        t = _PhaseTimer(self.model.device.device) if self.trace else None
         local = self.solver.backup(self.model, local_belief_set, value_function, append=False,
                                    belief_dominance_prune=belief_dominance_prune)
+        if t: t.mark('local backup')
         rows, actions, hashes, counts = allgather_rows(local.alpha_vector_array, local.actions, local.row_hashes, self.group)
+        if t: t.mark('all-gather')
         self.last_payload_bytes = int(counts.max()) * (rows.shape[1] + 3) * 8 * self.world
         rows, actions, hashes = merge_gathered(rows, actions, hashes, self.model.device.rows_equal)
+        if t: t.mark('merge')
         merged = ValueFunction(self.model, rows, actions, _trusted=True, _hashes=hashes)
         if append:
             merged.extend(value_function)
+        if t:
+            t.mark('extend')
+            self.last_phases = t.phases
         return merged
 
     def compute_change(self, value_function, new_value_function, local_belief_set) -> float:
