@@ -5,7 +5,8 @@
 // Pipeline of pbvi_backup_select:
 //   transpose_kernel          alphas [V][S] -> alphaT [S][Vp]          (so a gathered successor row is one coalesced line)
 //   belief_mask_kernel        row-group occupancy bits of every (belief tile, K chunk)
-//   build_chunk_lists_kernel  per (tile, a, o): ordered list of chunks live in both the beliefs and RTO[a][o]
+//   alpha_row_mask_kernel, chunk_alpha_mask_kernel   which chunks gather a non-zero alpha-tile row
+//   build_chunk_lists_kernel  per (tile, a, o, alpha tile): ordered list of chunks live in the beliefs, RTO[a][o] and the alpha tile
 //   (R > 1) gamma_project_kernel  GammaT[a,o][s][v] = sum_r RTO * alphaT[reach]   (HBM-bound gather)
 //   score_kernel              block-sparse DMMA + fused first-index argmax over v
 //   combine_tiles_kernel      argmax across the alpha tiles (ascending, strict >)
@@ -91,12 +92,49 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
     }
 }
 
-// ---- ordered live-chunk list of every (tile, z); one warp per list ------------------------------------------------
+// ---- rowLive[nt][s] = 1 iff alphaT[s][nt*BN .. nt*BN + BN) holds a non-zero: an all-zero row of the B operand (an alpha tile
+//      that vanishes at a landing state -- the rule for value functions of goal-reward models, whose support grows by one
+//      step per backup) contributes exact zeros to every score.  Warp per (s, nt).
+__global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __restrict__ alphaT, int S, int Vp, int nNt,
+                                                             uint8_t* __restrict__ rowLive) {
+    const size_t gw = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (gw >= (size_t)S * nNt) return;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)(gw / nNt), nt = (int)(gw % nNt);
+    const double* row = alphaT + (size_t)s * Vp + (size_t)nt * BN;
+    bool nz = false;
+#pragma unroll
+    for (int j = 0; j < BN / 32; j++) nz |= row[j * 32 + lane] != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) rowLive[(size_t)nt * S + s] = bal ? 1 : 0;
+}
+
+// ---- bLive[nt][g][c] = 1 iff some state k of chunk c gathers a live alphaT row: row index reach[g][k] (g = action) for the
+//      gather path, k itself when reach == nullptr (plain path, one group)
+__global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __restrict__ rowLive, const int32_t* __restrict__ reachP,
+                                                               int S, int Sp, int nChunks, int nG, int nNt, uint8_t* __restrict__ bLive) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)nNt * nG * nChunks) return;
+    const int c = (int)(i % nChunks), g = (int)((i / nChunks) % nG), nt = (int)(i / ((size_t)nChunks * nG));
+    const uint8_t* live = rowLive + (size_t)nt * S;
+    unsigned any = 0;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+        const int k = c * KC + kk;
+        if (k < S) any |= live[reachP ? reachP[(size_t)g * Sp + k] : k];
+    }
+    bLive[i] = any ? 1 : 0;
+}
+
+// ---- ordered live-chunk list of every (tile, z, alpha tile); one warp per list.  A chunk is live iff some belief of the tile
+//      is non-zero on it AND RTO[a][o] is non-zero on it AND the alpha tile is non-zero at some state it lands on.
 __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ zMask,
-                                                               int nChunks, int nZ, uint32_t* __restrict__ lists,
-                                                               int32_t* __restrict__ counts) {
-    const int z = blockIdx.x, mt = blockIdx.y, lane = threadIdx.x;
-    uint32_t* list = lists + ((size_t)mt * nZ + z) * nChunks;
+                                                               const uint8_t* __restrict__ bLive, int nG, int zPerG, int nChunks, int nZ,
+                                                               int nNt, uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
+    const int z = blockIdx.x / nNt, nt = blockIdx.x % nNt, mt = blockIdx.y, lane = threadIdx.x;
+    const size_t slot = ((size_t)mt * nZ + z) * nNt + nt;
+    uint32_t* list = lists + slot * nChunks;
+    const uint8_t* bl = bLive ? bLive + ((size_t)nt * nG + z / zPerG) * nChunks : nullptr;
     int base = 0;
     for (int c0 = 0; c0 < nChunks; c0 += 32) {
         const int c = c0 + lane;
@@ -104,12 +142,13 @@ __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __
         if (c < nChunks) {
             b = bits[(size_t)mt * nChunks + c];
             if (zMask && !zMask[(size_t)z * nChunks + c]) b = 0u;
+            if (bl && !bl[c]) b = 0u;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, b != 0u);
         if (b) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c | (b << 24);
         base += __popc(bal);
     }
-    if (lane == 0) counts[mt * nZ + z] = base;
+    if (lane == 0) counts[slot] = base;
 }
 
 // ---- argmax across alpha tiles: ascending tile order, strict > keeps the lowest index on ties ----------------------
@@ -306,9 +345,25 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
     belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP);
     m->last_launches++;
-    PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nC);
-    PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ);
-    build_chunk_lists_kernel<<<dim3(nZ, nMt), 32, 0, st>>>(bits, backup ? m->zMask : nullptr, nC, nZ, lists, counts);
+    // alpha-side occupancy (gather path: per action; plain max_v path: one group; Gamma path: not masked)
+    uint8_t* bLive = nullptr;
+    int nG = 1, zPerG = 1;
+    if (!backup || R == 1) {
+        nG = backup ? m->A : 1;
+        zPerG = backup ? m->O : 1;
+        PBVI_TAKE(rowLive, uint8_t, (size_t)nNt * S);
+        alpha_row_mask_kernel<<<(unsigned)ceil_div_sz((size_t)S * nNt * 32, 256), 256, 0, st>>>(alphaT, S, Vp, nNt, rowLive);
+        bLive = m->arena.take<uint8_t>((size_t)nNt * nG * nC);
+        if (!bLive) return PBVI_ERR_OOM;
+        chunk_alpha_mask_kernel<<<(unsigned)ceil_div_sz((size_t)nNt * nG * nC, 256), 256, 0, st>>>(rowLive, backup ? m->reachP : nullptr, S,
+                                                                                                  m->Sp, nC, nG, nNt, bLive);
+        m->last_launches += 2;
+    }
+    PBVI_REQUIRE((size_t)nZ * nNt <= 2147483647u, "too many (z, alpha tile) pairs");
+    PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nNt * nC);
+    PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ * nNt);
+    build_chunk_lists_kernel<<<dim3(nZ * nNt, nMt), 32, 0, st>>>(bits, backup ? m->zMask : nullptr, bLive, nG, zPerG, nC, nZ, nNt, lists,
+                                                                 counts);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
 

@@ -11,7 +11,8 @@
 //   GammaT[a,o] built by gamma_project_kernel for models with reachable_state_count > 1.
 //
 // One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 16 source states) in which
-// some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero (list built by build_chunk_lists_kernel).
+// some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero AND some alpha of the tile is non-zero at a
+// state the chunk lands on (list built by build_chunk_lists_kernel): every skipped term is an exact zero.
 //
 // Warp specialisation (N_CONSUMER_WARPS + 1 warps):
 //   warp 8      producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
@@ -59,8 +60,8 @@ struct ScoreParams {
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
     const double* rtoP;        // [A*O][Sp]        (GATHER)
-    const uint32_t* lists;     // [nMt][nZ][nChunks]  chunk | row-group bits << 24
-    const int32_t* listCount;  // [nMt][nZ]
+    const uint32_t* lists;     // [nMt][nZ][nNt][nChunks]  chunk | row-group bits << 24
+    const int32_t* listCount;  // [nMt][nZ][nNt]
     const int32_t* zOrder;     // [nZ] heavy-first processing order (nullptr: identity)
     double* pval;              // [nNt][nB][nZ]
     int32_t* pidx;             // [nNt][nB][nZ]
@@ -124,8 +125,9 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
     const int nt = blockIdx.x, mt = blockIdx.y;
     const int z = p.zOrder ? p.zOrder[blockIdx.z] : (int)blockIdx.z;
     const int m0 = mt * BM, n0 = nt * BN;
-    const uint32_t* __restrict__ list = p.lists + ((size_t)mt * p.nZ + z) * p.nChunks;
-    const int nAct = p.listCount[mt * p.nZ + z];
+    const size_t listSlot = ((size_t)mt * p.nZ + z) * gridDim.x + nt;
+    const uint32_t* __restrict__ list = p.lists + listSlot * p.nChunks;
+    const int nAct = p.listCount[listSlot];
 
     if (tid == 0) {
 #pragma unroll
