@@ -43,8 +43,9 @@ UNIT = 'belief*alpha pairs/s'
 GAMMA = 0.99
 FP64_PEAK_TFLOPS = 37.1        # DMMA m8n8k4 / m16n8k16 on this pool's B200, profiles/r01_fp64_pipe_microbench.txt
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch on the default workload (B=10000, V=1000), from
-# `ncu --set full` (profiles/r01_score_kernel_v6_ncu_summary.txt); compulsory bytes are 8*S*(B+V) = 1.94e9
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 28.09e9
+# `ncu --set full` (profiles/r01_score_kernel_v8_ncu_summary.txt); dense compulsory bytes would be 8*S*(B+V) = 1.94e9 -- chunks
+# that are skipped are never read, so the kernel moves less than that
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 0.811e9
 
 
 def parse_args():
