@@ -4,9 +4,10 @@ Belief-sharded backup over the GPUs of one box (BASELINE.json north_star item 4;
 Every output row of the backup depends on one belief row, the whole (replicated) alpha set and the (replicated) model,
 so the belief set is split into contiguous row blocks, one per rank, with no collective on the data path.  The only
 exchange step is after the local backup: each rank holds n_r new alpha rows (after its local byte-dedup) and the ranks
-all-gather them -- counts first, then rows padded to the largest count -- over NCCL (NVLink 5 / NVSwitch).  Every rank
-then runs the same deterministic merge in rank order, which equals belief order, so the merged value function is
-identical on all ranks and identical to the single-GPU result (first position, last action).
+all-gather them over NCCL (NVLink 5 / NVSwitch) -- the 24-byte (action, key) records first, then only the globally first
+copy of every row (`exchange_new_rows`).  The merge is the same deterministic function of the rank-ordered records on every
+rank, and rank order equals belief order, so the merged value function is identical on all ranks and identical to the
+single-GPU result (first position, last action).
 
 One process per GPU (torchrun); `torch.distributed` must be initialised by the caller ("nccl" for CUDA tensors; the
 host-side logic is exercised with "gloo" on CPU in tests/test_parallel_gloo.py).
@@ -27,52 +28,73 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple:
     return lo, min(n_rows, lo + per)
 
 
-def allgather_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarray, group=None):
-    """
-    Variable-count all-gather of (rows [n_r,S] float64, actions [n_r], hashes [n_r,2]) in rank order.
-    Returns (rows [sum n_r, S], actions, hashes, counts).  Two collectives: counts (P int64) and the padded payload.
-    """
-    world = dist.get_world_size(group)
-    dev = rows.device
-    S = rows.shape[1]
-    n_local = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-    counts_t = torch.empty((world,), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts_t, n_local, group=group)
-    counts = counts_t.cpu().numpy()
+def _allgather_padded(local: torch.Tensor, counts: np.ndarray, group=None) -> torch.Tensor:
+    """All-gather of per-rank row blocks with different row counts (`counts`, already known everywhere): blocks are padded to
+    the largest count for ONE `all_gather_into_tensor`, then compacted.  Returns the rows of all ranks in rank order."""
+    world = counts.shape[0]
     n_max = int(counts.max())
+    width = local.shape[1]
     if n_max == 0:
-        return rows[:0], actions[:0], hashes[:0], counts
-    # payload per row: S doubles of alpha + 1 (action) + 2 (hash halves), all moved as raw 8-byte words
-    pad = torch.zeros((n_max, S + 3), dtype=torch.float64, device=dev)
-    n = rows.shape[0]
-    if n:
-        pad[:n, :S] = rows
-        meta = np.empty((n, 3), dtype=np.int64)
-        meta[:, 0] = actions
-        meta[:, 1:] = hashes
-        pad[:n, S:] = torch.from_numpy(meta).view(torch.float64).to(dev)
-    gathered = torch.empty((world * n_max, S + 3), dtype=torch.float64, device=dev)
+        return local[:0]
+    if local.shape[0] == n_max:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((n_max, width), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    gathered = torch.empty((world * n_max, width), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, pad, group=group)
-    keep = torch.cat([torch.arange(r * n_max, r * n_max + int(c), device=dev) for r, c in enumerate(counts)])
-    gathered = gathered[keep]
-    meta_all = gathered[:, S:].contiguous().view(torch.int64).cpu().numpy()
-    return gathered[:, :S].contiguous(), meta_all[:, 0].copy(), meta_all[:, 1:].copy(), counts
+    if np.all(counts == n_max):
+        return gathered
+    keep = np.concatenate([np.arange(r * n_max, r * n_max + int(c)) for r, c in enumerate(counts)])
+    return gathered[torch.as_tensor(keep, device=local.device)]
 
 
-def merge_gathered(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarray, rows_equal):
+def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarray, rows_equal, group=None):
     """
-    Dict-insertion merge of the rank-ordered rows: first position, last action (reference src/mdp.py:668-669).
-    `rows_equal(rows, ia, rows, ib) -> flags` confirms every 128-bit key match bytewise (DeviceModel.rows_equal).
+    The exchange step after a sharded backup.  Every rank holds its new alpha rows [n_r,S] (already byte-deduped locally) with
+    their actions and 128-bit keys; on return every rank holds the same merged set: the rank-ordered concatenation reduced with
+    the reference's dict semantics (first position, last action; src/mdp.py:668-669) -- what a single process computes over the
+    whole belief set.
+
+    Keys first, rows second: (1) the (action, key) records are all-gathered (24 bytes per row) and grouped identically on
+    every rank; (2) only the globally FIRST copy of each row travels -- each rank contributes the rows it owns to one NCCL
+    all-gather over NVLink, which then already is the merged set in order; (3) every rank confirms, bytewise on the device, that
+    its rows which lost to an earlier rank really equal the received copy (`rows_equal`), and the ranks agree on the outcome
+    with a scalar all-reduce.  Returns (rows, actions, hashes, payload_bytes).
     """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = rows.device
     n = rows.shape[0]
-    first, last, inverse = group_by_key(hashes)
-    if first.shape[0] != n:
-        dup = np.flatnonzero(first[inverse] != np.arange(n))
-        flags = rows_equal(rows, first[inverse[dup]].astype(np.int32), rows, dup.astype(np.int32))
-        if not bool(torch.as_tensor(flags).all()):
-            raise RuntimeError('128-bit row key collision between different alpha rows')
-        rows = rows[torch.as_tensor(first, device=rows.device)]
-    return rows, actions[last], hashes[first]
+    counts_t = torch.empty((world,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+    counts = counts_t.cpu().numpy()
+    meta = np.empty((n, 3), dtype=np.int64)
+    meta[:, 0] = actions
+    meta[:, 1:] = hashes
+    meta_all = _allgather_padded(torch.from_numpy(meta).to(dev), counts, group).cpu().numpy()
+    if meta_all.shape[0] == 0:
+        return rows[:0], actions[:0], hashes[:0], 0
+    first, last, inverse = group_by_key(meta_all[:, 1:])                     # identical on every rank
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    lo, hi = offsets[rank], offsets[rank + 1]
+    owner = np.searchsorted(offsets, first, side='right') - 1                # rank that holds the first copy of each group
+    owned_counts = np.bincount(owner, minlength=world)
+    mine = first[owner == rank] - lo                                         # ascending local positions
+    send = rows if mine.shape[0] == n else rows[torch.as_tensor(mine, device=dev)]
+    merged = _allgather_padded(send, owned_counts, group)                    # == rows of `first`, in order
+    # local rows that lost to an earlier rank: confirm they are byte-identical to the copy that won
+    local_groups = inverse[lo:hi]
+    lost = np.flatnonzero(first[local_groups] < lo)
+    ok = 1
+    if lost.shape[0]:
+        flags = rows_equal(rows, lost.astype(np.int32), merged, local_groups[lost].astype(np.int32))
+        ok = int(bool(torch.as_tensor(flags).all()))
+    ok_t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN, group=group)
+    if int(ok_t[0]) == 0:
+        raise RuntimeError('128-bit row key collision between different alpha rows of two ranks')
+    payload = int(owned_counts.max()) * rows.shape[1] * 8 * world + int(counts.max()) * 24 * world
+    return merged, meta_all[last, 0].copy(), meta_all[first, 1:].copy(), payload
 
 
 class _PhaseTimer:
@@ -117,11 +139,9 @@ class ShardedBackup:
         local = self.solver.backup(self.model, local_belief_set, value_function, append=False,
                                    belief_dominance_prune=belief_dominance_prune)
         if t: t.mark('local backup')
-        rows, actions, hashes, counts = allgather_rows(local.alpha_vector_array, local.actions, local.row_hashes, self.group)
-        if t: t.mark('all-gather')
-        self.last_payload_bytes = int(counts.max()) * (rows.shape[1] + 3) * 8 * self.world
-        rows, actions, hashes = merge_gathered(rows, actions, hashes, self.model.device.rows_equal)
-        if t: t.mark('merge')
+        rows, actions, hashes, self.last_payload_bytes = exchange_new_rows(local.alpha_vector_array, local.actions, local.row_hashes,
+                                                                          self.model.device.rows_equal, self.group)
+        if t: t.mark('exchange')
         merged = ValueFunction(self.model, rows, actions, _trusted=True, _hashes=hashes)
         if append:
             merged.extend(value_function)

@@ -24,23 +24,28 @@ def group_by_key(hashes: np.ndarray):
         z = np.zeros(0, dtype=np.int64)
         return z, z, z
     h = np.ascontiguousarray(hashes, dtype=np.int64)
-    srt = np.lexsort((np.arange(n), h[:, 1], h[:, 0]))      # by key, ties in original order (plain int64 sorts, no structured dtype)
-    hs = h[srt]
+    # one stable sort on a 64-bit mix of the two halves; the full 128-bit keys are then compared inside the sorted order, and the
+    # (never observed) case of two different keys sharing the mix falls back to a lexicographic sort on both halves
+    with np.errstate(over='ignore'):
+        mix = h[:, 0] ^ (h[:, 1] * np.int64(-7046029254386353131))
+    srt = np.argsort(mix, kind='stable')
+    hs, ms = h[srt], mix[srt]
     boundary = np.empty(n, dtype=bool)
     boundary[0] = True
-    boundary[1:] = np.any(hs[1:] != hs[:-1], axis=1)
-    group_sorted = np.cumsum(boundary) - 1                   # group id in key order
-    first = srt[boundary]                                    # first occurrence of each group (ties were kept in original order)
-    inverse = np.empty(n, dtype=np.int64)
-    inverse[srt] = group_sorted
-    order = np.argsort(first, kind='stable')                 # unique() sorts by key; renumber by first occurrence
+    boundary[1:] = (hs[1:, 0] != hs[:-1, 0]) | (hs[1:, 1] != hs[:-1, 1])
+    if np.any(boundary[1:] != (ms[1:] != ms[:-1])):
+        srt = np.lexsort((np.arange(n), h[:, 1], h[:, 0]))
+        hs = h[srt]
+        boundary[1:] = (hs[1:, 0] != hs[:-1, 0]) | (hs[1:, 1] != hs[:-1, 1])
+    starts = np.flatnonzero(boundary)
+    first = srt[starts]                                      # ties were kept in original order: first / last occurrence of a group
+    last = srt[np.append(starts[1:], n) - 1]
+    order = np.argsort(first, kind='stable')                 # renumber the groups by first occurrence
     rank = np.empty_like(order)
     rank[order] = np.arange(order.shape[0])
-    inverse = rank[inverse.reshape(n)]
-    first = first[order]
-    last = np.zeros_like(first)
-    np.maximum.at(last, inverse, np.arange(n))
-    return first.astype(np.int64), last.astype(np.int64), inverse.astype(np.int64)
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[srt] = rank[np.cumsum(boundary) - 1]
+    return first[order].astype(np.int64), last[order].astype(np.int64), inverse
 
 
 def dedup_rows(dev, rows: torch.Tensor, hashes: np.ndarray | None = None):

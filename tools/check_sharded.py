@@ -1,0 +1,48 @@
+"""
+torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_sharded.py
+Determinism check of the sharded backup on real GPUs: every rank's merged value function must equal, bit for bit and in
+order, the value function a single process computes over the whole belief set (rank 0 recomputes it locally).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ShardedBackup, ValueFunction  # noqa: E402
+from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    model = olfactory_wrap_model()
+    B = perseus_walk_beliefs(model, 1500, seed=5)                      # same beliefs on every rank (same seed)
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'backup_olfactory_wrap.npz')))
+    vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
+    solver = PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus')
+    sb = ShardedBackup(solver, model)
+    lo, hi = sb.bounds(B.shape[0])
+    for append in (False, True):
+        merged = sb.backup(BeliefSet(model, B[lo:hi]), vf, append=append)
+        rows, actions = merged.numpy()
+        single = solver.backup(model, BeliefSet(model, B), vf, append=append, belief_dominance_prune=False)
+        srows, sactions = single.numpy()
+        ok = rows.shape == srows.shape and np.array_equal(rows, srows) and np.array_equal(actions, sactions)
+        flag = torch.tensor([int(ok)], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f'append={append}: world={world} merged {rows.shape[0]} rows, single-process {srows.shape[0]} rows, identical on all ranks: {bool(flag[0])}',
+                  flush=True)
+        assert bool(flag[0])
+        chg = sb.compute_change(vf, merged, BeliefSet(model, B[lo:hi]))
+        ref = solver.compute_change(vf, single, BeliefSet(model, B))
+        assert chg == ref, (chg, ref)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
