@@ -250,6 +250,8 @@ def run_b200(args):
     A, O, S = model.action_count, model.observation_count, model.state_count
     belief_set = BeliefSet(model, beliefs)
     sharded = ShardedBackup(solver, model) if world > 1 else None
+    if sharded is not None:
+        sharded.set_capacity(B)            # every rank backs up exactly B beliefs
 
     def step_device():
         if sharded is not None:

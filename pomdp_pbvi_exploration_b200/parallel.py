@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .sets import group_by_key
+from .sets import group_by_key, unique_rows_first
 
 
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple:
@@ -97,6 +97,44 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
     return merged, meta_all[last, 0].copy(), meta_all[first, 1:].copy(), payload
 
 
+def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_local_beliefs: int, capacity: int, device, group=None):
+    """
+    The exchange step of the sharded backup in its compact form.  An alpha row of the backup is a deterministic function of
+    its generating tuple (a*, v*[a*, :]) and of the replicated (model, old value function), so the ranks all-gather the
+    distinct TUPLES of their shards (8*(1+O) bytes each instead of 8*S per row) together with the positions of the first / last
+    belief that chose them, and every rank then assembles the merged set itself (`PBVI_Solver.rows_from_tuples`) -- bitwise the
+    same rows on every rank, in the order a single process would produce.  One collective: block r of the gathered buffer
+    is [header (u_r, n_r); u_r records (tuple, first, last)], padded to `capacity` records.
+    Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set, positions in the rank-ordered concatenation.
+    """
+    world = dist.get_world_size(group)
+    u, w = tuples.shape
+    assert u <= capacity, (u, capacity)
+    buf = np.zeros((capacity + 1, w + 2), dtype=np.int64)
+    buf[0, 0], buf[0, 1] = u, n_local_beliefs
+    buf[1:u + 1, :w] = tuples
+    buf[1:u + 1, w] = first
+    buf[1:u + 1, w + 1] = last
+    local = torch.from_numpy(buf).to(device)
+    gathered = torch.empty((world * (capacity + 1), w + 2), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    allb = gathered.cpu().numpy().reshape(world, capacity + 1, w + 2)
+    counts, n_beliefs = allb[:, 0, 0], allb[:, 0, 1]
+    offsets = np.concatenate([[0], np.cumsum(n_beliefs)])
+    recs = np.concatenate([allb[r, 1:1 + counts[r]] + np.array([0] * w + [offsets[r], offsets[r]]) for r in range(world)], axis=0)
+    if recs.shape[0] == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return np.zeros((0, w), dtype=np.int64), z, z
+    gf, _, inv = unique_rows_first(recs[:, :w])
+    # records are rank-major and ascending in `first` inside a rank, so the first record of a group carries its smallest position
+    g_first = recs[gf, w]
+    order = np.lexsort((recs[:, w + 1], inv))
+    ends = np.append(np.flatnonzero(np.diff(inv[order])), order.shape[0] - 1)
+    g_last = np.empty(gf.shape[0], dtype=np.int64)
+    g_last[inv[order[ends]]] = recs[order[ends], w + 1]
+    return recs[gf, :w], g_first, g_last
+
+
 class _PhaseTimer:
     def __init__(self, device):
         import time
@@ -120,10 +158,13 @@ class ShardedBackup:
         vf = sb.backup(BeliefSet(model, B[lo:hi]), value_function, append=False)   # same ValueFunction on every rank
     """
 
-    def __init__(self, solver, model, group=None):
+    def __init__(self, solver, model, group=None, exchange: str = 'tuples'):
+        assert exchange in ('tuples', 'rows')
         self.solver = solver
         self.model = model
         self.group = group
+        self.exchange = exchange        # 'tuples': all-gather the generating tuples, assemble everywhere; 'rows': all-gather the rows
+        self._cap = (None, None)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.last_payload_bytes = 0
@@ -131,11 +172,29 @@ class ShardedBackup:
         self.last_phases = {}
 
     def bounds(self, n_rows: int) -> tuple:
+        self._fixed_cap = -(-n_rows // self.world)
         return shard_bounds(n_rows, self.world, self.rank)
 
     def backup(self, local_belief_set, value_function, append: bool = False, belief_dominance_prune: bool = False):
         from .value_function import ValueFunction
         t = _PhaseTimer(self.model.device.device) if self.trace else None
+        if self.exchange == 'tuples':
+            tuples, first, last = self.solver.select_tuples(self.model, local_belief_set, value_function, belief_dominance_prune)
+            if t: t.mark('local select')
+            n_local = len(local_belief_set)
+            g_tuples, _, g_last = exchange_tuples(tuples, first, last, n_local, self._capacity(n_local), self.model.device.device, self.group)
+            self.last_payload_bytes = (self._cap[1] + 1) * (tuples.shape[1] + 2) * 8 * self.world
+            if t: t.mark('exchange')
+            merged = self.solver.rows_from_tuples(self.model, value_function, g_tuples, g_last)
+            if t: t.mark('assemble + dedup')
+            if append:
+                n_new = len(merged)
+                merged.extend(value_function)
+                merged.parent_uid, merged.n_new = value_function.uid, n_new
+            if t:
+                t.mark('extend')
+                self.last_phases = t.phases
+            return merged
         local = self.solver.backup(self.model, local_belief_set, value_function, append=False,
                                    belief_dominance_prune=belief_dominance_prune)
         if t: t.mark('local backup')
@@ -149,6 +208,23 @@ class ShardedBackup:
             t.mark('extend')
             self.last_phases = t.phases
         return merged
+
+    def set_capacity(self, max_shard_rows: int) -> None:
+        """Declares the largest shard size of any rank (the same value on every rank), which saves the per-call agreement."""
+        self._fixed_cap = int(max_shard_rows)
+
+    def _capacity(self, n_local: int) -> int:
+        """Largest shard size over the ranks = upper bound on the records a rank contributes.  Known without communication after
+        `bounds(n_rows)` / `set_capacity`; otherwise agreed with one scalar all-reduce per call (every rank takes part)."""
+        fixed = getattr(self, '_fixed_cap', None)
+        if fixed is not None:
+            assert n_local <= fixed, f'shard of {n_local} rows exceeds the declared capacity {fixed}'
+            self._cap = (n_local, fixed)
+            return fixed
+        c = torch.tensor([n_local], dtype=torch.int64, device=self.model.device.device)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX, group=self.group)
+        self._cap = (n_local, int(c[0]))
+        return self._cap[1]
 
     def compute_change(self, value_function, new_value_function, local_belief_set) -> float:
         """max over all shards of the local change: one scalar all-reduce(max)."""

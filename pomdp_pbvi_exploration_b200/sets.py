@@ -48,6 +48,33 @@ def group_by_key(hashes: np.ndarray):
     return first[order].astype(np.int64), last[order].astype(np.int64), inverse
 
 
+def unique_rows_first(keys: np.ndarray):
+    """Unique rows of an int array in order of first occurrence: (first [u], last [u], inverse [n])."""
+    n = keys.shape[0]
+    if n == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    span = keys.max(axis=0) + 1
+    bits = np.ceil(np.log2(np.maximum(span, 2))).astype(np.int64)
+    if int(bits.sum()) <= 62 and keys.min() >= 0:          # pack a row into one int64 (the common case)
+        packed = np.zeros(n, dtype=np.int64)
+        for j in range(keys.shape[1]):
+            packed = (packed << int(bits[j])) | keys[:, j]
+        _, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
+    else:
+        _, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+    inverse = inverse.reshape(n)
+    order = np.argsort(first, kind='stable')
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.shape[0])
+    inverse = rank[inverse]
+    first = first[order]
+    last = np.zeros_like(first)
+    last[inverse] = np.arange(n)                             # ascending assignment: the largest position of each group wins
+    return first, last, inverse
+
+
 def dedup_rows(dev, rows: torch.Tensor, hashes: np.ndarray | None = None):
     """
     Dict-insertion dedup of device rows [n,S]: returns (first, last, hashes, inverse) where `first[g]` is the position of the

@@ -26,7 +26,7 @@ import torch
 
 from .belief import Belief, BeliefSet
 from .model import Model, log
-from .sets import dedup_rows, group_by_key
+from .sets import dedup_rows, group_by_key, unique_rows_first  # noqa: F401
 from .value_function import AlphaVector, ValueFunction  # noqa: F401
 
 
@@ -35,33 +35,6 @@ def _now_synced(model: Model) -> datetime:
     reads the clock without synchronising)."""
     torch.cuda.synchronize(model.device.device)
     return datetime.now()
-
-
-def unique_rows_first(keys: np.ndarray):
-    """Unique rows of an int array in order of first occurrence: (first [u], last [u], inverse [n])."""
-    n = keys.shape[0]
-    if n == 0:
-        z = np.zeros(0, dtype=np.int64)
-        return z, z, z
-    keys = np.ascontiguousarray(keys, dtype=np.int64)
-    span = keys.max(axis=0) + 1
-    bits = np.ceil(np.log2(np.maximum(span, 2))).astype(np.int64)
-    if int(bits.sum()) <= 62 and keys.min() >= 0:          # pack a row into one int64 (the common case)
-        packed = np.zeros(n, dtype=np.int64)
-        for j in range(keys.shape[1]):
-            packed = (packed << int(bits[j])) | keys[:, j]
-        _, first, inverse = np.unique(packed, return_index=True, return_inverse=True)
-    else:
-        _, first, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
-    inverse = inverse.reshape(n)
-    order = np.argsort(first, kind='stable')
-    rank = np.empty_like(order)
-    rank[order] = np.arange(order.shape[0])
-    inverse = rank[inverse]
-    first = first[order]
-    last = np.zeros_like(first)
-    np.maximum.at(last, inverse, np.arange(n))
-    return first, last, inverse
 
 
 # =====================================================================================================================
@@ -365,14 +338,28 @@ class PBVI_Solver:
         Two beliefs that select the same (a*, v*[a*,:]) tuple produce the same bytes, so only the distinct tuples are
         assembled; the byte-dedup then runs over those rows (different tuples can still give identical rows).
         """
+        tuples, _, last = self.select_tuples(model, belief_set, value_function, belief_dominance_prune)
+        new_vf = self.rows_from_tuples(model, value_function, tuples, last)
+        if append:
+            n_new = len(new_vf)
+            new_vf.extend(value_function)
+            # the union keeps the new rows first and every old row (bytewise): max over it = max(new rows, old value function)
+            new_vf.parent_uid, new_vf.n_new = value_function.uid, n_new
+        return new_vf
+
+    def select_tuples(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
+        """
+        First half of the backup: for every belief the tuple (a*, v*[a*, 0..O-1]) that generates its alpha row, reduced to the
+        DISTINCT tuples in order of first occurrence.  Returns host arrays (tuples [u, 1+O] int64, first [u], last [u]) where
+        first / last are the positions (in this belief set, after the optional dominance filter) of the first / last belief
+        that chose the tuple.  A tuple is 8*(1+O) bytes, the row it generates 8*S: the sharded backup exchanges these.
+        """
         dev = model.device
         V = value_function.alpha_vector_array
         nB = len(belief_set)
         if nB == 0:
-            new_vf = ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
-            if append:
-                new_vf.extend(value_function)
-            return new_vf
+            z = np.zeros(0, dtype=np.int64)
+            return np.zeros((0, 1 + dev.O), dtype=np.int64), z, z
         if belief_set._device is None and nB >= 2 * self.STREAM_FIRST_CHUNK:
             vstar, value, astar = self._select_streamed(model, belief_set, V)
         else:
@@ -381,39 +368,36 @@ class PBVI_Solver:
         ar = torch.arange(nB, device=dev.device)
         sel = vstar[ar, astar.long()]                                                    # [nB, O]
         keys = torch.cat([astar[:, None], sel], dim=1)
-        keep_idx = None
         if belief_dominance_prune:
             # keep b iff b.alpha_b > max_v b.alpha_v, strict (reference :1509-1515)
             best_old, _ = dev.max_values(B, V)
             keep = value[ar, astar.long()] > best_old
-            keep_idx = torch.nonzero(keep)[:, 0]
-            keys = keys[keep_idx]
-        keys_h = keys.cpu().numpy()
-        first, last, inverse = unique_rows_first(keys_h)
-        tuples = keys_h[first]
+            keys = keys[torch.nonzero(keep)[:, 0]]
+        keys_h = keys.cpu().numpy().astype(np.int64)
+        first, last, _ = unique_rows_first(keys_h)
+        return keys_h[first], first, last
+
+    def rows_from_tuples(self, model: Model, value_function: ValueFunction, tuples: np.ndarray, last: np.ndarray) -> ValueFunction:
+        """
+        Second half of the backup: assembles the alpha row of every distinct tuple (reference operation order, bit-identical for
+        R = 1) and applies the ValueFunction constructor's byte-dedup.  Different tuples can generate identical bytes; a byte
+        group keeps the position of its first tuple and the action of the tuple whose LAST belief comes latest (`last`).
+        """
+        dev = model.device
         if tuples.shape[0] == 0:
-            new_vf = ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
+            return ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
+        rows = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, tuples[:, 0], tuples[:, 1:])
+        gfirst, _, hashes, ginv = dedup_rows(dev, rows)
+        if gfirst.shape[0] == rows.shape[0]:
+            actions = tuples[:, 0].astype(np.int64)
         else:
-            rows = dev.backup_assemble(V, self.gamma, tuples[:, 0], tuples[:, 1:])
-            gfirst, _, hashes, ginv = dedup_rows(dev, rows)
-            # the surviving action of a byte group is the action of the LAST belief that produced those bytes
-            glast_belief = np.zeros(gfirst.shape[0], dtype=np.int64)
-            owner = np.zeros(gfirst.shape[0], dtype=np.int64)
-            for t in range(tuples.shape[0]):                         # tuples are few (distinct alpha rows of this backup)
-                g = ginv[t]
-                if last[t] >= glast_belief[g]:
-                    glast_belief[g] = last[t]
-                    owner[g] = t
+            order = np.lexsort((last, ginv))                         # within a byte group: ascending position of the last belief
+            ends = np.append(np.flatnonzero(np.diff(ginv[order])), order.shape[0] - 1)
+            owner = np.empty(gfirst.shape[0], dtype=np.int64)
+            owner[ginv[order[ends]]] = order[ends]
             actions = tuples[owner, 0].astype(np.int64)
-            if gfirst.shape[0] != rows.shape[0]:
-                rows = rows[torch.as_tensor(gfirst, device=rows.device)]
-            new_vf = ValueFunction(model, rows, actions, _trusted=True, _hashes=hashes[gfirst])
-        if append:
-            n_new = len(new_vf)
-            new_vf.extend(value_function)
-            # the union keeps the new rows first and every old row (bytewise): max over it = max(new rows, old value function)
-            new_vf.parent_uid, new_vf.n_new = value_function.uid, n_new
-        return new_vf
+            rows = rows[torch.as_tensor(gfirst, device=rows.device)]
+        return ValueFunction(model, rows, actions, _trusted=True, _hashes=hashes[gfirst])
 
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
     STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)

@@ -72,3 +72,42 @@ def test_sharded_merge_equals_single_process(n_rows, world):
         assert np.array_equal(rows, want_rows), rank
         assert np.array_equal(actions, want_actions), rank
         assert payload > 0
+
+
+def _tuple_worker(rank, world, port, keys_all, result_queue):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pomdp_pbvi_exploration_b200.parallel import exchange_tuples, shard_bounds
+    from pomdp_pbvi_exploration_b200.sets import unique_rows_first
+    lo, hi = shard_bounds(keys_all.shape[0], world, rank)
+    local = keys_all[lo:hi]
+    first, last, _ = unique_rows_first(local)
+    cap = -(-keys_all.shape[0] // world)
+    g_tuples, g_first, g_last = exchange_tuples(local[first], first, last, hi - lo, cap, torch.device('cpu'))
+    result_queue.put((rank, g_tuples, g_first, g_last))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_beliefs,world', [(50, 2), (3, 2), (64, 3)])
+def test_tuple_exchange_equals_single_process(n_beliefs, world):
+    """The compact exchange: distinct (a*, v*) tuples + first/last belief positions of every shard, merged identically on every
+    rank, must equal the distinct tuples (first occurrence order, first / last positions) of the whole belief set."""
+    from pomdp_pbvi_exploration_b200.sets import unique_rows_first
+    rng = np.random.default_rng(n_beliefs)
+    pool = rng.integers(0, 40, (7, 4))
+    keys_all = pool[rng.integers(0, 7, n_beliefs)]
+    f, l, _ = unique_rows_first(keys_all)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tuple_worker, args=(r, world, port, keys_all, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g_tuples, g_first, g_last in results:
+        assert np.array_equal(g_tuples, keys_all[f]) and np.array_equal(g_first, f) and np.array_equal(g_last, l), rank

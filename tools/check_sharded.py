@@ -24,9 +24,9 @@ def main():
     g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'backup_olfactory_wrap.npz')))
     vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
     solver = PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus')
-    sb = ShardedBackup(solver, model)
-    lo, hi = sb.bounds(B.shape[0])
-    for append in (False, True):
+    for mode, append in [('tuples', False), ('tuples', True), ('rows', False), ('rows', True)]:
+        sb = ShardedBackup(solver, model, exchange=mode)
+        lo, hi = sb.bounds(B.shape[0])
         merged = sb.backup(BeliefSet(model, B[lo:hi]), vf, append=append)
         rows, actions = merged.numpy()
         single = solver.backup(model, BeliefSet(model, B), vf, append=append, belief_dominance_prune=False)
@@ -35,7 +35,7 @@ def main():
         flag = torch.tensor([int(ok)], device='cuda')
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(f'append={append}: world={world} merged {rows.shape[0]} rows, single-process {srows.shape[0]} rows, identical on all ranks: {bool(flag[0])}',
+            print(f'exchange={mode} append={append}: world={world} merged {rows.shape[0]} rows, single-process {srows.shape[0]} rows, identical on all ranks: {bool(flag[0])}',
                   flush=True)
         assert bool(flag[0])
         chg = sb.compute_change(vf, merged, BeliefSet(model, B[lo:hi]))
