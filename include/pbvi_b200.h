@@ -75,10 +75,11 @@ PBVI_API int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB, 
 /* pbvi_backup_assemble: alpha_a rows for n (action, v_star[O]) tuples                    (:1497-1506)
  *   out[i][s] = Rbar[s,a_i] + ((G_0 + G_1) + ...),  G_o = gamma * sum_r RTO[s,a_i,o,r] * alpha[v_i[o]][reach[s,a_i,r]]
  * with the reference's operation order and no FMA contraction (bit-identical rows when R == 1).
- * d_actions [n] int32, d_vsel [n][O] int32, d_out [n][S].
+ * d_actions [n] int32, d_vsel [n][O] int32, d_out [n][S]; d_hash [n][2] uint64 (nullable) receives the 128-bit key of every
+ * row (the value pbvi_row_hash computes), accumulated while the row is being written.
  */
 PBVI_API int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int nV, double gamma, const int32_t* d_actions,
-                         const int32_t* d_vsel, int n, double* d_out, void* stream);
+                         const int32_t* d_vsel, int n, double* d_out, uint64_t* d_hash, void* stream);
 
 /* pbvi_backup: select + assemble for every belief (no dedup): d_out_alpha [nB][S], d_out_action [nB];
  * d_out_vstar [nB][A][O] and d_out_value [nB][A] may be NULL. */

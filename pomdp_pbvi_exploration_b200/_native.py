@@ -28,7 +28,7 @@ SIGNATURES = {
     'pbvi_model_destroy': [_P],
     'pbvi_model_dims': [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     'pbvi_backup_select': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P],
-    'pbvi_backup_assemble': [_P, _P, c_int, c_double, _P, _P, c_int, _P, _P],
+    'pbvi_backup_assemble': [_P, _P, c_int, c_double, _P, _P, c_int, _P, _P, _P],
     'pbvi_backup': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P, _P],
     'pbvi_backup_host': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P],
     'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
@@ -172,15 +172,18 @@ class DeviceModel:
                                             self._stream))
         return vstar, value, astar
 
-    def backup_assemble(self, alphas, gamma: float, actions, vsel) -> torch.Tensor:
-        """alpha_a rows for (action, v*[O]) tuples (reference src/pomdp.py:1497-1506)."""
+    def backup_assemble(self, alphas, gamma: float, actions, vsel, with_hash: bool = False):
+        """alpha_a rows for (action, v*[O]) tuples (reference src/pomdp.py:1497-1506); `with_hash` also returns their 128-bit
+        row keys (int64 [n,2], equal to `row_hash(rows)`) computed in the same pass."""
         al = self._beliefs(alphas)
         act, vs = _i32(actions, self.device), _i32(vsel, self.device)
         n = act.shape[0]
         assert vs.shape == (n, self.O)
         out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
-        self._call(self._lib.pbvi_backup_assemble(self._h, _ptr(al), al.shape[0], float(gamma), _ptr(act), _ptr(vs), n, _ptr(out), self._stream))
-        return out
+        keys = torch.empty((n, 2), dtype=torch.int64, device=self.device) if with_hash else None
+        self._call(self._lib.pbvi_backup_assemble(self._h, _ptr(al), al.shape[0], float(gamma), _ptr(act), _ptr(vs), n, _ptr(out),
+                                                  _ptr(keys), self._stream))
+        return (out, keys) if with_hash else out
 
     def backup(self, beliefs, alphas, gamma: float):
         """select + assemble for every belief, no dedup: (alpha [nB,S], action [nB], v* [nB,A,O], value [nB,A])."""

@@ -300,16 +300,48 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
                                                        const int32_t* __restrict__ vsel, size_t vselStride, int perAction,
                                                        const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                        const double* __restrict__ rbarT, double gamma, int S, int R, int O,
-                                                       double* __restrict__ out) {
+                                                       double* __restrict__ out, unsigned long long* __restrict__ hacc) {
     extern __shared__ int s_vsel[];
+    __shared__ unsigned long long sh[2][8];
     const int i = blockIdx.y, a = actions[i];
     const int32_t* vs = vsel + (size_t)i * vselStride + (perAction ? (size_t)a * O : 0);
     for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vs[o];
     __syncthreads();
     const int s = blockIdx.x * 256 + threadIdx.x;
-    if (s >= S) return;
-    out[(size_t)i * S + s] = alpha_a_entry(alphas, S, R, O, s_vsel, reachK + (size_t)a * S * R, rtoK + (size_t)a * O * S * R,
-                                           rbarT + (size_t)a * S, gamma, s);
+    unsigned long long h0 = 0, h1 = 0;
+    if (s < S) {
+        const double v = alpha_a_entry(alphas, S, R, O, s_vsel, reachK + (size_t)a * S * R, rtoK + (size_t)a * O * S * R,
+                                       rbarT + (size_t)a * S, gamma, s);
+        out[(size_t)i * S + s] = v;
+        if (hacc) {
+            const uint64_t w = (uint64_t)__double_as_longlong(v);
+            h0 = row_hash_term0(w, s);
+            h1 = row_hash_term1(w, s);
+        }
+    }
+    if (!hacc) return;
+    // the row's 128-bit key, accumulated while the row is still in registers (same value as row_hash_kernel over the finished row)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        h0 += __shfl_down_sync(0xffffffffu, h0, off);
+        h1 += __shfl_down_sync(0xffffffffu, h1, off);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = h0; sh[1][threadIdx.x >> 5] = h1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long x = 0, y = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { x += sh[0][w]; y += sh[1][w]; }
+        atomicAdd(&hacc[(size_t)i * 2], x);
+        atomicAdd(&hacc[(size_t)i * 2 + 1], y);
+    }
+}
+
+__global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* __restrict__ h, int n, int rowLen) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    h[(size_t)i * 2] = row_hash_final0(h[(size_t)i * 2], rowLen);
+    h[(size_t)i * 2 + 1] = row_hash_final1(h[(size_t)i * 2 + 1], rowLen);
 }
 
 // =====================================================================================================================
@@ -449,12 +481,18 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
 }
 
 static int assemble_impl(pbvi_model* m, const double* d_alphas, double gamma, const int32_t* d_actions, const int32_t* d_vsel,
-                         size_t vselStride, int perAction, int n, double* d_out, cudaStream_t st) {
+                         size_t vselStride, int perAction, int n, double* d_out, uint64_t* d_hash, cudaStream_t st) {
+    unsigned long long* hacc = reinterpret_cast<unsigned long long*>(d_hash);
+    if (hacc) PBVI_CUDA(cudaMemsetAsync(hacc, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
     for (int i0 = 0; i0 < n; i0 += 65535) {
         const int ni = std::min(65535, n - i0);
         assemble_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, m->O * sizeof(int), st>>>(
             d_alphas, d_actions + i0, d_vsel + (size_t)i0 * vselStride, vselStride, perAction, m->reachK, m->rtoK, m->rbarT, gamma,
-            m->S, m->R, m->O, d_out + (size_t)i0 * m->S);
+            m->S, m->R, m->O, d_out + (size_t)i0 * m->S, hacc ? hacc + (size_t)i0 * 2 : nullptr);
+        m->last_launches++;
+    }
+    if (hacc) {
+        hash_finalise_kernel<<<ceil_div(n, 256), 256, 0, st>>>(hacc, n, m->S);
         m->last_launches++;
     }
     PBVI_CUDA(cudaGetLastError());
@@ -476,14 +514,14 @@ extern "C" int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB
 }
 
 extern "C" int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int nV, double gamma, const int32_t* d_actions,
-                                    const int32_t* d_vsel, int n, double* d_out, void* stream) {
+                                    const int32_t* d_vsel, int n, double* d_out, uint64_t* d_hash, void* stream) {
     PBVI_REQUIRE(m != nullptr, "model handle is NULL");
     PBVI_REQUIRE(n >= 0 && nV > 0, "need n >= 0 tuples and nV > 0 alpha vectors");
     if (n == 0) return PBVI_OK;
     PBVI_REQUIRE(d_alphas && d_actions && d_vsel && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
-    return assemble_impl(m, d_alphas, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, (cudaStream_t)stream);
+    return assemble_impl(m, d_alphas, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, d_hash, (cudaStream_t)stream);
 }
 
 extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
@@ -500,7 +538,7 @@ extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const
         if (!d_out_vstar) return PBVI_ERR_OOM;
     }
     PBVI_TRY(select_impl(m, d_beliefs, nB, d_alphas, nV, gamma, d_out_vstar, d_out_value, d_out_action, st));
-    return assemble_impl(m, d_alphas, gamma, d_out_action, d_out_vstar, (size_t)m->nZ, 1, nB, d_out_alpha, st);
+    return assemble_impl(m, d_alphas, gamma, d_out_action, d_out_vstar, (size_t)m->nZ, 1, nB, d_out_alpha, nullptr, st);
 }
 
 extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
@@ -521,7 +559,7 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     PBVI_CUDA(cudaMemcpyAsync(d_b, h_beliefs, (size_t)nB * S * sizeof(double), cudaMemcpyHostToDevice, st));
     PBVI_CUDA(cudaMemcpyAsync(d_a, h_alphas, (size_t)nV * S * sizeof(double), cudaMemcpyHostToDevice, st));
     PBVI_TRY(select_impl(m, d_b, nB, d_a, nV, gamma, d_vs, nullptr, d_act, st));
-    PBVI_TRY(assemble_impl(m, d_a, gamma, d_act, d_vs, (size_t)m->nZ, 1, nB, d_out, st));
+    PBVI_TRY(assemble_impl(m, d_a, gamma, d_act, d_vs, (size_t)m->nZ, 1, nB, d_out, nullptr, st));
     PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, d_out, (size_t)nB * S * sizeof(double), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaMemcpyAsync(h_out_action, d_act, (size_t)nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));

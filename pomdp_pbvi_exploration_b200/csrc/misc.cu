@@ -7,13 +7,6 @@
 
 namespace pbvi {
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27; x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
-    return x;
-}
-
 // 128-bit hash of the raw 8-byte words of each row: position-salted mixes combined by wrapping addition (associative,
 // so any reduction shape gives the same value).  Block per row.
 __global__ void __launch_bounds__(256) row_hash_kernel(const uint64_t* __restrict__ rows, int rowLen, uint64_t* __restrict__ out) {
@@ -22,8 +15,8 @@ __global__ void __launch_bounds__(256) row_hash_kernel(const uint64_t* __restric
     uint64_t h0 = 0, h1 = 0;
     for (int i = threadIdx.x; i < rowLen; i += 256) {
         const uint64_t w = row[i];
-        h0 += mix64(w ^ (0x9e3779b97f4a7c15ull * (uint64_t)(i + 1)));
-        h1 += mix64((w + 0xd6e8feb86659fd93ull) ^ (0xc2b2ae3d27d4eb4full * (uint64_t)(i + 1)));
+        h0 += row_hash_term0(w, i);
+        h1 += row_hash_term1(w, i);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -36,8 +29,8 @@ __global__ void __launch_bounds__(256) row_hash_kernel(const uint64_t* __restric
         uint64_t a = 0, b = 0;
 #pragma unroll
         for (int w = 0; w < 8; w++) { a += sh[0][w]; b += sh[1][w]; }
-        out[(size_t)blockIdx.x * 2] = mix64(a + (uint64_t)rowLen);
-        out[(size_t)blockIdx.x * 2 + 1] = mix64(b ^ (uint64_t)rowLen);
+        out[(size_t)blockIdx.x * 2] = row_hash_final0(a, rowLen);
+        out[(size_t)blockIdx.x * 2 + 1] = row_hash_final1(b, rowLen);
     }
 }
 

@@ -61,6 +61,21 @@ struct Arena {
     T* var = m->arena.take<T>(n);                    \
     if (!var) return PBVI_ERR_OOM
 
+// 128-bit row key = two position-salted sums of mixed 8-byte words (wrapping addition: any reduction shape, including
+// atomics, gives the same value), finalised with the row length.  Shared by row_hash_kernel and the hashing assemble kernel.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t row_hash_term0(uint64_t w, int i) { return mix64(w ^ (0x9e3779b97f4a7c15ull * (uint64_t)(i + 1))); }
+__host__ __device__ __forceinline__ uint64_t row_hash_term1(uint64_t w, int i) {
+    return mix64((w + 0xd6e8feb86659fd93ull) ^ (0xc2b2ae3d27d4eb4full * (uint64_t)(i + 1)));
+}
+__host__ __device__ __forceinline__ uint64_t row_hash_final0(uint64_t a, int rowLen) { return mix64(a + (uint64_t)rowLen); }
+__host__ __device__ __forceinline__ uint64_t row_hash_final1(uint64_t b, int rowLen) { return mix64(b ^ (uint64_t)rowLen); }
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
 

@@ -97,6 +97,9 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
     return merged, meta_all[last, 0].copy(), meta_all[first, 1:].copy(), payload
 
 
+_LAST_MAX_COUNT = [512]
+
+
 def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_local_beliefs: int, capacity: int, device, group=None):
     """
     The exchange step of the sharded backup in its compact form.  An alpha row of the backup is a deterministic function of
@@ -110,15 +113,24 @@ def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_l
     world = dist.get_world_size(group)
     u, w = tuples.shape
     assert u <= capacity, (u, capacity)
-    buf = np.zeros((capacity + 1, w + 2), dtype=np.int64)
-    buf[0, 0], buf[0, 1] = u, n_local_beliefs
-    buf[1:u + 1, :w] = tuples
-    buf[1:u + 1, w] = first
-    buf[1:u + 1, w + 1] = last
-    local = torch.from_numpy(buf).to(device)
-    gathered = torch.empty((world * (capacity + 1), w + 2), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(gathered, local, group=group)
-    allb = gathered.cpu().numpy().reshape(world, capacity + 1, w + 2)
+    # Most beliefs share their tuple with others, so the blocks are first sized by a guess (twice the largest count seen in the
+    # previous exchange); the header carries the true count, and if any rank overflowed -- every rank sees that in the gathered
+    # headers, so the decision is consistent -- the exchange is repeated once at full capacity.
+    guess = min(capacity, max(256, 2 * _LAST_MAX_COUNT[0]))
+    while True:
+        buf = np.zeros((guess + 1, w + 2), dtype=np.int64)
+        buf[0, 0], buf[0, 1] = u, n_local_beliefs
+        k = min(u, guess)
+        buf[1:k + 1, :w] = tuples[:k]
+        buf[1:k + 1, w] = first[:k]
+        buf[1:k + 1, w + 1] = last[:k]
+        gathered = torch.empty((world * (guess + 1), w + 2), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered, torch.from_numpy(buf).to(device), group=group)
+        allb = gathered.cpu().numpy().reshape(world, guess + 1, w + 2)
+        _LAST_MAX_COUNT[0] = int(allb[:, 0, 0].max())
+        if _LAST_MAX_COUNT[0] <= guess:
+            break
+        guess = capacity
     counts, n_beliefs = allb[:, 0, 0], allb[:, 0, 1]
     offsets = np.concatenate([[0], np.cumsum(n_beliefs)])
     recs = np.concatenate([allb[r, 1:1 + counts[r]] + np.array([0] * w + [offsets[r], offsets[r]]) for r in range(world)], axis=0)
@@ -183,7 +195,7 @@ class ShardedBackup:
             if t: t.mark('local select')
             n_local = len(local_belief_set)
             g_tuples, _, g_last = exchange_tuples(tuples, first, last, n_local, self._capacity(n_local), self.model.device.device, self.group)
-            self.last_payload_bytes = (self._cap[1] + 1) * (tuples.shape[1] + 2) * 8 * self.world
+            self.last_payload_bytes = (min(self._cap[1], max(256, 2 * _LAST_MAX_COUNT[0])) + 1) * (tuples.shape[1] + 2) * 8 * self.world
             if t: t.mark('exchange')
             merged = self.solver.rows_from_tuples(self.model, value_function, g_tuples, g_last)
             if t: t.mark('assemble + dedup')

@@ -386,8 +386,8 @@ class PBVI_Solver:
         dev = model.device
         if tuples.shape[0] == 0:
             return ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
-        rows = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, tuples[:, 0], tuples[:, 1:])
-        gfirst, _, hashes, ginv = dedup_rows(dev, rows)
+        rows, keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, tuples[:, 0], tuples[:, 1:], with_hash=True)
+        gfirst, _, hashes, ginv = dedup_rows(dev, rows, keys.cpu().numpy())
         if gfirst.shape[0] == rows.shape[0]:
             actions = tuples[:, 0].astype(np.int64)
         else:

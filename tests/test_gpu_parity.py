@@ -100,6 +100,9 @@ def test_backup_golden(torch_cuda, tag):
     sel = np.take_along_axis(vstar, act[:, None, None].astype(np.int64), axis=1)[:, 0, :]
     rows = dev.backup_assemble(g['alphas'], gamma, act, sel).cpu().numpy()
     assert np.array_equal(rows, alpha)
+    # keys accumulated while the rows are written == keys of a separate pass over the finished rows
+    rows_t, keys = dev.backup_assemble(g['alphas'], gamma, act, sel, with_hash=True)
+    assert torch_cuda.equal(keys, dev.row_hash(rows_t)) and np.array_equal(rows_t.cpu().numpy(), alpha)
 
 
 def _sparse_beliefs(rng, n, S, ks):
