@@ -140,10 +140,9 @@ def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_l
     gf, _, inv = unique_rows_first(recs[:, :w])
     # records are rank-major and ascending in `first` inside a rank, so the first record of a group carries its smallest position
     g_first = recs[gf, w]
-    order = np.lexsort((recs[:, w + 1], inv))
-    ends = np.append(np.flatnonzero(np.diff(inv[order])), order.shape[0] - 1)
+    # a higher rank holds later beliefs, and a rank lists a tuple once: the last record of a group carries its largest position
     g_last = np.empty(gf.shape[0], dtype=np.int64)
-    g_last[inv[order[ends]]] = recs[order[ends], w + 1]
+    g_last[inv] = recs[:, w + 1]
     return recs[gf, :w], g_first, g_last
 
 
