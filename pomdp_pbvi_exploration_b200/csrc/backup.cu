@@ -55,13 +55,14 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
 //      so that the A operand of one (tile, chunk, row group) is ONE contiguous, 128-byte aligned block of RG*LDA doubles that a
 //      single bulk async copy drops into shared memory already in its bank-conflict-free layout.
 __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
-                                                          uint8_t* __restrict__ bits, double* __restrict__ beliefsP) {
+                                                          uint8_t* __restrict__ bits, double* __restrict__ beliefsP, int* __restrict__ signs) {
     __shared__ unsigned smask[NRG];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cb = blockIdx.x, mt = blockIdx.y;
     if (tid < NRG) smask[tid] = 0u;
     __syncthreads();
     unsigned mask = 0u;
+    bool bad = false;
     for (int rr = 0; rr < MASK_ROWS_PER_WARP; rr++) {
         const int m = w * MASK_ROWS_PER_WARP + rr;           // row inside the tile
         const int row = mt * BM + m;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
             const int s = cb * 512 + j * 32 + lane;
             const int c = s / KC;
             const double v = (live && s < S) ? brow[s] : 0.0;
+            bad |= !(v >= 0.0);                                  // negative or NaN entry: no exact-zero shortcut for this call
             if (c < nChunks)
                 beliefsP[(((size_t)mt * nChunks + c) * NRG + m / RG) * A_GROUP_DOUBLES + (m % RG) * LDA + (s % KC)] = v;
             const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
             if (bal >> 16) mask |= 1u << (2 * j + 1);
         }
     }
+    if (bad) signs[1] = 1;
     if (lane == 0 && mask) atomicOr(&smask[(w * MASK_ROWS_PER_WARP) / RG], mask);
     __syncthreads();
     if (tid < 32) {
@@ -96,17 +99,22 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
 //      that vanishes at a landing state -- the rule for value functions of goal-reward models, whose support grows by one
 //      step per backup) contributes exact zeros to every score.  Warp per (s, nt).
 __global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __restrict__ alphaT, int S, int Vp, int nNt,
-                                                             uint8_t* __restrict__ rowLive) {
+                                                             uint8_t* __restrict__ rowLive, int* __restrict__ signs) {
     const size_t gw = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     if (gw >= (size_t)S * nNt) return;
     const int lane = threadIdx.x & 31;
     const int s = (int)(gw / nNt), nt = (int)(gw % nNt);
     const double* row = alphaT + (size_t)s * Vp + (size_t)nt * BN;
-    bool nz = false;
+    bool nz = false, neg = false;
 #pragma unroll
-    for (int j = 0; j < BN / 32; j++) nz |= row[j * 32 + lane] != 0.0;
+    for (int j = 0; j < BN / 32; j++) {
+        const double v = row[j * 32 + lane];
+        nz |= v != 0.0;
+        neg |= !(v >= 0.0);
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) rowLive[(size_t)nt * S + s] = bal ? 1 : 0;
+    if (neg) signs[0] = 1;
 }
 
 // ---- bLive[nt][g][c] = 1 iff some state k of chunk c gathers a live alphaT row: row index reach[g][k] (g = action) for the
@@ -245,22 +253,34 @@ __global__ void __launch_bounds__(256) approx_value_kernel(const double* __restr
 }
 
 // ---- value[b][a] = sum_s b[s] * alpha_a[b,a,s] in the reference's operation order; block per (a, b); only the support of b
-//      is visited.  Screening: an action whose approximate value is more than 1e-9 (relative to max(1, |best|)) below the
-//      best approximate value of its belief cannot be the argmax -- the two sums differ by rounding only -- so it keeps the
-//      approximate value and the block exits; every action that could win or tie is evaluated exactly.
+//      is visited.  Screening: an action whose approximate value lies below the best approximate value of its belief by more
+//      than the two summation orders can differ cannot be the argmax, so it keeps the approximate value and the block exits;
+//      every action that could win or tie is evaluated exactly.
 __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restrict__ beliefs, const double* __restrict__ alphas,
                                                            const int32_t* __restrict__ vstar, const int32_t* __restrict__ reachK,
                                                            const double* __restrict__ rtoK, const double* __restrict__ rbarT,
-                                                           const double* __restrict__ approx, double gamma, int S, int R, int A, int O,
-                                                           double* __restrict__ value) {
+                                                           const double* __restrict__ approx, const int* __restrict__ signs, int modelNonneg,
+                                                           const uint8_t* __restrict__ bits, int nChunks, int b0, double gamma, int S, int R,
+                                                           int A, int O, double* __restrict__ value) {
     extern __shared__ int s_vsel[];
     __shared__ double sh[8];
-    const int a = blockIdx.x, b = blockIdx.y;
+    const int a = blockIdx.x, b = b0 + blockIdx.y;
     {
         const double mine = approx[(size_t)b * A + a];
+        // every term of the sum is >= 0 (model, beliefs and alphas are non-negative) and the score-order sum is exactly 0:
+        // all terms are zero, so the reference-order sum is exactly +0.0 too
+        if (mine == 0.0 && modelNonneg && gamma > 0.0 && !signs[0] && !signs[1]) {
+            if (threadIdx.x == 0) value[(size_t)b * A + a] = 0.0;
+            return;
+        }
         double best = -INFINITY;
         for (int aa = 0; aa < A; aa++) best = fmax(best, approx[(size_t)b * A + aa]);
-        if (!(mine >= best - 1e-9 * fmax(1.0, fabs(best)))) {
+        // how far the score-order sum can be from the reference-order sum: with non-negative terms the rounding error of both is
+        // below n * eps * value (2.4e-12 relative for S = 22021), so 1e-10 * |best| separates safely; with mixed signs the terms
+        // can cancel and only the looser absolute bound is used
+        const bool nonneg = modelNonneg && !signs[0] && !signs[1];
+        const double margin = nonneg ? 1e-10 * fabs(best) : 1e-9 * fmax(1.0, fabs(best));
+        if (!(mine >= best - margin)) {
             if (threadIdx.x == 0) value[(size_t)b * A + a] = mine;
             return;
         }
@@ -272,7 +292,14 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
     const double* rtoA = rtoK + (size_t)a * O * S * R;
     const double* rbarA = rbarT + (size_t)a * S;
     double part = 0.0;
-    for (int s = threadIdx.x; s < S; s += 256) {
+    // a half-warp per 16-state chunk; chunks on which the belief's row group is all-zero (occupancy bits of belief_mask_kernel)
+    // are skipped without touching the belief row.  The state -> thread mapping is the same for every action of a belief.
+    const uint8_t* live = bits + (size_t)(b / BM) * nChunks;
+    const unsigned gbit = 1u << ((b % BM) / RG);
+    for (int c = threadIdx.x >> 4; c < nChunks; c += 16) {
+        if (!(live[c] & gbit)) continue;
+        const int s = c * KC + (threadIdx.x & 15);
+        if (s >= S) continue;
         const double bs = brow[s];
         if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s), part);
     }
@@ -374,8 +401,10 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
 
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
+    m->last_bits = bits;           // read again by the value pass of the same call
     PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
-    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP);
+    PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 2 * sizeof(int), st));
+    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs);
     m->last_launches++;
     // alpha-side occupancy (gather path: per action; plain max_v path: one group; Gamma path: not masked)
     uint8_t* bLive = nullptr;
@@ -384,12 +413,16 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
         nG = backup ? m->A : 1;
         zPerG = backup ? m->O : 1;
         PBVI_TAKE(rowLive, uint8_t, (size_t)nNt * S);
-        alpha_row_mask_kernel<<<(unsigned)ceil_div_sz((size_t)S * nNt * 32, 256), 256, 0, st>>>(alphaT, S, Vp, nNt, rowLive);
+        alpha_row_mask_kernel<<<(unsigned)ceil_div_sz((size_t)S * nNt * 32, 256), 256, 0, st>>>(alphaT, S, Vp, nNt, rowLive, m->d_signs);
         bLive = m->arena.take<uint8_t>((size_t)nNt * nG * nC);
         if (!bLive) return PBVI_ERR_OOM;
         chunk_alpha_mask_kernel<<<(unsigned)ceil_div_sz((size_t)nNt * nG * nC, 256), 256, 0, st>>>(rowLive, backup ? m->reachP : nullptr, S,
                                                                                                   m->Sp, nC, nG, nNt, bLive);
         m->last_launches += 2;
+    }
+    else {
+        const int one = 1;                 // Gamma path: the alpha signs are not scanned, so no exact-zero shortcut
+        PBVI_CUDA(cudaMemcpyAsync(m->d_signs, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     PBVI_REQUIRE((size_t)nZ * nNt <= 2147483647u, "too many (z, alpha tile) pairs");
     PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nNt * nC);
@@ -468,8 +501,8 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
     for (int b0 = 0; b0 < nB; b0 += 65535) {
         const int nb = std::min(65535, nB - b0);
         backup_value_kernel<<<dim3(m->A, nb), 256, m->O * sizeof(int), st>>>(
-            d_beliefs + (size_t)b0 * m->S, d_alphas, d_vstar + (size_t)b0 * m->nZ, m->reachK, m->rtoK, m->rbarT, approx + (size_t)b0 * m->A,
-            gamma, m->S, m->R, m->A, m->O, d_value + (size_t)b0 * m->A);
+            d_beliefs, d_alphas, d_vstar, m->reachK, m->rtoK, m->rbarT, approx, m->d_signs, m->model_nonneg ? 1 : 0, m->last_bits, m->nChunks,
+            b0, gamma, m->S, m->R, m->A, m->O, d_value);
         m->last_launches++;
     }
     if (d_astar) {

@@ -151,6 +151,10 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
             }
         }
 
+    m->model_nonneg = true;
+    for (double v : rtoK) if (!(v >= 0.0)) { m->model_nonneg = false; break; }
+    for (double v : rbarT) if (!(v >= 0.0)) { m->model_nonneg = false; break; }
+
     // ---- CSR of the non-zero expected rewards
     std::vector<int32_t> rbarNzPtr(A + 1, 0), rbarNzIdx;
     std::vector<double> rbarNzVal;
@@ -209,6 +213,10 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
     up(&m->predPtr, predPtr); up(&m->predK, predK);
     up(&m->pwLeaves, leaves); up(&m->pwNodes, nodes);
+    if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 2 * sizeof(int)) != cudaSuccess) {
+        set_error("cudaMalloc(signs) failed");
+        rc = PBVI_ERR_CUDA;
+    }
     if (rc == PBVI_OK && cudaMalloc(&m->d_stats, sizeof(unsigned long long)) != cudaSuccess) {
         set_error("cudaMalloc(stats) failed");
         rc = PBVI_ERR_CUDA;
@@ -227,6 +235,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->reachP); cudaFree(m->rtoP); cudaFree(m->zMask); cudaFree(m->zOrder);
     cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes);
     cudaFree(m->d_stats);
+    cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
     m->arena.release();
     delete m;

@@ -116,6 +116,11 @@ struct pbvi_model {
     pbvi::Arena arena;
     // instrumentation of the last select / max_values call
     unsigned long long* d_stats = nullptr;   // [1] live (tile, z, chunk, row group) quadruples visited by the score launch
+    // sign information for the exact-zero shortcut of the value pass: with RTO, Rbar, every belief and every alpha >= 0 a sum
+    // that comes out exactly 0 consists of zero terms only, so the reference-order value is exactly 0 as well
+    bool model_nonneg = false;               // RTO >= 0 and Rbar >= 0 (checked once on the host)
+    const uint8_t* last_bits = nullptr;      // belief occupancy bits of the running select call (arena memory)
+    int* d_signs = nullptr;                  // [2] set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN
     double last_dense_flops = 0.0;
     double last_exec_scale = 0.0;            // flops per visited quadruple
     int last_launches = 0;

@@ -298,3 +298,41 @@ def test_olfactory_full_size_properties(torch_cuda):
     decided = (top[..., -1] - top[..., -2]) > GAP_TOL * np.maximum(1.0, np.abs(top[..., -1]))
     rev = vs4[:24].cpu().numpy()
     assert np.array_equal((V.shape[0] - 1 - rev)[decided], ref['v_star'][decided])
+
+
+@pytest.mark.parametrize('negative', [False, True])
+def test_backup_sparse_alphas_and_sign_flags(torch_cuda, negative):
+    """
+    Alpha-side zero skipping and the exact-zero shortcut of the value pass: alpha vectors that vanish on most states (whole
+    256-wide alpha tiles are zero on most chunks), beliefs that miss their support entirely (all values exactly 0), and --
+    with `negative` -- alphas of mixed sign, for which the shortcut must stay off.  Parity contract as everywhere else.
+    """
+    from pomdp_pbvi_exploration_b200._native import DeviceModel
+    rng = np.random.default_rng(17 + int(negative))
+    S, A, O, nB, nV = 700, 3, 3, 150, 530
+    reach = rng.integers(0, S, (S, A, 1))
+    obs = rng.random((S, A, O)); obs /= obs.sum(2, keepdims=True)
+    obs[rng.random((S, A, O)) < 0.25] = 0.0
+    rto = orc.build_rto(reach, np.ones(reach.shape), obs)
+    rbar = orc.expected_rewards(rto, orc.end_state_reachable_rewards(reach, O, [S // 2]))
+    V = np.zeros((nV, S))
+    for v in range(nV):                                           # support: a window of states that depends on the alpha TILE
+        lo = (v // 256) * 200 + rng.integers(0, 40)
+        V[v, lo:lo + 60] = rng.random(60)
+    if negative:
+        V[rng.random(V.shape) < 0.02] *= -1.0
+    B = _sparse_beliefs(rng, nB, S, [S, 40, 5, 1])
+    B[::7] = 0.0
+    B[::7, 650:660] = 0.1                                         # beliefs far from every alpha support -> all-zero scores
+    dev = DeviceModel(reach, None, rto, rbar)
+    alpha, act, vstar, value, ref = check_backup_against_oracle(dev, reach, rto, rbar, 0.95, B, V, exact_rows=True)
+    far = np.arange(0, nB, 7)
+    if not negative:
+        assert np.all(value[far][ref['values'][far] == 0.0] == 0.0)
+    mx, arg = [t.cpu().numpy() for t in dev.max_values(B, V)]
+    rmx, rarg = orc.max_values(B, V)
+    np.testing.assert_allclose(mx, rmx, rtol=1e-12, atol=1e-15)
+    prod = np.sort(B @ V.T, axis=1)
+    decided = prod[:, -1] - prod[:, -2] > GAP_TOL * np.maximum(1, np.abs(prod[:, -1]))
+    assert np.array_equal(arg[decided], rarg[decided])
+    dev.close()
