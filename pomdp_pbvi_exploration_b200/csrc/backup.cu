@@ -364,6 +364,100 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
     }
 }
 
+// ---- order[] = tuple indices grouped by action (counting sort in one block; the order inside an action is irrelevant)
+__global__ void __launch_bounds__(256) action_order_kernel(const int32_t* __restrict__ actions, int n, int A, int32_t* __restrict__ order) {
+    extern __shared__ int s_cnt[];     // [A] counts, then running bases
+    for (int a = threadIdx.x; a < A; a += 256) s_cnt[a] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&s_cnt[actions[i]], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int a = 0; a < A; a++) { const int c = s_cnt[a]; s_cnt[a] = run; run += c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) order[atomicAdd(&s_cnt[actions[i]], 1)] = i;
+}
+
+// ---- assemble for reachable_state_count == 1 and O <= OM: a block writes the same 256-state slice of G tuples that share
+//      (mostly) one action, so reach / RTO / Rbar of the slice are read once per action instead of once per tuple; what is
+//      left per element is the O gathered alpha values and the store.  Same arithmetic as alpha_a_entry (bit-identical rows).
+template <int G, int OM>
+__global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __restrict__ alphas, const int32_t* __restrict__ actions,
+                                                               const int32_t* __restrict__ vsel, const int32_t* __restrict__ order, int n,
+                                                               const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
+                                                               const double* __restrict__ rbarT, double gamma, int S, int O,
+                                                               double* __restrict__ out, unsigned long long* __restrict__ hacc) {
+    __shared__ int s_idx[G], s_act[G], s_v[G][OM];
+    __shared__ unsigned long long sh[2][8];
+    const int slot0 = blockIdx.y * G;
+    if (threadIdx.x < G) {
+        const int j = slot0 + threadIdx.x;
+        const int idx = j < n ? order[j] : -1;
+        s_idx[threadIdx.x] = idx;
+        s_act[threadIdx.x] = idx >= 0 ? actions[idx] : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x < G * OM) {
+        const int g = threadIdx.x / OM, o = threadIdx.x % OM;
+        s_v[g][o] = (s_idx[g] >= 0 && o < O) ? vsel[(size_t)s_idx[g] * O + o] : 0;
+    }
+    __syncthreads();
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = s < S;
+    int prevA = -1, landing = 0;
+    double rb = 0.0, rto[OM];
+#pragma unroll
+    for (int o = 0; o < OM; o++) rto[o] = 0.0;
+    for (int g = 0; g < G; g++) {
+        const int idx = s_idx[g];
+        if (idx < 0) break;
+        const int a = s_act[g];
+        if (a != prevA && valid) {
+            landing = reachK[(size_t)a * S + s];
+            rb = rbarT[(size_t)a * S + s];
+#pragma unroll
+            for (int o = 0; o < OM; o++)
+                if (o < O) rto[o] = rtoK[((size_t)a * O + o) * S + s];
+        }
+        prevA = a;
+        unsigned long long h0 = 0, h1 = 0;
+        if (valid) {
+            double tot = 0.0;
+#pragma unroll
+            for (int o = 0; o < OM; o++)
+                if (o < O) {
+                    const double term = __dmul_rn(gamma, __dmul_rn(rto[o], alphas[(size_t)s_v[g][o] * S + landing]));
+                    tot = (o == 0) ? term : __dadd_rn(tot, term);
+                }
+            const double v = __dadd_rn(rb, tot);
+            out[(size_t)idx * S + s] = v;
+            if (hacc) {
+                const uint64_t w = (uint64_t)__double_as_longlong(v);
+                h0 = row_hash_term0(w, s);
+                h1 = row_hash_term1(w, s);
+            }
+        }
+        if (hacc) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                h0 += __shfl_down_sync(0xffffffffu, h0, off);
+                h1 += __shfl_down_sync(0xffffffffu, h1, off);
+            }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = h0; sh[1][threadIdx.x >> 5] = h1; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long x = 0, y = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { x += sh[0][w]; y += sh[1][w]; }
+                atomicAdd(&hacc[(size_t)idx * 2], x);
+                atomicAdd(&hacc[(size_t)idx * 2 + 1], y);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* __restrict__ h, int n, int rowLen) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -517,6 +611,21 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, double gamma, co
                          size_t vselStride, int perAction, int n, double* d_out, uint64_t* d_hash, cudaStream_t st) {
     unsigned long long* hacc = reinterpret_cast<unsigned long long*>(d_hash);
     if (hacc) PBVI_CUDA(cudaMemsetAsync(hacc, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
+    constexpr int G = 8, OM = 4;
+    if (m->R == 1 && m->O <= OM && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024) {
+        m->arena.reset();
+        PBVI_TAKE(order, int32_t, (size_t)n);
+        action_order_kernel<<<1, 256, m->A * sizeof(int), st>>>(d_actions, n, m->A, order);
+        assemble_grouped_kernel<G, OM><<<dim3(ceil_div(m->S, 256), ceil_div(n, G)), 256, 0, st>>>(
+            d_alphas, d_actions, d_vsel, order, n, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc);
+        m->last_launches += 2;
+        if (hacc) {
+            hash_finalise_kernel<<<ceil_div(n, 256), 256, 0, st>>>(hacc, n, m->S);
+            m->last_launches++;
+        }
+        PBVI_CUDA(cudaGetLastError());
+        return PBVI_OK;
+    }
     for (int i0 = 0; i0 < n; i0 += 65535) {
         const int ni = std::min(65535, n - i0);
         assemble_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, m->O * sizeof(int), st>>>(
