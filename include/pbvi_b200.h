@@ -67,7 +67,9 @@ PBVI_API int pbvi_model_dims(const pbvi_model* m, int* S, int* A, int* O, int* R
  *   value[b][a]     = belief_b . (Rbar[:,a] + sum_o Gamma[a,o,v_star[b][a][o]])          (:1502-1505)
  *   a_star[b]       = first index of max_a value[b][a]                                   (:1505)
  * d_beliefs [nB][S], d_alphas [nV][S]; outputs d_vstar [nB][A][O] int32, d_value [nB][A] (nullable),
- * d_astar [nB] int32.
+ * d_astar [nB] int32.  value[b][a] is summed in the reference's operation order for every action that can win or tie
+ * (approximate value within the rounding margin of the best one); actions that cannot win carry their approximate value.
+ * With d_value == NULL only a_star is produced, and beliefs with a single possible winner skip the exact sum.
  */
 PBVI_API int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV,
                        double gamma, int32_t* d_vstar, double* d_value, int32_t* d_astar, void* stream);
@@ -124,6 +126,21 @@ PBVI_API int pbvi_observation_probabilities(pbvi_model* m, const double* d_belie
 PBVI_API int pbvi_row_hash(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, void* stream);
 PBVI_API int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int32_t* d_ia, const double* d_rows_b, const int32_t* d_ib,
                     int n, int row_len, int32_t* d_flags, void* stream);
+
+/* pbvi_group_keys: the insertion order of the reference's `{row.tobytes(): alpha_vector}` dicts (ValueFunction ctor
+ * src/mdp.py:668-669; BeliefSet src/pomdp.py:581,600) for n fixed-width keys, computed on the device: the (a*, v*[a*,:]) tuples
+ * of a backup and the 128-bit keys of its alpha rows are grouped without leaving HBM.  d_keys [n][words] uint32.  Groups are
+ * numbered by first occurrence; d_first[g] = index of the group's first record (ascending in g), d_last[g] = index of its
+ * record with the largest (d_rank[i], i) -- the last occurrence when d_rank is NULL ("first position, last action") --,
+ * d_inverse[i] (nullable) = group of record i.  d_first / d_last have room for n entries; *h_count receives the number of
+ * groups.  Synchronises `stream`. */
+PBVI_API int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first,
+                    int32_t* d_last, int32_t* d_inverse, int* h_count, void* stream);
+
+/* pbvi_confirm_groups: *h_all_equal = 1 iff every row equals, bytewise, the first row of its group (d_first, d_inverse from
+ * pbvi_group_keys over the rows' 128-bit keys): makes the key-based dedup exact.  Synchronises `stream`. */
+PBVI_API int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first,
+                        const int32_t* d_inverse, int* h_all_equal, void* stream);
 
 /* ---- MDP value iteration sweep (src/mdp.py:1507) ---------------------------------------------------
  * d_alpha_out[a][s] = Rbar[s,a] + gamma * sum_r P[s,a,r] * d_vopt[reach[s,a,r]];  d_vopt_out[s] = max_a (nullable) */

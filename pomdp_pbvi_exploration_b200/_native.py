@@ -38,6 +38,8 @@ SIGNATURES = {
     'pbvi_observation_probabilities': [_P, _P, c_int, _P, _P],
     'pbvi_row_hash': [_P, _P, c_int, c_int, _P, _P],
     'pbvi_rows_equal': [_P, _P, _P, _P, _P, c_int, c_int, _P, _P],
+    'pbvi_group_keys': [_P, _P, c_int, c_int, _P, _P, _P, _P, POINTER(c_int), _P],
+    'pbvi_confirm_groups': [_P, _P, c_int, c_int, _P, _P, POINTER(c_int), _P],
     'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
@@ -272,6 +274,34 @@ class DeviceModel:
         flags = torch.empty((ia.shape[0],), dtype=torch.int32, device=self.device)
         self._call(self._lib.pbvi_rows_equal(self._h, _ptr(ra), _ptr(ia), _ptr(rb), _ptr(ib), ia.shape[0], ra.shape[1], _ptr(flags), self._stream))
         return flags
+
+    def group_keys(self, keys: torch.Tensor, rank: torch.Tensor | None = None, want_inverse: bool = False):
+        """
+        Dict-insertion grouping of fixed-width integer keys on the device (reference src/mdp.py:668-669): `keys` is an int32
+        [n,w] or int64 [n,w] CUDA tensor (viewed as 32-bit words).  Returns (first [g], last [g], inverse [n] | None) as int32
+        CUDA tensors: groups in order of first occurrence, `last` = the record with the largest (rank, index).
+        """
+        k = keys.to(device=self.device).contiguous()
+        n = k.shape[0]
+        assert k.dim() == 2 and k.dtype in (torch.int32, torch.int64)
+        words = k.shape[1] * (2 if k.dtype == torch.int64 else 1)
+        first = torch.empty((n,), dtype=torch.int32, device=self.device)
+        last = torch.empty((n,), dtype=torch.int32, device=self.device)
+        inverse = torch.empty((n,), dtype=torch.int32, device=self.device) if want_inverse else None
+        r = None if rank is None else _i32(rank, self.device)
+        assert r is None or r.shape == (n,)
+        count = c_int()
+        self._call(self._lib.pbvi_group_keys(self._h, _ptr(k), n, words, _ptr(r), _ptr(first), _ptr(last), _ptr(inverse), byref(count),
+                                             self._stream))
+        return first[:count.value], last[:count.value], inverse
+
+    def confirm_groups(self, rows: torch.Tensor, first: torch.Tensor, inverse: torch.Tensor) -> bool:
+        """True iff every row is bytewise equal to the first row of its group (exactness check of a key-based dedup)."""
+        r = _f64(rows, self.device)
+        ok = c_int()
+        self._call(self._lib.pbvi_confirm_groups(self._h, _ptr(r), r.shape[0], r.shape[1], _ptr(_i32(first, self.device)),
+                                                 _ptr(_i32(inverse, self.device)), byref(ok), self._stream))
+        return bool(ok.value)
 
     def vi_sweep(self, vopt, gamma: float):
         v = _f64(vopt, self.device)

@@ -105,16 +105,18 @@ __global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __res
     const int lane = threadIdx.x & 31;
     const int s = (int)(gw / nNt), nt = (int)(gw % nNt);
     const double* row = alphaT + (size_t)s * Vp + (size_t)nt * BN;
-    bool nz = false, neg = false;
+    bool nz = false, neg = false, nonfinite = false;
 #pragma unroll
     for (int j = 0; j < BN / 32; j++) {
         const double v = row[j * 32 + lane];
         nz |= v != 0.0;
         neg |= !(v >= 0.0);
+        nonfinite |= !(fabs(v) <= 1.79769313486231570e308);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) rowLive[(size_t)nt * S + s] = bal ? 1 : 0;
     if (neg) signs[0] = 1;
+    if (nonfinite) signs[2] = 1;
 }
 
 // ---- bLive[nt][g][c] = 1 iff some state k of chunk c gathers a live alphaT row: row index reach[g][k] (g = action) for the
@@ -211,9 +213,16 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 
 // alpha_a[s] of the reference for one (action, v*[O]) tuple: Rbar[s,a] + ((G_0 + G_1) + ...),
 // G_o = gamma * sum_r RTO[s,a,o,r] * alpha[v_o][reach[s,a,r]]  (src/pomdp.py:1489-1502), no FMA contraction.
+// skipZero: a term whose RTO factor is zero is taken as +0.0 without gathering the alpha value.  With finite alphas and gamma
+// the reference's term is +-0.0; the sign of a zero term changes no partial sum that is non-zero and at most the sign of one
+// that is zero, and Rbar + (+-0.0) is the same double unless Rbar is -0.0 -- in which case nothing is skipped.  So the
+// result is bit-identical while most gathers of a sparse observation model (2 of 3 observations impossible from most states of
+// the olfactory model) are never issued.
 __device__ __forceinline__ double alpha_a_entry(const double* __restrict__ alphas, int S, int R, int O, const int* vsel,
                                                 const int32_t* __restrict__ reach, const double* __restrict__ rtoA,
-                                                const double* __restrict__ rbarA, double gamma, int s) {
+                                                const double* __restrict__ rbarA, double gamma, int s, bool skipZero) {
+    const double rb = rbarA[s];
+    const bool skip = skipZero && !(rb == 0.0 && signbit(rb));
     double tot = 0.0;
     for (int o = 0; o < O; o++) {
         const double* arow = alphas + (size_t)vsel[o] * S;
@@ -221,13 +230,21 @@ __device__ __forceinline__ double alpha_a_entry(const double* __restrict__ alpha
         double inner = 0.0;
         for (int r = 0; r < R; r++) {
             const size_t k = (size_t)s * R + r;
-            const double prod = __dmul_rn(rto[k], arow[reach[k]]);
+            const double w = rto[k];
+            const double prod = (skip && w == 0.0) ? 0.0 : __dmul_rn(w, arow[reach[k]]);
             inner = (r == 0) ? prod : __dadd_rn(inner, prod);
         }
         const double term = __dmul_rn(gamma, inner);
         tot = (o == 0) ? term : __dadd_rn(tot, term);
     }
-    return __dadd_rn(rbarA[s], tot);
+    return __dadd_rn(rb, tot);
+}
+
+// sets *flag when some entry is NaN or +-inf (the zero-skip of the assemble kernels needs finite alphas)
+__global__ void __launch_bounds__(256) nonfinite_scan_kernel(const double* __restrict__ x, size_t n, int* __restrict__ flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) bad |= !(fabs(x[i]) <= 1.79769313486231570e308);
+    if (bad) *flag = 1;
 }
 
 // ---- approx[b][a] = b . Rbar[:,a] + gamma * sum_o max_v score[b,a,o,v]: the same quantity as value[b][a] below, but summed
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
                                                            const double* __restrict__ rtoK, const double* __restrict__ rbarT,
                                                            const double* __restrict__ approx, const int* __restrict__ signs, int modelNonneg,
                                                            const uint8_t* __restrict__ bits, int nChunks, int b0, double gamma, int S, int R,
-                                                           int A, int O, double* __restrict__ value) {
+                                                           int A, int O, int needExact, double* __restrict__ value) {
     extern __shared__ int s_vsel[];
     __shared__ double sh[8];
     const int a = blockIdx.x, b = b0 + blockIdx.y;
@@ -284,6 +301,16 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
             if (threadIdx.x == 0) value[(size_t)b * A + a] = mine;
             return;
         }
+        // the only action that can win: a* is decided, and when the caller did not ask for the values themselves the exact sum
+        // would change nothing (about 70 % of the beliefs of the olfactory workload)
+        if (!needExact) {
+            int contenders = 0;
+            for (int aa = 0; aa < A; aa++) contenders += (approx[(size_t)b * A + aa] >= best - margin) ? 1 : 0;
+            if (contenders == 1) {
+                if (threadIdx.x == 0) value[(size_t)b * A + a] = mine;
+                return;
+            }
+        }
     }
     for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vstar[((size_t)b * A + a) * O + o];
     __syncthreads();
@@ -291,6 +318,9 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
     const int32_t* reach = reachK + (size_t)a * S * R;
     const double* rtoA = rtoK + (size_t)a * O * S * R;
     const double* rbarA = rbarT + (size_t)a * S;
+    // no zero-term skipping here: the pass is latency-bound (a few support states per thread), and a gather that waits for its RTO
+    // factor serialises two dependent loads (measured: 1.22 -> 1.53 ms with the skip)
+    const bool skipZero = false;
     double part = 0.0;
     // a half-warp per 16-state chunk; chunks on which the belief's row group is all-zero (occupancy bits of belief_mask_kernel)
     // are skipped without touching the belief row.  The state -> thread mapping is the same for every action of a belief.
@@ -301,7 +331,7 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
         const int s = c * KC + (threadIdx.x & 15);
         if (s >= S) continue;
         const double bs = brow[s];
-        if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s), part);
+        if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s, skipZero), part);
     }
     const double tot = block_sum_256(part, sh);
     if (threadIdx.x == 0) value[(size_t)b * A + a] = tot;
@@ -327,7 +357,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
                                                        const int32_t* __restrict__ vsel, size_t vselStride, int perAction,
                                                        const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                        const double* __restrict__ rbarT, double gamma, int S, int R, int O,
-                                                       double* __restrict__ out, unsigned long long* __restrict__ hacc) {
+                                                       double* __restrict__ out, unsigned long long* __restrict__ hacc,
+                                                       const int* __restrict__ nonfinite) {
     extern __shared__ int s_vsel[];
     __shared__ unsigned long long sh[2][8];
     const int i = blockIdx.y, a = actions[i];
@@ -338,7 +369,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
     unsigned long long h0 = 0, h1 = 0;
     if (s < S) {
         const double v = alpha_a_entry(alphas, S, R, O, s_vsel, reachK + (size_t)a * S * R, rtoK + (size_t)a * O * S * R,
-                                       rbarT + (size_t)a * S, gamma, s);
+                                       rbarT + (size_t)a * S, gamma, s, !*nonfinite);
         out[(size_t)i * S + s] = v;
         if (hacc) {
             const uint64_t w = (uint64_t)__double_as_longlong(v);
@@ -387,7 +418,8 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
                                                                const int32_t* __restrict__ vsel, const int32_t* __restrict__ order, int n,
                                                                const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                                const double* __restrict__ rbarT, double gamma, int S, int O,
-                                                               double* __restrict__ out, unsigned long long* __restrict__ hacc) {
+                                                               double* __restrict__ out, unsigned long long* __restrict__ hacc,
+                                                               const int* __restrict__ nonfinite) {
     __shared__ int s_idx[G], s_act[G], s_v[G][OM];
     __shared__ unsigned long long sh[2][8];
     const int slot0 = blockIdx.y * G;
@@ -405,6 +437,8 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
     __syncthreads();
     const int s = blockIdx.x * 256 + threadIdx.x;
     const bool valid = s < S;
+    const bool skipZero = !*nonfinite;              // finite alphas: a zero RTO factor makes the term +-0.0 (see alpha_a_entry)
+    bool skip = false;
     int prevA = -1, landing = 0;
     double rb = 0.0, rto[OM];
 #pragma unroll
@@ -416,6 +450,7 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
         if (a != prevA && valid) {
             landing = reachK[(size_t)a * S + s];
             rb = rbarT[(size_t)a * S + s];
+            skip = skipZero && !(rb == 0.0 && signbit(rb));
 #pragma unroll
             for (int o = 0; o < OM; o++)
                 if (o < O) rto[o] = rtoK[((size_t)a * O + o) * S + s];
@@ -427,7 +462,7 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
 #pragma unroll
             for (int o = 0; o < OM; o++)
                 if (o < O) {
-                    const double term = __dmul_rn(gamma, __dmul_rn(rto[o], alphas[(size_t)s_v[g][o] * S + landing]));
+                    const double term = (skip && rto[o] == 0.0) ? 0.0 : __dmul_rn(gamma, __dmul_rn(rto[o], alphas[(size_t)s_v[g][o] * S + landing]));
                     tot = (o == 0) ? term : __dadd_rn(tot, term);
                 }
             const double v = __dadd_rn(rb, tot);
@@ -497,7 +532,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
     m->last_bits = bits;           // read again by the value pass of the same call
     PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
-    PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 2 * sizeof(int), st));
+    PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 3 * sizeof(int), st));
     belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs);
     m->last_launches++;
     // alpha-side occupancy (gather path: per action; plain max_v path: one group; Gamma path: not masked)
@@ -515,8 +550,9 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
         m->last_launches += 2;
     }
     else {
-        const int one = 1;                 // Gamma path: the alpha signs are not scanned, so no exact-zero shortcut
+        static const int one = 1;          // Gamma path: the alphas are not scanned, so no exact-zero shortcut and no zero-term skip
         PBVI_CUDA(cudaMemcpyAsync(m->d_signs, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        PBVI_CUDA(cudaMemcpyAsync(m->d_signs + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     PBVI_REQUIRE((size_t)nZ * nNt <= 2147483647u, "too many (z, alpha tile) pairs");
     PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nNt * nC);
@@ -582,6 +618,7 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
     }
     PBVI_TRY(score_argmax(m, d_beliefs, nB, d_alphas, nV, true, maxscore, d_vstar, st));
     if (!d_value && !d_astar) return PBVI_OK;
+    const int needExact = d_value ? 1 : 0;        // values requested: every action that could win is summed in reference order
     if (!d_value) {
         d_value = m->arena.take<double>((size_t)nB * m->A);
         if (!d_value) return PBVI_ERR_OOM;
@@ -596,7 +633,7 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
         const int nb = std::min(65535, nB - b0);
         backup_value_kernel<<<dim3(m->A, nb), 256, m->O * sizeof(int), st>>>(
             d_beliefs, d_alphas, d_vstar, m->reachK, m->rtoK, m->rbarT, approx, m->d_signs, m->model_nonneg ? 1 : 0, m->last_bits, m->nChunks,
-            b0, gamma, m->S, m->R, m->A, m->O, d_value);
+            b0, gamma, m->S, m->R, m->A, m->O, needExact, d_value);
         m->last_launches++;
     }
     if (d_astar) {
@@ -607,17 +644,23 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
     return PBVI_OK;
 }
 
-static int assemble_impl(pbvi_model* m, const double* d_alphas, double gamma, const int32_t* d_actions, const int32_t* d_vsel,
+static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double gamma, const int32_t* d_actions, const int32_t* d_vsel,
                          size_t vselStride, int perAction, int n, double* d_out, uint64_t* d_hash, cudaStream_t st) {
     unsigned long long* hacc = reinterpret_cast<unsigned long long*>(d_hash);
     if (hacc) PBVI_CUDA(cudaMemsetAsync(hacc, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
+    // zero-RTO terms are skipped only when every alpha (and gamma) is finite: one streaming pass over the alphas decides
+    int* nonfinite = m->d_signs + 3;
+    const int gammaBad = (fabs(gamma) <= 1.79769313486231570e308) ? 0 : 1;
+    PBVI_CUDA(cudaMemsetAsync(nonfinite, gammaBad, sizeof(int), st));
+    nonfinite_scan_kernel<<<m->sm_count * 8, 256, 0, st>>>(d_alphas, (size_t)nV * m->S, nonfinite);
+    m->last_launches++;
     constexpr int G = 8, OM = 4;
     if (m->R == 1 && m->O <= OM && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024) {
         m->arena.reset();
         PBVI_TAKE(order, int32_t, (size_t)n);
         action_order_kernel<<<1, 256, m->A * sizeof(int), st>>>(d_actions, n, m->A, order);
         assemble_grouped_kernel<G, OM><<<dim3(ceil_div(m->S, 256), ceil_div(n, G)), 256, 0, st>>>(
-            d_alphas, d_actions, d_vsel, order, n, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc);
+            d_alphas, d_actions, d_vsel, order, n, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, nonfinite);
         m->last_launches += 2;
         if (hacc) {
             hash_finalise_kernel<<<ceil_div(n, 256), 256, 0, st>>>(hacc, n, m->S);
@@ -630,7 +673,7 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, double gamma, co
         const int ni = std::min(65535, n - i0);
         assemble_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, m->O * sizeof(int), st>>>(
             d_alphas, d_actions + i0, d_vsel + (size_t)i0 * vselStride, vselStride, perAction, m->reachK, m->rtoK, m->rbarT, gamma,
-            m->S, m->R, m->O, d_out + (size_t)i0 * m->S, hacc ? hacc + (size_t)i0 * 2 : nullptr);
+            m->S, m->R, m->O, d_out + (size_t)i0 * m->S, hacc ? hacc + (size_t)i0 * 2 : nullptr, nonfinite);
         m->last_launches++;
     }
     if (hacc) {
@@ -663,7 +706,7 @@ extern "C" int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int n
     PBVI_REQUIRE(d_alphas && d_actions && d_vsel && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
-    return assemble_impl(m, d_alphas, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, d_hash, (cudaStream_t)stream);
+    return assemble_impl(m, d_alphas, nV, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, d_hash, (cudaStream_t)stream);
 }
 
 extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
@@ -680,7 +723,7 @@ extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const
         if (!d_out_vstar) return PBVI_ERR_OOM;
     }
     PBVI_TRY(select_impl(m, d_beliefs, nB, d_alphas, nV, gamma, d_out_vstar, d_out_value, d_out_action, st));
-    return assemble_impl(m, d_alphas, gamma, d_out_action, d_out_vstar, (size_t)m->nZ, 1, nB, d_out_alpha, nullptr, st);
+    return assemble_impl(m, d_alphas, nV, gamma, d_out_action, d_out_vstar, (size_t)m->nZ, 1, nB, d_out_alpha, nullptr, st);
 }
 
 extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
@@ -701,7 +744,7 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     PBVI_CUDA(cudaMemcpyAsync(d_b, h_beliefs, (size_t)nB * S * sizeof(double), cudaMemcpyHostToDevice, st));
     PBVI_CUDA(cudaMemcpyAsync(d_a, h_alphas, (size_t)nV * S * sizeof(double), cudaMemcpyHostToDevice, st));
     PBVI_TRY(select_impl(m, d_b, nB, d_a, nV, gamma, d_vs, nullptr, d_act, st));
-    PBVI_TRY(assemble_impl(m, d_a, gamma, d_act, d_vs, (size_t)m->nZ, 1, nB, d_out, nullptr, st));
+    PBVI_TRY(assemble_impl(m, d_a, nV, gamma, d_act, d_vs, (size_t)m->nZ, 1, nB, d_out, nullptr, st));
     PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, d_out, (size_t)nB * S * sizeof(double), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaMemcpyAsync(h_out_action, d_act, (size_t)nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));

@@ -45,6 +45,110 @@ __global__ void __launch_bounds__(256) rows_equal_kernel(const uint64_t* __restr
     if (threadIdx.x == 0) flags[blockIdx.x] = any ? 0 : 1;
 }
 
+// ---- first-occurrence grouping of fixed-width keys: the insertion order of a Python dict (src/mdp.py:668-669, src/pomdp.py:600)
+//      computed on the device, so the (a*, v*) tuples of a backup and the 128-bit keys of its rows never travel to the host.
+//      Open-addressing table of representatives; per slot an atomicMin of the record index (first position) and an atomicMax of
+//      (rank << 32 | index) (the record that defines the group's action: last occurrence, or largest caller-supplied rank).
+//      Which record becomes the representative of a slot depends on scheduling; first / last / inverse do not.
+__device__ __forceinline__ uint32_t key_hash(const uint32_t* __restrict__ k, int w) {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (int j = 0; j < w; j++) h = mix64(h ^ (uint64_t)k[j]) + 0xd6e8feb86659fd93ull;
+    return (uint32_t)(h >> 29);
+}
+
+__global__ void __launch_bounds__(256) group_init_kernel(int32_t* __restrict__ rep, int32_t* __restrict__ gfirst,
+                                                         unsigned long long* __restrict__ glast, int T) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= T) return;
+    rep[i] = -1;
+    gfirst[i] = 0x7fffffff;
+    glast[i] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) group_insert_kernel(const uint32_t* __restrict__ keys, int n, int w, const int32_t* __restrict__ rank,
+                                                           int T, int32_t* rep, int32_t* __restrict__ gfirst,
+                                                           unsigned long long* __restrict__ glast, int32_t* __restrict__ slotOf) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* k = keys + (size_t)i * w;
+    uint32_t h = key_hash(k, w) & (uint32_t)(T - 1);
+    for (;;) {
+        int cur = *reinterpret_cast<volatile int32_t*>(rep + h);
+        if (cur == -1) {
+            cur = atomicCAS(rep + h, -1, i);
+            if (cur == -1) break;                       // this record now represents the slot
+        }
+        const uint32_t* kc = keys + (size_t)cur * w;
+        bool eq = true;
+        for (int j = 0; j < w; j++) eq &= (kc[j] == k[j]);
+        if (eq) break;
+        h = (h + 1) & (uint32_t)(T - 1);
+    }
+    slotOf[i] = (int32_t)h;
+    atomicMin(gfirst + h, i);
+    atomicMax(glast + h, ((unsigned long long)(uint32_t)(rank ? rank[i] : i) << 32) | (unsigned long long)(uint32_t)i);
+}
+
+// one block: stream compaction of the group-first records in ascending index order (tiles of 1024, ballot scan)
+__global__ void __launch_bounds__(1024) group_compact_kernel(const int32_t* __restrict__ slotOf, const int32_t* __restrict__ gfirst,
+                                                             const unsigned long long* __restrict__ glast, int n,
+                                                             int32_t* __restrict__ groupOfSlot, int32_t* __restrict__ first,
+                                                             int32_t* __restrict__ last, int32_t* __restrict__ count) {
+    __shared__ int warpCount[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        int slot = 0;
+        bool isFirst = false;
+        if (i < n) {
+            slot = slotOf[i];
+            isFirst = gfirst[slot] == i;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, isFirst);
+        if (lane == 0) warpCount[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int c = warpCount[j];
+            before += (j < w) ? c : 0;
+            total += c;
+        }
+        const int b0 = base;
+        if (isFirst) {
+            const int g = b0 + before + __popc(bal & ((1u << lane) - 1u));
+            first[g] = i;
+            last[g] = (int32_t)(glast[slot] & 0xffffffffull);
+            groupOfSlot[slot] = g;
+        }
+        __syncthreads();
+        if (tid == 0) base = b0 + total;
+        __syncthreads();
+    }
+    if (tid == 0) *count = base;
+}
+
+__global__ void __launch_bounds__(256) group_inverse_kernel(const int32_t* __restrict__ slotOf, const int32_t* __restrict__ groupOfSlot, int n,
+                                                            int32_t* __restrict__ inverse) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) inverse[i] = groupOfSlot[slotOf[i]];
+}
+
+// block per record: a record that is not the first of its group must equal that first row bytewise (confirms the 128-bit key match)
+__global__ void __launch_bounds__(256) group_confirm_kernel(const uint64_t* __restrict__ rows, int rowLen, const int32_t* __restrict__ first,
+                                                            const int32_t* __restrict__ inverse, int32_t* __restrict__ mismatch) {
+    const int i = blockIdx.x, f = first[inverse[i]];
+    if (f == i) return;
+    const uint64_t* a = rows + (size_t)i * rowLen;
+    const uint64_t* b = rows + (size_t)f * rowLen;
+    int diff = 0;
+    for (int s = threadIdx.x; s < rowLen; s += 256) diff |= (a[s] != b[s]);
+    if (diff) atomicOr(mismatch, 1);
+}
+
 // alpha[a][s] = Rbar[s,a] + gamma * sum_r P[s,a,r] * V*[reach[s,a,r]]; vopt_out[s] = max_a
 __global__ void __launch_bounds__(256) vi_sweep_kernel(const double* __restrict__ vopt, const int32_t* __restrict__ reachK,
                                                        const double* __restrict__ probK, const double* __restrict__ rbarT, double gamma,
@@ -234,6 +338,65 @@ extern "C" int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int3
                                                           reinterpret_cast<const uint64_t*>(d_rows_b), d_ib, row_len, d_flags);
     m->last_launches = 1;
     PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first,
+                               int32_t* d_last, int32_t* d_inverse, int* h_count, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0 && words > 0 && h_count != nullptr, "need n >= 0 records of positive width and a count output");
+    *h_count = 0;
+    m->last_launches = 0;
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_keys && d_first && d_last, "NULL pointer argument");
+    PBVI_REQUIRE(n <= (1 << 29), "too many records");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int T = 64;
+    while (T < 2 * n) T <<= 1;
+    m->arena.reset();
+    PBVI_TAKE(rep, int32_t, (size_t)T);
+    PBVI_TAKE(gfirst, int32_t, (size_t)T);
+    PBVI_TAKE(glast, unsigned long long, (size_t)T);
+    PBVI_TAKE(slotOf, int32_t, (size_t)n);
+    PBVI_TAKE(groupOfSlot, int32_t, (size_t)T);
+    PBVI_TAKE(count, int32_t, 1);
+    group_init_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, glast, T);
+    group_insert_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_keys, n, words, d_rank, T, rep, gfirst, glast, slotOf);
+    group_compact_kernel<<<1, 1024, 0, st>>>(slotOf, gfirst, glast, n, groupOfSlot, d_first, d_last, count);
+    m->last_launches = 3;
+    if (d_inverse) {
+        group_inverse_kernel<<<ceil_div(n, 256), 256, 0, st>>>(slotOf, groupOfSlot, n, d_inverse);
+        m->last_launches++;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    int32_t c = 0;
+    PBVI_CUDA(cudaMemcpyAsync(&c, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    *h_count = (int)c;
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first, const int32_t* d_inverse,
+                                   int* h_all_equal, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0 && row_len > 0 && h_all_equal != nullptr, "need n >= 0 rows of positive length and a result output");
+    *h_all_equal = 1;
+    m->last_launches = 0;
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_rows && d_first && d_inverse, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    m->arena.reset();
+    PBVI_TAKE(mismatch, int32_t, 1);
+    PBVI_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int32_t), st));
+    group_confirm_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_first, d_inverse, mismatch);
+    m->last_launches = 1;
+    PBVI_CUDA(cudaGetLastError());
+    int32_t bad = 0;
+    PBVI_CUDA(cudaMemcpyAsync(&bad, mismatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    *h_all_equal = bad ? 0 : 1;
     return PBVI_OK;
 }
 

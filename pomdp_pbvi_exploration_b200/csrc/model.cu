@@ -213,7 +213,7 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
     up(&m->predPtr, predPtr); up(&m->predK, predK);
     up(&m->pwLeaves, leaves); up(&m->pwNodes, nodes);
-    if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 2 * sizeof(int)) != cudaSuccess) {
+    if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 4 * sizeof(int)) != cudaSuccess) {
         set_error("cudaMalloc(signs) failed");
         rc = PBVI_ERR_CUDA;
     }

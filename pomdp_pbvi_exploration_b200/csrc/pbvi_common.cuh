@@ -120,7 +120,8 @@ struct pbvi_model {
     // that comes out exactly 0 consists of zero terms only, so the reference-order value is exactly 0 as well
     bool model_nonneg = false;               // RTO >= 0 and Rbar >= 0 (checked once on the host)
     const uint8_t* last_bits = nullptr;      // belief occupancy bits of the running select call (arena memory)
-    int* d_signs = nullptr;                  // [2] set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN
+    int* d_signs = nullptr;                  // [4] set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN,
+                                             //     [2] some alpha NaN or +-inf; [3] the same for the alphas of the last assemble call
     double last_dense_flops = 0.0;
     double last_exec_scale = 0.0;            // flops per visited quadruple
     int last_launches = 0;

@@ -100,17 +100,42 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
 _LAST_MAX_COUNT = [512]
 
 
-def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_local_beliefs: int, capacity: int, device, group=None):
+def group_records_host(keys: torch.Tensor, rank: torch.Tensor):
+    """
+    `DeviceModel.group_keys` for records held in CPU tensors: (first [g], last [g], None), groups in order of first occurrence,
+    `last` = the record with the largest (rank, index).  Host logic only -- used where the exchange runs over gloo on CPU
+    (tests/test_parallel_gloo.py); on a GPU the records never leave the device (`pbvi_group_keys`).
+    """
+    k = keys.numpy().astype(np.int64)
+    n = k.shape[0]
+    first, _, inv = unique_rows_first(k)
+    order = np.lexsort((np.arange(n), rank.numpy(), inv))
+    ends = np.append(np.flatnonzero(np.diff(inv[order])), n - 1)
+    last = np.empty(first.shape[0], dtype=np.int64)
+    last[inv[order[ends]]] = order[ends]
+    return torch.from_numpy(first), torch.from_numpy(last), None
+
+
+def exchange_tuples(tuples, first, last, n_local_beliefs: int, capacity: int, device, group=None, group_fn=None):
     """
     The exchange step of the sharded backup in its compact form.  An alpha row of the backup is a deterministic function of
     its generating tuple (a*, v*[a*, :]) and of the replicated (model, old value function), so the ranks all-gather the
-    distinct TUPLES of their shards (8*(1+O) bytes each instead of 8*S per row) together with the positions of the first / last
+    distinct TUPLES of their shards (4*(1+O) bytes each instead of 8*S per row) together with the positions of the first / last
     belief that chose them, and every rank then assembles the merged set itself (`PBVI_Solver.rows_from_tuples`) -- bitwise the
-    same rows on every rank, in the order a single process would produce.  One collective: block r of the gathered buffer
-    is [header (u_r, n_r); u_r records (tuple, first, last)], padded to `capacity` records.
-    Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set, positions in the rank-ordered concatenation.
+    same rows on every rank, in the order a single process would produce.  One collective: block r of the gathered int32 buffer
+    is [header (u_r, n_r); u_r records (tuple, first, last)], padded to `capacity` records.  The records stay on `device`: only
+    the per-rank headers are read by the host, the merge is `group_fn` (the device's `group_keys`; host twin for CPU tensors).
+    Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set as tensors on `device`, positions in the rank-ordered
+    concatenation of the shards.
     """
     world = dist.get_world_size(group)
+    device = torch.device(device)
+    tuples = torch.as_tensor(tuples).to(device=device, dtype=torch.int32)
+    first = torch.as_tensor(first).to(device=device, dtype=torch.int32)
+    last = torch.as_tensor(last).to(device=device, dtype=torch.int32)
+    if group_fn is None:
+        assert device.type == 'cpu', 'pass the device grouping (DeviceModel.group_keys) for records in device memory'
+        group_fn = group_records_host
     u, w = tuples.shape
     assert u <= capacity, (u, capacity)
     # Most beliefs share their tuple with others, so the blocks are first sized by a guess (twice the largest count seen in the
@@ -118,32 +143,36 @@ def exchange_tuples(tuples: np.ndarray, first: np.ndarray, last: np.ndarray, n_l
     # headers, so the decision is consistent -- the exchange is repeated once at full capacity.
     guess = min(capacity, max(256, 2 * _LAST_MAX_COUNT[0]))
     while True:
-        buf = np.zeros((guess + 1, w + 2), dtype=np.int64)
-        buf[0, 0], buf[0, 1] = u, n_local_beliefs
         k = min(u, guess)
+        buf = torch.zeros((guess + 1, w + 2), dtype=torch.int32, device=device)
+        buf[0, :2] = torch.tensor([u, n_local_beliefs], dtype=torch.int32)
         buf[1:k + 1, :w] = tuples[:k]
         buf[1:k + 1, w] = first[:k]
         buf[1:k + 1, w + 1] = last[:k]
-        gathered = torch.empty((world * (guess + 1), w + 2), dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(gathered, torch.from_numpy(buf).to(device), group=group)
-        allb = gathered.cpu().numpy().reshape(world, guess + 1, w + 2)
-        _LAST_MAX_COUNT[0] = int(allb[:, 0, 0].max())
+        gathered = torch.empty((world * (guess + 1), w + 2), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+        hdr = gathered.view(world, guess + 1, w + 2)[:, 0, :2].cpu().numpy().astype(np.int64)
+        _LAST_MAX_COUNT[0] = int(hdr[:, 0].max())
         if _LAST_MAX_COUNT[0] <= guess:
             break
         guess = capacity
-    counts, n_beliefs = allb[:, 0, 0], allb[:, 0, 1]
+    counts, n_beliefs = hdr[:, 0], hdr[:, 1]
+    total = int(counts.sum())
+    if total == 0:
+        z = torch.zeros((0,), dtype=torch.int32, device=device)
+        return torch.zeros((0, w), dtype=torch.int32, device=device), z, z
     offsets = np.concatenate([[0], np.cumsum(n_beliefs)])
-    recs = np.concatenate([allb[r, 1:1 + counts[r]] + np.array([0] * w + [offsets[r], offsets[r]]) for r in range(world)], axis=0)
-    if recs.shape[0] == 0:
-        z = np.zeros(0, dtype=np.int64)
-        return np.zeros((0, w), dtype=np.int64), z, z
-    gf, _, inv = unique_rows_first(recs[:, :w])
-    # records are rank-major and ascending in `first` inside a rank, so the first record of a group carries its smallest position
-    g_first = recs[gf, w]
-    # a higher rank holds later beliefs, and a rank lists a tuple once: the last record of a group carries its largest position
-    g_last = np.empty(gf.shape[0], dtype=np.int64)
-    g_last[inv] = recs[:, w + 1]
-    return recs[gf, :w], g_first, g_last
+    # rows of the valid records in the gathered buffer and the position offset of their shard
+    idx = np.concatenate([r * (guess + 1) + 1 + np.arange(counts[r]) for r in range(world)])
+    meta = torch.from_numpy(np.stack([idx, np.repeat(offsets[:-1], counts)])).to(device)
+    recs = gathered[meta[0]]
+    off = meta[1].to(torch.int32)
+    keys = recs[:, :w].contiguous()
+    pos_first, pos_last = recs[:, w] + off, recs[:, w + 1] + off
+    # records are rank-major and ascending in `first` inside a rank, so the first record of a group carries its smallest
+    # position; its largest position is the largest `last` of the group
+    gf, gl, _ = group_fn(keys, pos_last)
+    return keys[gf.long()], pos_first[gf.long()], pos_last[gl.long()]
 
 
 class _PhaseTimer:
@@ -190,11 +219,13 @@ class ShardedBackup:
         from .value_function import ValueFunction
         t = _PhaseTimer(self.model.device.device) if self.trace else None
         if self.exchange == 'tuples':
-            tuples, first, last = self.solver.select_tuples(self.model, local_belief_set, value_function, belief_dominance_prune)
+            dev = self.model.device
+            tuples, first, last = self.solver.select_tuples_device(self.model, local_belief_set, value_function, belief_dominance_prune)
             if t: t.mark('local select')
             n_local = len(local_belief_set)
-            g_tuples, _, g_last = exchange_tuples(tuples, first, last, n_local, self._capacity(n_local), self.model.device.device, self.group)
-            self.last_payload_bytes = (min(self._cap[1], max(256, 2 * _LAST_MAX_COUNT[0])) + 1) * (tuples.shape[1] + 2) * 8 * self.world
+            g_tuples, _, g_last = exchange_tuples(tuples, first, last, n_local, self._capacity(n_local), dev.device, self.group,
+                                                  group_fn=dev.group_keys)
+            self.last_payload_bytes = (min(self._cap[1], max(256, 2 * _LAST_MAX_COUNT[0])) + 1) * (tuples.shape[1] + 2) * 4 * self.world
             if t: t.mark('exchange')
             merged = self.solver.rows_from_tuples(self.model, value_function, g_tuples, g_last)
             if t: t.mark('assemble + dedup')

@@ -26,7 +26,7 @@ import torch
 
 from .belief import Belief, BeliefSet
 from .model import Model, log
-from .sets import dedup_rows, group_by_key, unique_rows_first  # noqa: F401
+from .sets import _dedup_exact_host, dedup_rows, group_by_key, unique_rows_first  # noqa: F401
 from .value_function import AlphaVector, ValueFunction  # noqa: F401
 
 
@@ -338,7 +338,7 @@ class PBVI_Solver:
         Two beliefs that select the same (a*, v*[a*,:]) tuple produce the same bytes, so only the distinct tuples are
         assembled; the byte-dedup then runs over those rows (different tuples can still give identical rows).
         """
-        tuples, _, last = self.select_tuples(model, belief_set, value_function, belief_dominance_prune)
+        tuples, _, last = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune)
         new_vf = self.rows_from_tuples(model, value_function, tuples, last)
         if append:
             n_new = len(new_vf)
@@ -347,23 +347,26 @@ class PBVI_Solver:
             new_vf.parent_uid, new_vf.n_new = value_function.uid, n_new
         return new_vf
 
-    def select_tuples(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
+    def select_tuples_device(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
         """
         First half of the backup: for every belief the tuple (a*, v*[a*, 0..O-1]) that generates its alpha row, reduced to the
-        DISTINCT tuples in order of first occurrence.  Returns host arrays (tuples [u, 1+O] int64, first [u], last [u]) where
-        first / last are the positions (in this belief set, after the optional dominance filter) of the first / last belief
-        that chose the tuple.  A tuple is 8*(1+O) bytes, the row it generates 8*S: the sharded backup exchanges these.
+        DISTINCT tuples in order of first occurrence -- on the device (`pbvi_group_keys`), nothing but the count comes back.
+        Returns CUDA int32 tensors (tuples [u, 1+O], first [u], last [u]) where first / last are the positions (in this belief
+        set, after the optional dominance filter) of the first / last belief that chose the tuple.  A tuple is 4*(1+O) bytes,
+        the row it generates 8*S: the sharded backup exchanges these.
         """
         dev = model.device
         V = value_function.alpha_vector_array
         nB = len(belief_set)
         if nB == 0:
-            z = np.zeros(0, dtype=np.int64)
-            return np.zeros((0, 1 + dev.O), dtype=np.int64), z, z
+            z = torch.zeros((0,), dtype=torch.int32, device=dev.device)
+            return torch.zeros((0, 1 + dev.O), dtype=torch.int32, device=dev.device), z, z
+        # value[b][a] itself is only read by the dominance filter; without it a* alone is asked for and beliefs with a single
+        # possible winner skip the exact reference-order sum
         if belief_set._device is None and nB >= 2 * self.STREAM_FIRST_CHUNK:
-            vstar, value, astar = self._select_streamed(model, belief_set, V)
+            vstar, value, astar = self._select_streamed(model, belief_set, V, want_value=belief_dominance_prune)
         else:
-            vstar, value, astar = dev.backup_select(belief_set.belief_array, V, self.gamma)
+            vstar, value, astar = dev.backup_select(belief_set.belief_array, V, self.gamma, want_value=belief_dominance_prune)
         B = belief_set.belief_array
         ar = torch.arange(nB, device=dev.device)
         sel = vstar[ar, astar.long()]                                                    # [nB, O]
@@ -373,36 +376,50 @@ class PBVI_Solver:
             best_old, _ = dev.max_values(B, V)
             keep = value[ar, astar.long()] > best_old
             keys = keys[torch.nonzero(keep)[:, 0]]
-        keys_h = keys.cpu().numpy().astype(np.int64)
-        first, last, _ = unique_rows_first(keys_h)
-        return keys_h[first], first, last
+        first, last, _ = dev.group_keys(keys)
+        return keys[first.long()], first, last
 
-    def rows_from_tuples(self, model: Model, value_function: ValueFunction, tuples: np.ndarray, last: np.ndarray) -> ValueFunction:
+    def select_tuples(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
+        """`select_tuples_device` as host int64 arrays (tuples [u, 1+O], first [u], last [u])."""
+        t, f, l = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune)
+        return tuple(x.cpu().numpy().astype(np.int64) for x in (t, f, l))
+
+    def rows_from_tuples(self, model: Model, value_function: ValueFunction, tuples, last) -> ValueFunction:
         """
         Second half of the backup: assembles the alpha row of every distinct tuple (reference operation order, bit-identical for
-        R = 1) and applies the ValueFunction constructor's byte-dedup.  Different tuples can generate identical bytes; a byte
-        group keeps the position of its first tuple and the action of the tuple whose LAST belief comes latest (`last`).
+        R = 1) and applies the ValueFunction constructor's byte-dedup on the device: rows are grouped by their 128-bit keys
+        (accumulated by the assemble kernel), every key match is confirmed bytewise.  Different tuples can generate identical
+        bytes; a byte group keeps the position of its first tuple and the action of the tuple whose LAST belief comes latest
+        (`last`).  `tuples` [u, 1+O] / `last` [u]: CUDA tensors (from `select_tuples_device`) or host arrays.
         """
         dev = model.device
-        if tuples.shape[0] == 0:
+        t = torch.as_tensor(tuples).to(device=dev.device, dtype=torch.int32)
+        n = t.shape[0]
+        if n == 0:
             return ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
-        rows, keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, tuples[:, 0], tuples[:, 1:], with_hash=True)
-        gfirst, _, hashes, ginv = dedup_rows(dev, rows, keys.cpu().numpy())
-        if gfirst.shape[0] == rows.shape[0]:
-            actions = tuples[:, 0].astype(np.int64)
-        else:
-            order = np.lexsort((last, ginv))                         # within a byte group: ascending position of the last belief
+        rank = torch.as_tensor(last).to(device=dev.device, dtype=torch.int32)
+        rows, keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, t[:, 0], t[:, 1:], with_hash=True)
+        gfirst, owner, inverse = dev.group_keys(keys, rank=rank, want_inverse=True)
+        if gfirst.shape[0] == n:
+            actions, hashes = t[:, 0], keys
+        elif dev.confirm_groups(rows, gfirst, inverse):
+            gf = gfirst.long()
+            actions, rows, hashes = t[owner.long(), 0], rows[gf], keys[gf]
+        else:                                                        # 128-bit key collision (never observed): group on the bytes
+            first_h, _, _, ginv = _dedup_exact_host(rows, keys.cpu().numpy())
+            last_h = rank.cpu().numpy()
+            order = np.lexsort((last_h, ginv))                       # within a byte group: ascending position of the last belief
             ends = np.append(np.flatnonzero(np.diff(ginv[order])), order.shape[0] - 1)
-            owner = np.empty(gfirst.shape[0], dtype=np.int64)
-            owner[ginv[order[ends]]] = order[ends]
-            actions = tuples[owner, 0].astype(np.int64)
-            rows = rows[torch.as_tensor(gfirst, device=rows.device)]
-        return ValueFunction(model, rows, actions, _trusted=True, _hashes=hashes[gfirst])
+            own = np.empty(first_h.shape[0], dtype=np.int64)
+            own[ginv[order[ends]]] = order[ends]
+            gf = torch.as_tensor(first_h, device=dev.device)
+            actions, rows, hashes = t[torch.as_tensor(own, device=dev.device), 0], rows[gf], keys[gf]
+        return ValueFunction(model, rows, actions.cpu().numpy().astype(np.int64), _trusted=True, _hashes=hashes)
 
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
     STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
 
-    def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor):
+    def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor, want_value: bool = True):
         """
         Select step for a belief set that still lives in (pinned) host memory: the rows are uploaded in chunks on a
         copy stream while the compute stream runs `pbvi_backup_select` on the chunks that have landed (rows are
@@ -413,7 +430,7 @@ class PBVI_Solver:
         nB, S = host.shape
         full = torch.empty((nB, S), dtype=torch.float64, device=dev.device)
         vstar = torch.empty((nB, dev.A, dev.O), dtype=torch.int32, device=dev.device)
-        value = torch.empty((nB, dev.A), dtype=torch.float64, device=dev.device)
+        value = torch.empty((nB, dev.A), dtype=torch.float64, device=dev.device) if want_value else None
         astar = torch.empty((nB,), dtype=torch.int32, device=dev.device)
         bounds, lo = [], 0
         while lo < nB:
@@ -436,8 +453,10 @@ class PBVI_Solver:
                 events.append(ev)
         for (lo, hi), ev in zip(bounds, events):
             compute.wait_event(ev)
-            v, val, a = dev.backup_select(full[lo:hi], V, self.gamma)
-            vstar[lo:hi], value[lo:hi], astar[lo:hi] = v, val, a
+            v, val, a = dev.backup_select(full[lo:hi], V, self.gamma, want_value=want_value)
+            vstar[lo:hi], astar[lo:hi] = v, a
+            if want_value:
+                value[lo:hi] = val
         belief_set._device = full
         return vstar, value, astar
 

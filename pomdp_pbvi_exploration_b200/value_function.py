@@ -103,6 +103,8 @@ class ValueFunction:
     def row_hashes(self) -> np.ndarray:
         if self._hashes is None:
             self._hashes = self.model.device.row_hash(self._array).cpu().numpy() if len(self) else np.zeros((0, 2), dtype=np.int64)
+        elif isinstance(self._hashes, torch.Tensor):              # keys left on the device by the backup: fetched on first use
+            self._hashes = self._hashes.cpu().numpy()
         return self._hashes
 
     def __len__(self) -> int:
@@ -211,7 +213,7 @@ class ValueFunction:
             idx = np.flatnonzero(keep)
             self._array = self._array[torch.as_tensor(idx, device=self._array.device)]
             self._actions = self._actions[idx]
-            self._hashes = None if self._hashes is None else self._hashes[idx]
+            self._hashes = None if self._hashes is None else self.row_hashes[idx]
             self._vector_list = None
             self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
             self._buf = None

@@ -336,3 +336,54 @@ def test_backup_sparse_alphas_and_sign_flags(torch_cuda, negative):
     decided = prod[:, -1] - prod[:, -2] > GAP_TOL * np.maximum(1, np.abs(prod[:, -1]))
     assert np.array_equal(arg[decided], rarg[decided])
     dev.close()
+
+
+@pytest.mark.parametrize('n,pool,width,dtype', [(1, 1, 4, 'int32'), (7, 3, 1, 'int32'), (1000, 37, 4, 'int32'), (5000, 5000, 2, 'int64'),
+                                                (20000, 900, 5, 'int32'), (3001, 2, 2, 'int64')])
+def test_group_keys_device_equals_dict_insertion(torch_cuda, n, pool, width, dtype):
+    """`pbvi_group_keys` == the reference's `{row.tobytes(): value}` dict (src/mdp.py:668-669): groups in order of first
+    occurrence, first position, last occurrence (or the record of largest rank)."""
+    torch = torch_cuda
+    dev, m, reach, _ = device_model('tiger')
+    rng = np.random.default_rng(n + width)
+    hi = 2 ** 31 - 1 if dtype == 'int32' else 2 ** 62
+    base = rng.integers(-hi, hi, (pool, width)).astype(dtype)
+    keys = base[rng.integers(0, pool, n)]
+    table = {}
+    for i, k in enumerate(keys):
+        kb = k.tobytes()
+        if kb in table:
+            table[kb][1] = i
+        else:
+            table[kb] = [i, i, len(table)]
+    want_first = np.array([v[0] for v in table.values()])
+    want_last = np.array([v[1] for v in table.values()])
+    want_inv = np.array([table[k.tobytes()][2] for k in keys])
+    first, last, inv = dev.group_keys(torch.as_tensor(keys).cuda(), want_inverse=True)
+    assert np.array_equal(first.cpu().numpy(), want_first) and np.array_equal(last.cpu().numpy(), want_last)
+    assert np.array_equal(inv.cpu().numpy(), want_inv)
+    # with ranks: `last` is the record of largest rank inside the group
+    rank = rng.permutation(n).astype(np.int32)
+    first2, owner, _ = dev.group_keys(torch.as_tensor(keys).cuda(), rank=torch.as_tensor(rank).cuda())
+    want_owner = np.array([np.flatnonzero(want_inv == g)[np.argmax(rank[want_inv == g])] for g in range(len(table))]) if n <= 5000 else None
+    assert np.array_equal(first2.cpu().numpy(), want_first)
+    if want_owner is not None:
+        assert np.array_equal(owner.cpu().numpy(), want_owner)
+
+
+def test_confirm_groups_and_backup_dedup(torch_cuda):
+    """Byte confirmation of key groups, and PBVI_Solver.rows_from_tuples on tuples that generate identical rows: first position,
+    action of the tuple whose last belief comes latest (reference ValueFunction ctor semantics)."""
+    torch = torch_cuda
+    dev, m, reach, _ = device_model('hallway')
+    rng = np.random.default_rng(5)
+    rows = rng.random((30, dev.S))
+    rows[11] = rows[4]; rows[29] = rows[4]; rows[17] = rows[16]
+    t = torch.as_tensor(rows).cuda()
+    keys = dev.row_hash(t)
+    first, last, inv = dev.group_keys(keys, want_inverse=True)
+    assert first.shape[0] == 27 and dev.confirm_groups(t, first, inv)
+    bad = keys.clone()
+    bad[20] = bad[2]                                            # a forged key match between different rows
+    first_b, _, inv_b = dev.group_keys(bad, want_inverse=True)
+    assert first_b.shape[0] == 26 and not dev.confirm_groups(t, first_b, inv_b)
