@@ -20,8 +20,10 @@
 
 namespace pbvi {
 
-static_assert(KC == 16 && BM % RG == 0 && (BM / 8) <= RG && RG % (BM / 8) == 0, "belief_mask_kernel: 16-state chunks, a warp's rows inside one row group");
-constexpr int MASK_ROWS_PER_WARP = BM / 8;   // 8 warps cover the tile; a warp's rows lie inside one row group
+constexpr int MASK_COLS = 256;                         // states per belief_mask_kernel block
+constexpr int MASK_SLABS = MASK_COLS / 32;             // 32-state slabs (one warp load per row)
+constexpr int MASK_CHUNKS = MASK_COLS / KC;            // chunks per block
+static_assert(NRG == 4 && RG == 16 && 32 % KC == 0 && MASK_SLABS % 2 == 0, "belief_mask_kernel: 8 warps = 4 row groups x 2 slab phases");
 
 // ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out) {
@@ -51,47 +53,50 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
 
 // ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c.  The same pass writes
 //      beliefsP, the belief tiles re-laid out as the shared-memory image the score kernel wants:
-//          beliefsP[mt][chunk][row group][RG rows][LDA]      (LDA = KC + 4 padded row stride, zero beyond nB rows / S columns)
-//      so that the A operand of one (tile, chunk, row group) is ONE contiguous, 128-byte aligned block of RG*LDA doubles that a
-//      single bulk async copy drops into shared memory already in its bank-conflict-free layout.
+//          beliefsP[mt][chunk][row group][RG rows][KC]      (columns of row r XOR-swizzled by a_swizzle(r); zero beyond nB rows / S)
+//      so that the A operand of one (tile, chunk, row group) is ONE contiguous, 128-byte aligned block of RG*KC doubles that a
+//      single bulk async copy drops into shared memory already in its bank-conflict-free layout.  Images of row groups that
+//      are all-zero on a chunk are NOT written (the score kernel never fetches them): on the bench workload that is 60 % of
+//      the image.  A warp owns one row group and a 32-state slab at a time: 16 independent row loads in flight per lane.
 __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
                                                           uint8_t* __restrict__ bits, double* __restrict__ beliefsP, int* __restrict__ signs) {
-    __shared__ unsigned smask[NRG];
+    __shared__ unsigned smask[MASK_CHUNKS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cb = blockIdx.x, mt = blockIdx.y;
-    if (tid < NRG) smask[tid] = 0u;
+    const int rg = w & 3;
+    if (tid < MASK_CHUNKS) smask[tid] = 0u;
     __syncthreads();
-    unsigned mask = 0u;
     bool bad = false;
-    for (int rr = 0; rr < MASK_ROWS_PER_WARP; rr++) {
-        const int m = w * MASK_ROWS_PER_WARP + rr;           // row inside the tile
-        const int row = mt * BM + m;
-        const bool live = row < nB;
-        const double* brow = beliefs + (size_t)(live ? row : 0) * S;
-#pragma unroll 4
-        for (int j = 0; j < 16; j++) {
-            const int s = cb * 512 + j * 32 + lane;
-            const int c = s / KC;
-            const double v = (live && s < S) ? brow[s] : 0.0;
-            bad |= !(v >= 0.0);                                  // negative or NaN entry: no exact-zero shortcut for this call
-            if (c < nChunks)
-                beliefsP[(((size_t)mt * nChunks + c) * NRG + m / RG) * A_GROUP_DOUBLES + (m % RG) * LDA + (s % KC)] = v;
-            const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
-            if (bal & 0xFFFFu) mask |= 1u << (2 * j);
-            if (bal >> 16) mask |= 1u << (2 * j + 1);
+    const int row0 = mt * BM + rg * RG;
+    constexpr int CPS = 32 / KC;                         // chunks per slab
+    for (int sl = (w >> 2); sl < MASK_SLABS; sl += 2) {
+        const int s = cb * MASK_COLS + sl * 32 + lane;
+        double v[RG];
+#pragma unroll
+        for (int r = 0; r < RG; r++) v[r] = (row0 + r < nB && s < S) ? beliefs[(size_t)(row0 + r) * S + s] : 0.0;
+        bool nz = false;
+#pragma unroll
+        for (int r = 0; r < RG; r++) {
+            nz |= v[r] != 0.0;
+            bad |= !(v[r] >= 0.0);                       // negative or NaN entry: no exact-zero shortcut for this call
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        const int cl = lane / KC;                        // this lane's chunk inside the slab
+        const bool live = ((bal >> (cl * KC)) & ((1u << KC) - 1u)) != 0u;
+        const int c = (cb * MASK_COLS + sl * 32) / KC + cl;
+        if (live && c < nChunks) {
+            double* dst = beliefsP + (((size_t)mt * nChunks + c) * NRG + rg) * A_GROUP_DOUBLES;
+            const int col = lane % KC;
+#pragma unroll
+            for (int r = 0; r < RG; r++) dst[r * KC + (col ^ a_swizzle(r))] = v[r];
+            if (col == 0) atomicOr(&smask[sl * CPS + cl], 1u << rg);
         }
     }
     if (bad) signs[1] = 1;
-    if (lane == 0 && mask) atomicOr(&smask[(w * MASK_ROWS_PER_WARP) / RG], mask);
     __syncthreads();
-    if (tid < 32) {
-        const int c = cb * 32 + tid;
-        if (c < nChunks) {
-            unsigned b = 0u;
-#pragma unroll
-            for (int g = 0; g < NRG; g++) b |= ((smask[g] >> tid) & 1u) << g;
-            bits[(size_t)mt * nChunks + c] = (uint8_t)b;
-        }
+    if (tid < MASK_CHUNKS) {
+        const int c = cb * MASK_CHUNKS + tid;
+        if (c < nChunks) bits[(size_t)mt * nChunks + c] = (uint8_t)smask[tid];
     }
 }
 
@@ -322,13 +327,13 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
     // factor serialises two dependent loads (measured: 1.22 -> 1.53 ms with the skip)
     const bool skipZero = false;
     double part = 0.0;
-    // a half-warp per 16-state chunk; chunks on which the belief's row group is all-zero (occupancy bits of belief_mask_kernel)
+    // KC threads per chunk; chunks on which the belief's row group is all-zero (occupancy bits of belief_mask_kernel)
     // are skipped without touching the belief row.  The state -> thread mapping is the same for every action of a belief.
     const uint8_t* live = bits + (size_t)(b / BM) * nChunks;
     const unsigned gbit = 1u << ((b % BM) / RG);
-    for (int c = threadIdx.x >> 4; c < nChunks; c += 16) {
+    for (int c = threadIdx.x / KC; c < nChunks; c += 256 / KC) {
         if (!(live[c] & gbit)) continue;
-        const int s = c * KC + (threadIdx.x & 15);
+        const int s = c * KC + (threadIdx.x % KC);
         if (s >= S) continue;
         const double bs = brow[s];
         if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s, skipZero), part);
@@ -533,7 +538,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     m->last_bits = bits;           // read again by the value pass of the same call
     PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
     PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 3 * sizeof(int), st));
-    belief_mask_kernel<<<dim3(ceil_div(nC, 32), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs);
+    belief_mask_kernel<<<dim3(ceil_div(nC, MASK_CHUNKS), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs);
     m->last_launches++;
     // alpha-side occupancy (gather path: per action; plain max_v path: one group; Gamma path: not masked)
     uint8_t* bLive = nullptr;

@@ -12,7 +12,8 @@
 namespace pbvi {
 
 // ---- tiling constants of the score kernel (see score_kernel.cuh) --------------------------------
-constexpr int KC = 16;         // source states per K chunk -- the sparsity-skipping granule along K
+constexpr int KC = 8;          // source states per K chunk -- the sparsity-skipping granule along K (4, 8 or 16).  On the bench workload
+                               // a 16-state granule executes 1.46x the flops of an 8-state one (tools/sparsity_analysis.py)
 constexpr int BM = 64;         // beliefs per block tile
 constexpr int BN = 256;        // alpha vectors per block tile
 constexpr int RG = 16;         // beliefs per row group (one warp's rows) -- the skipping granule along M

@@ -10,16 +10,16 @@
 //   bmat is alphaT (z stride 0: max_v b.alpha_v of compute_change / SSGA / GER) or the transposed Gamma projection
 //   GammaT[a,o] built by gamma_project_kernel for models with reachable_state_count > 1.
 //
-// One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 16 source states) in which
+// One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 8 source states) in which
 // some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero AND some alpha of the tile is non-zero at a
 // state the chunk lands on (list built by build_chunk_lists_kernel): every skipped term is an exact zero.
 //
 // Warp specialisation (N_CONSUMER_WARPS + 1 warps):
-//   warp 8      producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
-//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (16), ONE 5 KB
-//               copy per live row group (belief_mask_kernel stores the belief tiles as ready-made shared-memory images,
-//               padded row stride included) and the RTO chunk: 19 copies per chunk.  List entries and gathered row
-//               indices are prefetched one chunk ahead, so the producer never waits on a dependent global load.
+//   last warp   producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
+//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (KC of them), ONE
+//               1 KB copy per live row group (belief_mask_kernel stores the belief tiles as ready-made, bank-swizzled
+//               shared-memory images) and the RTO chunk.  List entries and gathered row indices are prefetched one chunk
+//               ahead, so the producer never waits on a dependent global load.
 //   the rest    consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
 //               Warp w owns row group w / 4 (RG beliefs) and column quarter w % 4, so each SM sub-partition
 //               (warp id mod 4) holds one warp of EACH row group: a row group that is all-zero on the chunk is skipped
@@ -33,29 +33,34 @@
 
 namespace pbvi {
 
-constexpr int STAGES = 5;
-constexpr int LDA = KC + 4;   // 20: row stride 4 mod 16 doubles -> conflict-free 8-byte fragment loads
 constexpr int LDB = BN + 4;   // 260
 constexpr int NCW = BN / 64;  // 4 column warps, 64 columns each
 constexpr int MT = RG / 8;    // m8 row tiles per consumer warp
-constexpr int A_GROUP_DOUBLES = RG * LDA;   // one row group of one chunk in beliefsP == its shared-memory image (640 doubles, 5 KB)
-constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 8
+// One row group of one chunk in beliefsP == its shared-memory image: RG rows of KC doubles, dense, with the columns of row r
+// XOR-swizzled by a_swizzle(r) so that the 8-byte fragment loads of a half-warp (4 rows x 4 columns) hit 16 different banks
+// whatever KC is (row r starts at 8-byte slot r*KC mod 16).
+constexpr int A_GROUP_DOUBLES = RG * KC;
+__host__ __device__ constexpr int a_swizzle(int row) { return KC == 16 ? ((row & 3) << 2) : KC == 8 ? (((row >> 1) & 1) << 2) : 0; }
+static_assert(KC == 4 || KC == 8 || KC == 16, "a_swizzle covers KC = 4, 8, 16");
+constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 16
 constexpr int SCORE_THREADS_TOTAL = (N_CONSUMER_WARPS + 1) * 32;   // + the producer warp
 
 struct __align__(128) ScoreStage {
     double Bs[KC * LDB];
-    double As[BM * LDA];
-    double Rs[KC];
+    double As[BM * KC];
+    double Rs[KC < 16 ? 16 : KC];
 };
+constexpr int STAGES = (int)((212 * 1024) / sizeof(ScoreStage)) < 12 ? (int)((212 * 1024) / sizeof(ScoreStage)) : 12;
 constexpr size_t SCORE_SMEM = sizeof(ScoreStage) * STAGES;
 static_assert(sizeof(ScoreStage) % 128 == 0, "stage alignment");
-static_assert(SCORE_SMEM <= 226 * 1024, "score pipeline exceeds shared memory");
+static_assert(SCORE_SMEM <= 226 * 1024 && STAGES >= 3, "score pipeline exceeds shared memory");
 static_assert(BM == NRG * RG && N_CONSUMER_WARPS * 32 == SCORE_THREADS, "warp layout: NRG row groups x NCW column warps");
 static_assert(2 * sizeof(double) * NCW * BM <= sizeof(ScoreStage), "argmax staging reuses the first stage");
 static_assert(KC + NRG + 1 <= 32, "producer lane mapping: lanes [0,KC) B rows, [KC,KC+NRG) A row groups, KC+NRG the RTO chunk");
+static_assert((A_GROUP_DOUBLES * 8) % 16 == 0 && (KC * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 struct ScoreParams {
-    const double* beliefsP;    // [nMt][nChunks][NRG][RG][LDA]  belief tiles as shared-memory images (written by belief_mask_kernel)
+    const double* beliefsP;    // [nMt][nChunks][NRG][RG][KC]  belief tiles as swizzled shared-memory images (belief_mask_kernel)
     const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [gridDim.z][S][Vp], matrix of block z at blockIdx.z * zStrideB
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
@@ -203,13 +208,14 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             const ScoreStage& st = stages[slot];
             const uint32_t rg = s_meta[slot] >> 24;
             if ((rg >> warp_m) & 1u) {
-                const double* Ab = st.As + (warp_m * RG + g) * LDA + t;
+                const double* Ab = st.As + (warp_m * RG + g) * KC;
                 const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
+                const int swz = a_swizzle(g);                 // == a_swizzle(i * 8 + g)
 #pragma unroll
                 for (int ks = 0; ks < KC / 4; ks++) {
                     double af[MT], bf[8];
 #pragma unroll
-                    for (int i = 0; i < MT; i++) af[i] = Ab[i * 8 * LDA + ks * 4];
+                    for (int i = 0; i < MT; i++) af[i] = Ab[i * 8 * KC + ((ks * 4 + t) ^ swz)];
                     if (GATHER) {
                         const double r = st.Rs[ks * 4 + t];
 #pragma unroll
