@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpbvi_b200.so')
+LIB_PATH = os.environ.get('PBVI_B200_LIB', os.path.join(_HERE, 'libpbvi_b200.so'))     # override: A/B builds of the same engine
 
 PBVI_OK, PBVI_ERR_BAD_ARG, PBVI_ERR_CUDA, PBVI_ERR_OOM, PBVI_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 

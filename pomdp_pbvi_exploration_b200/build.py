@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libpbvi_b200.so')
+LIB = os.environ.get('PBVI_B200_LIB', os.path.join(HERE, 'libpbvi_b200.so'))
 SOURCES = ['model.cu', 'backup.cu', 'belief.cu', 'misc.cu']
 HEADERS = ['pbvi_common.cuh', 'score_kernel.cuh', os.path.join('..', '..', 'include', 'pbvi_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
@@ -35,12 +35,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs = []
     os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
-    flags = [f for f in FLAGS if not f.startswith('--use_fast_math')]
+    flags = [f for f in FLAGS if not f.startswith('--use_fast_math')] + os.environ.get('PBVI_B200_DEFS', '').split()
     if verbose:
         flags += ['-Xptxas', '-v']
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, '_build', src.replace('.cu', '.o'))
+        obj = os.path.join(HERE, '_build', os.path.basename(LIB).replace('.so', '_') + src.replace('.cu', '.o'))
         objs.append(obj)
         cmd = [NVCC, *flags, '-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -24,6 +24,7 @@ constexpr int MASK_COLS = 256;                         // states per belief_mask
 constexpr int MASK_SLABS = MASK_COLS / 32;             // 32-state slabs (one warp load per row)
 constexpr int MASK_CHUNKS = MASK_COLS / KC;            // chunks per block
 static_assert(NRG == 4 && RG == 16 && 32 % KC == 0 && MASK_SLABS % 2 == 0, "belief_mask_kernel: 8 warps = 4 row groups x 2 slab phases");
+static_assert(BN == 256 && NCW == 4, "alpha_row_mask_kernel: four 64-column quarters per alpha tile");
 
 // ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out) {
@@ -100,9 +101,9 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
     }
 }
 
-// ---- rowLive[nt][s] = 1 iff alphaT[s][nt*BN .. nt*BN + BN) holds a non-zero: an all-zero row of the B operand (an alpha tile
-//      that vanishes at a landing state -- the rule for value functions of goal-reward models, whose support grows by one
-//      step per backup) contributes exact zeros to every score.  Warp per (s, nt).
+// ---- rowLive[nt][s]: bit q set iff alphaT[s][nt*BN + q*64 .. + 64) holds a non-zero: an all-zero piece of a row of the B operand
+//      (an alpha tile that vanishes at a landing state -- the rule for value functions of goal-reward models, whose support
+//      grows by one step per backup) contributes exact zeros to every score.  Warp per (s, nt).
 __global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __restrict__ alphaT, int S, int Vp, int nNt,
                                                              uint8_t* __restrict__ rowLive, int* __restrict__ signs) {
     const size_t gw = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -110,22 +111,22 @@ __global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __res
     const int lane = threadIdx.x & 31;
     const int s = (int)(gw / nNt), nt = (int)(gw % nNt);
     const double* row = alphaT + (size_t)s * Vp + (size_t)nt * BN;
-    bool nz = false, neg = false, nonfinite = false;
+    bool neg = false, nonfinite = false;
+    unsigned live = 0u;
 #pragma unroll
     for (int j = 0; j < BN / 32; j++) {
         const double v = row[j * 32 + lane];
-        nz |= v != 0.0;
         neg |= !(v >= 0.0);
         nonfinite |= !(fabs(v) <= 1.79769313486231570e308);
+        if (__ballot_sync(0xffffffffu, v != 0.0)) live |= 1u << (j / 2);      // columns j*32 .. j*32+31 lie in quarter j / 2
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, nz);
-    if (lane == 0) rowLive[(size_t)nt * S + s] = bal ? 1 : 0;
+    if (lane == 0) rowLive[(size_t)nt * S + s] = (uint8_t)live;
     if (neg) signs[0] = 1;
     if (nonfinite) signs[2] = 1;
 }
 
-// ---- bLive[nt][g][c] = 1 iff some state k of chunk c gathers a live alphaT row: row index reach[g][k] (g = action) for the
-//      gather path, k itself when reach == nullptr (plain path, one group)
+// ---- bLive[nt][g][c]: bit q set iff some state k of chunk c gathers an alphaT row that is live in column quarter q: row index
+//      reach[g][k] (g = action) for the gather path, k itself when reach == nullptr (plain path, one group)
 __global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __restrict__ rowLive, const int32_t* __restrict__ reachP,
                                                                int S, int Sp, int nChunks, int nG, int nNt, uint8_t* __restrict__ bLive) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -138,11 +139,12 @@ __global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __
         const int k = c * KC + kk;
         if (k < S) any |= live[reachP ? reachP[(size_t)g * Sp + k] : k];
     }
-    bLive[i] = any ? 1 : 0;
+    bLive[i] = (uint8_t)any;
 }
 
 // ---- ordered live-chunk list of every (tile, z, alpha tile); one warp per list.  A chunk is live iff some belief of the tile
 //      is non-zero on it AND RTO[a][o] is non-zero on it AND the alpha tile is non-zero at some state it lands on.
+//      Entry = chunk | live row groups << 24 | live column quarters << 28.
 __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ zMask,
                                                                const uint8_t* __restrict__ bLive, int nG, int zPerG, int nChunks, int nZ,
                                                                int nNt, uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
@@ -153,14 +155,17 @@ __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __
     int base = 0;
     for (int c0 = 0; c0 < nChunks; c0 += 32) {
         const int c = c0 + lane;
-        unsigned b = 0u;
+        unsigned b = 0u, q = 0xFu;
         if (c < nChunks) {
             b = bits[(size_t)mt * nChunks + c];
             if (zMask && !zMask[(size_t)z * nChunks + c]) b = 0u;
-            if (bl && !bl[c]) b = 0u;
+            if (bl) {
+                q = bl[c];
+                if (!q) b = 0u;
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, b != 0u);
-        if (b) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c | (b << 24);
+        if (b) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c | (b << 24) | (q << 28);
         base += __popc(bal);
     }
     if (lane == 0) counts[slot] = base;
@@ -570,7 +575,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_TAKE(pval, double, (size_t)nNt * nB * nZ);
     PBVI_TAKE(pidx, int32_t, (size_t)nNt * nB * nZ);
     PBVI_CUDA(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), st));
-    m->last_exec_scale = 2.0 * RG * BN * KC;
+    m->last_exec_scale = 2.0 * RG * (BN / NCW) * KC;     // per visited (chunk, row group, column quarter)
     m->last_dense_flops = 2.0 * nB * (double)nV * nZ * S;
 
     if (m->profile) PBVI_CUDA(cudaEventRecord(m->evScore0, st));

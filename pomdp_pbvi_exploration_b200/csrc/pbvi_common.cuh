@@ -12,7 +12,10 @@
 namespace pbvi {
 
 // ---- tiling constants of the score kernel (see score_kernel.cuh) --------------------------------
-constexpr int KC = 8;          // source states per K chunk -- the sparsity-skipping granule along K (4, 8 or 16).  On the bench workload
+#ifndef PBVI_KC
+#define PBVI_KC 4
+#endif
+constexpr int KC = PBVI_KC;         // source states per K chunk -- the sparsity-skipping granule along K (4, 8 or 16).  On the bench workload
                                // a 16-state granule executes 1.46x the flops of an 8-state one (tools/sparsity_analysis.py)
 constexpr int BM = 64;         // beliefs per block tile
 constexpr int BN = 256;        // alpha vectors per block tile

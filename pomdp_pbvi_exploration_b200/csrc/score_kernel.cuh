@@ -50,7 +50,7 @@ struct __align__(128) ScoreStage {
     double As[BM * KC];
     double Rs[KC < 16 ? 16 : KC];
 };
-constexpr int STAGES = (int)((212 * 1024) / sizeof(ScoreStage)) < 12 ? (int)((212 * 1024) / sizeof(ScoreStage)) : 12;
+constexpr int STAGES = (int)((212 * 1024) / sizeof(ScoreStage)) < 16 ? (int)((212 * 1024) / sizeof(ScoreStage)) : 16;
 constexpr size_t SCORE_SMEM = sizeof(ScoreStage) * STAGES;
 static_assert(sizeof(ScoreStage) % 128 == 0, "stage alignment");
 static_assert(SCORE_SMEM <= 226 * 1024 && STAGES >= 3, "score pipeline exceeds shared memory");
@@ -65,12 +65,12 @@ struct ScoreParams {
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
     const double* rtoP;        // [A*O][Sp]        (GATHER)
-    const uint32_t* lists;     // [nMt][nZ][nNt][nChunks]  chunk | row-group bits << 24
+    const uint32_t* lists;     // [nMt][nZ][nNt][nChunks]  chunk | row-group bits << 24 | column-quarter bits << 28
     const int32_t* listCount;  // [nMt][nZ][nNt]
     const int32_t* zOrder;     // [nZ] heavy-first processing order (nullptr: identity)
     double* pval;              // [nNt][nB][nZ]
     int32_t* pidx;             // [nNt][nB][nZ]
-    unsigned long long* stats; // visited (chunk, row group) pairs, summed over blocks
+    unsigned long long* stats; // visited (chunk, row group, column quarter) triples, summed over blocks
     int nB, S, Sp, V, Vp, nChunks, nZ, O;
 };
 
@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
     double best[MT];
     int bidx[MT];
     const int g = lane >> 2, t = lane & 3;
-    const int warp_m = warp / NCW, warp_n = warp % NCW;     // meaningful for consumer warps only
+    // Consumer warp w = 4 m + j sits on SM sub-partition j; it owns row group m and column quarter (j + m) % 4 -- a Latin square, so
+    // every sub-partition holds one warp of EACH row group and one of EACH column quarter: a skipped row group or a skipped
+    // column quarter takes the same share of work off all four FP64 pipes.
+    const int warp_m = warp / NCW, warp_n = (warp + warp_m) % NCW;     // meaningful for consumer warps only
 
     if (warp == N_CONSUMER_WARPS) {
         // =============================== producer warp ===============================
@@ -161,26 +164,31 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             return GATHER ? reach[k] : min(k, p.S - 1);
         };
         uint32_t e0 = 0, e1 = 0;
-        int row0 = 0;
+        int row0n = 0;
         if (nAct > 0) {
             e0 = list[0];
             e1 = list[min(1, nAct - 1)];
-            row0 = gathered_row(e0);
+            row0n = gathered_row(e0);
         }
         unsigned long long visited = 0;
         for (int q = 0; q < nAct; q++) {
             const int slot = q % STAGES;
             const unsigned use = (unsigned)(q / STAGES);
+            const uint32_t e = e0;
+            const int row0 = row0n;
+            // prefetch for the next chunk (consumed one iteration from now)
+            e0 = e1;
+            row0n = gathered_row(e0);
+            e1 = list[min(q + 2, nAct - 1)];
             mbar_wait(&s_empty[slot], (use & 1u) ^ 1u);          // first use of a slot passes immediately
             ScoreStage& st = stages[slot];
-            const uint32_t e = e0;
             const int k0 = (int)(e & 0xFFFFFFu) * KC;
-            const uint32_t rg = e >> 24;
+            const uint32_t rg = (e >> 24) & ((1u << NRG) - 1u);
             if (lane == 0) {
                 s_meta[slot] = e;
-                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg & ((1u << NRG) - 1u)) * A_GROUP_DOUBLES * 8;
+                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg) * A_GROUP_DOUBLES * 8;
                 mbar_arrive_expect_tx(&s_full[slot], bytes);
-                visited += __popc(rg & ((1u << NRG) - 1u));
+                visited += __popc(rg) * __popc(e >> 28);
             }
             __syncwarp();
             if (lane < KC) bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
@@ -188,10 +196,6 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
                 bulk_g2s(&st.As[(lane - KC) * A_GROUP_DOUBLES], atile + ((size_t)(k0 / KC) * NRG + (lane - KC)) * A_GROUP_DOUBLES,
                          A_GROUP_DOUBLES * 8, &s_full[slot]);
             if (GATHER && lane == KC + NRG) bulk_g2s(&st.Rs[0], rto + k0, KC * 8, &s_full[slot]);
-            // prefetch for the next chunk (consumed one iteration from now)
-            e0 = e1;
-            row0 = gathered_row(e0);
-            e1 = list[min(q + 2, nAct - 1)];
         }
         if (lane == 0 && p.stats && visited) atomicAdd(p.stats, visited);
     } else {
@@ -206,8 +210,8 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             const int slot = it % STAGES;
             mbar_wait(&s_full[slot], (unsigned)(it / STAGES) & 1u);
             const ScoreStage& st = stages[slot];
-            const uint32_t rg = s_meta[slot] >> 24;
-            if ((rg >> warp_m) & 1u) {
+            const uint32_t meta = s_meta[slot];
+            if (((meta >> (24 + warp_m)) & 1u) && ((meta >> (28 + warp_n)) & 1u)) {
                 const double* Ab = st.As + (warp_m * RG + g) * KC;
                 const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
                 const int swz = a_swizzle(g);                 // == a_swizzle(i * 8 + g)
