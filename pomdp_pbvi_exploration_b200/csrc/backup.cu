@@ -142,36 +142,40 @@ __global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __
     bLive[i] = (uint8_t)any;
 }
 
-// ---- ordered live-chunk list of every (tile, z, alpha tile); one warp per list.  A chunk is live iff some belief of the tile
-//      is non-zero on it AND RTO[a][o] is non-zero on it AND the alpha tile is non-zero at some state it lands on.
-//      Entry = chunk | live row groups << 24 | live column quarters << 28.
+// ---- ordered list of the live pipeline stages (SUB consecutive chunks) of every (tile, z, alpha tile); one warp per list.  A
+//      chunk is live iff some belief of the tile is non-zero on it AND RTO[a][o] is non-zero on it AND the alpha tile is non-zero
+//      at some state it lands on.  Entry = (stage index, flags): byte h of flags = live row groups | live column quarters << 4
+//      of chunk h of the stage (0 when the chunk is dead).
 __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ zMask,
                                                                const uint8_t* __restrict__ bLive, int nG, int zPerG, int nChunks, int nZ,
-                                                               int nNt, uint32_t* __restrict__ lists, int32_t* __restrict__ counts) {
+                                                               int nNt, uint2* __restrict__ lists, int32_t* __restrict__ counts) {
     const int z = blockIdx.x / nNt, nt = blockIdx.x % nNt, mt = blockIdx.y, lane = threadIdx.x;
     const size_t slot = ((size_t)mt * nZ + z) * nNt + nt;
-    uint32_t* list = lists + slot * nChunks;
+    const int nStages = nChunks / SUB;
+    uint2* list = lists + slot * nStages;
     const uint8_t* bl = bLive ? bLive + ((size_t)nt * nG + z / zPerG) * nChunks : nullptr;
     int base = 0;
-    for (int c0 = 0; c0 < nChunks; c0 += 32) {
-        const int c = c0 + lane;
-        unsigned b = 0u, q = 0xFu;
-        if (c < nChunks) {
-            b = bits[(size_t)mt * nChunks + c];
-            if (zMask && !zMask[(size_t)z * nChunks + c]) b = 0u;
-            if (bl) {
-                q = bl[c];
-                if (!q) b = 0u;
+    for (int s0 = 0; s0 < nStages; s0 += 32) {
+        const int sg = s0 + lane;
+        unsigned flags = 0u;
+        if (sg < nStages) {
+#pragma unroll
+            for (int h = 0; h < SUB; h++) {
+                const int c = sg * SUB + h;
+                unsigned b = bits[(size_t)mt * nChunks + c], q = 0xFu;
+                if (zMask && !zMask[(size_t)z * nChunks + c]) b = 0u;
+                if (bl) q = bl[c];
+                if (b && q) flags |= (b | (q << 4)) << (8 * h);
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, b != 0u);
-        if (b) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c | (b << 24) | (q << 28);
+        const unsigned bal = __ballot_sync(0xffffffffu, flags != 0u);
+        if (flags) list[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)sg, flags);
         base += __popc(bal);
     }
     if (lane == 0) counts[slot] = base;
 }
 
-// ---- argmax across alpha tiles: ascending tile order, strict > keeps the lowest index on ties ----------------------
+// ---- argmax across the column quarters of all alpha tiles: ascending column order, strict > keeps the lowest index on ties ----------------------
 __global__ void __launch_bounds__(256) combine_tiles_kernel(const double* __restrict__ pval, const int32_t* __restrict__ pidx, int nNt,
                                                             size_t n, double* __restrict__ outVal, int32_t* __restrict__ outIdx) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,14 +515,19 @@ __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* 
 }
 
 // =====================================================================================================================
-static int launch_score(pbvi_model* m, bool gather, const ScoreParams& p, int nNt, int nMt, int nZ, cudaStream_t st) {
+static int launch_score(pbvi_model* m, bool gather, ScoreParams& p, int nNt, int nMt, int nZ, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         PBVI_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
         PBVI_CUDA(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
         configured = true;
     }
-    dim3 grid(nNt, nMt, nZ);
+    // persistent: one block per SM pulls (z, belief tile, alpha tile) tiles from a queue
+    PBVI_REQUIRE((long long)nNt * nMt * nZ < (1ll << 31), "too many score tiles");
+    p.nMt = nMt; p.nNt = nNt; p.nzLaunch = nZ;
+    p.tileCounter = m->d_signs + 4;
+    PBVI_CUDA(cudaMemsetAsync(p.tileCounter, 0, sizeof(int), st));
+    const int grid = std::min(m->sm_count, nNt * nMt * nZ);
     if (gather) score_kernel<true><<<grid, SCORE_THREADS_TOTAL, SCORE_SMEM, st>>>(p);
     else score_kernel<false><<<grid, SCORE_THREADS_TOTAL, SCORE_SMEM, st>>>(p);
     m->last_launches++;
@@ -565,15 +574,15 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
         PBVI_CUDA(cudaMemcpyAsync(m->d_signs + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     PBVI_REQUIRE((size_t)nZ * nNt <= 2147483647u, "too many (z, alpha tile) pairs");
-    PBVI_TAKE(lists, uint32_t, (size_t)nMt * nZ * nNt * nC);
+    PBVI_TAKE(lists, uint2, (size_t)nMt * nZ * nNt * (nC / SUB));
     PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ * nNt);
     build_chunk_lists_kernel<<<dim3(nZ * nNt, nMt), 32, 0, st>>>(bits, backup ? m->zMask : nullptr, bLive, nG, zPerG, nC, nZ, nNt, lists,
                                                                  counts);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
 
-    PBVI_TAKE(pval, double, (size_t)nNt * nB * nZ);
-    PBVI_TAKE(pidx, int32_t, (size_t)nNt * nB * nZ);
+    PBVI_TAKE(pval, double, (size_t)nNt * NCW * nB * nZ);
+    PBVI_TAKE(pidx, int32_t, (size_t)nNt * NCW * nB * nZ);
     PBVI_CUDA(cudaMemsetAsync(m->d_stats, 0, sizeof(unsigned long long), st));
     m->last_exec_scale = 2.0 * RG * (BN / NCW) * KC;     // per visited (chunk, row group, column quarter)
     m->last_dense_flops = 2.0 * nB * (double)nV * nZ * S;
@@ -581,7 +590,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     if (m->profile) PBVI_CUDA(cudaEventRecord(m->evScore0, st));
     ScoreParams p{};
     p.beliefsP = beliefsP; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
-    p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nZ = nZ; p.O = m->O;
+    p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nStages = nC / SUB; p.nZ = nZ; p.O = m->O;
     if (!backup) {
         p.bmat = alphaT; p.zStrideB = 0; p.zOrder = nullptr;
         PBVI_TRY(launch_score(m, false, p, nNt, nMt, 1, st));
@@ -603,7 +612,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     }
     if (m->profile) { PBVI_CUDA(cudaEventRecord(m->evScore1, st)); m->score_timed = true; }
     const size_t n = (size_t)nB * nZ;
-    combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt, n, outVal, outIdx);
+    combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt * NCW, n, outVal, outIdx);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;

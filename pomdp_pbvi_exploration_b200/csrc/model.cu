@@ -119,7 +119,7 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     pbvi_model* m = new pbvi_model();
     m->S = S; m->A = A; m->O = O; m->R = R;
     m->K = S * R;
-    m->Sp = ceil_div(S, KC) * KC;
+    m->Sp = ceil_div(S, 16) * 16;          // whole pipeline stages (SUB * KC <= 16 states); pad states land on state 0 with RTO 0
     m->nChunks = m->Sp / KC;
     m->nZ = A * O;
     m->device = device;
@@ -213,7 +213,7 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
     up(&m->predPtr, predPtr); up(&m->predK, predK);
     up(&m->pwLeaves, leaves); up(&m->pwNodes, nodes);
-    if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 4 * sizeof(int)) != cudaSuccess) {
+    if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 8 * sizeof(int)) != cudaSuccess) {
         set_error("cudaMalloc(signs) failed");
         rc = PBVI_ERR_CUDA;
     }

@@ -17,6 +17,12 @@ namespace pbvi {
 #endif
 constexpr int KC = PBVI_KC;         // source states per K chunk -- the sparsity-skipping granule along K (4, 8 or 16).  On the bench workload
                                // a 16-state granule executes 1.46x the flops of an 8-state one (tools/sparsity_analysis.py)
+#ifndef PBVI_SUB
+#define PBVI_SUB 4
+#endif
+constexpr int SUB = PBVI_SUB;  // chunks per pipeline stage of the score kernel: zeros are skipped per KC-state chunk, the mbarrier handshake
+                               // is paid per SUB chunks (a dense workload runs like a kernel with SUB*KC-state chunks)
+constexpr int SKC = SUB * KC;  // source states per stage
 constexpr int BM = 64;         // beliefs per block tile
 constexpr int BN = 256;        // alpha vectors per block tile
 constexpr int RG = 16;         // beliefs per row group (one warp's rows) -- the skipping granule along M
@@ -124,7 +130,7 @@ struct pbvi_model {
     // that comes out exactly 0 consists of zero terms only, so the reference-order value is exactly 0 as well
     bool model_nonneg = false;               // RTO >= 0 and Rbar >= 0 (checked once on the host)
     const uint8_t* last_bits = nullptr;      // belief occupancy bits of the running select call (arena memory)
-    int* d_signs = nullptr;                  // [4] set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN,
+    int* d_signs = nullptr;                  // [8] ([4]: tile queue counter of the score kernel) set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN,
                                              //     [2] some alpha NaN or +-inf; [3] the same for the alphas of the last assemble call
     double last_dense_flops = 0.0;
     double last_exec_scale = 0.0;            // flops per visited quadruple

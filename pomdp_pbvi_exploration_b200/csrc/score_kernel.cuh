@@ -46,32 +46,34 @@ constexpr int N_CONSUMER_WARPS = NRG * NCW;                 // 16
 constexpr int SCORE_THREADS_TOTAL = (N_CONSUMER_WARPS + 1) * 32;   // + the producer warp
 
 struct __align__(128) ScoreStage {
-    double Bs[KC * LDB];
-    double As[BM * KC];
-    double Rs[KC < 16 ? 16 : KC];
+    double Bs[SKC * LDB];
+    double As[SUB * BM * KC];          // [chunk of the stage][row group][RG rows][KC]
+    double Rs[SKC < 16 ? 16 : SKC];
 };
 constexpr int STAGES = (int)((212 * 1024) / sizeof(ScoreStage)) < 16 ? (int)((212 * 1024) / sizeof(ScoreStage)) : 16;
 constexpr size_t SCORE_SMEM = sizeof(ScoreStage) * STAGES;
 static_assert(sizeof(ScoreStage) % 128 == 0, "stage alignment");
 static_assert(SCORE_SMEM <= 226 * 1024 && STAGES >= 3, "score pipeline exceeds shared memory");
 static_assert(BM == NRG * RG && N_CONSUMER_WARPS * 32 == SCORE_THREADS, "warp layout: NRG row groups x NCW column warps");
-static_assert(2 * sizeof(double) * NCW * BM <= sizeof(ScoreStage), "argmax staging reuses the first stage");
-static_assert(KC + NRG + 1 <= 32, "producer lane mapping: lanes [0,KC) B rows, [KC,KC+NRG) A row groups, KC+NRG the RTO chunk");
+static_assert(SKC <= 16 && SKC + SUB * NRG <= 32 && NRG == 4 && NCW == 4 && SUB * 8 <= 32,
+              "producer lane mapping: lanes [0,SKC) B rows, [SKC, SKC + SUB*NRG) A row groups; flags: 4 + 4 bits per chunk");
 static_assert((A_GROUP_DOUBLES * 8) % 16 == 0 && (KC * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 struct ScoreParams {
     const double* beliefsP;    // [nMt][nChunks][NRG][RG][KC]  belief tiles as swizzled shared-memory images (belief_mask_kernel)
-    const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [gridDim.z][S][Vp], matrix of block z at blockIdx.z * zStrideB
+    const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [nzLaunch][S][Vp], matrix of queue position zi at zi * zStrideB
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
     const double* rtoP;        // [A*O][Sp]        (GATHER)
-    const uint32_t* lists;     // [nMt][nZ][nNt][nChunks]  chunk | row-group bits << 24 | column-quarter bits << 28
+    const uint2* lists;        // [nMt][nZ][nNt][nStages]  (stage index, flags): flags byte h = live row groups | live column quarters << 4 of chunk h
     const int32_t* listCount;  // [nMt][nZ][nNt]
-    const int32_t* zOrder;     // [nZ] heavy-first processing order (nullptr: identity)
-    double* pval;              // [nNt][nB][nZ]
-    int32_t* pidx;             // [nNt][nB][nZ]
+    const int32_t* zOrder;     // [nzLaunch] z of queue position zi, heavy first (nullptr: identity)
+    double* pval;              // [nNt * NCW][nB][nZ]  partial maxima per 64-column quarter, ascending columns
+    int32_t* pidx;             // [nNt * NCW][nB][nZ]
+    int* tileCounter;          // zeroed before the launch: next tile of the queue
+    int nMt, nNt, nzLaunch;    // tile queue = nzLaunch x nMt x nNt, z-major (heavy z first through zOrder)
     unsigned long long* stats; // visited (chunk, row group, column quarter) triples, summed over blocks
-    int nB, S, Sp, V, Vp, nChunks, nZ, O;
+    int nB, S, Sp, V, Vp, nChunks, nStages, nZ, O;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -118,21 +120,27 @@ __device__ __forceinline__ void argmax_combine(double& v, int& i, double ov, int
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+constexpr uint32_t META_TILE_END = 0xFFFFFFFFu;   // ring item that closes a tile (no stage has this index)
+constexpr uint32_t META_STOP = 0xFFFFFFFEu;       // ring item that ends the stream
+
+// Persistent, streaming form: one block per SM walks a queue of (z, belief tile, alpha tile) tiles (heavy z first, handed out by
+// an atomic counter).  The producer warp turns the queue into ONE stream of ring items -- the live chunks of a tile followed
+// by a TILE_END item -- and runs ahead across tile boundaries, so the first loads of the next tile overlap the last DMMAs
+// of the current one and a tile with an empty list costs one ring item instead of a block launch.  A consumer warp that meets
+// TILE_END reduces its own 16 x 64 accumulator block to (max, first argmax) per row, writes that partial result straight to
+// global memory (the column quarters are merged by combine_tiles_kernel) and clears its accumulators: no block-wide barrier
+// anywhere after the mbarrier initialisation.
 template <bool GATHER>
 __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const ScoreParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScoreStage* stages = reinterpret_cast<ScoreStage*>(smem_raw);
     __shared__ __align__(8) uint64_t s_full[STAGES];
     __shared__ __align__(8) uint64_t s_empty[STAGES];
-    __shared__ uint32_t s_meta[STAGES];
+    __shared__ uint2 s_meta[STAGES];               // (stage index or META_*, flags or tile id)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nt = blockIdx.x, mt = blockIdx.y;
-    const int z = p.zOrder ? p.zOrder[blockIdx.z] : (int)blockIdx.z;
-    const int m0 = mt * BM, n0 = nt * BN;
-    const size_t listSlot = ((size_t)mt * p.nZ + z) * gridDim.x + nt;
-    const uint32_t* __restrict__ list = p.lists + listSlot * p.nChunks;
-    const int nAct = p.listCount[listSlot];
+    const int nTiles = p.nzLaunch * p.nMt * p.nNt;
+    const int tilesPerZ = p.nMt * p.nNt;
 
     if (tid == 0) {
 #pragma unroll
@@ -144,89 +152,183 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
     }
     __syncthreads();
 
-    double best[MT];
-    int bidx[MT];
-    const int g = lane >> 2, t = lane & 3;
-    // Consumer warp w = 4 m + j sits on SM sub-partition j; it owns row group m and column quarter (j + m) % 4 -- a Latin square, so
-    // every sub-partition holds one warp of EACH row group and one of EACH column quarter: a skipped row group or a skipped
-    // column quarter takes the same share of work off all four FP64 pipes.
-    const int warp_m = warp / NCW, warp_n = (warp + warp_m) % NCW;     // meaningful for consumer warps only
-
     if (warp == N_CONSUMER_WARPS) {
         // =============================== producer warp ===============================
-        const int a = GATHER ? z / p.O : 0;
-        const double* __restrict__ bsrc = (GATHER ? p.bmat : p.bmat + (size_t)blockIdx.z * p.zStrideB) + n0;
-        const int32_t* __restrict__ reach = GATHER ? p.reachP + (size_t)a * p.Sp : nullptr;
-        const double* __restrict__ rto = GATHER ? p.rtoP + (size_t)z * p.Sp : nullptr;
-        const double* __restrict__ atile = p.beliefsP + (size_t)mt * p.nChunks * NRG * A_GROUP_DOUBLES;
-        auto gathered_row = [&](uint32_t e) -> int {
-            const int k = (int)(e & 0xFFFFFFu) * KC + (lane & (KC - 1));
-            return GATHER ? reach[k] : min(k, p.S - 1);
-        };
-        uint32_t e0 = 0, e1 = 0;
-        int row0n = 0;
-        if (nAct > 0) {
-            e0 = list[0];
-            e1 = list[min(1, nAct - 1)];
-            row0n = gathered_row(e0);
-        }
+        int q = 0;                                            // ring items issued so far
         unsigned long long visited = 0;
-        for (int q = 0; q < nAct; q++) {
-            const int slot = q % STAGES;
-            const unsigned use = (unsigned)(q / STAGES);
-            const uint32_t e = e0;
-            const int row0 = row0n;
-            // prefetch for the next chunk (consumed one iteration from now)
-            e0 = e1;
-            row0n = gathered_row(e0);
-            e1 = list[min(q + 2, nAct - 1)];
-            mbar_wait(&s_empty[slot], (use & 1u) ^ 1u);          // first use of a slot passes immediately
-            ScoreStage& st = stages[slot];
-            const int k0 = (int)(e & 0xFFFFFFu) * KC;
-            const uint32_t rg = (e >> 24) & ((1u << NRG) - 1u);
-            if (lane == 0) {
-                s_meta[slot] = e;
-                const unsigned bytes = KC * BN * 8 + (GATHER ? KC * 8 : 0) + __popc(rg) * A_GROUP_DOUBLES * 8;
-                mbar_arrive_expect_tx(&s_full[slot], bytes);
-                visited += __popc(rg) * __popc(e >> 28);
+        auto fetch_tile = [&]() -> int { return lane == 0 ? atomicAdd(p.tileCounter, 1) : 0; };
+        struct Hdr { int nAct; uint2 e0, e1; };
+        auto slot_of = [&](int t) -> size_t {
+            const int zi = t / tilesPerZ, rem = t - zi * tilesPerZ;
+            const int z = p.zOrder ? p.zOrder[zi] : zi;
+            return ((size_t)(rem / p.nNt) * p.nZ + z) * p.nNt + (rem % p.nNt);
+        };
+        auto load_hdr = [&](int t) -> Hdr {
+            Hdr h{0, make_uint2(0u, 0u), make_uint2(0u, 0u)};
+            if (t < nTiles) {
+                const size_t listSlot = slot_of(t);
+                h.nAct = p.listCount[listSlot];
+                const uint2* l = p.lists + listSlot * p.nStages;
+                h.e0 = l[0];
+                h.e1 = l[1 < p.nStages ? 1 : 0];
             }
-            __syncwarp();
-            if (lane < KC) bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
-            if (lane >= KC && lane < KC + NRG && ((rg >> (lane - KC)) & 1u))
-                bulk_g2s(&st.As[(lane - KC) * A_GROUP_DOUBLES], atile + ((size_t)(k0 / KC) * NRG + (lane - KC)) * A_GROUP_DOUBLES,
-                         A_GROUP_DOUBLES * 8, &s_full[slot]);
-            if (GATHER && lane == KC + NRG) bulk_g2s(&st.Rs[0], rto + k0, KC * 8, &s_full[slot]);
+            return h;
+        };
+        int rawNext2 = fetch_tile();
+        int tCur = __shfl_sync(0xffffffffu, rawNext2, 0);
+        rawNext2 = fetch_tile();
+        Hdr hNext = load_hdr(tCur);
+        while (tCur < nTiles) {
+            const int t = tCur;
+            const Hdr h = hNext;
+            tCur = __shfl_sync(0xffffffffu, rawNext2, 0);     // requested one tile ago
+            rawNext2 = fetch_tile();
+            hNext = load_hdr(tCur);                           // consumed one tile from now
+            const int zi = t / tilesPerZ, rem = t - zi * tilesPerZ;
+            const int mt = rem / p.nNt, nt = rem % p.nNt;
+            const int z = p.zOrder ? p.zOrder[zi] : zi;
+            const int a = GATHER ? z / p.O : 0;
+            const double* __restrict__ bsrc = (GATHER ? p.bmat : p.bmat + (size_t)zi * p.zStrideB) + nt * BN;
+            const int32_t* __restrict__ reach = GATHER ? p.reachP + (size_t)a * p.Sp : nullptr;
+            const double* __restrict__ rto = GATHER ? p.rtoP + (size_t)z * p.Sp : nullptr;
+            const double* __restrict__ atile = p.beliefsP + (size_t)mt * p.nChunks * NRG * A_GROUP_DOUBLES;
+            const uint2* __restrict__ list = p.lists + slot_of(t) * p.nStages;
+            const int nAct = h.nAct;
+            auto gathered_row = [&](uint32_t stage) -> int {
+                const int k = (int)stage * SKC + (lane & (SKC - 1));
+                return GATHER ? reach[k] : min(k, p.S - 1);
+            };
+            uint2 e0 = h.e0, e1 = h.e1;
+            int row0n = nAct > 0 ? gathered_row(e0.x) : 0;
+            for (int c = 0; c < nAct; c++, q++) {
+                const int slot = q % STAGES;
+                const unsigned use = (unsigned)(q / STAGES);
+                const uint2 e = e0;
+                const int row0 = row0n;
+                // prefetch for the next stage (consumed one iteration from now)
+                e0 = e1;
+                row0n = c + 1 < nAct ? gathered_row(e0.x) : 0;
+                e1 = list[min(c + 2, nAct - 1)];
+                mbar_wait(&s_empty[slot], (use & 1u) ^ 1u);          // first use of a slot passes immediately
+                ScoreStage& st = stages[slot];
+                const int k0 = (int)e.x * SKC;
+                const uint32_t flags = e.y;
+                if (lane == 0) {
+                    s_meta[slot] = e;
+                    unsigned bytes = GATHER ? SKC * 8 : 0;
+                    unsigned work = 0;
+#pragma unroll
+                    for (int hh = 0; hh < SUB; hh++) {
+                        const unsigned rg = (flags >> (8 * hh)) & 0xFu, cq = (flags >> (8 * hh + 4)) & 0xFu;
+                        bytes += (rg ? KC * BN * 8 : 0) + __popc(rg) * A_GROUP_DOUBLES * 8;
+                        work += __popc(rg) * __popc(cq);
+                    }
+                    mbar_arrive_expect_tx(&s_full[slot], bytes);
+                    visited += work;
+                }
+                __syncwarp();
+                if (lane < SKC && ((flags >> (8 * (lane / KC))) & 0xFu))
+                    bulk_g2s(&st.Bs[lane * LDB], bsrc + (size_t)row0 * p.Vp, BN * 8, &s_full[slot]);
+                if (lane >= SKC && lane < SKC + SUB * NRG && ((flags >> (8 * ((lane - SKC) / NRG) + (lane - SKC) % NRG)) & 1u))
+                    bulk_g2s(&st.As[(lane - SKC) * A_GROUP_DOUBLES],
+                             atile + ((size_t)(k0 / KC + (lane - SKC) / NRG) * NRG + (lane - SKC) % NRG) * A_GROUP_DOUBLES, A_GROUP_DOUBLES * 8,
+                             &s_full[slot]);
+                if (GATHER && lane == 31) bulk_g2s(&st.Rs[0], rto + k0, SKC * 8, &s_full[slot]);
+            }
+            {   // TILE_END
+                const int slot = q % STAGES;
+                mbar_wait(&s_empty[slot], (((unsigned)(q / STAGES)) & 1u) ^ 1u);
+                if (lane == 0) {
+                    s_meta[slot] = make_uint2(META_TILE_END, (unsigned)t);
+                    mbar_arrive(&s_full[slot]);
+                }
+                __syncwarp();
+                q++;
+            }
+        }
+        {   // STOP
+            const int slot = q % STAGES;
+            mbar_wait(&s_empty[slot], (((unsigned)(q / STAGES)) & 1u) ^ 1u);
+            if (lane == 0) {
+                s_meta[slot] = make_uint2(META_STOP, 0u);
+                mbar_arrive(&s_full[slot]);
+            }
         }
         if (lane == 0 && p.stats && visited) atomicAdd(p.stats, visited);
     } else {
         // =============================== consumer warps ===============================
+        const int g = lane >> 2, t = lane & 3;
+        // Consumer warp w = 4 m + j sits on SM sub-partition j; it owns row group m and column quarter (j + m) % 4 -- a Latin
+        // square, so every sub-partition holds one warp of EACH row group and one of EACH column quarter: a skipped row group or
+        // a skipped column quarter takes the same share of work off all four FP64 pipes.
+        const int warp_m = warp / NCW, warp_n = (warp + warp_m) % NCW;
         double acc[MT][8][2];
 #pragma unroll
         for (int i = 0; i < MT; i++)
 #pragma unroll
             for (int n = 0; n < 8; n++) { acc[i][n][0] = 0.0; acc[i][n][1] = 0.0; }
 
-        for (int it = 0; it < nAct; it++) {
+        const int swz = a_swizzle(g);                 // == a_swizzle(i * 8 + g)
+        const int aOff = (warp_m * RG + g) * KC, bOff = t * LDB + warp_n * 64 + g;
+        for (int it = 0;; it++) {
             const int slot = it % STAGES;
             mbar_wait(&s_full[slot], (unsigned)(it / STAGES) & 1u);
             const ScoreStage& st = stages[slot];
-            const uint32_t meta = s_meta[slot];
-            if (((meta >> (24 + warp_m)) & 1u) && ((meta >> (28 + warp_n)) & 1u)) {
-                const double* Ab = st.As + (warp_m * RG + g) * KC;
-                const double* Bb = st.Bs + t * LDB + warp_n * 64 + g;
-                const int swz = a_swizzle(g);                 // == a_swizzle(i * 8 + g)
+            const uint2 meta = s_meta[slot];
+            if (meta.x >= META_STOP) {
+                if (meta.x == META_STOP) break;
+                // ---- TILE_END: fused argmax of this warp's block (ascending columns per thread, then the quad, which holds disjoint
+                //      columns of the same rows).  A tile without live chunks leaves acc == 0: every score is 0, first column wins.
+                const int tile = (int)meta.y;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[slot]);
+                const int zi = tile / tilesPerZ, rem = tile - zi * tilesPerZ;
+                const int mt = rem / p.nNt, nt = rem % p.nNt;
+                const int z = p.zOrder ? p.zOrder[zi] : zi;
+                const int cbase = nt * BN + warp_n * 64 + 2 * t;
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    double best = -INFINITY;
+                    int bidx = 0x7fffffff;
+#pragma unroll
+                    for (int n = 0; n < 8; n++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int col = cbase + n * 8 + j;
+                            const double v = acc[i][n][j];
+                            if (col < p.V && v > best) { best = v; bidx = col; }
+                            acc[i][n][j] = 0.0;
+                        }
+#pragma unroll
+                    for (int off = 1; off <= 2; off <<= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+                        argmax_combine(best, bidx, ov, oi);
+                    }
+                    const int row = mt * BM + warp_m * RG + i * 8 + g;
+                    if (t == 0 && row < p.nB) {
+                        const size_t out = ((size_t)(nt * NCW + warp_n) * p.nB + row) * p.nZ + z;
+                        p.pval[out] = best;
+                        p.pidx[out] = bidx;
+                    }
+                }
+                continue;
+            }
+#pragma unroll
+            for (int hh = 0; hh < SUB; hh++) {
+                if (!(((meta.y >> (8 * hh + warp_m)) & 1u) && ((meta.y >> (8 * hh + 4 + warp_n)) & 1u))) continue;
 #pragma unroll
                 for (int ks = 0; ks < KC / 4; ks++) {
                     double af[MT], bf[8];
 #pragma unroll
-                    for (int i = 0; i < MT; i++) af[i] = Ab[i * 8 * KC + ((ks * 4 + t) ^ swz)];
+                    for (int i = 0; i < MT; i++) af[i] = st.As[hh * BM * KC + aOff + i * 8 * KC + ((ks * 4 + t) ^ swz)];
                     if (GATHER) {
-                        const double r = st.Rs[ks * 4 + t];
+                        const double r = st.Rs[hh * KC + ks * 4 + t];
 #pragma unroll
                         for (int i = 0; i < MT; i++) af[i] *= r;
                     }
 #pragma unroll
-                    for (int n = 0; n < 8; n++) bf[n] = Bb[ks * 4 * LDB + n * 8];
+                    for (int n = 0; n < 8; n++) bf[n] = st.Bs[bOff + (hh * KC + ks * 4) * LDB + n * 8];
 #pragma unroll
                     for (int i = 0; i < MT; i++)
 #pragma unroll
@@ -236,52 +338,6 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[slot]);
         }
-
-        // ---- fused argmax, part 1: ascending columns per thread, then the quad (disjoint columns of the same rows).
-        //      An empty list leaves acc == 0: every score is 0, first column wins.
-        const int cbase = n0 + warp_n * 64 + 2 * t;
-#pragma unroll
-        for (int i = 0; i < MT; i++) {
-            best[i] = -INFINITY;
-            bidx[i] = 0x7fffffff;
-#pragma unroll
-            for (int n = 0; n < 8; n++)
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const int col = cbase + n * 8 + j;
-                    const double v = acc[i][n][j];
-                    if (col < p.V && v > best[i]) { best[i] = v; bidx[i] = col; }
-                }
-#pragma unroll
-            for (int off = 1; off <= 2; off <<= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best[i], off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], off);
-                argmax_combine(best[i], bidx[i], ov, oi);
-            }
-        }
-    }
-
-    // ---- fused argmax, part 2: the column warps through shared memory (every stage has been consumed by now)
-    __syncthreads();
-    double* sval = reinterpret_cast<double*>(smem_raw);                           // [NCW][BM]
-    int* sidx = reinterpret_cast<int*>(smem_raw + sizeof(double) * NCW * BM);     // [NCW][BM]
-    if (warp < N_CONSUMER_WARPS && t == 0) {
-#pragma unroll
-        for (int i = 0; i < MT; i++) {
-            const int row = warp_m * RG + i * 8 + g;
-            sval[warp_n * BM + row] = best[i];
-            sidx[warp_n * BM + row] = bidx[i];
-        }
-    }
-    __syncthreads();
-    if (tid < BM && m0 + tid < p.nB) {
-        double v = sval[tid];
-        int i = sidx[tid];
-#pragma unroll
-        for (int w = 1; w < NCW; w++) argmax_combine(v, i, sval[w * BM + tid], sidx[w * BM + tid]);
-        const size_t out = ((size_t)nt * p.nB + (m0 + tid)) * p.nZ + z;
-        p.pval[out] = v;
-        p.pidx[out] = i;
     }
 }
 
