@@ -137,6 +137,16 @@ PBVI_API int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int32_
 PBVI_API int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first,
                     int32_t* d_last, int32_t* d_inverse, int* h_count, void* stream);
 
+/* pbvi_group_record_blocks: the merge step of the sharded backup's tuple exchange (all-gather of each rank's new alpha vectors,
+ * in generating-tuple form).  d_blocks is the gathered buffer: `world` blocks of block_rows rows of (words + 2) int32; row 0 of a
+ * block is its header (word 0 = number of records u_r of rank r), rows 1..u_r are records (key[words], first position, last
+ * position).  Records are grouped by key in buffer order (rank-major = belief order), like one dict over the whole belief set:
+ * d_first[g] = row of the group's first record, d_last[g] = row of its record with the largest last position (rows index the
+ * whole buffer; outputs have room for world*block_rows entries).  *h_count = number of groups, *h_max_records = max_r u_r
+ * (a value above block_rows - 1 means a rank overflowed its block: repeat the exchange with larger blocks).  Synchronises. */
+PBVI_API int pbvi_group_record_blocks(pbvi_model* m, const int32_t* d_blocks, int world, int block_rows, int words, int32_t* d_first,
+                             int32_t* d_last, int* h_count, int* h_max_records, void* stream);
+
 /* pbvi_confirm_groups: *h_all_equal = 1 iff every row equals, bytewise, the first row of its group (d_first, d_inverse from
  * pbvi_group_keys over the rows' 128-bit keys): makes the key-based dedup exact.  Synchronises `stream`. */
 PBVI_API int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first,

@@ -39,6 +39,7 @@ SIGNATURES = {
     'pbvi_row_hash': [_P, _P, c_int, c_int, _P, _P],
     'pbvi_rows_equal': [_P, _P, _P, _P, _P, c_int, c_int, _P, _P],
     'pbvi_group_keys': [_P, _P, c_int, c_int, _P, _P, _P, _P, POINTER(c_int), _P],
+    'pbvi_group_record_blocks': [_P, _P, c_int, c_int, c_int, _P, _P, POINTER(c_int), POINTER(c_int), _P],
     'pbvi_confirm_groups': [_P, _P, c_int, c_int, _P, _P, POINTER(c_int), _P],
     'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
@@ -294,6 +295,22 @@ class DeviceModel:
         self._call(self._lib.pbvi_group_keys(self._h, _ptr(k), n, words, _ptr(r), _ptr(first), _ptr(last), _ptr(inverse), byref(count),
                                              self._stream))
         return first[:count.value], last[:count.value], inverse
+
+    def group_record_blocks(self, blocks: torch.Tensor, world: int, block_rows: int, words: int):
+        """
+        Merge of the all-gathered tuple blocks of a sharded backup (`parallel.exchange_tuples`): `blocks` is the int32 CUDA buffer
+        [world * block_rows, words + 2]; returns (first_rows [g], last_rows [g], max_records) -- rows of the buffer holding the
+        first record of every distinct key (ascending) and the record with the largest last position, and the largest record
+        count any rank announced in its header.
+        """
+        assert blocks.dtype == torch.int32 and blocks.is_contiguous() and tuple(blocks.shape) == (world * block_rows, words + 2)
+        n = world * block_rows
+        first = torch.empty((n,), dtype=torch.int32, device=self.device)
+        last = torch.empty((n,), dtype=torch.int32, device=self.device)
+        count, mx = c_int(), c_int()
+        self._call(self._lib.pbvi_group_record_blocks(self._h, _ptr(blocks), world, block_rows, words, _ptr(first), _ptr(last), byref(count),
+                                                      byref(mx), self._stream))
+        return first[:count.value], last[:count.value], mx.value
 
     def confirm_groups(self, rows: torch.Tensor, first: torch.Tensor, inverse: torch.Tensor) -> bool:
         """True iff every row is bytewise equal to the first row of its group (exactness check of a key-based dedup)."""

@@ -89,6 +89,40 @@ __global__ void __launch_bounds__(256) group_insert_kernel(const uint32_t* __res
     atomicMax(glast + h, ((unsigned long long)(uint32_t)(rank ? rank[i] : i) << 32) | (unsigned long long)(uint32_t)i);
 }
 
+// The same insertion over the all-gathered blocks of the sharded backup's tuple exchange: `world` blocks of blockRows rows of
+// (w + 2) int32 words; row 0 of a block is its header (word 0 = number of records u_r), rows 1..u_r are records
+// (key[w], first position, last position).  The record index is the row index in the whole buffer (rank-major = belief order);
+// the rank of a record for `last` is its last-position word.  maxCount receives max_r u_r (overflow check of the caller).
+__global__ void __launch_bounds__(256) group_insert_blocks_kernel(const int32_t* __restrict__ blocks, int world, int blockRows, int w, int T,
+                                                                  int32_t* rep, int32_t* __restrict__ gfirst,
+                                                                  unsigned long long* __restrict__ glast, int32_t* __restrict__ slotOf,
+                                                                  int32_t* __restrict__ maxCount) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= world * blockRows) return;
+    const int stride = w + 2;
+    const int r = i / blockRows, j = i - r * blockRows;
+    const int count = blocks[(size_t)r * blockRows * stride];
+    if (j == 0) atomicMax(maxCount, count);
+    if (j == 0 || j > count) { slotOf[i] = -1; return; }
+    const uint32_t* k = reinterpret_cast<const uint32_t*>(blocks) + (size_t)i * stride;
+    uint32_t h = key_hash(k, w) & (uint32_t)(T - 1);
+    for (;;) {
+        int cur = *reinterpret_cast<volatile int32_t*>(rep + h);
+        if (cur == -1) {
+            cur = atomicCAS(rep + h, -1, i);
+            if (cur == -1) break;
+        }
+        const uint32_t* kc = reinterpret_cast<const uint32_t*>(blocks) + (size_t)cur * stride;
+        bool eq = true;
+        for (int x = 0; x < w; x++) eq &= (kc[x] == k[x]);
+        if (eq) break;
+        h = (h + 1) & (uint32_t)(T - 1);
+    }
+    slotOf[i] = (int32_t)h;
+    atomicMin(gfirst + h, i);
+    atomicMax(glast + h, ((unsigned long long)k[w + 1] << 32) | (unsigned long long)(uint32_t)i);
+}
+
 // one block: stream compaction of the group-first records in ascending index order (tiles of 1024, ballot scan)
 __global__ void __launch_bounds__(1024) group_compact_kernel(const int32_t* __restrict__ slotOf, const int32_t* __restrict__ gfirst,
                                                              const unsigned long long* __restrict__ glast, int n,
@@ -105,7 +139,7 @@ __global__ void __launch_bounds__(1024) group_compact_kernel(const int32_t* __re
         bool isFirst = false;
         if (i < n) {
             slot = slotOf[i];
-            isFirst = gfirst[slot] == i;
+            isFirst = slot >= 0 && gfirst[slot] == i;       // slot < 0: not a record (header / padding row of a gathered block)
         }
         const unsigned bal = __ballot_sync(0xffffffffu, isFirst);
         if (lane == 0) warpCount[w] = __popc(bal);
@@ -374,6 +408,38 @@ extern "C" int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int
     PBVI_CUDA(cudaMemcpyAsync(&c, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));
     *h_count = (int)c;
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_group_record_blocks(pbvi_model* m, const int32_t* d_blocks, int world, int block_rows, int words, int32_t* d_first,
+                                       int32_t* d_last, int* h_count, int* h_max_records, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(world > 0 && block_rows > 1 && words > 0 && h_count && h_max_records, "need world > 0 blocks of more than one row");
+    PBVI_REQUIRE(d_blocks && d_first && d_last, "NULL pointer argument");
+    const long long n = (long long)world * block_rows;
+    PBVI_REQUIRE(n <= (1 << 29), "too many records");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int T = 64;
+    while (T < 2 * n) T <<= 1;
+    m->arena.reset();
+    PBVI_TAKE(rep, int32_t, (size_t)T);
+    PBVI_TAKE(gfirst, int32_t, (size_t)T);
+    PBVI_TAKE(glast, unsigned long long, (size_t)T);
+    PBVI_TAKE(slotOf, int32_t, (size_t)n);
+    PBVI_TAKE(groupOfSlot, int32_t, (size_t)T);
+    PBVI_TAKE(count, int32_t, 2);
+    PBVI_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st));
+    group_init_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, glast, T);
+    group_insert_blocks_kernel<<<ceil_div((int)n, 256), 256, 0, st>>>(d_blocks, world, block_rows, words, T, rep, gfirst, glast, slotOf, count + 1);
+    group_compact_kernel<<<1, 1024, 0, st>>>(slotOf, gfirst, glast, (int)n, groupOfSlot, d_first, d_last, count);
+    m->last_launches = 3;
+    PBVI_CUDA(cudaGetLastError());
+    int32_t c[2] = {0, 0};
+    PBVI_CUDA(cudaMemcpyAsync(c, count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    *h_count = (int)c[0];
+    *h_max_records = (int)c[1];
     return PBVI_OK;
 }
 

@@ -100,79 +100,74 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
 _LAST_MAX_COUNT = [512]
 
 
-def group_records_host(keys: torch.Tensor, rank: torch.Tensor):
+def merge_blocks_host(blocks: torch.Tensor, world: int, block_rows: int, words: int):
     """
-    `DeviceModel.group_keys` for records held in CPU tensors: (first [g], last [g], None), groups in order of first occurrence,
-    `last` = the record with the largest (rank, index).  Host logic only -- used where the exchange runs over gloo on CPU
-    (tests/test_parallel_gloo.py); on a GPU the records never leave the device (`pbvi_group_keys`).
+    `DeviceModel.group_record_blocks` for a gathered buffer held in a CPU tensor: (first_rows [g], last_rows [g], max_records).
+    Host logic only -- used where the exchange runs over gloo on CPU (tests/test_parallel_gloo.py); on a GPU the records never
+    leave the device (`pbvi_group_record_blocks`).
     """
-    k = keys.numpy().astype(np.int64)
-    n = k.shape[0]
-    first, _, inv = unique_rows_first(k)
-    order = np.lexsort((np.arange(n), rank.numpy(), inv))
+    b = blocks.numpy().reshape(world, block_rows, words + 2).astype(np.int64)
+    counts = b[:, 0, 0]
+    rows = np.concatenate([r * block_rows + 1 + np.arange(min(int(counts[r]), block_rows - 1)) for r in range(world)])
+    if rows.shape[0] == 0:
+        z = torch.zeros((0,), dtype=torch.int64)
+        return z, z, int(counts.max())
+    recs = b.reshape(-1, words + 2)[rows]
+    first, _, inv = unique_rows_first(recs[:, :words])
+    n = recs.shape[0]
+    order = np.lexsort((np.arange(n), recs[:, words + 1], inv))          # per group: ascending (last position, index)
     ends = np.append(np.flatnonzero(np.diff(inv[order])), n - 1)
     last = np.empty(first.shape[0], dtype=np.int64)
     last[inv[order[ends]]] = order[ends]
-    return torch.from_numpy(first), torch.from_numpy(last), None
+    return torch.from_numpy(rows[first]), torch.from_numpy(rows[last]), int(counts.max())
 
 
-def exchange_tuples(tuples, first, last, n_local_beliefs: int, capacity: int, device, group=None, group_fn=None):
+def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merge_fn=None):
     """
     The exchange step of the sharded backup in its compact form.  An alpha row of the backup is a deterministic function of
     its generating tuple (a*, v*[a*, :]) and of the replicated (model, old value function), so the ranks all-gather the
     distinct TUPLES of their shards (4*(1+O) bytes each instead of 8*S per row) together with the positions of the first / last
     belief that chose them, and every rank then assembles the merged set itself (`PBVI_Solver.rows_from_tuples`) -- bitwise the
     same rows on every rank, in the order a single process would produce.  One collective: block r of the gathered int32 buffer
-    is [header (u_r, n_r); u_r records (tuple, first, last)], padded to `capacity` records.  The records stay on `device`: only
-    the per-rank headers are read by the host, the merge is `group_fn` (the device's `group_keys`; host twin for CPU tensors).
-    Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set as tensors on `device`, positions in the rank-ordered
-    concatenation of the shards.
+    is [header (u_r); u_r records (tuple, first, last)], padded to a common number of rows.  Positions travel globalised as
+    rank * capacity + local position (`capacity` = the largest shard size, the same on every rank): that is the position in the
+    whole belief set when the shards are the contiguous blocks of `shard_bounds`, and order-preserving in any case.  The
+    records stay on `device`; the merge is `merge_fn` (the device's `group_record_blocks`; host twin for CPU tensors), which
+    also returns the largest record count of any rank.
+    Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set as int32 tensors on `device`.
     """
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     device = torch.device(device)
     tuples = torch.as_tensor(tuples).to(device=device, dtype=torch.int32)
     first = torch.as_tensor(first).to(device=device, dtype=torch.int32)
     last = torch.as_tensor(last).to(device=device, dtype=torch.int32)
-    if group_fn is None:
-        assert device.type == 'cpu', 'pass the device grouping (DeviceModel.group_keys) for records in device memory'
-        group_fn = group_records_host
+    if merge_fn is None:
+        assert device.type == 'cpu', 'pass the device merge (DeviceModel.group_record_blocks) for records in device memory'
+        merge_fn = merge_blocks_host
     u, w = tuples.shape
     assert u <= capacity, (u, capacity)
+    assert capacity * world < 2 ** 31
+    offset = rank * capacity
     # Most beliefs share their tuple with others, so the blocks are first sized by a guess (twice the largest count seen in the
     # previous exchange); the header carries the true count, and if any rank overflowed -- every rank sees that in the gathered
     # headers, so the decision is consistent -- the exchange is repeated once at full capacity.
     guess = min(capacity, max(256, 2 * _LAST_MAX_COUNT[0]))
     while True:
         k = min(u, guess)
-        buf = torch.zeros((guess + 1, w + 2), dtype=torch.int32, device=device)
-        buf[0, :2] = torch.tensor([u, n_local_beliefs], dtype=torch.int32)
+        buf = torch.empty((guess + 1, w + 2), dtype=torch.int32, device=device)
+        buf[0].fill_(u)
         buf[1:k + 1, :w] = tuples[:k]
-        buf[1:k + 1, w] = first[:k]
-        buf[1:k + 1, w + 1] = last[:k]
+        buf[1:k + 1, w] = first[:k] + offset
+        buf[1:k + 1, w + 1] = last[:k] + offset
         gathered = torch.empty((world * (guess + 1), w + 2), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(gathered, buf, group=group)
-        hdr = gathered.view(world, guess + 1, w + 2)[:, 0, :2].cpu().numpy().astype(np.int64)
-        _LAST_MAX_COUNT[0] = int(hdr[:, 0].max())
-        if _LAST_MAX_COUNT[0] <= guess:
+        first_rows, last_rows, max_count = merge_fn(gathered, world, guess + 1, w)
+        _LAST_MAX_COUNT[0] = max_count
+        if max_count <= guess:
             break
         guess = capacity
-    counts, n_beliefs = hdr[:, 0], hdr[:, 1]
-    total = int(counts.sum())
-    if total == 0:
-        z = torch.zeros((0,), dtype=torch.int32, device=device)
-        return torch.zeros((0, w), dtype=torch.int32, device=device), z, z
-    offsets = np.concatenate([[0], np.cumsum(n_beliefs)])
-    # rows of the valid records in the gathered buffer and the position offset of their shard
-    idx = np.concatenate([r * (guess + 1) + 1 + np.arange(counts[r]) for r in range(world)])
-    meta = torch.from_numpy(np.stack([idx, np.repeat(offsets[:-1], counts)])).to(device)
-    recs = gathered[meta[0]]
-    off = meta[1].to(torch.int32)
-    keys = recs[:, :w].contiguous()
-    pos_first, pos_last = recs[:, w] + off, recs[:, w + 1] + off
-    # records are rank-major and ascending in `first` inside a rank, so the first record of a group carries its smallest
-    # position; its largest position is the largest `last` of the group
-    gf, gl, _ = group_fn(keys, pos_last)
-    return keys[gf.long()], pos_first[gf.long()], pos_last[gl.long()]
+    fr = first_rows.long()
+    return gathered[fr, :w], gathered[fr, w], gathered[last_rows.long(), w + 1]
 
 
 class _PhaseTimer:
@@ -223,8 +218,8 @@ class ShardedBackup:
             tuples, first, last = self.solver.select_tuples_device(self.model, local_belief_set, value_function, belief_dominance_prune)
             if t: t.mark('local select')
             n_local = len(local_belief_set)
-            g_tuples, _, g_last = exchange_tuples(tuples, first, last, n_local, self._capacity(n_local), dev.device, self.group,
-                                                  group_fn=dev.group_keys)
+            g_tuples, _, g_last = exchange_tuples(tuples, first, last, self._capacity(n_local), dev.device, self.group,
+                                                  merge_fn=dev.group_record_blocks)
             self.last_payload_bytes = (min(self._cap[1], max(256, 2 * _LAST_MAX_COUNT[0])) + 1) * (tuples.shape[1] + 2) * 4 * self.world
             if t: t.mark('exchange')
             merged = self.solver.rows_from_tuples(self.model, value_function, g_tuples, g_last)

@@ -387,3 +387,38 @@ def test_confirm_groups_and_backup_dedup(torch_cuda):
     bad[20] = bad[2]                                            # a forged key match between different rows
     first_b, _, inv_b = dev.group_keys(bad, want_inverse=True)
     assert first_b.shape[0] == 26 and not dev.confirm_groups(t, first_b, inv_b)
+
+
+@pytest.mark.parametrize('world,block_rows,width', [(1, 5, 3), (2, 40, 4), (8, 257, 4), (3, 9, 1)])
+def test_group_record_blocks_equals_host_merge(torch_cuda, world, block_rows, width):
+    """`pbvi_group_record_blocks` (merge of the all-gathered tuple blocks of a sharded backup) == the host twin used by the gloo
+    tests: ragged record counts per rank (including an empty and an overflowing block), duplicate tuples across ranks."""
+    from pomdp_pbvi_exploration_b200.parallel import merge_blocks_host
+    torch = torch_cuda
+    dev, m, reach, _ = device_model('tiger')
+    rng = np.random.default_rng(world * 100 + block_rows)
+    pool = rng.integers(0, 50, (max(3, block_rows // 2), width))
+    blocks = rng.integers(0, 1000, (world, block_rows, width + 2)).astype(np.int32)     # padding rows hold garbage
+    pos = 0
+    for r in range(world):
+        u = int(rng.integers(0, block_rows)) if r else block_rows - 1
+        if r == 1:
+            u = 0
+        blocks[r, 0, :] = u
+        pick = rng.choice(pool.shape[0], min(u, pool.shape[0]), replace=False)
+        u = pick.shape[0]
+        blocks[r, 0, :] = u
+        blocks[r, 1:1 + u, :width] = pool[pick]
+        firsts = pos + np.sort(rng.choice(10 * block_rows, u, replace=False))
+        blocks[r, 1:1 + u, width] = firsts
+        blocks[r, 1:1 + u, width + 1] = firsts + rng.integers(0, 5, u)
+        pos += 10 * block_rows + 5
+    flat = torch.as_tensor(blocks.reshape(world * block_rows, width + 2))
+    want_first, want_last, want_max = merge_blocks_host(flat, world, block_rows, width)
+    first, last, mx = dev.group_record_blocks(flat.cuda(), world, block_rows, width)
+    assert mx == want_max
+    assert np.array_equal(first.cpu().numpy(), want_first.numpy()) and np.array_equal(last.cpu().numpy(), want_last.numpy())
+    # an overflowing header is reported, not silently truncated
+    blocks[0, 0, :] = block_rows + 3
+    _, _, mx2 = dev.group_record_blocks(torch.as_tensor(blocks.reshape(world * block_rows, width + 2)).cuda(), world, block_rows, width)
+    assert mx2 == block_rows + 3

@@ -84,7 +84,7 @@ def _tuple_worker(rank, world, port, keys_all, result_queue):
     local = keys_all[lo:hi]
     first, last, _ = unique_rows_first(local)
     cap = -(-keys_all.shape[0] // world)
-    g_tuples, g_first, g_last = exchange_tuples(local[first], first, last, hi - lo, cap, torch.device('cpu'))
+    g_tuples, g_first, g_last = exchange_tuples(local[first], first, last, cap, torch.device('cpu'))
     result_queue.put((rank, g_tuples.numpy(), g_first.numpy(), g_last.numpy()))
     dist.barrier()
     dist.destroy_process_group()
