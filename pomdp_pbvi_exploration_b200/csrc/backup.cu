@@ -387,8 +387,9 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
         out[(size_t)i * S + s] = v;
         if (hacc) {
             const uint64_t w = (uint64_t)__double_as_longlong(v);
-            h0 = row_hash_term0(w, s);
-            h1 = row_hash_term1(w, s);
+            const uint4 k = row_key_words(s);
+            h0 = row_hash_term0(w, k);
+            h1 = row_hash_term1(w, k);
         }
     }
     if (!hacc) return;
@@ -409,8 +410,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
     }
 }
 
-// ---- order[] = tuple indices grouped by action (counting sort in one block; the order inside an action is irrelevant)
-__global__ void __launch_bounds__(256) action_order_kernel(const int32_t* __restrict__ actions, int n, int A, int32_t* __restrict__ order) {
+// ---- order[] = tuple indices grouped by action, every group padded with -1 to a multiple of G (so that a block of the grouped
+//      assemble kernel sees one action only); counting sort in one block, the order inside an action is irrelevant.
+//      order has room for n + A * (G - 1) entries and is pre-filled with -1.
+__global__ void __launch_bounds__(256) action_order_kernel(const int32_t* __restrict__ actions, int n, int A, int G, int32_t* __restrict__ order) {
     extern __shared__ int s_cnt[];     // [A] counts, then running bases
     for (int a = threadIdx.x; a < A; a += 256) s_cnt[a] = 0;
     __syncthreads();
@@ -418,73 +421,85 @@ __global__ void __launch_bounds__(256) action_order_kernel(const int32_t* __rest
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int a = 0; a < A; a++) { const int c = s_cnt[a]; s_cnt[a] = run; run += c; }
+        for (int a = 0; a < A; a++) { const int c = s_cnt[a]; s_cnt[a] = run; run += (c + G - 1) / G * G; }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += 256) order[atomicAdd(&s_cnt[actions[i]], 1)] = i;
 }
 
-// ---- assemble for reachable_state_count == 1 and O <= OM: a block writes the same 256-state slice of G tuples that share
-//      (mostly) one action, so reach / RTO / Rbar of the slice are read once per action instead of once per tuple; what is
-//      left per element is the O gathered alpha values and the store.  Same arithmetic as alpha_a_entry (bit-identical rows).
-template <int G, int OM>
+// ---- assemble for reachable_state_count == 1 and O <= OM: a block writes the same SPT*256-state slice of G tuples of ONE
+//      action, so reach / RTO / Rbar of the slice are read once per block instead of once per tuple; what is left per element
+//      is the O gathered alpha values, the two hash terms and the store.  The gathers of tuple g+1 are issued before the
+//      arithmetic of tuple g (the loop is otherwise one exposed memory latency per tuple).  A thread owns SPT states (256 apart:
+//      coalesced), which amortises the per-tuple reduction of the 128-bit key; the warp partials of all G tuples meet in shared
+//      memory once, at the end.  Same arithmetic as alpha_a_entry (bit-identical rows).
+template <int G, int OM, int SPT>
 __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __restrict__ alphas, const int32_t* __restrict__ actions,
-                                                               const int32_t* __restrict__ vsel, const int32_t* __restrict__ order, int n,
+                                                               const int32_t* __restrict__ vsel, const int32_t* __restrict__ order,
                                                                const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                                const double* __restrict__ rbarT, double gamma, int S, int O,
                                                                double* __restrict__ out, unsigned long long* __restrict__ hacc,
-                                                               const int* __restrict__ nonfinite) {
-    __shared__ int s_idx[G], s_act[G], s_v[G][OM];
-    __shared__ unsigned long long sh[2][8];
+                                                               const uint4* __restrict__ hashKeys, const int* __restrict__ nonfinite) {
+    __shared__ int s_idx[G], s_v[G][OM];
+    __shared__ unsigned long long sh[G][8][2];
     const int slot0 = blockIdx.y * G;
-    if (threadIdx.x < G) {
-        const int j = slot0 + threadIdx.x;
-        const int idx = j < n ? order[j] : -1;
-        s_idx[threadIdx.x] = idx;
-        s_act[threadIdx.x] = idx >= 0 ? actions[idx] : -1;
-    }
+    if (threadIdx.x < G) s_idx[threadIdx.x] = order[slot0 + threadIdx.x];
     __syncthreads();
+    if (s_idx[0] < 0) return;                        // padding block (uniform)
     if (threadIdx.x < G * OM) {
         const int g = threadIdx.x / OM, o = threadIdx.x % OM;
         s_v[g][o] = (s_idx[g] >= 0 && o < O) ? vsel[(size_t)s_idx[g] * O + o] : 0;
     }
+    const int a = actions[s_idx[0]];
     __syncthreads();
-    const int s = blockIdx.x * 256 + threadIdx.x;
-    const bool valid = s < S;
+    const int sBase = blockIdx.x * (SPT * 256) + threadIdx.x;
     const bool skipZero = !*nonfinite;              // finite alphas: a zero RTO factor makes the term +-0.0 (see alpha_a_entry)
-    bool skip = false;
-    int prevA = -1, landing = 0;
-    double rb = 0.0, rto[OM];
+    bool need[SPT][OM], live[SPT];
+    int landing[SPT];
+    double rb[SPT], rto[SPT][OM];
+    uint4 hk[SPT];
 #pragma unroll
-    for (int o = 0; o < OM; o++) rto[o] = 0.0;
-    for (int g = 0; g < G; g++) {
+    for (int j = 0; j < SPT; j++) {
+        const int s = sBase + j * 256;
+        live[j] = s < S;
+        landing[j] = live[j] ? reachK[(size_t)a * S + s] : 0;
+        rb[j] = live[j] ? rbarT[(size_t)a * S + s] : 0.0;
+        hk[j] = (hacc && live[j]) ? hashKeys[s] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int o = 0; o < OM; o++) rto[j][o] = (live[j] && o < O) ? rtoK[((size_t)a * O + o) * S + s] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < SPT; j++) {
+        const bool skip = skipZero && !(rb[j] == 0.0 && signbit(rb[j]));
+#pragma unroll
+        for (int o = 0; o < OM; o++) need[j][o] = live[j] && o < O && !(skip && rto[j][o] == 0.0);
+    }
+    auto gather = [&](int g, double (&av)[SPT][OM]) {
+#pragma unroll
+        for (int j = 0; j < SPT; j++)
+#pragma unroll
+            for (int o = 0; o < OM; o++) av[j][o] = need[j][o] ? alphas[(size_t)s_v[g][o] * S + landing[j]] : 0.0;
+    };
+    auto finish = [&](int g, const double (&av)[SPT][OM]) {
         const int idx = s_idx[g];
-        if (idx < 0) break;
-        const int a = s_act[g];
-        if (a != prevA && valid) {
-            landing = reachK[(size_t)a * S + s];
-            rb = rbarT[(size_t)a * S + s];
-            skip = skipZero && !(rb == 0.0 && signbit(rb));
-#pragma unroll
-            for (int o = 0; o < OM; o++)
-                if (o < O) rto[o] = rtoK[((size_t)a * O + o) * S + s];
-        }
-        prevA = a;
         unsigned long long h0 = 0, h1 = 0;
-        if (valid) {
-            double tot = 0.0;
 #pragma unroll
-            for (int o = 0; o < OM; o++)
-                if (o < O) {
-                    const double term = (skip && rto[o] == 0.0) ? 0.0 : __dmul_rn(gamma, __dmul_rn(rto[o], alphas[(size_t)s_v[g][o] * S + landing]));
-                    tot = (o == 0) ? term : __dadd_rn(tot, term);
+        for (int j = 0; j < SPT; j++) {
+            if (live[j]) {
+                double tot = 0.0;
+#pragma unroll
+                for (int o = 0; o < OM; o++)
+                    if (o < O) {
+                        const double term = need[j][o] ? __dmul_rn(gamma, __dmul_rn(rto[j][o], av[j][o])) : 0.0;
+                        tot = (o == 0) ? term : __dadd_rn(tot, term);
+                    }
+                const double v = __dadd_rn(rb[j], tot);
+                out[(size_t)idx * S + sBase + j * 256] = v;
+                if (hacc) {
+                    const uint64_t w = (uint64_t)__double_as_longlong(v);
+                    h0 += row_hash_term0(w, hk[j]);
+                    h1 += row_hash_term1(w, hk[j]);
                 }
-            const double v = __dadd_rn(rb, tot);
-            out[(size_t)idx * S + s] = v;
-            if (hacc) {
-                const uint64_t w = (uint64_t)__double_as_longlong(v);
-                h0 = row_hash_term0(w, s);
-                h1 = row_hash_term1(w, s);
             }
         }
         if (hacc) {
@@ -493,18 +508,42 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
                 h0 += __shfl_down_sync(0xffffffffu, h0, off);
                 h1 += __shfl_down_sync(0xffffffffu, h1, off);
             }
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = h0; sh[1][threadIdx.x >> 5] = h1; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long x = 0, y = 0;
+            if ((threadIdx.x & 31) == 0) { sh[g][threadIdx.x >> 5][0] = h0; sh[g][threadIdx.x >> 5][1] = h1; }
+        }
+    };
+    static_assert(G % 2 == 0, "the tuple loop is unrolled in pairs (two gather buffers)");
+    double avA[SPT][OM], avB[SPT][OM];
+    gather(0, avA);
 #pragma unroll
-                for (int w = 0; w < 8; w++) { x += sh[0][w]; y += sh[1][w]; }
-                atomicAdd(&hacc[(size_t)idx * 2], x);
-                atomicAdd(&hacc[(size_t)idx * 2 + 1], y);
-            }
+    for (int g = 0; g < G; g += 2) {
+        const bool has1 = s_idx[g + 1] >= 0;                               // uniform over the block
+        if (has1) gather(g + 1, avB);
+        finish(g, avA);
+        if (!has1) break;
+        const bool has2 = g + 2 < G && s_idx[g + 2 < G ? g + 2 : 0] >= 0;
+        if (has2) gather(g + 2, avA);
+        finish(g + 1, avB);
+        if (!has2) break;
+    }
+    if (!hacc) return;
+    __syncthreads();
+    if (threadIdx.x < G * 2) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const int idx = s_idx[g];
+        if (idx >= 0) {
+            unsigned long long x = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) x += sh[g][w][which];
+            atomicAdd(&hacc[(size_t)idx * 2 + which], x);
         }
     }
+}
+
+template <int G, int OM, int SPT>
+static void launch_assemble_grouped(pbvi_model* m, const double* d_alphas, const int32_t* d_actions, const int32_t* d_vsel, const int32_t* order,
+                                    int nPad, double gamma, double* d_out, unsigned long long* hacc, const int* nonfinite, cudaStream_t st) {
+    assemble_grouped_kernel<G, OM, SPT><<<dim3(ceil_div(m->S, SPT * 256), nPad / G), 256, 0, st>>>(
+        d_alphas, d_actions, d_vsel, order, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, m->hashKeys, nonfinite);
 }
 
 __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* __restrict__ h, int n, int rowLen) {
@@ -673,13 +712,16 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
     PBVI_CUDA(cudaMemsetAsync(nonfinite, gammaBad, sizeof(int), st));
     nonfinite_scan_kernel<<<m->sm_count * 8, 256, 0, st>>>(d_alphas, (size_t)nV * m->S, nonfinite);
     m->last_launches++;
-    constexpr int G = 8, OM = 4;
-    if (m->R == 1 && m->O <= OM && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024) {
+    constexpr int G = 8, SPT = 2;
+    if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024) {
         m->arena.reset();
-        PBVI_TAKE(order, int32_t, (size_t)n);
-        action_order_kernel<<<1, 256, m->A * sizeof(int), st>>>(d_actions, n, m->A, order);
-        assemble_grouped_kernel<G, OM><<<dim3(ceil_div(m->S, 256), ceil_div(n, G)), 256, 0, st>>>(
-            d_alphas, d_actions, d_vsel, order, n, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, nonfinite);
+        const int nPad = ceil_div(n + m->A * (G - 1), G) * G;
+        PBVI_TAKE(order, int32_t, (size_t)nPad);
+        PBVI_CUDA(cudaMemsetAsync(order, 0xFF, (size_t)nPad * sizeof(int32_t), st));
+        action_order_kernel<<<1, 256, m->A * sizeof(int), st>>>(d_actions, n, m->A, G, order);
+        if (m->O <= 2) launch_assemble_grouped<G, 2, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
+        else if (m->O == 3) launch_assemble_grouped<G, 3, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
+        else launch_assemble_grouped<G, 4, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
         m->last_launches += 2;
         if (hacc) {
             hash_finalise_kernel<<<ceil_div(n, 256), 256, 0, st>>>(hacc, n, m->S);

@@ -7,16 +7,16 @@
 
 namespace pbvi {
 
-// 128-bit hash of the raw 8-byte words of each row: position-salted mixes combined by wrapping addition (associative,
-// so any reduction shape gives the same value).  Block per row.
+// 128-bit key of the raw 8-byte words of each row (NH hashes with position keys, pbvi_common.cuh).  Block per row.
 __global__ void __launch_bounds__(256) row_hash_kernel(const uint64_t* __restrict__ rows, int rowLen, uint64_t* __restrict__ out) {
     __shared__ uint64_t sh[2][8];
     const uint64_t* row = rows + (size_t)blockIdx.x * rowLen;
     uint64_t h0 = 0, h1 = 0;
     for (int i = threadIdx.x; i < rowLen; i += 256) {
         const uint64_t w = row[i];
-        h0 += row_hash_term0(w, i);
-        h1 += row_hash_term1(w, i);
+        const uint4 k = row_key_words(i);
+        h0 += row_hash_term0(w, k);
+        h1 += row_hash_term1(w, k);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

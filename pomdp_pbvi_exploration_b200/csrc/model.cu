@@ -213,6 +213,9 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
     up(&m->predPtr, predPtr); up(&m->predK, predK);
     up(&m->pwLeaves, leaves); up(&m->pwNodes, nodes);
+    std::vector<uint4> hashKeys((size_t)S);
+    for (int s = 0; s < S; s++) hashKeys[s] = row_key_words(s);
+    up(&m->hashKeys, hashKeys);
     if (rc == PBVI_OK && cudaMalloc(&m->d_signs, 8 * sizeof(int)) != cudaSuccess) {
         set_error("cudaMalloc(signs) failed");
         rc = PBVI_ERR_CUDA;
@@ -233,7 +236,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->reachK); cudaFree(m->rtoK); cudaFree(m->probK); cudaFree(m->rbarT);
     cudaFree(m->rbarNzPtr); cudaFree(m->rbarNzIdx); cudaFree(m->rbarNzVal);
     cudaFree(m->reachP); cudaFree(m->rtoP); cudaFree(m->zMask); cudaFree(m->zOrder);
-    cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes);
+    cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes); cudaFree(m->hashKeys);
     cudaFree(m->d_stats);
     cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }

@@ -71,17 +71,29 @@ struct Arena {
     T* var = m->arena.take<T>(n);                    \
     if (!var) return PBVI_ERR_OOM
 
-// 128-bit row key = two position-salted sums of mixed 8-byte words (wrapping addition: any reduction shape, including
-// atomics, gives the same value), finalised with the row length.  Shared by row_hash_kernel and the hashing assemble kernel.
+// 128-bit row key = two independent NH hashes (the almost-universal hash of UMAC) over the 8-byte words of the row:
+//     h_j = sum_i (lo(w_i) + k_{j,0}(i)) * (hi(w_i) + k_{j,1}(i))     32-bit wrapping adds, 32x32 -> 64-bit product, sum mod 2^64
+// with four 32-bit position keys per word index drawn from splitmix64 (row_key_words), finalised with the row length.  Wrapping
+// addition makes the value independent of the reduction shape (shuffles, shared memory, atomics).  A word costs one wide
+// multiply per hash once its keys are at hand: the assemble kernel, which computes the key of a row while writing it, loads the
+// keys of its states from a per-model table once per block instead of running the mixer per element.  Every key match is
+// confirmed bytewise before rows are merged, so the key only has to make false matches rare, not impossible.
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
     x ^= x >> 27; x *= 0x94d049bb133111ebull;
     x ^= x >> 31;
     return x;
 }
-__host__ __device__ __forceinline__ uint64_t row_hash_term0(uint64_t w, int i) { return mix64(w ^ (0x9e3779b97f4a7c15ull * (uint64_t)(i + 1))); }
-__host__ __device__ __forceinline__ uint64_t row_hash_term1(uint64_t w, int i) {
-    return mix64((w + 0xd6e8feb86659fd93ull) ^ (0xc2b2ae3d27d4eb4full * (uint64_t)(i + 1)));
+__host__ __device__ __forceinline__ uint4 row_key_words(int i) {
+    const uint64_t a = mix64(0x9e3779b97f4a7c15ull * (uint64_t)(2 * (int64_t)i + 1));
+    const uint64_t b = mix64(0xc2b2ae3d27d4eb4full * (uint64_t)(2 * (int64_t)i + 2) + 0xd6e8feb86659fd93ull);
+    return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+}
+__host__ __device__ __forceinline__ uint64_t row_hash_term0(uint64_t w, const uint4& k) {
+    return (uint64_t)((uint32_t)w + k.x) * (uint64_t)((uint32_t)(w >> 32) + k.y);
+}
+__host__ __device__ __forceinline__ uint64_t row_hash_term1(uint64_t w, const uint4& k) {
+    return (uint64_t)((uint32_t)w + k.z) * (uint64_t)((uint32_t)(w >> 32) + k.w);
 }
 __host__ __device__ __forceinline__ uint64_t row_hash_final0(uint64_t a, int rowLen) { return mix64(a + (uint64_t)rowLen); }
 __host__ __device__ __forceinline__ uint64_t row_hash_final1(uint64_t b, int rowLen) { return mix64(b ^ (uint64_t)rowLen); }
@@ -121,6 +133,7 @@ struct pbvi_model {
     // NumPy pairwise-sum tree over a length-S row
     int2* pwLeaves = nullptr;    // [nLeaves] (offset, length)
     int2* pwNodes = nullptr;     // [nNodes]  (left, right); child >= 0: node id, < 0: leaf ~id; root is the last node
+    uint4* hashKeys = nullptr;   // [S] row_key_words(s): position keys of the 128-bit row key
     int nLeaves = 0, nNodes = 0;
 
     pbvi::Arena arena;
