@@ -43,9 +43,9 @@ UNIT = 'belief*alpha pairs/s'
 GAMMA = 0.99
 FP64_PEAK_TFLOPS = 37.1        # DMMA m8n8k4 / m16n8k16 on this pool's B200, profiles/r01_fp64_pipe_microbench.txt
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch on the default workload (B=10000, V=1000), from
-# `ncu --set full` (profiles/r01_score_kernel_v8_ncu_summary.txt); dense compulsory bytes would be 8*S*(B+V) = 1.94e9 -- chunks
-# that are skipped are never read, so the kernel moves less than that
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 0.811e9
+# `ncu --set full` (profiles/r01_score_kernel_v12_ncu_summary.txt); dense compulsory bytes would be 8*S*(B+V) = 1.94e9 -- chunks
+# that are skipped are never read, so the kernel moves far less than that
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 0.2346e9
 
 
 def parse_args():
@@ -368,7 +368,7 @@ def run_b200(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy()'},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (FP64 DMMA m8n8k4 + fused argmax)', 'achieved': achieved,
+            'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (persistent block-sparse FP64 DMMA m8n8k4 GEMM + fused argmax)', 'achieved': achieved,
                          'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,
                          'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH if (B == 10000 and V == 1000) else None,
                          'peak_source': 'own FP64 DMMA microbenchmark on this pool (profiles/r01_fp64_pipe_microbench.txt); '
