@@ -343,7 +343,10 @@ def run_b200(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) if e2e_steps else 0.0   # device clock; every step ends with the blocking D2H read
-    h2d = int(h_beliefs.numel() * 8 + h_alphas.numel() * 8)
+    # bytes that actually crossed PCIe per step: the belief rows travel packed (bitmap + non-zero 4-double chunks, packed by host
+    # threads inside the timed region and rebuilt bytewise on the device), the alpha rows as they are
+    h2d_dense = int(h_beliefs.numel() * 8 + h_alphas.numel() * 8)
+    h2d = int(getattr(solver, 'last_h2d_bytes', h_beliefs.numel() * 8) + h_alphas.numel() * 8) if e2e_steps else h2d_dense
     d2h = int(rows.size * 8 + acts.size * 8)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------------
@@ -366,7 +369,9 @@ def run_b200(args):
             'data': 'synthetic', 'config': workload_config(args, world),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
-                    'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy()'},
+                    'host_input_bytes_per_step': h2d_dense, 'host_threads': min(32, os.cpu_count() or 1),
+                    'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy(); sparse belief rows are packed by '
+                           'host threads (pbvi_pack_rows_host) for the upload and unpacked on the device'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (persistent block-sparse FP64 DMMA m8n8k4 GEMM + fused argmax)', 'achieved': achieved,
                          'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,

@@ -152,6 +152,20 @@ PBVI_API int pbvi_group_record_blocks(pbvi_model* m, const int32_t* d_blocks, in
 PBVI_API int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first,
                         const int32_t* d_inverse, int* h_all_equal, void* stream);
 
+/* ---- host -> device transport of sparse rows (the reference's GPU path copies the dense belief array: Model.gpu_model /
+ * `cp.array(belief_array)`, src/pomdp.py:1482) ---------------------------------------------------------------------------
+ * pbvi_pack_rows_host (pure host code, thread-safe, no handle): packs n rows of row_len doubles into a bitmap over 4-double
+ * chunks (h_bitmap [n][W] uint32, W = ceil(ceil(row_len/4)/32)), the chunks that contain a non-zero BIT (so -0.0 survives)
+ * back to back in h_packed (room for n*ceil(row_len/4)*4 doubles) and the first chunk of every row in h_row_start [n+1];
+ * *h_chunks = number of chunks written (h_packed needs one chunk of slack beyond that).  Rows are packed in slabs (one call per
+ * slab, slabs in parallel on host threads).  pbvi_unpack_rows rebuilds n dense rows [n][row_len] in device memory from device
+ * copies of the arrays of consecutive slabs of slab_rows rows each, byte for byte: row i belongs to slab i / slab_rows, whose
+ * chunks start at slab * region_chunks in d_packed and whose row offsets are d_row_start[slab * (slab_rows + 1) + i % slab_rows]. */
+PBVI_API int pbvi_pack_rows_host(const double* h_rows, int n, int row_len, uint32_t* h_bitmap, int32_t* h_row_start, double* h_packed,
+                        int64_t* h_chunks);
+PBVI_API int pbvi_unpack_rows(pbvi_model* m, const uint32_t* d_bitmap, const int32_t* d_row_start, const double* d_packed, int n,
+                     int row_len, int slab_rows, int64_t region_chunks, double* d_out, void* stream);
+
 /* ---- MDP value iteration sweep (src/mdp.py:1507) ---------------------------------------------------
  * d_alpha_out[a][s] = Rbar[s,a] + gamma * sum_r P[s,a,r] * d_vopt[reach[s,a,r]];  d_vopt_out[s] = max_a (nullable) */
 PBVI_API int pbvi_vi_sweep(pbvi_model* m, const double* d_vopt, double gamma, double* d_alpha_out, double* d_vopt_out, void* stream);

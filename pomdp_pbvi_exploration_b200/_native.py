@@ -41,6 +41,8 @@ SIGNATURES = {
     'pbvi_group_keys': [_P, _P, c_int, c_int, _P, _P, _P, _P, POINTER(c_int), _P],
     'pbvi_group_record_blocks': [_P, _P, c_int, c_int, c_int, _P, _P, POINTER(c_int), POINTER(c_int), _P],
     'pbvi_confirm_groups': [_P, _P, c_int, c_int, _P, _P, POINTER(c_int), _P],
+    'pbvi_pack_rows_host': [_P, c_int, c_int, _P, _P, _P, POINTER(c_int64)],
+    'pbvi_unpack_rows': [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P],
     'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
@@ -320,6 +322,68 @@ class DeviceModel:
                                                  _ptr(_i32(inverse, self.device)), byref(ok), self._stream))
         return bool(ok.value)
 
+    @staticmethod
+    def pack_geometry(row_len: int) -> tuple:
+        """(chunks per row, bitmap words per row) of the packed row format."""
+        n_c = -(-row_len // 4)
+        return n_c, -(-n_c // 32)
+
+    def pack_rows_host(self, rows: torch.Tensor, bitmap: torch.Tensor, row_start: torch.Tensor, packed: torch.Tensor) -> int:
+        """Packs host rows [n,L] (float64 CPU tensor) into the given host buffers (pure host code; releases the GIL, so slabs can be
+        packed by a thread pool).  Returns the number of 4-double chunks written."""
+        n, L = rows.shape
+        assert rows.dtype == torch.float64 and rows.is_contiguous() and not rows.is_cuda
+        total = c_int64()
+        _check(self._lib.pbvi_pack_rows_host(rows.data_ptr(), n, L, bitmap.data_ptr(), row_start.data_ptr(), packed.data_ptr(), byref(total)))
+        return int(total.value)
+
+    def unpack_rows(self, bitmap: torch.Tensor, row_start: torch.Tensor, packed: torch.Tensor, out: torch.Tensor,
+                    slab_rows: int | None = None, region_chunks: int = 0) -> None:
+        """Rebuilds dense rows `out` [n,L] (CUDA float64, contiguous) from device copies of the packed arrays of consecutive slabs
+        of `slab_rows` rows (default: one slab), each slab's chunks starting at slab * region_chunks in `packed`."""
+        n, L = out.shape
+        assert out.is_contiguous() and out.dtype == torch.float64
+        self._call(self._lib.pbvi_unpack_rows(self._h, _ptr(bitmap), _ptr(row_start), _ptr(packed), n, L, int(slab_rows or max(n, 1)),
+                                              int(region_chunks), _ptr(out), self._stream))
+
+    # ---- packed upload of host-resident rows: persistent staging + packer threads --------------------------------------------
+    PACK_SLAB = 64                 # rows packed by one host task (small: the first chunk is ready after a few milliseconds)
+
+    def start_pack(self, host: torch.Tensor):
+        """
+        Starts packing the pinned host rows [n,L] on the packer threads and returns a job handle (or None when the staging
+        buffers are in use by another pending job).  Called when a host-resident BeliefSet is created, so that the host work
+        overlaps whatever the caller does before the backup; `PBVI_Solver._select_streamed` consumes the job.
+        """
+        import os
+        import weakref
+        from concurrent.futures import ThreadPoolExecutor
+        n, L = host.shape
+        st = self.__dict__.get('_pack')
+        if st is not None and st['job'] is not None and st['job']() is not None and not st['job']().consumed:
+            return None
+        if st is None or st['key'] != (n, L):
+            n_c, W = self.pack_geometry(L)
+            SL = self.PACK_SLAB
+            n_slabs = -(-n // SL)
+            region = SL * n_c * 4 + 4              # doubles per slab: worst case + the packer's one-chunk slack
+            pool = st['pool'] if st is not None else ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
+            st = self._pack = {
+                'key': (n, L), 'n_c': n_c, 'W': W, 'SL': SL, 'n_slabs': n_slabs, 'region': region, 'pool': pool, 'job': None, 'copies_done': None,
+                'h_bm': torch.empty((n, W), dtype=torch.int32).pin_memory(),
+                'h_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32).pin_memory(),
+                'h_pk': torch.empty((n_slabs * region,), dtype=torch.float64).pin_memory(),
+                'd_bm': torch.empty((n, W), dtype=torch.int32, device=self.device),
+                'd_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32, device=self.device),
+                'd_pk': torch.empty((n_slabs * region,), dtype=torch.float64, device=self.device)}
+        for f in st.get('futures') or ():          # packers of an abandoned job may still be writing the staging buffers
+            f.result()
+        if st['copies_done'] is not None:
+            st['copies_done'].synchronize()        # the copies of the previous job may still be reading the pinned staging
+        job = _PackJob(self, st, host)
+        st['job'], st['futures'] = weakref.ref(job), job.futures
+        return job
+
     def vi_sweep(self, vopt, gamma: float):
         v = _f64(vopt, self.device)
         assert v.shape == (self.S,)
@@ -381,3 +445,20 @@ class DeviceModel:
         e, d, n = c_double(), c_double(), c_int()
         _check(self._lib.pbvi_last_stats(self._h, byref(e), byref(d), byref(n)))
         return dict(executed_flops=e.value, dense_flops=d.value, launches=n.value)
+
+
+class _PackJob:
+    """Slabs of host rows being packed by the thread pool; `result(i)` = number of chunks of slab i (blocks until it is packed)."""
+
+    def __init__(self, dev: 'DeviceModel', st: dict, host: torch.Tensor):
+        self.st, self.host, self.consumed = st, host, False
+        n, SL, region = host.shape[0], st['SL'], st['region']
+
+        def pack(i):
+            r0, r1 = i * SL, min(n, (i + 1) * SL)
+            return dev.pack_rows_host(host[r0:r1], st['h_bm'][r0:r1], st['h_rs'][i], st['h_pk'][i * region:(i + 1) * region])
+
+        self.futures = [st['pool'].submit(pack, i) for i in range(st['n_slabs'])]
+
+    def result(self, i: int) -> int:
+        return self.futures[i].result()

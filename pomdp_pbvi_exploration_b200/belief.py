@@ -145,6 +145,10 @@ class BeliefSet:
                 # host tensor: kept on the host and uploaded on first device use, or streamed chunk by chunk behind the score
                 # kernel by PBVI_Solver.backup (pin it -- `tensor.pin_memory()` -- for the copies to overlap the compute)
                 self._host = beliefs.to(torch.float64).contiguous()
+                if self._host.is_pinned() and self._host.shape[0] >= 2048:
+                    # large pinned host set: the packer threads start now, so the host half of the sparse-row upload overlaps
+                    # whatever the caller does before the backup (PBVI_Solver._select_streamed consumes the job)
+                    self._pack_job = model.device.start_pack(self._host)
             else:
                 self._device = _to_device(model, beliefs)
             if not isinstance(beliefs, torch.Tensor):
@@ -157,6 +161,9 @@ class BeliefSet:
     def belief_array(self) -> torch.Tensor:
         """[N,S] CUDA float64 tensor."""
         if self._device is None:
+            job = self.__dict__.pop('_pack_job', None)
+            if job is not None:
+                job.consumed = True                 # plain upload: the packed form is not used (the staging buffers become free)
             self._device = _to_device(self.model, self._host)
         return self._device
 

@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.environ.get('PBVI_B200_LIB', os.path.join(HERE, 'libpbvi_b200.so'))
-SOURCES = ['model.cu', 'backup.cu', 'belief.cu', 'misc.cu']
+SOURCES = ['model.cu', 'backup.cu', 'belief.cu', 'misc.cu', 'hostpack.cu']
+HOST_SOURCES = ['hostpack_host.cpp']
 HEADERS = ['pbvi_common.cuh', 'score_kernel.cuh', os.path.join('..', '..', 'include', 'pbvi_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
@@ -26,7 +27,7 @@ def _stale() -> bool:
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HOST_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -44,12 +45,17 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         cmd = [NVCC, *flags, '-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src in HOST_SOURCES:                      # plain C++ (host-only code paths of the C ABI)
+        obj = os.path.join(HERE, '_build', os.path.basename(LIB).replace('.so', '_') + src.replace('.cpp', '.o'))
+        objs.append(obj)
+        cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-fPIC', '-fvisibility=hidden', '-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             print(out)
         if p.returncode:
-            raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
+            raise RuntimeError('compilation failed: ' + ' '.join(cmd))
     cmd = [NVCC, '-shared', '-o', LIB, *objs, '-cudart', 'static']
     subprocess.run(cmd, check=True)
     return LIB

@@ -418,12 +418,17 @@ class PBVI_Solver:
 
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
     STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
+    PACK_MAX_DENSITY = 0.6         # above this share of non-zero 4-double chunks the rows are uploaded as they are
 
     def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor, want_value: bool = True):
         """
         Select step for a belief set that still lives in (pinned) host memory: the rows are uploaded in chunks on a
         copy stream while the compute stream runs `pbvi_backup_select` on the chunks that have landed (rows are
         independent given V), so the PCIe transfer hides behind the score kernel instead of preceding it.
+
+        Sparse rows travel packed: host threads turn slabs of rows into [bitmap | non-zero 4-double chunks]
+        (`pbvi_pack_rows_host`), only that crosses the bus and `pbvi_unpack_rows` rebuilds the dense rows in HBM, byte for
+        byte.  The packers run ahead of the copies, the copies ahead of the kernels.  `last_h2d_bytes` = bytes copied.
         """
         dev = model.device
         host = belief_set._host
@@ -443,20 +448,44 @@ class PBVI_Solver:
         copy = getattr(self, '_copy_stream', None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(device=dev.device)
-        copy.wait_stream(compute)                       # `full` must be allocated before the copies touch it
-        events = []
-        with torch.cuda.stream(copy):
-            for lo, hi in bounds:
-                full[lo:hi].copy_(host[lo:hi], non_blocking=True)
+        copy.wait_stream(compute)                       # `full` and the staging buffers must be free before the copies touch them
+
+        # the packers were started when the host-resident BeliefSet was created (`DeviceModel.start_pack`); start them now otherwise
+        job = belief_set.__dict__.pop('_pack_job', None) or dev.start_pack(host)
+        packed = False
+        if job is not None:
+            st = job.st
+            SL, region, n_c = st['SL'], st['region'], st['n_c']
+            packed = job.result(0) <= self.PACK_MAX_DENSITY * min(SL, nB) * n_c
+        self.last_h2d_bytes = 0
+        for lo, hi in bounds:
+            with torch.cuda.stream(copy):
+                if packed:
+                    s0, s1 = lo // SL, -(-hi // SL)
+                    for i in range(s0, s1):
+                        total = job.result(i)                                        # the packers run ahead of the copies
+                        st['d_pk'][i * region:i * region + total * 4].copy_(st['h_pk'][i * region:i * region + total * 4], non_blocking=True)
+                        self.last_h2d_bytes += total * 32
+                    st['d_bm'][lo:hi].copy_(st['h_bm'][lo:hi], non_blocking=True)
+                    st['d_rs'][s0:s1].copy_(st['h_rs'][s0:s1], non_blocking=True)
+                    self.last_h2d_bytes += (hi - lo) * st['W'] * 4 + (s1 - s0) * (SL + 1) * 4
+                else:
+                    full[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                    self.last_h2d_bytes += (hi - lo) * S * 8
                 ev = torch.cuda.Event()
                 ev.record(copy)
-                events.append(ev)
-        for (lo, hi), ev in zip(bounds, events):
-            compute.wait_event(ev)
+            compute.wait_event(ev)                      # the kernels of this chunk are enqueued while later slabs are still being packed
+            if packed:
+                dev.unpack_rows(st['d_bm'][lo:hi], st['d_rs'][s0:s1], st['d_pk'][s0 * region:], full[lo:hi], slab_rows=SL, region_chunks=region // 4)
             v, val, a = dev.backup_select(full[lo:hi], V, self.gamma, want_value=want_value)
             vstar[lo:hi], astar[lo:hi] = v, a
             if want_value:
                 value[lo:hi] = val
+        if job is not None:
+            job.consumed = True
+            done = torch.cuda.Event()
+            done.record(copy)
+            job.st['copies_done'] = done
         belief_set._device = full
         return vstar, value, astar
 

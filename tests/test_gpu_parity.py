@@ -422,3 +422,47 @@ def test_group_record_blocks_equals_host_merge(torch_cuda, world, block_rows, wi
     blocks[0, 0, :] = block_rows + 3
     _, _, mx2 = dev.group_record_blocks(torch.as_tensor(blocks.reshape(world * block_rows, width + 2)).cuda(), world, block_rows, width)
     assert mx2 == block_rows + 3
+
+
+@pytest.mark.parametrize('n,L', [(1, 1), (5, 3), (300, 130), (257, 22021), (64, 4096)])
+def test_pack_unpack_rows_bytewise(torch_cuda, n, L):
+    """Sparse-row transport: host pack (pbvi_pack_rows_host) + device unpack (pbvi_unpack_rows) reproduces the rows byte for byte,
+    including -0.0, NaN payloads, all-zero rows, dense rows and a ragged last chunk."""
+    torch = torch_cuda
+    dev, m, reach, _ = device_model('tiger')
+    rng = np.random.default_rng(n * 31 + L)
+    rows = np.zeros((n, L))
+    for i in range(n):
+        k = int(rng.integers(0, L + 1))
+        if i % 3 == 0:
+            lo = int(rng.integers(0, L))
+            rows[i, lo:lo + k] = rng.random(min(k, L - lo))
+        elif i % 3 == 1:
+            rows[i, rng.choice(L, min(L, 7), replace=False)] = rng.random(min(L, 7))
+    rows[0, -1] = -0.0
+    if n > 2:
+        rows[2] = rng.random(L)                                    # dense row
+        rows[1, 0] = np.nan
+    t = torch.from_numpy(rows)
+    n_c, W = dev.pack_geometry(L)
+    bm = torch.empty((n, W), dtype=torch.int32)
+    rs = torch.empty((n + 1,), dtype=torch.int32)
+    pk = torch.empty((n * n_c * 4 + 4,), dtype=torch.float64)
+    total = dev.pack_rows_host(t, bm, rs, pk)
+    assert total == int(rs[n]) and total <= n * n_c
+    out = torch.full((n, L), 7.0, dtype=torch.float64, device='cuda')
+    dev.unpack_rows(bm.cuda(), rs.cuda(), pk[:max(4, total * 4)].cuda(), out)
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), rows.view(np.uint64))
+    # the same rows packed in slabs of 7 (regions at a fixed stride), unpacked by one launch
+    SL = 7
+    n_slabs = -(-n // SL)
+    region = SL * n_c * 4 + 4
+    bm2 = torch.empty((n, W), dtype=torch.int32)
+    rs2 = torch.zeros((n_slabs, SL + 1), dtype=torch.int32)
+    pk2 = torch.zeros((n_slabs * region,), dtype=torch.float64)
+    for i in range(n_slabs):
+        r0, r1 = i * SL, min(n, (i + 1) * SL)
+        dev.pack_rows_host(t[r0:r1], bm2[r0:r1], rs2[i], pk2[i * region:(i + 1) * region])
+    out2 = torch.full((n, L), 7.0, dtype=torch.float64, device='cuda')
+    dev.unpack_rows(bm2.cuda(), rs2.cuda(), pk2.cuda(), out2, slab_rows=SL, region_chunks=region // 4)
+    assert np.array_equal(out2.cpu().numpy().view(np.uint64), rows.view(np.uint64))

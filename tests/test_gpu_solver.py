@@ -225,6 +225,33 @@ def test_streamed_host_beliefs_equal_device_resident():
     assert torch.equal(host_set.belief_array.cpu(), torch.as_tensor(B))
 
 
+def test_streamed_dense_host_beliefs_take_the_plain_upload():
+    """Dense rows are not worth packing: the streamed select falls back to plain chunked copies (same results, bytes counted)."""
+    import torch
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    from pomdp_pbvi_exploration_b200.recipes import synthetic_sparse_model
+    model = synthetic_sparse_model(600, 3, 2, 1, seed=4)
+    rng = np.random.default_rng(8)
+    B = rng.dirichlet(np.ones(600), size=2100)
+    vf = ValueFunction(model, rng.random((40, 600)), rng.integers(0, 3, 40))
+    solver = PBVI_Solver(gamma=0.95, eps=1e-6, expand_function='perseus')
+    dev_out = solver.backup(model, BeliefSet(model, B), vf, append=False, belief_dominance_prune=False)
+    host_set = BeliefSet(model, torch.as_tensor(B).pin_memory())
+    host_out = solver.backup(model, host_set, vf, append=False, belief_dominance_prune=False)
+    assert solver.last_h2d_bytes == B.size * 8
+    r0, a0 = dev_out.numpy()
+    r1, a1 = host_out.numpy()
+    assert np.array_equal(r0, r1) and np.array_equal(a0, a1)
+    sparse = B.copy()
+    sparse[:, 40:] = 0.0
+    sparse /= sparse.sum(1, keepdims=True)
+    host_sparse = BeliefSet(model, torch.as_tensor(sparse).pin_memory())
+    out_sparse = solver.backup(model, host_sparse, vf, append=False, belief_dominance_prune=False)
+    assert solver.last_h2d_bytes < sparse.size * 8 // 4
+    want = solver.backup(model, BeliefSet(model, sparse), vf, append=False, belief_dominance_prune=False)
+    assert np.array_equal(out_sparse.numpy()[0], want.numpy()[0]) and torch.equal(host_sparse.belief_array.cpu(), torch.as_tensor(sparse))
+
+
 def test_olfactory_fsvi_solve_and_backup_parity():
     """FSVI on the 22021-state model: one expansion trajectory + backup with the engine, every step checked against the oracle."""
     from pomdp_pbvi_exploration_b200 import BeliefSet, FSVI_Solver, ValueFunction
