@@ -163,6 +163,11 @@ PBVI_API int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, int
  * chunks start at slab * region_chunks in d_packed and whose row offsets are d_row_start[slab * (slab_rows + 1) + i % slab_rows]. */
 PBVI_API int pbvi_pack_rows_host(const double* h_rows, int n, int row_len, uint32_t* h_bitmap, int32_t* h_row_start, double* h_packed,
                         int64_t* h_chunks);
+/* One packer thread's share of a row set: slabs first_slab, first_slab + slab_step, ... (slab i = rows [i*slab_rows, ...)); slab i's
+ * chunks go to h_packed + i*region_doubles, its offsets to h_row_start + i*(slab_rows+1) and, last, its chunk count to h_totals[i]
+ * (release store; initialise to -1 and poll: -2 = failed). */
+PBVI_API int pbvi_pack_slabs_host(const double* h_rows, int n, int row_len, int slab_rows, int first_slab, int slab_step, uint32_t* h_bitmap,
+                         int32_t* h_row_start, double* h_packed, int64_t region_doubles, int64_t* h_totals);
 PBVI_API int pbvi_unpack_rows(pbvi_model* m, const uint32_t* d_bitmap, const int32_t* d_row_start, const double* d_packed, int n,
                      int row_len, int slab_rows, int64_t region_chunks, double* d_out, void* stream);
 

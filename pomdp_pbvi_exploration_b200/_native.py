@@ -42,6 +42,7 @@ SIGNATURES = {
     'pbvi_group_record_blocks': [_P, _P, c_int, c_int, c_int, _P, _P, POINTER(c_int), POINTER(c_int), _P],
     'pbvi_confirm_groups': [_P, _P, c_int, c_int, _P, _P, POINTER(c_int), _P],
     'pbvi_pack_rows_host': [_P, c_int, c_int, _P, _P, _P, POINTER(c_int64)],
+    'pbvi_pack_slabs_host': [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P],
     'pbvi_unpack_rows': [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P],
     'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
@@ -381,7 +382,8 @@ class DeviceModel:
         if st['copies_done'] is not None:
             st['copies_done'].synchronize()        # the copies of the previous job may still be reading the pinned staging
         job = _PackJob(self, st, host)
-        st['job'], st['futures'] = weakref.ref(job), job.futures
+        # the staging dict keeps what the packer threads touch alive for as long as they may run
+        st['job'], st['futures'], st['alive'] = weakref.ref(job), job.futures, (job.totals, host)
         return job
 
     def vi_sweep(self, vopt, gamma: float):
@@ -448,17 +450,26 @@ class DeviceModel:
 
 
 class _PackJob:
-    """Slabs of host rows being packed by the thread pool; `result(i)` = number of chunks of slab i (blocks until it is packed)."""
+    """Slabs of host rows being packed by the packer threads; `result(i)` = number of chunks of slab i (waits until it is packed).
+    Every thread makes ONE library call (slabs t, t + T, t + 2T, ... in a C loop, GIL released throughout) and publishes a
+    slab's chunk count as its last store, so finished slabs are shipped without any thread having to return to Python."""
 
     def __init__(self, dev: 'DeviceModel', st: dict, host: torch.Tensor):
         self.st, self.host, self.consumed = st, host, False
-        n, SL, region = host.shape[0], st['SL'], st['region']
-
-        def pack(i):
-            r0, r1 = i * SL, min(n, (i + 1) * SL)
-            return dev.pack_rows_host(host[r0:r1], st['h_bm'][r0:r1], st['h_rs'][i], st['h_pk'][i * region:(i + 1) * region])
-
-        self.futures = [st['pool'].submit(pack, i) for i in range(st['n_slabs'])]
+        n, L = host.shape
+        self.totals = np.full((st['n_slabs'],), -1, dtype=np.int64)
+        lib, pool = dev._lib, st['pool']
+        T = max(1, min(pool._max_workers, st['n_slabs']))
+        args = (host.data_ptr(), n, L, st['SL'])
+        tail = (st['h_bm'].data_ptr(), st['h_rs'].data_ptr(), st['h_pk'].data_ptr(), st['region'], self.totals.ctypes.data)
+        self.futures = [pool.submit(lib.pbvi_pack_slabs_host, *args, t, T, *tail) for t in range(T)]
 
     def result(self, i: int) -> int:
-        return self.futures[i].result()
+        import time
+        while True:
+            v = int(self.totals[i])
+            if v >= 0:
+                return v
+            if v == -2 or all(f.done() for f in self.futures) and int(self.totals[i]) < 0:
+                raise PBVIError('packing the host rows failed')
+            time.sleep(2e-5)

@@ -89,3 +89,26 @@ extern "C" int pbvi_pack_rows_host(const double* h_rows, int n, int row_len, uin
     *h_chunks = total;
     return PBVI_OK;
 }
+
+// One packer thread: slabs first_slab, first_slab + slab_step, ... of slab_rows rows each.  Slab i writes its bitmap rows, its
+// row offsets h_row_start[i * (slab_rows + 1) ..], its chunks at h_packed + i * region_doubles and, LAST, its chunk count to
+// h_totals[i] (initialised to -1 by the caller, who polls it): the caller never needs this thread to come back before it
+// can ship a finished slab.
+extern "C" int pbvi_pack_slabs_host(const double* h_rows, int n, int row_len, int slab_rows, int first_slab, int slab_step, uint32_t* h_bitmap,
+                                    int32_t* h_row_start, double* h_packed, int64_t region_doubles, int64_t* h_totals) {
+    if (n < 0 || row_len <= 0 || slab_rows <= 0 || first_slab < 0 || slab_step <= 0 || !h_totals) return PBVI_ERR_BAD_ARG;
+    const int nC = (row_len + PACK - 1) / PACK, W = (nC + 31) / 32;
+    const int n_slabs = (n + slab_rows - 1) / slab_rows;
+    for (int i = first_slab; i < n_slabs; i += slab_step) {
+        const int r0 = i * slab_rows, r1 = r0 + slab_rows < n ? r0 + slab_rows : n;
+        int64_t total = 0;
+        const int rc = pbvi_pack_rows_host(h_rows + (size_t)r0 * row_len, r1 - r0, row_len, h_bitmap + (size_t)r0 * W,
+                                           h_row_start + (size_t)i * (slab_rows + 1), h_packed + (size_t)i * region_doubles, &total);
+        if (rc != PBVI_OK) {
+            __atomic_store_n(&h_totals[i], (int64_t)-2, __ATOMIC_RELEASE);
+            return rc;
+        }
+        __atomic_store_n(&h_totals[i], total, __ATOMIC_RELEASE);
+    }
+    return PBVI_OK;
+}
