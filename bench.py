@@ -369,7 +369,7 @@ def run_b200(args):
             'data': 'synthetic', 'config': workload_config(args, world),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
-                    'host_input_bytes_per_step': h2d_dense, 'host_threads': min(32, os.cpu_count() or 1),
+                    'host_input_bytes_per_step': h2d_dense, 'host_threads': min(32, os.cpu_count() or 1) if (e2e_steps and h2d < h2d_dense) else 1,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy(); sparse belief rows are packed by '
                            'host threads (pbvi_pack_rows_host) for the upload and unpacked on the device'},
             'gpu_launches': int(launches),
