@@ -625,8 +625,13 @@ class PBVI_Solver:
         """
         HSVI exploration (reference src/pomdp.py:1768-1868): a = argmax of the upper-bound Q, o = argmax P(o|b,a) * (upper - lower),
         recursing until the gap closes or `max_generation` is reached.  Observations with P(o|b,a) = 0 are skipped
-        (their successor is 0/0 in the reference).
+        (their successor is 0/0 in the reference).  The reference rebuilds a BeliefSet at every level of the unwinding
+        recursion (:1862-1868); here the levels hand a list up and the set is stacked once -- same beliefs, same order.
         """
+        return BeliefSet(model, self._expand_hsvi_list(model, b, value_function, upper_bound_belief_value_map, conv_term, max_generation))
+
+    def _expand_hsvi_list(self, model: Model, b: Belief, value_function: ValueFunction, upper_bound_belief_value_map: BeliefValueMapping,
+                          conv_term: Union[float, None], max_generation: int) -> list:
         dev = model.device
         if conv_term is None:
             conv_term = self.eps
@@ -661,16 +666,16 @@ class PBVI_Solver:
             o_val = probs[best_a, o] * v_diff
             if o_val > max_o_val:
                 max_o_val, best_v_diff = o_val, v_diff
-                next_b = Belief._from_device(model, succ[best_a, o])
+                next_b = succ[best_a, o]
+        if next_b is not b:
+            # own storage for the chosen successor: a view would keep the whole [A,O,S] successor block of every level alive
+            next_b = Belief._from_device(model, next_b.clone())
         if best_v_diff < conv_term or max_generation <= 1:
-            return BeliefSet(model, [next_b])
+            return [next_b]
         upper_bound_belief_value_map.add(b, max_qv)
-        b_set = self.expand_hsvi(model=model, b=next_b, value_function=value_function,
-                                 upper_bound_belief_value_map=upper_bound_belief_value_map, conv_term=conv_term,
-                                 max_generation=max_generation - 1)
-        new_belief_list = list(b_set.belief_list)
+        new_belief_list = self._expand_hsvi_list(model, next_b, value_function, upper_bound_belief_value_map, conv_term, max_generation - 1)
         new_belief_list.append(next_b)
-        return BeliefSet(model, new_belief_list)
+        return new_belief_list
 
     def _trajectory(self, model: Model, b0: Belief, mdp_policy: ValueFunction, max_generation: int, eps_greedy=None) -> BeliefSet:
         """

@@ -466,3 +466,25 @@ def test_pack_unpack_rows_bytewise(torch_cuda, n, L):
     out2 = torch.full((n, L), 7.0, dtype=torch.float64, device='cuda')
     dev.unpack_rows(bm2.cuda(), rs2.cuda(), pk2.cuda(), out2, slab_rows=SL, region_chunks=region // 4)
     assert np.array_equal(out2.cpu().numpy().view(np.uint64), rows.view(np.uint64))
+
+
+@pytest.mark.parametrize('S,n_ub,n_q', [(60, 5, 3), (9000, 40, 18), (20011, 33, 7)])
+def test_sawtooth_sparse_stored_beliefs(torch_cuda, S, n_ub, n_q):
+    """HSVI upper bound on sparse stored beliefs (support compacted per 8192-state range in shared memory, one block per stored
+    belief): equals the oracle's support-restricted sawtooth; a query equal to a stored belief, a stored belief whose support
+    misses the query (ratio 0), supports spanning several ranges."""
+    from pomdp_pbvi_exploration_b200._native import DeviceModel
+    rng = np.random.default_rng(S + n_ub)
+    reach = rng.integers(0, S, (S, 2, 1))
+    obs = np.full((S, 2, 2), 0.5)
+    rto = orc.build_rto(reach, np.ones(reach.shape), obs)
+    dev = DeviceModel(reach, None, rto, np.zeros((S, 2)))
+    corner = rng.random(S) * 10
+    ub = _sparse_beliefs(rng, n_ub, S, [S, min(S, 300), 17, 1])
+    queries = _sparse_beliefs(rng, n_q, S, [S, min(S, 500), 40])
+    queries[0] = ub[1]
+    ub_v = ub @ corner - rng.random(n_ub)                         # stored values below the corner interpolation
+    got = dev.sawtooth(corner, ub, ub_v, queries).cpu().numpy()
+    want = np.array([orc.sawtooth_intended(corner, ub, ub_v, q) for q in queries])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)
+    dev.close()
