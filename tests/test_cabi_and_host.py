@@ -5,8 +5,10 @@ CPU-only checks of the drop-in boundary and the host logic:
   * the error convention (negative status + pbvi_last_error) works without touching a device;
   * host-side set bookkeeping (dict-insertion order on 128-bit row keys, first position / last action) and the belief sharding
     bounds behave as the reference's dict semantics require;
+  * the host half of the sparse-row transport (pbvi_pack_rows_host / pbvi_pack_slabs_host: plain C++, no device) and the host
+    twin of the sharded merge reproduce bytes / dict order;
   * the product package never imports the oracle.
-No compute entry point is called here.
+No DEVICE entry point is called here.
 """
 import ctypes
 import os
@@ -143,3 +145,94 @@ def test_olfactory_recipe_matches_reference_model():
     assert np.array_equal(model.reachable_transitional_observation_table, m['rto'])
     assert np.array_equal(model.expected_rewards_table, m['rbar'])
     assert np.array_equal(model.start_probabilities, m['start'])
+
+
+def _unpack_numpy(bitmap, row_start, packed, n, L):
+    """Reference unpacking of the sparse-row transport format (what pbvi_unpack_rows does on the device)."""
+    n_c = -(-L // 4)
+    out = np.zeros((n, n_c * 4))
+    chunks = packed.reshape(-1, 4)
+    for i in range(n):
+        bits = np.unpackbits(bitmap[i].view(np.uint8), bitorder='little')[:n_c].astype(bool)
+        assert bits.sum() == row_start[i + 1] - row_start[i]
+        out[i].reshape(n_c, 4)[bits] = chunks[row_start[i]:row_start[i + 1]]
+    return out[:, :L]
+
+
+@pytest.mark.parametrize('n,L', [(0, 5), (1, 1), (7, 6), (100, 257), (33, 22021)])
+def test_host_row_packer_round_trip(lib_path, n, L):
+    """pbvi_pack_rows_host / pbvi_pack_slabs_host are pure host code (no device needed): bitmap + non-zero 4-double chunks, and
+    the packed form unpacks to the same BYTES (-0.0, NaN payloads, ragged last chunk, all-zero and dense rows)."""
+    import ctypes
+    lib = ctypes.CDLL(lib_path)
+    rng = np.random.default_rng(n + L)
+    rows = np.zeros((n, L))
+    for i in range(n):
+        if i % 4 == 0:
+            lo = int(rng.integers(0, L)); k = int(rng.integers(0, L - lo + 1))
+            rows[i, lo:lo + k] = rng.random(k)
+        elif i % 4 == 1:
+            rows[i, rng.choice(L, min(L, 5), replace=False)] = rng.random(min(L, 5))
+        elif i % 4 == 2:
+            rows[i] = rng.random(L)
+    if n > 1:
+        rows[0, -1] = -0.0
+        rows[1, 0] = np.nan
+    n_c = -(-L // 4); W = -(-n_c // 32)
+    bm = np.zeros((max(n, 1), W), dtype=np.uint32)
+    rs = np.zeros(n + 1, dtype=np.int32)
+    pk = np.zeros(n * n_c * 4 + 4)
+    total = ctypes.c_int64(-1)
+    rc = lib.pbvi_pack_rows_host(ctypes.c_void_p(rows.ctypes.data), n, L, ctypes.c_void_p(bm.ctypes.data), ctypes.c_void_p(rs.ctypes.data),
+                                 ctypes.c_void_p(pk.ctypes.data), ctypes.byref(total))
+    assert rc == 0 and total.value == rs[n]
+    got = _unpack_numpy(bm, rs, pk[:total.value * 4], n, L)
+    assert np.array_equal(got.view(np.uint64), rows.view(np.uint64))
+    if n == 0:
+        return
+    # slabs of 3 rows, two "threads" (slabs 0,2,4,.. and 1,3,5,..): same bytes, counts published per slab
+    SL = 3
+    n_slabs = -(-n // SL)
+    region = SL * n_c * 4 + 4
+    bm2 = np.zeros((n, W), dtype=np.uint32)
+    rs2 = np.zeros((n_slabs, SL + 1), dtype=np.int32)
+    pk2 = np.zeros(n_slabs * region)
+    totals = np.full(n_slabs, -1, dtype=np.int64)
+    lib.pbvi_pack_slabs_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    for t in range(2):
+        assert lib.pbvi_pack_slabs_host(rows.ctypes.data, n, L, SL, t, 2, bm2.ctypes.data, rs2.ctypes.data, pk2.ctypes.data, region,
+                                        totals.ctypes.data) == 0
+    assert np.all(totals >= 0)
+    for i in range(n_slabs):
+        r0, r1 = i * SL, min(n, (i + 1) * SL)
+        got = _unpack_numpy(bm2[r0:r1], rs2[i], pk2[i * region:i * region + totals[i] * 4], r1 - r0, L)
+        assert np.array_equal(got.view(np.uint64), rows[r0:r1].view(np.uint64))
+
+
+def test_merge_blocks_host_matches_a_dict_over_all_records():
+    """Host twin of pbvi_group_record_blocks (used by the gloo tests of the tuple exchange): grouping of the valid records of the
+    gathered blocks == one dict over them in buffer order; `last` = record with the largest last-position."""
+    import torch
+    from pomdp_pbvi_exploration_b200.parallel import merge_blocks_host
+    rng = np.random.default_rng(2)
+    world, block_rows, w = 3, 9, 2
+    blocks = rng.integers(0, 99, (world, block_rows, w + 2)).astype(np.int32)
+    counts = [8, 0, 5]
+    pool = rng.integers(0, 4, (6, w))
+    for r in range(world):
+        blocks[r, 0, :] = counts[r]
+        blocks[r, 1:1 + counts[r], :w] = pool[rng.integers(0, 6, counts[r])]
+        blocks[r, 1:1 + counts[r], w + 1] = rng.permutation(100)[:counts[r]] + 100 * r
+    first, last, mx = merge_blocks_host(torch.as_tensor(blocks.reshape(-1, w + 2)), world, block_rows, w)
+    table = {}
+    for r in range(world):
+        for j in range(1, 1 + counts[r]):
+            row = r * block_rows + j
+            key = blocks[r, j, :w].tobytes()
+            if key not in table:
+                table[key] = [row, row]
+            elif blocks.reshape(-1, w + 2)[row, w + 1] > blocks.reshape(-1, w + 2)[table[key][1], w + 1]:
+                table[key][1] = row
+    assert mx == 8
+    assert first.tolist() == [v[0] for v in table.values()] and last.tolist() == [v[1] for v in table.values()]
