@@ -367,7 +367,11 @@ class DeviceModel:
         st = self.__dict__.get('_pack')
         if st is not None and st['job'] is not None and st['job']() is not None and not st['job']().consumed:
             return None
+        for f in (st or {}).get('futures') or ():  # packers of an abandoned job may still be writing the staging buffers
+            f.result()
         if st is None or st['key'] != (n, L):
+            if st is not None and st['copies_done'] is not None:
+                st['copies_done'].synchronize()    # copy-stream writes into the old device staging must land before it is released
             n_c, W = self.pack_geometry(L)
             SL = self.PACK_SLAB
             n_slabs = -(-n // SL)
@@ -375,14 +379,13 @@ class DeviceModel:
             pool = st['pool'] if st is not None else ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
             st = self._pack = {
                 'key': (n, L), 'n_c': n_c, 'W': W, 'SL': SL, 'n_slabs': n_slabs, 'region': region, 'pool': pool, 'job': None, 'copies_done': None,
+                'futures': None, 'alive': None,
                 'h_bm': torch.empty((n, W), dtype=torch.int32).pin_memory(),
                 'h_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32).pin_memory(),
                 'h_pk': torch.empty((n_slabs * region,), dtype=torch.float64).pin_memory(),
                 'd_bm': torch.empty((n, W), dtype=torch.int32, device=self.device),
                 'd_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32, device=self.device),
                 'd_pk': torch.empty((n_slabs * region,), dtype=torch.float64, device=self.device)}
-        for f in st.get('futures') or ():          # packers of an abandoned job may still be writing the staging buffers
-            f.result()
         if st['copies_done'] is not None:
             st['copies_done'].synchronize()        # the copies of the previous job may still be reading the pinned staging
         job = _PackJob(self, st, host)
