@@ -83,6 +83,59 @@ __global__ void __launch_bounds__(256) pairwise_normalise_kernel(double* __restr
     }
 }
 
+// The same normalisation split in two for a CHAIN of updates (one row per step, every step waiting for the previous one): with
+// one block per row the 256 threads of a single SM walk 170 leaves and 22 000 divisions alone (80 us per step on the olfactory
+// model, the whole cost of an FSVI expansion).  pairwise_leaf_kernel spreads the leaf sums over ceil(nLeaves / 32) blocks,
+// pairwise_finish_kernel walks the (tiny) combine tree in every block and divides that block's slice.  Same additions in the
+// same order: bit-identical to pairwise_normalise_kernel.
+__global__ void __launch_bounds__(256) pairwise_leaf_kernel(const double* __restrict__ row, const int2* __restrict__ leaves, int nLeaves,
+                                                            double* __restrict__ leafSums) {
+    const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int l = blockIdx.x * 32 + grp;
+    const bool valid = l < nLeaves;
+    const int off = valid ? leaves[l].x : 0, n = valid ? leaves[l].y : 0;
+    const double* a = row + off;
+    const int lim = n - (n % 8);
+    double r = (n >= 8) ? a[j] : 0.0;
+    for (int i = 8; i < lim; i += 8) r = __dadd_rn(r, a[i + j]);
+    const double p = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));
+    const double q = __dadd_rn(p, __shfl_down_sync(0xffffffffu, p, 2, 8));
+    double res = __dadd_rn(q, __shfl_down_sync(0xffffffffu, q, 4, 8));
+    if (valid && j == 0) {
+        if (n < 8) {
+            res = 0.0;
+            for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+        } else {
+            for (int i = lim; i < n; i++) res = __dadd_rn(res, a[i]);
+        }
+        leafSums[l] = res;
+    }
+}
+
+constexpr int FINISH_SLICE = 2048;   // elements divided per block
+
+__global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict__ row, int S, const double* __restrict__ leafSums, int nLeaves,
+                                                              const int2* __restrict__ nodes, int nNodes) {
+    extern __shared__ double s_sum[];   // [nLeaves] leaf sums, then [nNodes] node sums
+    __shared__ double s_total;
+    for (int l = threadIdx.x; l < nLeaves; l += 256) s_sum[l] = leafSums[l];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* nsum = s_sum + nLeaves;
+        for (int j = 0; j < nNodes; j++) {
+            const int l = nodes[j].x, r = nodes[j].y;
+            const double lv = l < 0 ? s_sum[~l] : nsum[l];
+            const double rv = r < 0 ? s_sum[~r] : nsum[r];
+            nsum[j] = __dadd_rn(lv, rv);
+        }
+        s_total = nNodes ? nsum[nNodes - 1] : s_sum[0];
+    }
+    __syncthreads();
+    const double tot = s_total;
+    const int s1 = min(S, (int)(blockIdx.x + 1) * FINISH_SLICE);
+    for (int s = blockIdx.x * FINISH_SLICE + threadIdx.x; s < s1; s += 256) row[s] = row[s] / tot;   // 0/0 = NaN, as in the reference
+}
+
 // out[i][a][o] = sum_k RTO[a][o][k] * belief_i[k / R]; block per (z, i)
 __global__ void __launch_bounds__(256) observation_probability_kernel(const double* __restrict__ beliefs, const double* __restrict__ rtoK,
                                                                       int S, int R, int nZ, double* __restrict__ out) {
@@ -167,13 +220,16 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
+    m->arena.reset();
+    PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
     const double* src = d_b0;
     for (int i = 0; i < n; i++) {
         double* out = d_out + (size_t)i * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
                                                                            m->O, out, h_actions[i], h_observations[i]);
-        pairwise_normalise_kernel<<<1, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, 1, nullptr);
-        m->last_launches += 2;
+        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
+        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes);
+        m->last_launches += 3;
         src = (h_reset && h_reset[i]) ? d_b0 : out;
     }
     PBVI_CUDA(cudaGetLastError());

@@ -144,8 +144,12 @@ class ValueFunction:
         if n_self == 0 or n_other == 0:
             return None
         hashes = np.concatenate([self.row_hashes, other.row_hashes], axis=0)
-        keys = set(map(tuple, hashes.tolist()))
-        if len(keys) != n_self + n_other:
+        # all keys distinct?  Checked on a 64-bit mix of the two halves with one SIMD sort (0.1 ms at 9000 rows; a set of Python
+        # tuples costs 5 ms there, every backup of a long solve): distinct mixes imply distinct keys, and a repeated mix -- a real
+        # duplicate or a 2^-64 accident -- just takes the general path below.
+        with np.errstate(over='ignore'):
+            mix = np.sort(hashes[:, 0] ^ (hashes[:, 1] * np.int64(-7046029254386353131)))
+        if np.any(mix[1:] == mix[:-1]):
             return None
         S = self.model.state_count
         buf, start = other.__dict__.get('_buf'), other.__dict__.get('_buf_start')

@@ -488,3 +488,29 @@ def test_sawtooth_sparse_stored_beliefs(torch_cuda, S, n_ub, n_q):
     want = np.array([orc.sawtooth_intended(corner, ub, ub_v, q) for q in queries])
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13)
     dev.close()
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'hallway', 'olfactory_wrap'])
+def test_belief_trajectory_equals_chained_updates(torch_cuda, tag):
+    """pbvi_belief_trajectory (the FSVI chain: project + multi-block pairwise normaliser per step, restarts from b0) is bit-identical
+    to chaining pbvi_belief_update one step at a time."""
+    torch = torch_cuda
+    dev, m, reach, _ = device_model(tag)
+    g = load_golden('backup_' + tag)
+    rng = np.random.default_rng(11)
+    b0 = torch.as_tensor(g['beliefs'][0]).cuda()
+    n = 25
+    actions, observations, resets = [], [], []
+    cur = b0
+    want = []
+    for i in range(n):
+        a = int(rng.integers(dev.A))
+        probs = dev.observation_probabilities(cur[None, :])[0, a].cpu().numpy()
+        o = int(rng.choice(np.flatnonzero(probs > 0)))
+        nxt, _ = dev.belief_update(cur[None, :], [a], [o])
+        want.append(nxt[0])
+        reset = i % 9 == 8
+        actions.append(a); observations.append(o); resets.append(reset)
+        cur = b0 if reset else nxt[0]
+    chain = dev.belief_trajectory(b0, actions, observations, resets)
+    assert torch.equal(chain, torch.stack(want))
