@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) pairwise_leaf_kernel(const double* __rest
 constexpr int FINISH_SLICE = 2048;   // elements divided per block
 
 __global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict__ row, int S, const double* __restrict__ leafSums, int nLeaves,
-                                                              const int2* __restrict__ nodes, int nNodes) {
+                                                              const int2* __restrict__ nodes, int nNodes, double* __restrict__ norm) {
     extern __shared__ double s_sum[];   // [nLeaves] leaf sums, then [nNodes] node sums
     __shared__ double s_total;
     for (int l = threadIdx.x; l < nLeaves; l += 256) s_sum[l] = leafSums[l];
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict
             nsum[j] = __dadd_rn(lv, rv);
         }
         s_total = nNodes ? nsum[nNodes - 1] : s_sum[0];
+        if (norm && blockIdx.x == 0) *norm = s_total;
     }
     __syncthreads();
     const double tot = s_total;
@@ -185,7 +186,17 @@ static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t bel
                                                                             d_observations + i0, beliefStride, m->predPtr, m->predK,
                                                                             m->rtoK, m->S, m->R, m->O, out, 0, 0);
         m->last_launches++;
-        if (normalise || d_norm) {
+        if (normalise && ni <= 4 && smem <= 48 * 1024) {
+            // a few rows (one step of a Perseus walk, a single Belief.update): the multi-block form of the normaliser, row by row
+            double* leafSums = m->arena.take<double>((size_t)m->nLeaves);
+            if (!leafSums) return PBVI_ERR_OOM;
+            for (int r = 0; r < ni; r++) {
+                pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out + (size_t)r * m->S, m->pwLeaves, m->nLeaves, leafSums);
+                pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out + (size_t)r * m->S, m->S, leafSums, m->nLeaves,
+                                                                                        m->pwNodes, m->nNodes, d_norm ? d_norm + i0 + r : nullptr);
+                m->last_launches += 2;
+            }
+        } else if (normalise || d_norm) {
             pairwise_normalise_kernel<<<ni, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
                                                             d_norm ? d_norm + i0 : nullptr);
             m->last_launches++;
@@ -202,6 +213,7 @@ extern "C" int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const 
     if (n == 0) return PBVI_OK;
     PBVI_REQUIRE(d_beliefs && d_actions && d_observations && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
     m->last_launches = 0;
     return belief_update_impl(m, d_beliefs, (size_t)m->S, d_actions, d_observations, n, normalise, d_out, d_norm, (cudaStream_t)stream);
 }
@@ -228,7 +240,7 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
                                                                            m->O, out, h_actions[i], h_observations[i]);
         pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
-        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes);
+        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
         m->last_launches += 3;
         src = (h_reset && h_reset[i]) ? d_b0 : out;
     }

@@ -186,6 +186,11 @@ def test_belief_update_bit_exact(torch_cuda, tag):
         out, mass = dev.belief_update(bb, aa, oo)
         got = out.cpu().numpy().reshape(len(B), len(pairs), -1)
         assert np.array_equal(got, g['ref_updates'], equal_nan=True)
+        # one to four rows take the multi-block normaliser: same bytes, same masses
+        for k in (1, 3):
+            out_k, mass_k = dev.belief_update(bb[:k], aa[:k], oo[:k])
+            assert np.array_equal(out_k.cpu().numpy(), out[:k].cpu().numpy(), equal_nan=True)
+            assert np.array_equal(mass_k.cpu().numpy(), mass[:k].cpu().numpy(), equal_nan=True)
     else:
         succ, mass = dev.belief_successors(B)
         assert np.array_equal(succ.cpu().numpy(), g['ref_updates'], equal_nan=True)
