@@ -4,16 +4,17 @@
 //
 // Pipeline of pbvi_backup_select:
 //   transpose_kernel          alphas [V][S] -> alphaT [S][Vp]          (so a gathered successor row is one coalesced line)
-//   belief_mask_kernel        row-group occupancy bits of every (belief tile, K chunk)
-//   alpha_row_mask_kernel, chunk_alpha_mask_kernel   which chunks gather a non-zero alpha-tile row
-//   build_chunk_lists_kernel  per (tile, a, o, alpha tile): ordered list of chunks live in the beliefs, RTO[a][o] and the alpha tile
+//   belief_mask_kernel        row-group occupancy bits of every (belief tile, 4-state chunk) + the belief tiles as shared-memory images
+//   alpha_row_mask_kernel, chunk_alpha_mask_kernel   which chunks gather a non-zero row of each 64-alpha column quarter
+//   build_chunk_lists_kernel  per (tile, a, o, alpha tile): ordered list of live pipeline stages with per-chunk flag bytes
 //   (R > 1) gamma_project_kernel  GammaT[a,o][s][v] = sum_r RTO * alphaT[reach]   (HBM-bound gather)
-//   score_kernel              block-sparse DMMA + fused first-index argmax over v
-//   combine_tiles_kernel      argmax across the alpha tiles (ascending, strict >)
-//   backup_value_kernel       value[b][a] = b . (Rbar[:,a] + sum_o Gamma[a,o,v*]) in the reference's operation order
+//   score_kernel              persistent block-sparse DMMA GEMM + fused first-index argmax per 64-alpha column quarter
+//   combine_tiles_kernel      argmax across the column quarters of all alpha tiles (ascending, strict >)
+//   approx_value_kernel, backup_value_kernel   value[b][a] = b . (Rbar[:,a] + sum_o Gamma[a,o,v*]): screened, exact where it matters
 //   first_argmax_kernel       a*[b]
 // pbvi_backup_assemble:
-//   assemble_kernel           alpha_a rows for (action, v*[O]) tuples, reference operation order, no FMA contraction
+//   action_order_kernel + assemble_grouped_kernel (R = 1) / assemble_kernel   alpha_a rows for (action, v*[O]) tuples in the
+//                             reference's operation order, no FMA contraction, 128-bit row keys accumulated on the way
 #include <algorithm>
 
 #include "score_kernel.cuh"

@@ -10,21 +10,24 @@
 //   bmat is alphaT (z stride 0: max_v b.alpha_v of compute_change / SSGA / GER) or the transposed Gamma projection
 //   GammaT[a,o] built by gamma_project_kernel for models with reachable_state_count > 1.
 //
-// One block owns a BM x BN = 64 x 256 tile of one z = (a,o) and walks only the K chunks (KC = 8 source states) in which
-// some belief of the tile is non-zero AND some RTO entry of (a,o) is non-zero AND some alpha of the tile is non-zero at a
-// state the chunk lands on (list built by build_chunk_lists_kernel): every skipped term is an exact zero.
+// Tiles are BM x BN = 64 beliefs x 256 alphas of one z = (a,o).  A tile touches only the CHUNKS (KC = 4 consecutive source
+// states) in which some belief of a row group (RG = 16 beliefs) is non-zero AND some RTO entry of (a,o) is non-zero AND some alpha
+// of a column quarter (64 alphas) is non-zero at a state the chunk lands on: every skipped term is an exact zero.  SUB = 4 chunks
+// form a pipeline STAGE (16 states): zeros are skipped per chunk, the mbarrier handshake is paid per stage, so a dense
+// workload runs like a kernel with 16-state chunks.  build_chunk_lists_kernel writes, per tile, the ordered list of live stages
+// with 8 flag bits per chunk (live row groups | live column quarters << 4).
 //
-// Warp specialisation (N_CONSUMER_WARPS + 1 warps):
-//   last warp   producer.  Per chunk it arms the stage's `full` mbarrier with the byte count and issues the stage as
-//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row (KC of them), ONE
-//               1 KB copy per live row group (belief_mask_kernel stores the belief tiles as ready-made, bank-swizzled
-//               shared-memory images) and the RTO chunk.  List entries and gathered row indices are prefetched one chunk
-//               ahead, so the producer never waits on a dependent global load.
-//   the rest    consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier inside the K loop.
-//               Warp w owns row group w / 4 (RG beliefs) and column quarter w % 4, so each SM sub-partition
-//               (warp id mod 4) holds one warp of EACH row group: a row group that is all-zero on the chunk is skipped
-//               and the saving is spread over all four FP64 pipes (the first, 128 x 128 layout stalled on the barrier
-//               instead: profiles/r01_score_kernel_v1_ncu_summary.txt).
+// The kernel is persistent (see score_kernel below): one block per SM pulls tiles from a queue.  Warp specialisation
+// (N_CONSUMER_WARPS + 1 warps):
+//   last warp   producer.  Per live stage it arms the stage's `full` mbarrier with the byte count and issues the stage as
+//               bulk async copies (cp.async.bulk, the TMA engine): one 2 KB copy per gathered alphaT row of a live chunk, ONE
+//               512-byte copy per live (chunk, row group) (belief_mask_kernel stores the belief tiles as ready-made
+//               shared-memory images) and the RTO values of the stage.  List entries and gathered row indices are prefetched
+//               one stage ahead, so the producer never waits on a dependent global load.
+//   the rest    consumers: wait on `full`, DMMA, arrive on `empty`.  No block-wide barrier anywhere in the stream.
+//               Warp 4m + j owns row group m and column quarter (j + m) mod 4 -- a Latin square over the SM sub-partitions
+//               (warp id mod 4), so a skipped row group or column quarter takes the same share of work off all four FP64
+//               pipes (the first, 128 x 128 layout stalled on the barrier instead: profiles/r01_score_kernel_v1_ncu_summary.txt).
 // gamma > 0 scales every score equally and is left out (argmax invariant; exact-zero rows stay exactly zero, so "first
 // index of the maximum" is preserved).
 // Bound: the FP64 pipe (DMMA.8x8x4 runs at the FP64 peak on sm_100a, see profiles/r01_fp64_pipe_microbench.txt).

@@ -3,8 +3,11 @@ Raw-byte set semantics of the reference's containers, on device-resident rows.
 
 The reference keys Python dicts by `values.tobytes()` (ValueFunction ctor src/mdp.py:668-669, `extend` :773-774,
 BeliefSet.union src/pomdp.py:585-606) -- on its GPU path that is one D2H copy per row.  Here rows stay on the
-device: `pbvi_row_hash` gives a 128-bit key per row, the grouping runs on the host over 16 bytes per row, and every
-key match is confirmed bytewise on the device (`pbvi_rows_equal`), so the result is exact, not probabilistic.
+device: `pbvi_row_hash` gives a 128-bit key per row and every key match is confirmed bytewise on the device
+(`pbvi_rows_equal` / `pbvi_confirm_groups`), so the result is exact, not probabilistic.  The backup itself groups its
+tuples and row keys on the device (`DeviceModel.group_keys`); the helpers below are the host form of the same grouping,
+used by the container classes (constructor dedup, `extend`, `union`), by the 'rows' exchange of the sharded backup and as
+the reference implementation the device grouping is tested against.
 """
 from __future__ import annotations
 

@@ -6,7 +6,9 @@ Host Python keeps what the reference keeps in Python -- the expand/backup loop, 
 host RNG draws (same generators, same draw order as the reference's CPU path, so seeded runs pick the same states /
 actions / observations) -- and every array operation of the hot path is a kernel of the library:
 
-    backup            pbvi_backup_select + pbvi_backup_assemble (+ pbvi_row_hash / pbvi_rows_equal for the byte-dedup)
+    backup            pbvi_backup_select + pbvi_group_keys (distinct generating tuples) + pbvi_backup_assemble + pbvi_group_keys /
+                      pbvi_confirm_groups (the byte-dedup, on the device); host-resident belief sets travel packed
+                      (pbvi_pack_slabs_host + pbvi_unpack_rows)
     compute_change    pbvi_max_values
     Belief.update     pbvi_belief_update (bit-identical to the reference, NaN rows included)
     SSEA / GER / HSVI pbvi_belief_successors, pbvi_min_l2_distance, pbvi_ger_scores, pbvi_sawtooth,
