@@ -67,46 +67,67 @@ def parse_args():
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """
+    nvidia-smi clocks / throttle reasons, sampled every 100 ms from the warm-up on.  `begin()` / `end()` bracket the timed
+    regions; the reported SM clock is the median of the samples that fall inside them (under load), or -- when a region is
+    shorter than the sampling period -- of the samples of the 300 ms after it; throttle reasons come from the same samples.
+    """
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
               'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, line)
+        self.windows = []        # [begin, end] of the timed regions
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
-                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
+        time.sleep(0.3)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        inside, after, mx, reasons = [], [], [], set()
+        for t, ln in list(self.lines):
             parts = [p.strip() for p in ln.split(',')]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                clk, top = float(parts[0]), float(parts[1])
             except ValueError:
                 continue
+            mx.append(top)
+            if any(b <= t <= (e if e is not None else t) for b, e in self.windows):
+                inside.append(clk)
+            elif any(e is not None and e < t <= e + 0.3 for b, e in self.windows):
+                after.append(clk)
+            else:
+                continue                                   # warm-up / set-up sample: neither its clock nor its reasons are reported
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith('active'):
                     reasons.add(name)
+        sm = inside if inside else after
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'samples': len(sm),
+                'samples_total': len(mx), 'sampled': 'inside the timed regions' if inside else 'within 300 ms after a timed region',
                 'reasons': sorted(reasons)}
 
 
@@ -264,22 +285,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()                     # started before the warm-up so that nvidia-smi is up when the timed regions run
     for _ in range(args.warmup):
         out = step_device()
     dev.set_profiling(True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     launches0 = dev.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     score_ms = []
+    sampler.begin()
     ev0.record()
     for _ in range(args.steps):
         out = step_device()
         score_ms.append(dev.last_score_ms())       # the step has already synchronised (dedup reads keys back)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.end()
     if args.trace_phases and sharded is not None:
         sharded.trace = True
         step_device()
@@ -302,12 +324,14 @@ def run_b200(args):
         barrier()
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dscore = []
+        sampler.begin()
         d0.record()
         for _ in range(dsteps):
             solver.backup(model, belief_set, vf_dense, append=False, belief_dominance_prune=False)
             dscore.append(dev.last_score_ms())
         d1.record()
         barrier()
+        sampler.end()
         dstats = dev.last_stats()
         dms = d0.elapsed_time(d1) / dsteps
         dense = {'what': 'same beliefs, the same alphas plus a strictly positive perturbation (every alpha non-zero at every state): only '
@@ -315,6 +339,8 @@ def run_b200(args):
                  'value_per_gpu': float(B) * V / (dms * 1e-3), 'ms_per_step': dms, 'kernel_ms': float(np.mean(dscore)),
                  'executed_flops_per_launch': dstats['executed_flops'],
                  'executed_tflops': dstats['executed_flops'] / (float(np.mean(dscore)) * 1e-3) / 1e12}
+
+    clocks = sampler.stop()       # before the e2e leg: that one is PCIe-bound, the GPU idles through most of it
 
     # ---- end to end from host buffers -----------------------------------------------------------------------------
     h_beliefs = beliefs.cpu().pin_memory()
