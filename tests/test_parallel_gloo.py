@@ -90,14 +90,20 @@ def _tuple_worker(rank, world, port, keys_all, result_queue):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_beliefs,world', [(50, 2), (3, 2), (64, 3)])
+@pytest.mark.parametrize('n_beliefs,world', [(50, 2), (3, 2), (64, 3), (1300, 2)])
 def test_tuple_exchange_equals_single_process(n_beliefs, world):
     """The compact exchange: distinct (a*, v*) tuples + first/last belief positions of every shard, merged identically on every
     rank, must equal the distinct tuples (first occurrence order, first / last positions) of the whole belief set."""
     from pomdp_pbvi_exploration_b200.sets import unique_rows_first
     rng = np.random.default_rng(n_beliefs)
-    pool = rng.integers(0, 40, (7, 4))
-    keys_all = pool[rng.integers(0, 7, n_beliefs)]
+    if n_beliefs > 1000:
+        # more distinct tuples per rank than the first-guess block size (256 records): the exchange must notice the overflow in the
+        # gathered headers on every rank and repeat once at full capacity
+        pool = np.unique(rng.integers(0, 40, (900, 4)), axis=0)
+        keys_all = pool[rng.integers(0, pool.shape[0], n_beliefs)]
+    else:
+        pool = rng.integers(0, 40, (7, 4))
+        keys_all = pool[rng.integers(0, 7, n_beliefs)]
     f, l, _ = unique_rows_first(keys_all)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
