@@ -714,7 +714,8 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
     nonfinite_scan_kernel<<<m->sm_count * 8, 256, 0, st>>>(d_alphas, (size_t)nV * m->S, nonfinite);
     m->last_launches++;
     constexpr int G = 8, SPT = 2;
-    if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024) {
+    if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024 &&
+        ((long long)n + (long long)m->A * (G - 1)) / G + 1 <= 65535) {            // grid.y of the grouped kernel
         m->arena.reset();
         const int nPad = ceil_div(n + m->A * (G - 1), G) * G;
         PBVI_TAKE(order, int32_t, (size_t)nPad);
