@@ -132,7 +132,10 @@ class BeliefSet:
         self._hashes = _hashes
         self._device = None
         self._host = None
-        self.lineage = next(_LINEAGE)       # sets grown from one another by union() share it (their rows are prefixes)
+        # identity of this (immutable) row sequence for per-row result caches; `union` links the result to its parents through
+        # `lineage_chain` = [(lineage, n)]: "my first n rows are the first n rows of the set with that lineage"
+        self.lineage = next(_LINEAGE)
+        self._chain = None
         S = model.state_count
         if isinstance(beliefs, list):
             assert all(b.values.shape[0] == S for b in beliefs), f"Beliefs in belief list provided dont all have shape ({S},)"
@@ -156,6 +159,16 @@ class BeliefSet:
                 sums = np.round(np.asarray(beliefs, dtype=np.float64).sum(axis=1), 3)
                 bad = np.flatnonzero(~(sums == 1.0))
                 assert bad.size == 0, f"States probabilities in belief must sum to 1 (found: {float(np.asarray(beliefs)[bad[0]].sum())})"
+
+    LINEAGE_DEPTH = 8
+
+    @property
+    def lineage_chain(self) -> list:
+        """[(lineage, n)], own identity first: the first n rows of this set equal the first n rows of the set `lineage`."""
+        return [(self.lineage, len(self))] + (self._chain or [])
+
+    def _inherit(self, parent: 'BeliefSet', n_prefix: int) -> None:
+        self._chain = [(l, min(n, n_prefix)) for l, n in parent.lineage_chain][:self.LINEAGE_DEPTH]
 
     @property
     def belief_array(self) -> torch.Tensor:
@@ -271,7 +284,7 @@ class BeliefSet:
         for j in fresh:
             index[other_keys[j]] = len(index)             # == its row position: the index held exactly n_self keys on entry
         out._keys, out._store, out._store_used = index, store, used
-        out.lineage = self.lineage
+        out._inherit(self, n_self)
         return out
 
     def _union_general(self, other_belief_set: 'BeliefSet') -> 'BeliefSet':
@@ -284,7 +297,7 @@ class BeliefSet:
         out = BeliefSet(self.model, rows, _hashes=hashes)
         n_self = len(self)
         if first.shape[0] >= n_self and np.array_equal(first[:n_self], np.arange(n_self)):
-            out.lineage = self.lineage          # own rows survive as a prefix: per-row results cached for `self` stay valid
+            out._inherit(self, n_self)          # own rows survive as a prefix: per-row results cached for `self` stay valid for it
         return out
 
     def to_gpu(self) -> 'BeliefSet':

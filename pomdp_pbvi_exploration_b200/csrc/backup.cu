@@ -60,14 +60,21 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
 //      single bulk async copy drops into shared memory already in its bank-conflict-free layout.  Images of row groups that
 //      are all-zero on a chunk are NOT written (the score kernel never fetches them): on the bench workload that is 60 % of
 //      the image.  A warp owns one row group and a 32-state slab at a time: 16 independent row loads in flight per lane.
+//      Non-finite input (np.argmax / NaN semantics of the reference): a row that holds a NaN or an infinity makes every one of its
+//      scores NaN in the reference (NaN * 0 = NaN), so it is only flagged here (rowBad) and combine_tiles_kernel writes the
+//      reference's result for it -- v* = 0, score NaN -- whatever the kernel accumulated.  Non-finite ALPHAS (signs[SIGN_DENSE], set
+//      by alpha_row_mask_kernel, which runs first) make every zero-skipping rule invalid (0 * inf = NaN): then every row group of
+//      every chunk is written and marked live and the score kernel runs the dense product.
 __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restrict__ beliefs, int nB, int S, int nChunks,
-                                                          uint8_t* __restrict__ bits, double* __restrict__ beliefsP, int* __restrict__ signs) {
+                                                          uint8_t* __restrict__ bits, double* __restrict__ beliefsP, int* __restrict__ signs,
+                                                          uint8_t* __restrict__ rowBad) {
     __shared__ unsigned smask[MASK_CHUNKS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cb = blockIdx.x, mt = blockIdx.y;
     const int rg = w & 3;
     if (tid < MASK_CHUNKS) smask[tid] = 0u;
     __syncthreads();
+    const bool dense = signs[SIGN_DENSE] != 0;
     bool bad = false;
     const int row0 = mt * BM + rg * RG;
     constexpr int CPS = 32 / KC;                         // chunks per slab
@@ -81,10 +88,11 @@ __global__ void __launch_bounds__(256) belief_mask_kernel(const double* __restri
         for (int r = 0; r < RG; r++) {
             nz |= v[r] != 0.0;
             bad |= !(v[r] >= 0.0);                       // negative or NaN entry: no exact-zero shortcut for this call
+            if (!(fabs(v[r]) <= 1.79769313486231570e308)) rowBad[row0 + r] = 1;     // NaN / inf (never a pad row: those read 0.0)
         }
         const unsigned bal = __ballot_sync(0xffffffffu, nz);
         const int cl = lane / KC;                        // this lane's chunk inside the slab
-        const bool live = ((bal >> (cl * KC)) & ((1u << KC) - 1u)) != 0u;
+        const bool live = dense || ((bal >> (cl * KC)) & ((1u << KC) - 1u)) != 0u;
         const int c = (cb * MASK_COLS + sl * 32) / KC + cl;
         if (live && c < nChunks) {
             double* dst = beliefsP + (((size_t)mt * nChunks + c) * NRG + rg) * A_GROUP_DOUBLES;
@@ -123,15 +131,17 @@ __global__ void __launch_bounds__(256) alpha_row_mask_kernel(const double* __res
     }
     if (lane == 0) rowLive[(size_t)nt * S + s] = (uint8_t)live;
     if (neg) signs[0] = 1;
-    if (nonfinite) signs[2] = 1;
+    if (nonfinite) signs[SIGN_DENSE] = 1;
 }
 
 // ---- bLive[nt][g][c]: bit q set iff some state k of chunk c gathers an alphaT row that is live in column quarter q: row index
 //      reach[g][k] (g = action) for the gather path, k itself when reach == nullptr (plain path, one group)
 __global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __restrict__ rowLive, const int32_t* __restrict__ reachP,
-                                                               int S, int Sp, int nChunks, int nG, int nNt, uint8_t* __restrict__ bLive) {
+                                                               int S, int Sp, int nChunks, int nG, int nNt, uint8_t* __restrict__ bLive,
+                                                               const int* __restrict__ signs) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= (size_t)nNt * nG * nChunks) return;
+    if (signs[SIGN_DENSE]) { bLive[i] = 0xFu; return; }          // non-finite alphas: nothing may be skipped
     const int c = (int)(i % nChunks), g = (int)((i / nChunks) % nG), nt = (int)(i / ((size_t)nChunks * nG));
     const uint8_t* live = rowLive + (size_t)nt * S;
     unsigned any = 0;
@@ -149,12 +159,14 @@ __global__ void __launch_bounds__(256) chunk_alpha_mask_kernel(const uint8_t* __
 //      of chunk h of the stage (0 when the chunk is dead).
 __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ zMask,
                                                                const uint8_t* __restrict__ bLive, int nG, int zPerG, int nChunks, int nZ,
-                                                               int nNt, uint2* __restrict__ lists, int32_t* __restrict__ counts) {
+                                                               int nNt, uint2* __restrict__ lists, int32_t* __restrict__ counts,
+                                                               const int* __restrict__ signs) {
     const int z = blockIdx.x / nNt, nt = blockIdx.x % nNt, mt = blockIdx.y, lane = threadIdx.x;
     const size_t slot = ((size_t)mt * nZ + z) * nNt + nt;
     const int nStages = nChunks / SUB;
     uint2* list = lists + slot * nStages;
     const uint8_t* bl = bLive ? bLive + ((size_t)nt * nG + z / zPerG) * nChunks : nullptr;
+    if (signs[SIGN_DENSE]) zMask = nullptr;             // non-finite alphas: a zero RTO factor does not make the term zero
     int base = 0;
     for (int s0 = 0; s0 < nStages; s0 += 32) {
         const int sg = s0 + lane;
@@ -177,25 +189,32 @@ __global__ void __launch_bounds__(32) build_chunk_lists_kernel(const uint8_t* __
 }
 
 // ---- argmax across the column quarters of all alpha tiles: ascending column order, strict > keeps the lowest index on ties ----------------------
+//      np.argmax semantics (argmax_append): the first NaN wins, an all -inf row yields column 0; a quarter that lies entirely beyond V carries
+//      ARG_NONE and is passed over.  Rows flagged non-finite by belief_mask_kernel get the reference's result outright: every score
+//      of such a row is NaN there, so v* = 0 and the maximum is NaN.
 __global__ void __launch_bounds__(256) combine_tiles_kernel(const double* __restrict__ pval, const int32_t* __restrict__ pidx, int nNt,
-                                                            size_t n, double* __restrict__ outVal, int32_t* __restrict__ outIdx) {
+                                                            size_t n, int nZ, int nV, const uint8_t* __restrict__ rowBad,
+                                                            double* __restrict__ outVal, int32_t* __restrict__ outIdx) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double best = pval[i];
     int idx = pidx[i];
     for (int t = 1; t < nNt; t++) {
-        const double v = pval[(size_t)t * n + i];
-        if (v > best) { best = v; idx = pidx[(size_t)t * n + i]; }
+        const int id = pidx[(size_t)t * n + i];
+        if (id != ARG_NONE) argmax_append(best, idx, pval[(size_t)t * n + i], id);
     }
+    if (rowBad[i / (size_t)nZ]) { best = __longlong_as_double(0x7ff8000000000000ll); idx = 0; }
     if (outVal) outVal[i] = best;
-    if (outIdx) outIdx[i] = idx;
+    if (outIdx) outIdx[i] = min(max(idx, 0), nV - 1);
 }
 
 // ---- R > 1: GammaT[j][s][v] = sum_r RTO[z][s*R+r] * alphaT[reach[a][s*R+r]][v] for z = zOrder[zBegin + j] ----------
 __global__ void __launch_bounds__(256) gamma_project_kernel(const double* __restrict__ alphaT, const int32_t* __restrict__ reachK,
                                                             const double* __restrict__ rtoK, const int32_t* __restrict__ zOrder,
-                                                            int zBegin, int S, int R, int O, int Vp, double* __restrict__ out) {
+                                                            int zBegin, int S, int R, int O, int Vp, double* __restrict__ out,
+                                                            const int* __restrict__ signs) {
     const int j = blockIdx.y, z = zOrder[zBegin + j], a = z / O;
+    const bool dense = signs[SIGN_DENSE] != 0;          // non-finite alphas: 0 * inf = NaN must survive, like in the reference's einsum
     const int s0 = blockIdx.x * 8;
     const int32_t* reach = reachK + (size_t)a * S * R;
     const double* rto = rtoK + (size_t)z * S * R;
@@ -206,9 +225,9 @@ __global__ void __launch_bounds__(256) gamma_project_kernel(const double* __rest
         for (int r = 0; r < R; r++) {
             const size_t k = (size_t)s * R + r;
             const double w = rto[k];
-            if (w != 0.0) acc += w * alphaT[(size_t)reach[k] * Vp + v];
+            if (w != 0.0 || dense) acc += w * alphaT[(size_t)reach[k] * Vp + v];
         }
-        out[((size_t)j * S + s) * Vp + v] = acc;
+        out[((size_t)j * (S + 1) + s) * Vp + v] = acc;
     }
 }
 
@@ -293,25 +312,30 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
                                                            const double* __restrict__ rtoK, const double* __restrict__ rbarT,
                                                            const double* __restrict__ approx, const int* __restrict__ signs, int modelNonneg,
                                                            const uint8_t* __restrict__ bits, int nChunks, int b0, double gamma, int S, int R,
-                                                           int A, int O, int needExact, double* __restrict__ value) {
+                                                           int A, int O, int nV, int needExact, double relMargin,
+                                                           double* __restrict__ value) {
     extern __shared__ int s_vsel[];
     __shared__ double sh[8];
     const int a = blockIdx.x, b = b0 + blockIdx.y;
-    {
+    // non-finite alphas: the reference's value is NaN / inf arithmetic over EVERY state (0 * inf = NaN), so nothing is screened or skipped
+    const bool dense = signs[SIGN_DENSE] != 0;
+    // Screening needs a bound on how far the score-order sum can be from the reference-order sum.  With non-negative terms both
+    // rounding errors are below n * eps * value, n = S*R*O terms (7.3e-12 relative for the olfactory model), so relMargin =
+    // max(1e-10, 4 * n * eps) times |best| separates safely.  With mixed
+    // signs the terms can cancel and the error is bounded by n * eps * sum |terms|, which is not known here: every action is
+    // then evaluated exactly (small / reward-penalty models: the pass is cheap there).
+    const bool nonneg = modelNonneg && !signs[0] && !signs[1];
+    if (!dense && nonneg) {
         const double mine = approx[(size_t)b * A + a];
         // every term of the sum is >= 0 (model, beliefs and alphas are non-negative) and the score-order sum is exactly 0:
         // all terms are zero, so the reference-order sum is exactly +0.0 too
-        if (mine == 0.0 && modelNonneg && gamma > 0.0 && !signs[0] && !signs[1]) {
+        if (mine == 0.0 && gamma > 0.0) {
             if (threadIdx.x == 0) value[(size_t)b * A + a] = 0.0;
             return;
         }
         double best = -INFINITY;
         for (int aa = 0; aa < A; aa++) best = fmax(best, approx[(size_t)b * A + aa]);
-        // how far the score-order sum can be from the reference-order sum: with non-negative terms the rounding error of both is
-        // below n * eps * value (2.4e-12 relative for S = 22021), so 1e-10 * |best| separates safely; with mixed signs the terms
-        // can cancel and only the looser absolute bound is used
-        const bool nonneg = modelNonneg && !signs[0] && !signs[1];
-        const double margin = nonneg ? 1e-10 * fabs(best) : 1e-9 * fmax(1.0, fabs(best));
+        const double margin = relMargin * fabs(best);
         if (!(mine >= best - margin)) {
             if (threadIdx.x == 0) value[(size_t)b * A + a] = mine;
             return;
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
             }
         }
     }
-    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vstar[((size_t)b * A + a) * O + o];
+    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = min(max(vstar[((size_t)b * A + a) * O + o], 0), nV - 1);
     __syncthreads();
     const double* brow = beliefs + (size_t)b * S;
     const int32_t* reach = reachK + (size_t)a * S * R;
@@ -342,11 +366,11 @@ __global__ void __launch_bounds__(256) backup_value_kernel(const double* __restr
     const uint8_t* live = bits + (size_t)(b / BM) * nChunks;
     const unsigned gbit = 1u << ((b % BM) / RG);
     for (int c = threadIdx.x / KC; c < nChunks; c += 256 / KC) {
-        if (!(live[c] & gbit)) continue;
+        if (!(live[c] & gbit)) continue;                 // (dense mode: belief_mask_kernel marked every chunk live)
         const int s = c * KC + (threadIdx.x % KC);
         if (s >= S) continue;
         const double bs = brow[s];
-        if (bs != 0.0) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s, skipZero), part);
+        if (bs != 0.0 || dense) part = fma(bs, alpha_a_entry(alphas, S, R, O, s_vsel, reach, rtoA, rbarA, gamma, s, skipZero), part);
     }
     const double tot = block_sum_256(part, sh);
     if (threadIdx.x == 0) value[(size_t)b * A + a] = tot;
@@ -373,12 +397,12 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double* __restrict_
                                                        const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                        const double* __restrict__ rbarT, double gamma, int S, int R, int O,
                                                        double* __restrict__ out, unsigned long long* __restrict__ hacc,
-                                                       const int* __restrict__ nonfinite) {
+                                                       const int* __restrict__ nonfinite, int A, int nV) {
     extern __shared__ int s_vsel[];
     __shared__ unsigned long long sh[2][8];
-    const int i = blockIdx.y, a = actions[i];
+    const int i = blockIdx.y, a = min(max(actions[i], 0), A - 1);       // indices are clamped: a bad tuple never reads out of bounds
     const int32_t* vs = vsel + (size_t)i * vselStride + (perAction ? (size_t)a * O : 0);
-    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = vs[o];
+    for (int o = threadIdx.x; o < O; o += 256) s_vsel[o] = min(max(vs[o], 0), nV - 1);
     __syncthreads();
     const int s = blockIdx.x * 256 + threadIdx.x;
     unsigned long long h0 = 0, h1 = 0;
@@ -418,14 +442,14 @@ __global__ void __launch_bounds__(256) action_order_kernel(const int32_t* __rest
     extern __shared__ int s_cnt[];     // [A] counts, then running bases
     for (int a = threadIdx.x; a < A; a += 256) s_cnt[a] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&s_cnt[actions[i]], 1);
+    for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&s_cnt[min(max(actions[i], 0), A - 1)], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         for (int a = 0; a < A; a++) { const int c = s_cnt[a]; s_cnt[a] = run; run += (c + G - 1) / G * G; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += 256) order[atomicAdd(&s_cnt[actions[i]], 1)] = i;
+    for (int i = threadIdx.x; i < n; i += 256) order[atomicAdd(&s_cnt[min(max(actions[i], 0), A - 1)], 1)] = i;
 }
 
 // ---- assemble for reachable_state_count == 1 and O <= OM: a block writes the same SPT*256-state slice of G tuples of ONE
@@ -440,7 +464,8 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
                                                                const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
                                                                const double* __restrict__ rbarT, double gamma, int S, int O,
                                                                double* __restrict__ out, unsigned long long* __restrict__ hacc,
-                                                               const uint4* __restrict__ hashKeys, const int* __restrict__ nonfinite) {
+                                                               const uint4* __restrict__ hashKeys, const int* __restrict__ nonfinite,
+                                                               int A, int nV) {
     __shared__ int s_idx[G], s_v[G][OM];
     __shared__ unsigned long long sh[G][8][2];
     const int slot0 = blockIdx.y * G;
@@ -449,9 +474,9 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
     if (s_idx[0] < 0) return;                        // padding block (uniform)
     if (threadIdx.x < G * OM) {
         const int g = threadIdx.x / OM, o = threadIdx.x % OM;
-        s_v[g][o] = (s_idx[g] >= 0 && o < O) ? vsel[(size_t)s_idx[g] * O + o] : 0;
+        s_v[g][o] = (s_idx[g] >= 0 && o < O) ? min(max(vsel[(size_t)s_idx[g] * O + o], 0), nV - 1) : 0;
     }
-    const int a = actions[s_idx[0]];
+    const int a = min(max(actions[s_idx[0]], 0), A - 1);
     __syncthreads();
     const int sBase = blockIdx.x * (SPT * 256) + threadIdx.x;
     const bool skipZero = !*nonfinite;              // finite alphas: a zero RTO factor makes the term +-0.0 (see alpha_a_entry)
@@ -541,10 +566,11 @@ __global__ void __launch_bounds__(256) assemble_grouped_kernel(const double* __r
 }
 
 template <int G, int OM, int SPT>
-static void launch_assemble_grouped(pbvi_model* m, const double* d_alphas, const int32_t* d_actions, const int32_t* d_vsel, const int32_t* order,
-                                    int nPad, double gamma, double* d_out, unsigned long long* hacc, const int* nonfinite, cudaStream_t st) {
+static void launch_assemble_grouped(pbvi_model* m, const double* d_alphas, int nV, const int32_t* d_actions, const int32_t* d_vsel,
+                                    const int32_t* order, int nPad, double gamma, double* d_out, unsigned long long* hacc, const int* nonfinite,
+                                    cudaStream_t st) {
     assemble_grouped_kernel<G, OM, SPT><<<dim3(ceil_div(m->S, SPT * 256), nPad / G), 256, 0, st>>>(
-        d_alphas, d_actions, d_vsel, order, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, m->hashKeys, nonfinite);
+        d_alphas, d_actions, d_vsel, order, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, m->hashKeys, nonfinite, m->A, nV);
 }
 
 __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* __restrict__ h, int n, int rowLen) {
@@ -555,13 +581,14 @@ __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* 
 }
 
 // =====================================================================================================================
+// Function attributes are per device: called by pbvi_model_create for the handle's device (current when called).
+int configure_backup_kernels() {
+    PBVI_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
+    PBVI_CUDA(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
+    return PBVI_OK;
+}
+
 static int launch_score(pbvi_model* m, bool gather, ScoreParams& p, int nNt, int nMt, int nZ, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        PBVI_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
-        PBVI_CUDA(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
-        configured = true;
-    }
     // persistent: one block per SM pulls (z, belief tile, alpha tile) tiles from a queue
     PBVI_REQUIRE((long long)nNt * nMt * nZ < (1ll << 31), "too many score tiles");
     p.nMt = nMt; p.nNt = nNt; p.nzLaunch = nZ;
@@ -585,39 +612,42 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
     PBVI_REQUIRE(nMt <= 65535, "too many beliefs in one call (limit 65535 * 64)");
     PBVI_REQUIRE(nZ <= 65535, "too many (action, observation) pairs");
 
-    PBVI_TAKE(alphaT, double, (size_t)S * Vp);
+    // S + 1 rows: row S is all zero.  The pad states of the last pipeline stage (S is rounded up to whole stages) gather THAT row, so
+    // their contribution is 0 * 0 whatever the alphas hold (a pad that re-read a real row would turn an infinite alpha into NaN).
+    PBVI_TAKE(alphaT, double, (size_t)(S + 1) * Vp);
     PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
+    PBVI_CUDA(cudaMemsetAsync(alphaT + (size_t)S * Vp, 0, (size_t)Vp * sizeof(double), st));
 
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
     m->last_bits = bits;           // read again by the value pass of the same call
     PBVI_TAKE(beliefsP, double, (size_t)nMt * nC * NRG * A_GROUP_DOUBLES);
-    PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 3 * sizeof(int), st));
-    belief_mask_kernel<<<dim3(ceil_div(nC, MASK_CHUNKS), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs);
-    m->last_launches++;
-    // alpha-side occupancy (gather path: per action; plain max_v path: one group; Gamma path: not masked)
+    PBVI_TAKE(rowBad, uint8_t, (size_t)nMt * BM);
+    PBVI_CUDA(cudaMemsetAsync(m->d_signs, 0, 8 * sizeof(int), st));
+    PBVI_CUDA(cudaMemsetAsync(rowBad, 0, (size_t)nMt * BM, st));
+    // alpha-side occupancy first: its scan also decides whether anything may be skipped at all (SIGN_DENSE: non-finite alphas).
+    // Gather path: per action; plain max_v path: one group; Gamma path (R > 1): scanned for the sign / finiteness flags only (a
+    // Gamma built from a non-negative model and non-negative alphas is non-negative), its B operand is not masked.
     uint8_t* bLive = nullptr;
     int nG = 1, zPerG = 1;
+    PBVI_TAKE(rowLive, uint8_t, (size_t)nNt * S);
+    alpha_row_mask_kernel<<<(unsigned)ceil_div_sz((size_t)S * nNt * 32, 256), 256, 0, st>>>(alphaT, S, Vp, nNt, rowLive, m->d_signs);
+    m->last_launches++;
     if (!backup || R == 1) {
         nG = backup ? m->A : 1;
         zPerG = backup ? m->O : 1;
-        PBVI_TAKE(rowLive, uint8_t, (size_t)nNt * S);
-        alpha_row_mask_kernel<<<(unsigned)ceil_div_sz((size_t)S * nNt * 32, 256), 256, 0, st>>>(alphaT, S, Vp, nNt, rowLive, m->d_signs);
         bLive = m->arena.take<uint8_t>((size_t)nNt * nG * nC);
         if (!bLive) return PBVI_ERR_OOM;
         chunk_alpha_mask_kernel<<<(unsigned)ceil_div_sz((size_t)nNt * nG * nC, 256), 256, 0, st>>>(rowLive, backup ? m->reachP : nullptr, S,
-                                                                                                  m->Sp, nC, nG, nNt, bLive);
-        m->last_launches += 2;
+                                                                                                  m->Sp, nC, nG, nNt, bLive, m->d_signs);
+        m->last_launches++;
     }
-    else {
-        static const int one = 1;          // Gamma path: the alphas are not scanned, so no exact-zero shortcut and no zero-term skip
-        PBVI_CUDA(cudaMemcpyAsync(m->d_signs, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-        PBVI_CUDA(cudaMemcpyAsync(m->d_signs + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-    }
+    belief_mask_kernel<<<dim3(ceil_div(nC, MASK_CHUNKS), nMt), 256, 0, st>>>(d_beliefs, nB, S, nC, bits, beliefsP, m->d_signs, rowBad);
+    m->last_launches++;
     PBVI_REQUIRE((size_t)nZ * nNt <= 2147483647u, "too many (z, alpha tile) pairs");
     PBVI_TAKE(lists, uint2, (size_t)nMt * nZ * nNt * (nC / SUB));
     PBVI_TAKE(counts, int32_t, (size_t)nMt * nZ * nNt);
     build_chunk_lists_kernel<<<dim3(nZ * nNt, nMt), 32, 0, st>>>(bits, backup ? m->zMask : nullptr, bLive, nG, zPerG, nC, nZ, nNt, lists,
-                                                                 counts);
+                                                                 counts, m->d_signs);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
 
@@ -639,20 +669,22 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
         PBVI_TRY(launch_score(m, true, p, nNt, nMt, nZ, st));
     } else {
         // Gamma projection in groups of z bounded by ~8 GB of scratch
-        const size_t perZ = (size_t)S * Vp * sizeof(double);
+        const size_t perZ = (size_t)(S + 1) * Vp * sizeof(double);             // + the zero row of the pad states
         const int zGroup = (int)std::max<size_t>(1, std::min<size_t>(nZ, (size_t(8) << 30) / perZ));
-        PBVI_TAKE(gammaT, double, (size_t)zGroup * S * Vp);
+        PBVI_TAKE(gammaT, double, (size_t)zGroup * (S + 1) * Vp);
+        PBVI_CUDA(cudaMemset2DAsync(gammaT + (size_t)S * Vp, perZ, 0, (size_t)Vp * sizeof(double), (size_t)zGroup, st));
         for (int z0 = 0; z0 < nZ; z0 += zGroup) {
             const int nz = std::min(zGroup, nZ - z0);
-            gamma_project_kernel<<<dim3(ceil_div(S, 8), nz), 256, 0, st>>>(alphaT, m->reachK, m->rtoK, m->zOrder, z0, S, R, m->O, Vp, gammaT);
+            gamma_project_kernel<<<dim3(ceil_div(S, 8), nz), 256, 0, st>>>(alphaT, m->reachK, m->rtoK, m->zOrder, z0, S, R, m->O, Vp, gammaT,
+                                                                           m->d_signs);
             m->last_launches++;
-            p.bmat = gammaT; p.zStrideB = (size_t)S * Vp; p.zOrder = m->zOrder + z0;
+            p.bmat = gammaT; p.zStrideB = (size_t)(S + 1) * Vp; p.zOrder = m->zOrder + z0;
             PBVI_TRY(launch_score(m, false, p, nNt, nMt, nz, st));
         }
     }
     if (m->profile) { PBVI_CUDA(cudaEventRecord(m->evScore1, st)); m->score_timed = true; }
     const size_t n = (size_t)nB * nZ;
-    combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt * NCW, n, outVal, outIdx);
+    combine_tiles_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(pval, pidx, nNt * NCW, n, nZ, nV, rowBad, outVal, outIdx);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
@@ -688,11 +720,12 @@ static int select_impl(pbvi_model* m, const double* d_beliefs, int nB, const dou
                                                                                           m->rbarNzVal, gamma, m->S, m->A, m->O, nB, approx);
     m->last_launches++;
     // grid.y is limited to 65535: walk the beliefs in slabs
+    const double relMargin = std::max(1e-10, 4.0 * (double)m->S * m->R * m->O * 1.1102230246251565e-16);
     for (int b0 = 0; b0 < nB; b0 += 65535) {
         const int nb = std::min(65535, nB - b0);
         backup_value_kernel<<<dim3(m->A, nb), 256, m->O * sizeof(int), st>>>(
             d_beliefs, d_alphas, d_vstar, m->reachK, m->rtoK, m->rbarT, approx, m->d_signs, m->model_nonneg ? 1 : 0, m->last_bits, m->nChunks,
-            b0, gamma, m->S, m->R, m->A, m->O, needExact, d_value);
+            b0, gamma, m->S, m->R, m->A, m->O, nV, needExact, relMargin, d_value);
         m->last_launches++;
     }
     if (d_astar) {
@@ -721,9 +754,9 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
         PBVI_TAKE(order, int32_t, (size_t)nPad);
         PBVI_CUDA(cudaMemsetAsync(order, 0xFF, (size_t)nPad * sizeof(int32_t), st));
         action_order_kernel<<<1, 256, m->A * sizeof(int), st>>>(d_actions, n, m->A, G, order);
-        if (m->O <= 2) launch_assemble_grouped<G, 2, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
-        else if (m->O == 3) launch_assemble_grouped<G, 3, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
-        else launch_assemble_grouped<G, 4, SPT>(m, d_alphas, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
+        if (m->O <= 2) launch_assemble_grouped<G, 2, SPT>(m, d_alphas, nV, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
+        else if (m->O == 3) launch_assemble_grouped<G, 3, SPT>(m, d_alphas, nV, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
+        else launch_assemble_grouped<G, 4, SPT>(m, d_alphas, nV, d_actions, d_vsel, order, nPad, gamma, d_out, hacc, nonfinite, st);
         m->last_launches += 2;
         if (hacc) {
             hash_finalise_kernel<<<ceil_div(n, 256), 256, 0, st>>>(hacc, n, m->S);
@@ -736,7 +769,7 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
         const int ni = std::min(65535, n - i0);
         assemble_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, m->O * sizeof(int), st>>>(
             d_alphas, d_actions + i0, d_vsel + (size_t)i0 * vselStride, vselStride, perAction, m->reachK, m->rtoK, m->rbarT, gamma,
-            m->S, m->R, m->O, d_out + (size_t)i0 * m->S, hacc ? hacc + (size_t)i0 * 2 : nullptr, nonfinite);
+            m->S, m->R, m->O, d_out + (size_t)i0 * m->S, hacc ? hacc + (size_t)i0 * 2 : nullptr, nonfinite, m->A, nV);
         m->last_launches++;
     }
     if (hacc) {

@@ -165,20 +165,20 @@ __global__ void __launch_bounds__(256) observation_probability_kernel(const doub
 
 }  // namespace pbvi
 
+namespace pbvi {
+int configure_belief_kernels() {
+    PBVI_CUDA(cudaFuncSetAttribute(pairwise_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return PBVI_OK;
+}
+}  // namespace pbvi
+
 using namespace pbvi;
 
 // belief_stride: doubles between consecutive source beliefs (S for one belief per (a,o) pair, 0 to update one belief n ways)
 static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t beliefStride, const int32_t* d_actions,
                               const int32_t* d_observations, int n, int normalise, double* d_out, double* d_norm, cudaStream_t st) {
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
-    if (smem > 48 * 1024) {
-        static bool configured = false;
-        PBVI_REQUIRE(smem <= 200 * 1024, "state space too large for the pairwise-sum kernel");
-        if (!configured) {
-            PBVI_CUDA(cudaFuncSetAttribute(pairwise_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = true;
-        }
-    }
+    PBVI_REQUIRE(smem <= 200 * 1024, "state space too large for the pairwise-sum kernel");      // opt-in set by configure_belief_kernels
     for (int i0 = 0; i0 < n; i0 += 65535) {
         const int ni = std::min(65535, n - i0);
         double* out = d_out + (size_t)i0 * m->S;

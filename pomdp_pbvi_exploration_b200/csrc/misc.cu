@@ -3,6 +3,8 @@
 // (src/pomdp.py:887-895) and SSEA's novelty distance (src/pomdp.py:1682-1686).  All HBM-bound streaming kernels.
 #include <algorithm>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pbvi_common.cuh"
 
 namespace pbvi {
@@ -91,19 +93,21 @@ __global__ void __launch_bounds__(256) group_insert_kernel(const uint32_t* __res
 
 // The same insertion over the all-gathered blocks of the sharded backup's tuple exchange: `world` blocks of blockRows rows of
 // (w + 2) int32 words; row 0 of a block is its header (word 0 = number of records u_r), rows 1..u_r are records
-// (key[w], first position, last position).  The record index is the row index in the whole buffer (rank-major = belief order);
-// the rank of a record for `last` is its last-position word.  maxCount receives max_r u_r (overflow check of the caller).
+// (key[w], first position, last position).  Positions are positions in the WHOLE belief set, so the merge does not depend on how
+// the beliefs are spread over the ranks (contiguous blocks, or the append-only interleaved ownership of the sharded solve): a
+// group's first record is the one with the smallest first position, its last record the one with the largest last position, and
+// the groups come out ordered by their first position (group_collect_kernel + a radix sort of the (position, row) words).
+// maxCount receives max_r u_r (overflow check of the caller).
 __global__ void __launch_bounds__(256) group_insert_blocks_kernel(const int32_t* __restrict__ blocks, int world, int blockRows, int w, int T,
-                                                                  int32_t* rep, int32_t* __restrict__ gfirst,
-                                                                  unsigned long long* __restrict__ glast, int32_t* __restrict__ slotOf,
-                                                                  int32_t* __restrict__ maxCount) {
+                                                                  int32_t* rep, unsigned long long* __restrict__ gfirst,
+                                                                  unsigned long long* __restrict__ glast, int32_t* __restrict__ maxCount) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= world * blockRows) return;
     const int stride = w + 2;
     const int r = i / blockRows, j = i - r * blockRows;
     const int count = blocks[(size_t)r * blockRows * stride];
     if (j == 0) atomicMax(maxCount, count);
-    if (j == 0 || j > count) { slotOf[i] = -1; return; }
+    if (j == 0 || j > count) return;
     const uint32_t* k = reinterpret_cast<const uint32_t*>(blocks) + (size_t)i * stride;
     uint32_t h = key_hash(k, w) & (uint32_t)(T - 1);
     for (;;) {
@@ -118,9 +122,42 @@ __global__ void __launch_bounds__(256) group_insert_blocks_kernel(const int32_t*
         if (eq) break;
         h = (h + 1) & (uint32_t)(T - 1);
     }
-    slotOf[i] = (int32_t)h;
-    atomicMin(gfirst + h, i);
+    atomicMin(gfirst + h, ((unsigned long long)k[w] << 32) | (unsigned long long)(uint32_t)i);
     atomicMax(glast + h, ((unsigned long long)k[w + 1] << 32) | (unsigned long long)(uint32_t)i);
+}
+
+__global__ void __launch_bounds__(256) group_blocks_init_kernel(int32_t* __restrict__ rep, unsigned long long* __restrict__ gfirst,
+                                                                unsigned long long* __restrict__ glast, int T,
+                                                                unsigned long long* __restrict__ sortKeys, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < T) { rep[i] = -1; gfirst[i] = ~0ull; glast[i] = 0ull; }
+    if (i < n) sortKeys[i] = ~0ull;                    // unused sort slots sink to the end
+}
+
+// occupied slots -> (first position << 32 | row of that record, slot), unordered; count[0] = number of groups
+__global__ void __launch_bounds__(256) group_collect_kernel(const int32_t* __restrict__ rep, const unsigned long long* __restrict__ gfirst, int T,
+                                                            unsigned long long* __restrict__ sortKeys, int32_t* __restrict__ sortSlots,
+                                                            int32_t* __restrict__ count) {
+    const int h = blockIdx.x * 256 + threadIdx.x;
+    const bool used = h < T && rep[h] != -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, used);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (used) {
+        const int at = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+        sortKeys[at] = gfirst[h];
+        sortSlots[at] = h;
+    }
+}
+
+__global__ void __launch_bounds__(256) group_emit_kernel(const unsigned long long* __restrict__ sortedKeys, const int32_t* __restrict__ sortedSlots,
+                                                         const unsigned long long* __restrict__ glast, const int32_t* __restrict__ count,
+                                                         int32_t* __restrict__ first, int32_t* __restrict__ last) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= *count) return;
+    first[g] = (int32_t)(sortedKeys[g] & 0xffffffffull);
+    last[g] = (int32_t)(glast[sortedSlots[g]] & 0xffffffffull);
 }
 
 // one block: stream compaction of the group-first records in ascending index order (tiles of 1024, ballot scan)
@@ -237,6 +274,7 @@ __global__ void __launch_bounds__(256) prune_dominated_kernel(const double* __re
 // forms were tried and are slower there: a warp per query with a reciprocal-screened two-pass minimum (12.2 s) and a dense walk
 // with eight query loads in flight per thread (12.9 s); the per-level host round trips now weigh as much as this kernel.
 constexpr int SAW_RANGE = 8192;
+constexpr int SAW_Q_SLAB = 4096;
 
 __global__ void __launch_bounds__(256) sawtooth_v0_kernel(const double* __restrict__ corner, const double* __restrict__ queries, int S,
                                                           double* __restrict__ v0) {
@@ -376,6 +414,12 @@ __global__ void __launch_bounds__(256) ger_eps_kernel(const double* __restrict__
     }
 }
 
+int configure_misc_kernels() {
+    PBVI_CUDA(cudaFuncSetAttribute(sawtooth_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((sizeof(double) + sizeof(int)) * SAW_RANGE + sizeof(double) * SAW_Q_SLAB)));
+    return PBVI_OK;
+}
+
 }  // namespace pbvi
 
 using namespace pbvi;
@@ -473,16 +517,23 @@ extern "C" int pbvi_group_record_blocks(pbvi_model* m, const int32_t* d_blocks, 
     while (T < 2 * n) T <<= 1;
     m->arena.reset();
     PBVI_TAKE(rep, int32_t, (size_t)T);
-    PBVI_TAKE(gfirst, int32_t, (size_t)T);
+    PBVI_TAKE(gfirst, unsigned long long, (size_t)T);
     PBVI_TAKE(glast, unsigned long long, (size_t)T);
-    PBVI_TAKE(slotOf, int32_t, (size_t)n);
-    PBVI_TAKE(groupOfSlot, int32_t, (size_t)T);
+    PBVI_TAKE(keysIn, unsigned long long, (size_t)n);
+    PBVI_TAKE(keysOut, unsigned long long, (size_t)n);
+    PBVI_TAKE(slotsIn, int32_t, (size_t)n);
+    PBVI_TAKE(slotsOut, int32_t, (size_t)n);
     PBVI_TAKE(count, int32_t, 2);
+    size_t sortBytes = 0;
+    PBVI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keysIn, keysOut, slotsIn, slotsOut, (int)n, 0, 64, st));
+    PBVI_TAKE(sortTemp, char, sortBytes);
     PBVI_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int32_t), st));
-    group_init_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, glast, T);
-    group_insert_blocks_kernel<<<ceil_div((int)n, 256), 256, 0, st>>>(d_blocks, world, block_rows, words, T, rep, gfirst, glast, slotOf, count + 1);
-    group_compact_kernel<<<1, 1024, 0, st>>>(slotOf, gfirst, glast, (int)n, groupOfSlot, d_first, d_last, count);
-    m->last_launches = 3;
+    group_blocks_init_kernel<<<ceil_div(std::max<int>(T, (int)n), 256), 256, 0, st>>>(rep, gfirst, glast, T, keysIn, (int)n);
+    group_insert_blocks_kernel<<<ceil_div((int)n, 256), 256, 0, st>>>(d_blocks, world, block_rows, words, T, rep, gfirst, glast, count + 1);
+    group_collect_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, T, keysIn, slotsIn, count);
+    PBVI_CUDA(cub::DeviceRadixSort::SortPairs(sortTemp, sortBytes, keysIn, keysOut, slotsIn, slotsOut, (int)n, 0, 64, st));
+    group_emit_kernel<<<ceil_div((int)n, 256), 256, 0, st>>>(keysOut, slotsOut, glast, count, d_first, d_last);
+    m->last_launches = 5;
     PBVI_CUDA(cudaGetLastError());
     int32_t c[2] = {0, 0};
     PBVI_CUDA(cudaMemcpyAsync(c, count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -558,13 +609,7 @@ extern "C" int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double
     PBVI_CUDA(cudaMemcpy2DAsync(terms + n_ub, (size_t)(n_ub + 1) * sizeof(double), v0, sizeof(double), sizeof(double), (size_t)n_q,
                                 cudaMemcpyDeviceToDevice, st));
     if (n_ub > 0) {
-        constexpr int Q_SLAB = 4096;                   // queries per launch (their running minima live in shared memory)
-        static bool configured = false;
-        if (!configured) {
-            PBVI_CUDA(cudaFuncSetAttribute(sawtooth_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((sizeof(double) + sizeof(int)) * SAW_RANGE + sizeof(double) * Q_SLAB)));
-            configured = true;
-        }
+        constexpr int Q_SLAB = SAW_Q_SLAB;             // queries per launch (their running minima live in shared memory)
         for (int q0 = 0; q0 < n_q; q0 += Q_SLAB) {
             const int nq = std::min(Q_SLAB, n_q - q0);
             const size_t smem = (sizeof(double) + sizeof(int)) * SAW_RANGE + sizeof(double) * (size_t)nq;

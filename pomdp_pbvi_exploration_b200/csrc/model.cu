@@ -116,10 +116,14 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
         return PBVI_ERR_UNSUPPORTED;
     }
 
+    PBVI_TRY(configure_backup_kernels());
+    PBVI_TRY(configure_belief_kernels());
+    PBVI_TRY(configure_misc_kernels());
+
     pbvi_model* m = new pbvi_model();
     m->S = S; m->A = A; m->O = O; m->R = R;
     m->K = S * R;
-    m->Sp = ceil_div(S, 16) * 16;          // whole pipeline stages (SUB * KC <= 16 states); pad states land on state 0 with RTO 0
+    m->Sp = ceil_div(S, 16) * 16;          // whole pipeline stages (SUB * KC <= 16 states); pad states land on the zero row S with RTO 0
     m->nChunks = m->Sp / KC;
     m->nZ = A * O;
     m->device = device;
@@ -183,7 +187,7 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     std::vector<int32_t> reachP;
     std::vector<double> rtoP;
     if (R == 1) {
-        reachP.assign((size_t)A * Sp, 0);
+        reachP.assign((size_t)A * Sp, S);           // pad states gather row S of alphaT, which the select call keeps all-zero
         rtoP.assign((size_t)nZ * Sp, 0.0);
         for (int a = 0; a < A; a++) std::copy_n(&reachK[(size_t)a * K], S, &reachP[(size_t)a * Sp]);
         for (int z = 0; z < nZ; z++) std::copy_n(&rtoK[(size_t)z * K], S, &rtoP[(size_t)z * Sp]);

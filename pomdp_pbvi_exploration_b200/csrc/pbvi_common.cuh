@@ -29,6 +29,11 @@ constexpr int RG = 16;         // beliefs per row group (one warp's rows) -- the
 constexpr int NRG = BM / RG;   // 4 row groups per tile
 constexpr int SCORE_THREADS = NRG * (BN / 64) * 32;   // consumer threads of the score kernel (+ one producer warp)
 
+// d_signs[SIGN_DENSE]: some alpha of the running select / max_values call is NaN or +-inf.  Every zero-skipping rule of the engine rests
+// on "0 * x = 0", which fails for non-finite x (the reference's NumPy arithmetic yields NaN there), so all of them are switched off
+// for such a call and the dense product is computed.
+constexpr int SIGN_DENSE = 6;
+
 void set_error(const char* fmt, ...);
 
 #define PBVI_CUDA(call)                                                                              \
@@ -144,7 +149,7 @@ struct pbvi_model {
     bool model_nonneg = false;               // RTO >= 0 and Rbar >= 0 (checked once on the host)
     const uint8_t* last_bits = nullptr;      // belief occupancy bits of the running select call (arena memory)
     int* d_signs = nullptr;                  // [8] ([4]: tile queue counter of the score kernel) set by the last select: [0] some alpha < 0 or NaN, [1] some belief < 0 or NaN,
-                                             //     [2] some alpha NaN or +-inf; [3] the same for the alphas of the last assemble call
+                                             //     [SIGN_DENSE] some alpha NaN or +-inf; [3] the same for the alphas of the last assemble call
     double last_dense_flops = 0.0;
     double last_exec_scale = 0.0;            // flops per visited quadruple
     int last_launches = 0;
@@ -157,4 +162,9 @@ struct pbvi_model {
 namespace pbvi {
 // implemented in backup.cu, used by other translation units
 int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st);
+// per-device function attributes (dynamic shared memory opt-ins) of each translation unit; pbvi_model_create calls them with the
+// handle's device current, so a second handle on another GPU of the same process is configured too
+int configure_backup_kernels();
+int configure_belief_kernels();
+int configure_misc_kernels();
 }

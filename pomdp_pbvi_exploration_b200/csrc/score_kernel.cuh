@@ -64,7 +64,7 @@ static_assert((A_GROUP_DOUBLES * 8) % 16 == 0 && (KC * 8) % 16 == 0, "bulk copie
 
 struct ScoreParams {
     const double* beliefsP;    // [nMt][nChunks][NRG][RG][KC]  belief tiles as swizzled shared-memory images (belief_mask_kernel)
-    const double* bmat;        // GATHER: alphaT [S][Vp];  PLAIN: [nzLaunch][S][Vp], matrix of queue position zi at zi * zStrideB
+    const double* bmat;        // GATHER: alphaT [S+1][Vp];  PLAIN: [nzLaunch][S+1][Vp], matrix of queue position zi at zi * zStrideB (row S: zeros)
     size_t zStrideB;
     const int32_t* reachP;     // [A][Sp]          (GATHER)
     const double* rtoP;        // [A*O][Sp]        (GATHER)
@@ -118,9 +118,17 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// (value, index) combine with NumPy argmax semantics: larger value wins, equal values keep the lower index
+// (value, index) combine with np.argmax semantics: a NaN counts as the maximum, among equals (and among NaNs) the lower index
+// wins.  Index ARG_NONE marks "no column seen" (a thread / column quarter that lies entirely beyond V) and loses to everything.
+constexpr int ARG_NONE = 0x7fffffff;
 __device__ __forceinline__ void argmax_combine(double& v, int& i, double ov, int oi) {
-    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    const bool on = ov != ov, vn = v != v;
+    const bool better = on ? (!vn || oi < i) : (!vn && (ov > v || (ov == v && oi < i)));
+    if (oi != ARG_NONE && (i == ARG_NONE || better)) { v = ov; i = oi; }
+}
+// the same for a candidate that comes AFTER everything seen so far (ascending index): only a strictly larger value or the first NaN replaces
+__device__ __forceinline__ void argmax_append(double& v, int& i, double ov, int oi) {
+    if (i == ARG_NONE || (v == v && (ov > v || ov != ov))) { v = ov; i = oi; }
 }
 
 constexpr uint32_t META_TILE_END = 0xFFFFFFFFu;   // ring item that closes a tile (no stage has this index)
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
             const int nAct = h.nAct;
             auto gathered_row = [&](uint32_t stage) -> int {
                 const int k = (int)stage * SKC + (lane & (SKC - 1));
-                return GATHER ? reach[k] : min(k, p.S - 1);
+                return GATHER ? reach[k] : min(k, p.S);         // pad states (k >= S) read the all-zero row S of the B matrix
             };
             uint2 e0 = h.e0, e1 = h.e1;
             int row0n = nAct > 0 ? gathered_row(e0.x) : 0;
@@ -292,14 +300,13 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
 #pragma unroll
                 for (int i = 0; i < MT; i++) {
                     double best = -INFINITY;
-                    int bidx = 0x7fffffff;
+                    int bidx = ARG_NONE;
 #pragma unroll
                     for (int n = 0; n < 8; n++)
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
                             const int col = cbase + n * 8 + j;
-                            const double v = acc[i][n][j];
-                            if (col < p.V && v > best) { best = v; bidx = col; }
+                            if (col < p.V) argmax_append(best, bidx, acc[i][n][j], col);
                             acc[i][n][j] = 0.0;
                         }
 #pragma unroll

@@ -21,6 +21,44 @@ import torch.distributed as dist
 from .sets import group_by_key, unique_rows_first
 
 
+def _host_backend(group=None) -> bool:
+    """True when the group's collectives run on CPU tensors (gloo): device tensors are staged through the host.  Used by the
+    tests that run two ranks of the real engine on ONE GPU (NCCL refuses two ranks per device)."""
+    return dist.get_backend(group) == 'gloo'
+
+
+def all_gather_rows(out: torch.Tensor, local: torch.Tensor, group=None) -> None:
+    """`all_gather_into_tensor` that also works for CUDA tensors over a gloo group (staged through the host)."""
+    if local.is_cuda and _host_backend(group):
+        tmp = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(tmp, local.cpu(), group=group)
+        out.copy_(tmp)
+    else:
+        dist.all_gather_into_tensor(out, local, group=group)
+
+
+def all_reduce_(t: torch.Tensor, op, group=None) -> torch.Tensor:
+    if t.is_cuda and _host_backend(group):
+        tmp = t.cpu()
+        dist.all_reduce(tmp, op=op, group=group)
+        t.copy_(tmp)
+    else:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def broadcast_(t: torch.Tensor, src: int, group=None) -> torch.Tensor:
+    """Broadcast from GROUP rank `src`."""
+    gsrc = dist.get_global_rank(group, src) if group is not None else src
+    if t.is_cuda and _host_backend(group):
+        tmp = t.cpu()
+        dist.broadcast(tmp, gsrc, group=group)
+        t.copy_(tmp)
+    else:
+        dist.broadcast(t, gsrc, group=group)
+    return t
+
+
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple:
     """Contiguous block [lo, hi) of rank `rank`: ceil(n/P) rows per rank, the tail ranks may be short or empty."""
     per = -(-n_rows // world_size)
@@ -42,7 +80,7 @@ def _allgather_padded(local: torch.Tensor, counts: np.ndarray, group=None) -> to
         pad = torch.zeros((n_max, width), dtype=local.dtype, device=local.device)
         pad[:local.shape[0]] = local
     gathered = torch.empty((world * n_max, width), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, pad, group=group)
+    all_gather_rows(gathered, pad, group)
     if np.all(counts == n_max):
         return gathered
     keep = np.concatenate([np.arange(r * n_max, r * n_max + int(c)) for r, c in enumerate(counts)])
@@ -66,7 +104,7 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
     dev = rows.device
     n = rows.shape[0]
     counts_t = torch.empty((world,), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts_t, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+    all_gather_rows(counts_t, torch.tensor([n], dtype=torch.int64, device=dev), group)
     counts = counts_t.cpu().numpy()
     meta = np.empty((n, 3), dtype=np.int64)
     meta[:, 0] = actions
@@ -90,21 +128,20 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
         flags = rows_equal(rows, lost.astype(np.int32), merged, local_groups[lost].astype(np.int32))
         ok = int(bool(torch.as_tensor(flags).all()))
     ok_t = torch.tensor([ok], dtype=torch.int32, device=dev)
-    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN, group=group)
+    all_reduce_(ok_t, dist.ReduceOp.MIN, group)
     if int(ok_t[0]) == 0:
         raise RuntimeError('128-bit row key collision between different alpha rows of two ranks')
     payload = int(owned_counts.max()) * rows.shape[1] * 8 * world + int(counts.max()) * 24 * world
     return merged, meta_all[last, 0].copy(), meta_all[first, 1:].copy(), payload
 
 
-_LAST_MAX_COUNT = [512]
-
-
 def merge_blocks_host(blocks: torch.Tensor, world: int, block_rows: int, words: int):
     """
     `DeviceModel.group_record_blocks` for a gathered buffer held in a CPU tensor: (first_rows [g], last_rows [g], max_records).
-    Host logic only -- used where the exchange runs over gloo on CPU (tests/test_parallel_gloo.py); on a GPU the records never
-    leave the device (`pbvi_group_record_blocks`).
+    Records are grouped by key; a group's first record is the one with the smallest FIRST POSITION word, its last record the one
+    with the largest (last position, row), and the groups are ordered by their first position -- the dict over the whole belief
+    set, whatever the assignment of beliefs to ranks.  Host logic only -- used where the exchange runs over gloo on CPU
+    (tests/test_parallel_gloo.py); on a GPU the records never leave the device (`pbvi_group_record_blocks`).
     """
     b = blocks.numpy().reshape(world, block_rows, words + 2).astype(np.int64)
     counts = b[:, 0, 0]
@@ -113,16 +150,22 @@ def merge_blocks_host(blocks: torch.Tensor, world: int, block_rows: int, words: 
         z = torch.zeros((0,), dtype=torch.int64)
         return z, z, int(counts.max())
     recs = b.reshape(-1, words + 2)[rows]
-    first, _, inv = unique_rows_first(recs[:, :words])
+    _, _, inv = unique_rows_first(recs[:, :words])
     n = recs.shape[0]
-    order = np.lexsort((np.arange(n), recs[:, words + 1], inv))          # per group: ascending (last position, index)
+    n_groups = int(inv.max()) + 1
+    order = np.lexsort((np.arange(n), recs[:, words], inv))              # per group: ascending (first position, row)
+    starts = np.append(0, np.flatnonzero(np.diff(inv[order])) + 1)
+    first = np.empty(n_groups, dtype=np.int64)
+    first[inv[order[starts]]] = order[starts]
+    order = np.lexsort((np.arange(n), recs[:, words + 1], inv))          # per group: ascending (last position, row)
     ends = np.append(np.flatnonzero(np.diff(inv[order])), n - 1)
-    last = np.empty(first.shape[0], dtype=np.int64)
+    last = np.empty(n_groups, dtype=np.int64)
     last[inv[order[ends]]] = order[ends]
-    return torch.from_numpy(rows[first]), torch.from_numpy(rows[last]), int(counts.max())
+    by_pos = np.argsort(recs[first, words], kind='stable')               # groups in order of their first position
+    return torch.from_numpy(rows[first[by_pos]]), torch.from_numpy(rows[last[by_pos]]), int(counts.max())
 
 
-def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merge_fn=None):
+def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merge_fn=None, positions=None, guess_state=None):
     """
     The exchange step of the sharded backup in its compact form.  An alpha row of the backup is a deterministic function of
     its generating tuple (a*, v*[a*, :]) and of the replicated (model, old value function), so the ranks all-gather the
@@ -133,7 +176,11 @@ def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merg
     rank * capacity + local position (`capacity` = the largest shard size, the same on every rank): that is the position in the
     whole belief set when the shards are the contiguous blocks of `shard_bounds`, and order-preserving in any case.  The
     records stay on `device`; the merge is `merge_fn` (the device's `group_record_blocks`; host twin for CPU tensors), which
-    also returns the largest record count of any rank.
+    also returns the largest record count of any rank.  `positions` (int32 [n_local], optional) gives the position of every
+    local belief in the whole belief set explicitly -- the sharded solve's append-only ownership interleaves the ranks' rows --
+    and replaces the rank * capacity + local rule; the merge orders by position either way.  `guess_state` is the caller's
+    one-element list holding the largest record count of its previous exchange (per `ShardedBackup`: every rank of a group
+    takes part in the same sequence of exchanges, so the block size guess is the same everywhere).
     Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set as int32 tensors on `device`.
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -147,22 +194,29 @@ def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merg
     u, w = tuples.shape
     assert u <= capacity, (u, capacity)
     assert capacity * world < 2 ** 31
-    offset = rank * capacity
+    if guess_state is None:
+        guess_state = [capacity // 2]               # no history: blocks at full capacity
+    if positions is not None:
+        pos = torch.as_tensor(positions).to(device=device, dtype=torch.int32)
+        g_first, g_last = pos[first.long()], pos[last.long()]
+    else:
+        offset = rank * capacity
+        g_first, g_last = first + offset, last + offset
     # Most beliefs share their tuple with others, so the blocks are first sized by a guess (twice the largest count seen in the
     # previous exchange); the header carries the true count, and if any rank overflowed -- every rank sees that in the gathered
     # headers, so the decision is consistent -- the exchange is repeated once at full capacity.
-    guess = min(capacity, max(256, 2 * _LAST_MAX_COUNT[0]))
+    guess = min(capacity, max(256, 2 * guess_state[0]))
     while True:
         k = min(u, guess)
         buf = torch.empty((guess + 1, w + 2), dtype=torch.int32, device=device)
         buf[0].fill_(u)
         buf[1:k + 1, :w] = tuples[:k]
-        buf[1:k + 1, w] = first[:k] + offset
-        buf[1:k + 1, w + 1] = last[:k] + offset
+        buf[1:k + 1, w] = g_first[:k]
+        buf[1:k + 1, w + 1] = g_last[:k]
         gathered = torch.empty((world * (guess + 1), w + 2), dtype=torch.int32, device=device)
-        dist.all_gather_into_tensor(gathered, buf, group=group)
+        all_gather_rows(gathered, buf, group)
         first_rows, last_rows, max_count = merge_fn(gathered, world, guess + 1, w)
-        _LAST_MAX_COUNT[0] = max_count
+        guess_state[0] = max_count
         if max_count <= guess:
             break
         guess = capacity
@@ -200,6 +254,7 @@ class ShardedBackup:
         self.group = group
         self.exchange = exchange        # 'tuples': all-gather the generating tuples, assemble everywhere; 'rows': all-gather the rows
         self._cap = (None, None)
+        self._guess = [256]             # largest record count of this instance's previous exchange (sizes the next blocks)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.last_payload_bytes = 0
@@ -210,7 +265,10 @@ class ShardedBackup:
         self._fixed_cap = -(-n_rows // self.world)
         return shard_bounds(n_rows, self.world, self.rank)
 
-    def backup(self, local_belief_set, value_function, append: bool = False, belief_dominance_prune: bool = False):
+    def backup(self, local_belief_set, value_function, append: bool = False, belief_dominance_prune: bool = False, positions=None,
+               capacity: int | None = None):
+        """`positions` / `capacity`: explicit positions of the local beliefs in the whole set and an upper bound on any rank's
+        shard size (the sharded solve); default: contiguous blocks of `bounds()` / `set_capacity()`."""
         from .value_function import ValueFunction
         t = _PhaseTimer(self.model.device.device) if self.trace else None
         if self.exchange == 'tuples':
@@ -218,9 +276,11 @@ class ShardedBackup:
             tuples, first, last = self.solver.select_tuples_device(self.model, local_belief_set, value_function, belief_dominance_prune)
             if t: t.mark('local select')
             n_local = len(local_belief_set)
-            g_tuples, _, g_last = exchange_tuples(tuples, first, last, self._capacity(n_local), dev.device, self.group,
-                                                  merge_fn=dev.group_record_blocks)
-            self.last_payload_bytes = (min(self._cap[1], max(256, 2 * _LAST_MAX_COUNT[0])) + 1) * (tuples.shape[1] + 2) * 4 * self.world
+            assert positions is None or not belief_dominance_prune, 'explicit positions index the unfiltered local belief set'
+            cap = int(capacity) if capacity is not None else self._capacity(n_local)
+            g_tuples, _, g_last = exchange_tuples(tuples, first, last, cap, dev.device, self.group, merge_fn=dev.group_record_blocks,
+                                                  positions=positions, guess_state=self._guess)
+            self.last_payload_bytes = (min(cap, max(256, 2 * self._guess[0])) + 1) * (tuples.shape[1] + 2) * 4 * self.world
             if t: t.mark('exchange')
             merged = self.solver.rows_from_tuples(self.model, value_function, g_tuples, g_last)
             if t: t.mark('assemble + dedup')
@@ -259,13 +319,140 @@ class ShardedBackup:
             self._cap = (n_local, fixed)
             return fixed
         c = torch.tensor([n_local], dtype=torch.int64, device=self.model.device.device)
-        dist.all_reduce(c, op=dist.ReduceOp.MAX, group=self.group)
+        all_reduce_(c, dist.ReduceOp.MAX, self.group)
         self._cap = (n_local, int(c[0]))
         return self._cap[1]
 
     def compute_change(self, value_function, new_value_function, local_belief_set) -> float:
         """max over all shards of the local change: one scalar all-reduce(max)."""
         local = self.solver.compute_change(value_function, new_value_function, local_belief_set)
-        t = torch.tensor([local], dtype=torch.float64, device=self.model.device.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        return float(t[0])
+        # np.max / torch.max propagate NaN (a NaN belief row makes the change NaN in the reference); MAX over ranks would drop it
+        t = torch.tensor([local if local == local else float('inf'), 1.0 if local != local else 0.0], dtype=torch.float64,
+                         device=self.model.device.device)
+        all_reduce_(t, dist.ReduceOp.MAX, self.group)
+        return float('nan') if float(t[1]) > 0 else float(t[0])
+
+
+class ShardedSolveState:
+    """
+    The distributed half of `PBVI_Solver.solve(..., group=...)` (reference loop src/pomdp.py:2306-2389) -- one process per GPU:
+
+      expand          runs on group rank 0 only (the reference's host RNG draws happen once) and the new belief rows are broadcast;
+                      every rank then forms the same union, so the whole belief set is replicated (50 000 beliefs of the olfactory
+                      model are 8.8 GB of 180 GB) and `expand_*` flavours that read all of it (SSEA, GER, SSGA, RA) work unchanged.
+      ownership       of the rows that the union appended, rank r owns a contiguous slice (`shard_bounds` over the fresh rows).
+                      A rank's owned rows only ever grow by appending, so its local BeliefSet keeps the lineage chain that makes
+                      `compute_change` incremental; `positions` remembers where every owned row sits in the whole set.
+      full backup     every rank selects the tuples of its owned rows; the tuple exchange carries explicit positions, the merge
+                      orders by position, every rank assembles the merged set: the value function is the single-process one, bit
+                      for bit and in order (first position, last action).
+      new-points backup (FSVI / HSVI / Perseus: <= max_belief_growth rows): sharded the same way when there are at least
+                      `replicate_below` rows per rank, otherwise every rank backs the few rows up itself -- same kernels on the same
+                      inputs give the same bytes, and no collective is cheaper than one.
+      compute_change  local maxima over the owned rows (incremental), one scalar all-reduce(max).
+    """
+
+    def __init__(self, solver, model, group=None, replicate_below: int = 64):
+        self.solver, self.model, self.group = solver, model, group
+        self.sb = ShardedBackup(solver, model, group)
+        self.sb_new = ShardedBackup(solver, model, group)      # its own block-size history: the two backups differ in size
+        self.world, self.rank = self.sb.world, self.sb.rank
+        self.replicate_below = int(replicate_below)
+        self.local_set = None
+        self._rows = None            # [capacity, S] owned rows
+        self._pos = None             # [capacity] int32 position of every owned row in the whole belief set
+        self.n_local = 0
+        self.n_global = 0
+        self.max_owned = 0           # upper bound on any rank's number of owned rows
+        self.stats = {'broadcast_rows': 0, 'sharded_backups': 0, 'replicated_backups': 0}
+
+    # ---- expansion on rank 0, rows broadcast ---------------------------------------------------------------------------
+    def expand(self, model, belief_set, value_function, max_generation, **params):
+        from .belief import BeliefSet
+        dev = model.device.device
+        head = torch.zeros((1,), dtype=torch.int64, device=dev)
+        new = None
+        if self.rank == 0:
+            new = self.solver.expand(model=model, belief_set=belief_set, value_function=value_function, max_generation=max_generation,
+                                     **params)
+            head[0] = len(new)
+        broadcast_(head, 0, self.group)
+        n = int(head[0])
+        if self.rank == 0:
+            rows = new.belief_array.contiguous()
+        else:
+            rows = torch.empty((n, model.state_count), dtype=torch.float64, device=dev)
+        if n:
+            broadcast_(rows, 0, self.group)
+        self.stats['broadcast_rows'] += n
+        return new if self.rank == 0 else BeliefSet(model, rows)
+
+    # ---- ownership of the rows a union appended ---------------------------------------------------------------------------
+    def absorb(self, belief_set) -> None:
+        """Called after every `belief_set = belief_set.union(new)` (and once for the initial set): rows [n_global, len) are new."""
+        from .belief import BeliefSet
+        n_prev, n_now = self.n_global, len(belief_set)
+        n_fresh = n_now - n_prev
+        assert n_fresh >= 0, 'the belief set of a solve only grows'
+        lo, hi = shard_bounds(n_fresh, self.world, self.rank)
+        self.max_owned += -(-n_fresh // self.world)
+        self.n_global = n_now
+        k = hi - lo
+        if k == 0 and self.local_set is not None:
+            return
+        S, dev = self.model.state_count, self.model.device.device
+        n0, n1 = self.n_local, self.n_local + k
+        if self._rows is None or self._rows.shape[0] < n1:
+            cap = max(256, 2 * n1)
+            rows = torch.empty((cap, S), dtype=torch.float64, device=dev)
+            pos = torch.empty((cap,), dtype=torch.int32, device=dev)
+            if n0:
+                rows[:n0], pos[:n0] = self._rows[:n0], self._pos[:n0]
+            self._rows, self._pos = rows, pos           # earlier local sets keep viewing the old store
+        if k:
+            self._rows[n0:n1] = belief_set.belief_array[n_prev + lo:n_prev + hi]
+            self._pos[n0:n1] = torch.arange(n_prev + lo, n_prev + hi, dtype=torch.int32, device=dev)
+        grown = BeliefSet(self.model, self._rows[:n1])
+        if self.local_set is not None:
+            grown._inherit(self.local_set, n0)
+        self.local_set, self.n_local = grown, n1
+
+    # ---- backups ------------------------------------------------------------------------------------------------------
+    def backup_full(self, value_function):
+        """Backup over the whole belief set (full_backup=True flavours), sharded by ownership."""
+        self.stats['sharded_backups'] += 1
+        return self.sb.backup(self.local_set, value_function, append=False, positions=self._pos[:self.n_local],
+                              capacity=max(self.max_owned, 1))
+
+    def backup_new(self, new_belief_set, value_function):
+        """New-points backup (append=True) over the expansion's rows: contiguous shards, or replicated when they are few."""
+        from .belief import BeliefSet
+        n = len(new_belief_set)
+        if n < self.replicate_below * self.world:
+            self.stats['replicated_backups'] += 1
+            return self.solver.backup(self.model, new_belief_set, value_function, append=True, belief_dominance_prune=False)
+        self.stats['sharded_backups'] += 1
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        self.sb_new.set_capacity(-(-n // self.world))
+        return self.sb_new.backup(BeliefSet(self.model, new_belief_set.belief_array[lo:hi]), value_function, append=True)
+
+    def compute_change(self, value_function, new_value_function) -> float:
+        return self.sb.compute_change(value_function, new_value_function, self.local_set)
+
+    # ---- the value-function size limiter draws on the host RNG: rank 0 decides, everyone applies ------------------------------
+    def limit_value_function(self, value_function, belief_set, max_belief_growth):
+        from .value_function import ValueFunction
+        dev = self.model.device.device
+        head = torch.zeros((2,), dtype=torch.int64, device=dev)
+        keep = None
+        if self.rank == 0:
+            limited, n_useful = self.solver._limit_value_function(self.model, value_function, belief_set, max_belief_growth, return_keep=True)
+            keep = torch.as_tensor(limited, dtype=torch.int64, device=dev)
+            head[0], head[1] = keep.shape[0], n_useful
+        broadcast_(head, 0, self.group)
+        if self.rank != 0:
+            keep = torch.empty((int(head[0]),), dtype=torch.int64, device=dev)
+        broadcast_(keep, 0, self.group)
+        k = keep.cpu().numpy()
+        rows = value_function.alpha_vector_array[keep]
+        return ValueFunction(self.model, rows, value_function.actions[k], _trusted=True, _hashes=value_function.row_hashes[k]), int(head[1])

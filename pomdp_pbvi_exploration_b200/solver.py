@@ -512,14 +512,23 @@ class PBVI_Solver:
         cache = self.__dict__.setdefault('_max_cache', {})
         B = belief_set.belief_array
         nB = B.shape[0]
+        chain = belief_set.lineage_chain        # every union result has its own lineage; the chain says which prefixes it shares
+
+        def known(uid):
+            """Longest cached prefix of per-belief maxima of value function `uid` that is valid for the rows of this set."""
+            for lineage, n in chain:
+                hit = cache.get((uid, lineage))
+                if hit is not None:
+                    return hit[:min(n, hit.shape[0], nB)]
+            return None
+
         key = (vf.uid, belief_set.lineage)
-        done = cache.get(key)
-        if done is None and vf.parent_uid is not None and (vf.parent_uid, belief_set.lineage) in cache and 0 < vf.n_new:
-            parent = cache[(vf.parent_uid, belief_set.lineage)]
-            n_p = min(parent.shape[0], nB)
-            if n_p > 0:
-                fresh, _ = dev.max_values(B[:n_p], vf.alpha_vector_array[:vf.n_new])
-                done = torch.maximum(parent[:n_p], fresh)
+        done = known(vf.uid)
+        if done is None and vf.parent_uid is not None and 0 < vf.n_new:
+            parent = known(vf.parent_uid)
+            if parent is not None and parent.shape[0] > 0:
+                fresh, _ = dev.max_values(B[:parent.shape[0]], vf.alpha_vector_array[:vf.n_new])
+                done = torch.maximum(parent, fresh)
         if done is None:
             done = torch.empty((0,), dtype=torch.float64, device=dev.device)
         if done.shape[0] > nB:
@@ -795,6 +804,7 @@ class PBVI_Solver:
             log(f'    > Value Iteration stopped or converged in {sum(hist.iteration_times):.3f}s, and after {len(hist.iteration_times)} iteration.\n')
             self.expand_function_params['mdp_policy'] = mdp_solution
 
+        self.__dict__.pop('_max_cache', None)        # per-belief maxima cached by compute_change belong to one solve
         max_allowed_change = self.eps * (self.gamma / (1 - self.gamma))
         solver_history = SolverHistory(tracking_level=history_tracking_level, model=model, gamma=self.gamma, eps=self.eps,
                                        expand_function=self.expand_function, expand_append=full_backup,
