@@ -778,11 +778,23 @@ class PBVI_Solver:
               max_belief_growth: int = 10, initial_belief: Union[BeliefSet, Belief, None] = None,
               initial_value_function: Union[ValueFunction, None] = None, prune_level: int = 1, prune_interval: int = 10,
               limit_value_function_size: int = -1, use_gpu: bool = True, history_tracking_level: int = 1,
-              print_progress: bool = True):
+              print_progress: bool = True, *, group=None, replicate_below: int = 64):
         """
         Expand / backup loop (reference src/pomdp.py:2172-2413), same arguments, same control flow.  Always runs on the device.
         Returns (ValueFunction, SolverHistory).
+
+        `group` (keyword-only, not in the reference): a torch.distributed process group (or True for the default group) over
+        which the loop is sharded, one process per GPU -- see `parallel.ShardedSolveState`: expansion on rank 0 + broadcast of
+        the new rows, append-only row ownership, belief-sharded backups with the tuple exchange, sharded `compute_change`.  Every
+        rank calls `solve` with the same arguments and gets the same value function and history counts as a single process
+        (host RNG draws happen on rank 0 only).
         """
+        shard = None
+        if group is not None and group is not False:
+            from .parallel import ShardedSolveState
+            shard = ShardedSolveState(self, model, None if group is True else group, replicate_below=replicate_below)
+            if shard.world == 1:
+                shard = None
         if initial_belief is None:
             belief_set = BeliefSet(model, [Belief(model)])
         elif isinstance(initial_belief, BeliefSet):
@@ -812,6 +824,9 @@ class PBVI_Solver:
         iteration = 0
         expand_value_function = value_function
         old_value_function = value_function
+        if shard is not None:
+            shard.absorb(belief_set)
+        self._shard_state = shard
         try:
             if print_progress:
                 from tqdm.auto import trange
@@ -822,16 +837,26 @@ class PBVI_Solver:
             for expansion_i in iterator:
                 # 1: expand the belief set
                 start_ts = _now_synced(model)
-                new_belief_set = self.expand(model=model, belief_set=belief_set, value_function=value_function,
-                                             max_generation=max_belief_growth, **self.expand_function_params)
+                if shard is None:
+                    new_belief_set = self.expand(model=model, belief_set=belief_set, value_function=value_function,
+                                                 max_generation=max_belief_growth, **self.expand_function_params)
+                else:
+                    new_belief_set = shard.expand(model, belief_set, value_function, max_belief_growth, **self.expand_function_params)
                 belief_set = belief_set.union(new_belief_set)
+                if shard is not None:
+                    shard.absorb(belief_set)
                 solver_history.add_expand_step(expansion_time=(_now_synced(model) - start_ts).total_seconds(), belief_set=belief_set)
 
                 # 2: backup
                 for _ in range(update_passes):
                     start_ts = _now_synced(model)
-                    value_function = self.backup(model, belief_set if full_backup else new_belief_set, value_function,
-                                                 append=(not full_backup), belief_dominance_prune=False)
+                    if shard is None:
+                        value_function = self.backup(model, belief_set if full_backup else new_belief_set, value_function,
+                                                     append=(not full_backup), belief_dominance_prune=False)
+                    elif full_backup:
+                        value_function = shard.backup_full(value_function)
+                    else:
+                        value_function = shard.backup_new(new_belief_set, value_function)
                     backup_time = (_now_synced(model) - start_ts).total_seconds()
 
                     if (iteration % prune_interval) == 0 and iteration > 0:
@@ -841,17 +866,22 @@ class PBVI_Solver:
                         solver_history.add_prune_step((_now_synced(model) - start_ts).total_seconds(), len(value_function) - vf_len)
 
                     if limit_value_function_size >= 0 and len(value_function) > limit_value_function_size:
-                        value_function, n_useful = self._limit_value_function(model, value_function, belief_set, max_belief_growth)
+                        if shard is None:
+                            value_function, n_useful = self._limit_value_function(model, value_function, belief_set, max_belief_growth)
+                        else:
+                            value_function, n_useful = shard.limit_value_function(value_function, belief_set, max_belief_growth)
                         iterator_postfix['|useful|'] = n_useful
 
-                    max_change = self.compute_change(value_function, old_value_function, belief_set)
+                    max_change = (self.compute_change(value_function, old_value_function, belief_set) if shard is None
+                                  else shard.compute_change(value_function, old_value_function))
                     solver_history.add_backup_step(backup_time, max_change, value_function)
                     if max_change < max_allowed_change:
                         break
                     old_value_function = value_function
                     iteration += 1
 
-                expand_max_change = self.compute_change(expand_value_function, value_function, belief_set)
+                expand_max_change = (self.compute_change(expand_value_function, value_function, belief_set) if shard is None
+                                     else shard.compute_change(expand_value_function, value_function))
                 if expand_max_change < max_allowed_change:
                     print('Converged!')
                     break
@@ -870,7 +900,8 @@ class PBVI_Solver:
         solver_history.add_prune_step((_now_synced(model) - start_ts).total_seconds(), len(value_function) - vf_len)
         return value_function, solver_history
 
-    def _limit_value_function(self, model: Model, value_function: ValueFunction, belief_set: BeliefSet, max_belief_growth: int):
+    def _limit_value_function(self, model: Model, value_function: ValueFunction, belief_set: BeliefSet, max_belief_growth: int,
+                              return_keep: bool = False):
         """Drops `max_belief_growth` randomly chosen alpha vectors that are best at no belief (reference src/pomdp.py:2347-2367;
         sampled WITH replacement and a linearly decaying weight, like the reference)."""
         _, best = model.device.max_values(belief_set.belief_array, value_function.alpha_vector_array)
@@ -879,6 +910,8 @@ class PBVI_Solver:
         weights = np.arange(len(unuseful))[::-1] / np.sum(np.arange(len(unuseful)))
         to_delete = np.random.choice(unuseful, size=max_belief_growth, p=weights)
         keep = np.delete(np.arange(len(value_function)), to_delete)
+        if return_keep:
+            return keep, useful.shape[0]
         rows = value_function.alpha_vector_array[torch.as_tensor(keep, device=model.device.device)]
         return ValueFunction(model, rows, value_function.actions[keep], _trusted=True, _hashes=value_function.row_hashes[keep]), useful.shape[0]
 
@@ -891,11 +924,11 @@ class HSVI_Solver(PBVI_Solver):
 
     def solve(self, model: Model, expansions: int, max_belief_growth: int = 10, initial_belief=None, initial_value_function=None,
               prune_level: int = 1, prune_interval: int = 10, limit_value_function_size: int = -1, use_gpu: bool = True,
-              history_tracking_level: int = 1, print_progress: bool = True):
+              history_tracking_level: int = 1, print_progress: bool = True, **sharding):
         return super().solve(model=model, expansions=expansions, full_backup=False, update_passes=1, max_belief_growth=max_belief_growth,
                              initial_belief=initial_belief, initial_value_function=initial_value_function, prune_level=prune_level,
                              prune_interval=prune_interval, limit_value_function_size=limit_value_function_size, use_gpu=use_gpu,
-                             history_tracking_level=history_tracking_level, print_progress=print_progress)
+                             history_tracking_level=history_tracking_level, print_progress=print_progress, **sharding)
 
 
 class FSVI_Solver(PBVI_Solver):
@@ -906,12 +939,12 @@ class FSVI_Solver(PBVI_Solver):
 
     def solve(self, model: Model, expansions: int, max_belief_growth: int = 10, initial_belief=None, initial_value_function=None,
               prune_level: int = 1, prune_interval: int = 10, limit_value_function_size: int = -1, use_gpu: bool = True,
-              history_tracking_level: int = 1, print_progress: bool = True):
+              history_tracking_level: int = 1, print_progress: bool = True, **sharding):
         return PBVI_Solver.solve(self, model=model, expansions=expansions, full_backup=False, update_passes=1,
                                  max_belief_growth=max_belief_growth, initial_belief=initial_belief,
                                  initial_value_function=initial_value_function, prune_level=prune_level, prune_interval=prune_interval,
                                  limit_value_function_size=limit_value_function_size, use_gpu=use_gpu,
-                                 history_tracking_level=history_tracking_level, print_progress=print_progress)
+                                 history_tracking_level=history_tracking_level, print_progress=print_progress, **sharding)
 
 
 class FSVI_EG_Solver(FSVI_Solver):

@@ -212,7 +212,8 @@ def test_host_row_packer_round_trip(lib_path, n, L):
 
 def test_merge_blocks_host_matches_a_dict_over_all_records():
     """Host twin of pbvi_group_record_blocks (used by the gloo tests of the tuple exchange): grouping of the valid records of the
-    gathered blocks == one dict over them in buffer order; `last` = record with the largest last-position."""
+    gathered blocks == one dict over the records visited in order of their first-position word (the position of the belief in the
+    whole set, which need not follow the buffer order); `last` = record with the largest last-position."""
     import torch
     from pomdp_pbvi_exploration_b200.parallel import merge_blocks_host
     rng = np.random.default_rng(2)
@@ -220,19 +221,21 @@ def test_merge_blocks_host_matches_a_dict_over_all_records():
     blocks = rng.integers(0, 99, (world, block_rows, w + 2)).astype(np.int32)
     counts = [8, 0, 5]
     pool = rng.integers(0, 4, (6, w))
+    firsts = rng.permutation(1000)                                # unique first positions, interleaved across the ranks
     for r in range(world):
         blocks[r, 0, :] = counts[r]
         blocks[r, 1:1 + counts[r], :w] = pool[rng.integers(0, 6, counts[r])]
+        blocks[r, 1:1 + counts[r], w] = firsts[r * 10:r * 10 + counts[r]]
         blocks[r, 1:1 + counts[r], w + 1] = rng.permutation(100)[:counts[r]] + 100 * r
-    first, last, mx = merge_blocks_host(torch.as_tensor(blocks.reshape(-1, w + 2)), world, block_rows, w)
+    flat = blocks.reshape(-1, w + 2)
+    first, last, mx = merge_blocks_host(torch.as_tensor(flat), world, block_rows, w)
+    rows = [r * block_rows + j for r in range(world) for j in range(1, 1 + counts[r])]
     table = {}
-    for r in range(world):
-        for j in range(1, 1 + counts[r]):
-            row = r * block_rows + j
-            key = blocks[r, j, :w].tobytes()
-            if key not in table:
-                table[key] = [row, row]
-            elif blocks.reshape(-1, w + 2)[row, w + 1] > blocks.reshape(-1, w + 2)[table[key][1], w + 1]:
-                table[key][1] = row
+    for row in sorted(rows, key=lambda x: flat[x, w]):
+        key = flat[row, :w].tobytes()
+        if key not in table:
+            table[key] = [row, row]
+        elif flat[row, w + 1] > flat[table[key][1], w + 1]:
+            table[key][1] = row
     assert mx == 8
     assert first.tolist() == [v[0] for v in table.values()] and last.tolist() == [v[1] for v in table.values()]

@@ -394,8 +394,9 @@ def test_confirm_groups_and_backup_dedup(torch_cuda):
     assert first_b.shape[0] == 26 and not dev.confirm_groups(t, first_b, inv_b)
 
 
+@pytest.mark.parametrize('interleaved', [False, True])
 @pytest.mark.parametrize('world,block_rows,width', [(1, 5, 3), (2, 40, 4), (8, 257, 4), (3, 9, 1)])
-def test_group_record_blocks_equals_host_merge(torch_cuda, world, block_rows, width):
+def test_group_record_blocks_equals_host_merge(torch_cuda, world, block_rows, width, interleaved):
     """`pbvi_group_record_blocks` (merge of the all-gathered tuple blocks of a sharded backup) == the host twin used by the gloo
     tests: ragged record counts per rank (including an empty and an overflowing block), duplicate tuples across ranks."""
     from pomdp_pbvi_exploration_b200.parallel import merge_blocks_host
@@ -418,6 +419,14 @@ def test_group_record_blocks_equals_host_merge(torch_cuda, world, block_rows, wi
         blocks[r, 1:1 + u, width] = firsts
         blocks[r, 1:1 + u, width + 1] = firsts + rng.integers(0, 5, u)
         pos += 10 * block_rows + 5
+    if interleaved:
+        # the sharded solve's ownership: positions of different ranks interleave (and do not follow the buffer order); the merge
+        # must order by position, not by where a record sits in the gathered buffer
+        valid = np.concatenate([r * block_rows + 1 + np.arange(int(blocks[r, 0, 0])) for r in range(world)]).astype(np.int64)
+        flat_v = blocks.reshape(world * block_rows, width + 2)
+        perm = rng.permutation(valid.shape[0])
+        flat_v[valid, width] = np.sort(flat_v[valid, width])[perm]
+        flat_v[valid, width + 1] = flat_v[valid, width] + rng.integers(0, 5, valid.shape[0])
     flat = torch.as_tensor(blocks.reshape(world * block_rows, width + 2))
     want_first, want_last, want_max = merge_blocks_host(flat, world, block_rows, width)
     first, last, mx = dev.group_record_blocks(flat.cuda(), world, block_rows, width)

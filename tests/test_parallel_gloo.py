@@ -84,7 +84,8 @@ def _tuple_worker(rank, world, port, keys_all, result_queue):
     local = keys_all[lo:hi]
     first, last, _ = unique_rows_first(local)
     cap = -(-keys_all.shape[0] // world)
-    g_tuples, g_first, g_last = exchange_tuples(local[first], first, last, cap, torch.device('cpu'))
+    # block-size history of 100 records -> first guess 256: the 1300-belief case overflows it and must retry consistently
+    g_tuples, g_first, g_last = exchange_tuples(local[first], first, last, cap, torch.device('cpu'), guess_state=[100])
     result_queue.put((rank, g_tuples.numpy(), g_first.numpy(), g_last.numpy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -109,6 +110,59 @@ def test_tuple_exchange_equals_single_process(n_beliefs, world):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_tuple_worker, args=(r, world, port, keys_all, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g_tuples, g_first, g_last in results:
+        assert np.array_equal(g_tuples, keys_all[f]) and np.array_equal(g_first, f) and np.array_equal(g_last, l), rank
+
+
+def _owned_positions(n_total, world, rank, growth):
+    """Positions owned by `rank` under the sharded solve's append-only ownership: of every batch of `growth` appended rows a rank
+    owns one contiguous slice (ShardedSolveState.absorb)."""
+    from pomdp_pbvi_exploration_b200.parallel import shard_bounds
+    pos, start = [], 0
+    while start < n_total:
+        n = min(growth, n_total - start)
+        lo, hi = shard_bounds(n, world, rank)
+        pos.extend(range(start + lo, start + hi))
+        start += n
+    return np.array(pos, dtype=np.int64)
+
+
+def _interleaved_worker(rank, world, port, keys_all, growth, result_queue):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pomdp_pbvi_exploration_b200.parallel import exchange_tuples
+    from pomdp_pbvi_exploration_b200.sets import unique_rows_first
+    pos = _owned_positions(keys_all.shape[0], world, rank, growth)
+    local = keys_all[pos]
+    first, last, _ = unique_rows_first(local) if pos.shape[0] else (np.zeros(0, dtype=np.int64),) * 3
+    cap = max(1, max(_owned_positions(keys_all.shape[0], world, r, growth).shape[0] for r in range(world)))
+    g_tuples, g_first, g_last = exchange_tuples(local[first].reshape(-1, keys_all.shape[1]), first, last, cap, torch.device('cpu'),
+                                                positions=pos.astype(np.int32), guess_state=[100])
+    result_queue.put((rank, g_tuples.numpy(), g_first.numpy(), g_last.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_beliefs,world,growth', [(50, 2, 7), (64, 3, 10), (5, 3, 1), (1300, 2, 100)])
+def test_tuple_exchange_with_interleaved_ownership(n_beliefs, world, growth):
+    """The sharded solve's ownership interleaves the ranks' rows in the whole belief set; the exchange then carries explicit
+    positions and the merge must still return the single-process grouping: tuples in order of first position, first / last positions."""
+    from pomdp_pbvi_exploration_b200.sets import unique_rows_first
+    rng = np.random.default_rng(n_beliefs + growth)
+    pool = np.unique(rng.integers(0, 40, (900 if n_beliefs > 1000 else 9, 4)), axis=0)
+    keys_all = pool[rng.integers(0, pool.shape[0], n_beliefs)]
+    f, l, _ = unique_rows_first(keys_all)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_interleaved_worker, args=(r, world, port, keys_all, growth, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]

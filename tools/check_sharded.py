@@ -5,6 +5,7 @@ order, the value function a single process computes over the whole belief set (r
 """
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -41,6 +42,31 @@ def main():
         chg = sb.compute_change(vf, merged, BeliefSet(model, B[lo:hi]))
         ref = solver.compute_change(vf, single, BeliefSet(model, B))
         assert chg == ref, (chg, ref)
+    # ---- the sharded solve loop: same value function, same history counts as one process (every rank checks against its own
+    #      single-process run with the same seeds; only rank 0's host RNG matters in the sharded run)
+    import random
+    from pomdp_pbvi_exploration_b200 import FSVI_Solver
+    cases = [('fsvi 40x100 (new-points backups)', lambda: FSVI_Solver(gamma=0.99, eps=1e-6), dict(expansions=40, max_belief_growth=100)),
+             ('perseus full backup 3x1500', lambda: PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus'),
+              dict(expansions=3, max_belief_growth=1500, full_backup=True))]
+    for name, make, kw in cases:
+        outs = []
+        for grp in (None, True):
+            np.random.seed(5 if (grp is None or rank == 0) else 1000 + rank)
+            random.seed(5 if (grp is None or rank == 0) else 1000 + rank)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            vf_s, hist = make().solve(model, print_progress=False, **kw, **({'group': True} if grp else {}))
+            torch.cuda.synchronize()
+            outs.append((vf_s.numpy(), hist.alpha_vector_counts, hist.beliefs_counts, hist.value_function_changes, time.perf_counter() - t0))
+        (r1, a1), (r2, a2) = outs[0][0], outs[1][0]
+        ok = r1.shape == r2.shape and np.array_equal(r1, r2) and np.array_equal(a1, a2) and outs[0][1:4] == outs[1][1:4]
+        flag = torch.tensor([int(ok)], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f'solve {name}: world={world} |V|={r2.shape[0]} |B|={outs[1][2][-1]} single {outs[0][4]:.2f}s sharded {outs[1][4]:.2f}s '
+                  f'identical on all ranks: {bool(flag[0])}', flush=True)
+        assert bool(flag[0])
     dist.destroy_process_group()
 
 
