@@ -3,30 +3,40 @@
 bench.py -- belief x alpha backups/sec of the PBVI backup on the olfactory-navigation POMDP (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--beliefs B] [--alphas V]
+                    [--legs backup,solve,configs] [--scaling weak|strong] [--headline late|young|dense]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU)
 
 Workload (config.workload): BASELINE.json configs[2] -- the 22021-state toroidal olfactory model (A=6, O=3, R=1),
-B = 10 000 belief points from Perseus random walks (100 walks x 100 steps from b0, the engine's own expand_perseus),
-V = 1 000 alpha vectors grown by the engine's own new-points backups over those walks.  One step = one full
-`PBVI_Solver.backup(model, belief_set, value_function)` pass = B*V belief x alpha units: v* per (b,a,o), a*, assembly of
-the distinct alpha rows and the byte-dedup that forms the new alpha set.  At N > 1 every rank backs up its own B
-beliefs (weak scaling) and the ranks all-gather + merge their new alpha rows (pomdp_pbvi_exploration_b200.parallel).
+B = 10 000 belief points from Perseus random walks (100 walks x 100 steps from b0, the engine's own expand_perseus) backed up
+against V = 1 000 alpha vectors.  One step = one full `PBVI_Solver.backup(model, belief_set, value_function)` pass = B*V
+belief x alpha units: v* per (b,a,o), a*, assembly of the distinct alpha rows and the byte-dedup that forms the new alpha set.
+Three value functions are measured, because the cost of a step depends on how much of the value function is exactly zero:
 
-`value`      device-resident inputs, CUDA-event timed, max over ranks.
-`e2e`        the same call from HOST (pinned) buffers: H2D of beliefs and alphas, backup, D2H of the new alpha rows and
-             actions, every step.
-`roofline`   the score kernel (block-sparse FP64 DMMA GEMM + fused argmax): ALGORITHMIC flops 2*A*O*S per unit over its
-             CUDA-event time, against the FP64 tensor-pipe peak measured by tools/fp64_microbench.cu on this pool
-             (profiles/r01_fp64_pipe_microbench.txt; MEASURED_PEAKS.json holds no FP64 figure).
-`cpu_baseline` the NumPy restatement of the reference's backup (oracle/pbvi_oracle.py, same primitives as the
-             reference) on the host cores, on a bounded sample.
---impl reference runs that CPU path as the reference arm.
+  late   (HEADLINE)  1 000 alphas produced by expansions >= 200 of the engine's own FSVI 300 x 100 solve of this model -- the
+                     value function of a solve that has been running for a while (alpha density stated in the line);
+  young              1 000 alphas grown by ~31 new-points backups from the initial value function (round-1 headline; 0.6 % dense);
+  dense              the late alphas plus a strictly positive perturbation (no alpha-side zero at all).
+
+At N > 1 every rank backs up its own B beliefs (weak scaling; `--scaling strong`: B beliefs in total, configs[3] uses 50 000) and
+the ranks exchange + merge their generating tuples (pomdp_pbvi_exploration_b200.parallel).
+
+`value`        device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`          the same call from HOST (pinned) buffers: H2D of beliefs and alphas, backup, D2H of the new alpha rows and actions.
+`roofline`     the score kernel (block-sparse FP64 DMMA GEMM + fused argmax): EXECUTED flops / kernel time / FP64 tensor-pipe peak.
+`parity_sample` the engine's v*, a* and alpha rows for a sample of the timed beliefs against the CPU oracle ON THE SAME ALPHAS, and the
+               oracle's rows looked up bytewise in the output of the timed step.  A mismatch makes the run exit non-zero.
+`cpu_baseline` the same oracle run (NumPy restatement of the reference's backup, oracle/pbvi_oracle.py), timed.
+`solve`        whole solves (FSVI 300 x 100 as published by the reference; a full-backup Perseus solve with >= 10 000 beliefs), sharded
+               over the ranks at N > 1 (`PBVI_Solver.solve(group=...)`).
+`configs`      the other BASELINE configs (tiger, 4x4 grid, synthetic sparse sweep, sea-robin size), each with its own parity sample.
+--impl reference runs the CPU oracle as the reference arm on the b200 arm's alphas.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import random
 import subprocess
 import sys
 import threading
@@ -41,11 +51,11 @@ if ROOT not in sys.path:
 METRIC = 'belief x alpha backups/sec (olfactory POMDP S=22021, PBVI backup)'
 UNIT = 'belief*alpha pairs/s'
 GAMMA = 0.99
+GAP_TOL = 1e-9                 # parity contract: indices identical wherever the oracle's top-2 gap exceeds GAP_TOL * max(1, |best|)
 FP64_PEAK_TFLOPS = 37.1        # DMMA m8n8k4 / m16n8k16 on this pool's B200, profiles/r01_fp64_pipe_microbench.txt
-# dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch on the default workload (B=10000, V=1000), from
-# `ncu --set full` (profiles/r01_score_kernel_v12_ncu_summary.txt); dense compulsory bytes would be 8*S*(B+V) = 1.94e9 -- chunks
-# that are skipped are never read, so the kernel moves far less than that
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 0.2346e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (`ncu --set full`, profiles/), per workload point at the
+# default sizes (B = 10000, V = 1000); None = not captured
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {'young': 0.2346e9, 'late': None, 'dense': None}
 
 
 def parse_args():
@@ -54,12 +64,16 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--beliefs', type=int, default=10000)
+    ap.add_argument('--beliefs', type=int, default=10000, help='beliefs per GPU (weak scaling) or in total (--scaling strong)')
     ap.add_argument('--alphas', type=int, default=1000)
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--headline', default='late', choices=['late', 'young', 'dense'])
+    ap.add_argument('--legs', default=None, help='comma list of backup,solve,configs (default: all three at N = 1, backup,solve at N > 1)')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the oracle run (no parity_sample / cpu_baseline)')
+    ap.add_argument('--parity-beliefs', type=int, default=None, help='beliefs of the oracle sample (default 512 at N = 1, 128 at N > 1)')
     ap.add_argument('--trace-phases', action='store_true', help='N > 1: print the phase times of the last sharded step to stderr')
-    ap.add_argument('--no-dense-variant', action='store_true', help='skip the secondary measurement against a dense value function')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (used for short ncu passes)')
+    ap.add_argument('--only-point', default=None, help='measure one value-function point only (ncu passes)')
     ap.add_argument('--save-workload', default=None, help='write the synthetic beliefs / alphas to this .pt file')
     ap.add_argument('--load-workload', default=None, help='read them back instead of regenerating (ncu passes: no setup kernels)')
     return ap.parse_args()
@@ -132,10 +146,53 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def build_workload(model, n_beliefs: int, n_alphas: int, seed: int):
-    """Synthetic inputs made by the engine itself: Perseus-walk beliefs and a value function grown by new-points backups."""
+def seed_all(seed: int) -> None:
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def timed_solve(solver, model, **kw):
+    """A whole `solve` with wall clock (device-synchronised) and the time spent in compute_change; returns (vf, hist, summary dict)."""
     import torch
-    from pomdp_pbvi_exploration_b200 import Belief, BeliefSet, PBVI_Solver, ValueFunction
+    change_s = [0.0]
+    shard_change = [None]
+    orig_change = solver.compute_change
+
+    def timed_change(*a, **k):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        out = orig_change(*a, **k)
+        torch.cuda.synchronize()
+        change_s[0] += time.perf_counter() - t
+        return out
+    solver.compute_change = timed_change
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vf, hist = solver.solve(model, print_progress=False, **kw)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    solver.compute_change = orig_change
+    full = hist.expand_append
+    nb = hist.beliefs_counts[1:] if full else np.diff(hist.beliefs_counts)
+    # units of a solve: every backup call processes (beliefs backed up) x (alphas of the value function it starts from)
+    pairs = float(sum(int(b) * int(v) for b, v in zip(nb, hist.alpha_vector_counts[:-1])))
+    out = dict(wall_s=wall, expand_s=float(sum(hist.expansion_times)), backup_s=float(sum(hist.backup_times)), change_s=change_s[0],
+               expansions=len(hist.expansion_times), backups=len(hist.backup_times), final_alphas=len(vf), final_beliefs=int(hist.beliefs_counts[-1]),
+               backup_pairs=pairs, backup_pairs_per_s=pairs / max(float(sum(hist.backup_times)), 1e-9))
+    st = getattr(solver, '_shard_state', None)
+    if st is not None:
+        out['sharding'] = dict(st.stats)
+    return vf, hist, out
+
+
+def build_workload(model, n_beliefs: int, n_alphas: int, seed: int):
+    """
+    Synthetic inputs made by the engine itself.  Beliefs: Perseus walks (`seed`: per rank).  Value functions (the same on every rank):
+    'young' grown by new-points backups from the initial one; 'late' taken from expansions >= 200 of an FSVI 300 x 100 solve.
+    Returns (solver, beliefs, {'young': vf, 'late': vf}, info dict).
+    """
+    import torch
+    from pomdp_pbvi_exploration_b200 import Belief, FSVI_Solver, PBVI_Solver, ValueFunction
     solver = PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus')
     np.random.seed(seed)
     walks = []
@@ -144,7 +201,19 @@ def build_workload(model, n_beliefs: int, n_alphas: int, seed: int):
     for _ in range(n_walks):
         walks.append(solver.expand_perseus(model, b0, max_generation=100).belief_array)
     beliefs = torch.cat(walks)[:n_beliefs].contiguous()
-    # value function: FSVI/Perseus-style new-points backups over the walks (append=True) until V >= n_alphas
+    info = {}
+
+    def pad_to(vf, rows, actions):
+        if rows.shape[0] < n_alphas:                                # top up (not expected): perturbed copies keep the shape of the data
+            g = torch.Generator(device='cpu').manual_seed(7)
+            need = n_alphas - rows.shape[0]
+            pick = torch.randint(0, rows.shape[0], (need,), generator=g)
+            scale = 1.0 + 1e-3 * torch.rand((need, 1), generator=g, dtype=torch.float64)
+            rows = torch.cat([rows, rows[pick.to(rows.device)] * scale.to(rows.device)])
+            actions = np.concatenate([actions, actions[pick.numpy()]])
+        return ValueFunction(model, rows[:n_alphas].contiguous(), actions[:n_alphas])
+
+    # ---- young: FSVI/Perseus-style new-points backups over walks (append=True) until V >= n_alphas
     np.random.seed(1000)                                  # the alpha set is the same on every rank
     grow_walks = [solver.expand_perseus(model, b0, max_generation=100) for _ in range(40)]
     vf = ValueFunction(model, model.expected_rewards_table.T, model.actions)
@@ -152,37 +221,52 @@ def build_workload(model, n_beliefs: int, n_alphas: int, seed: int):
     while len(vf) < n_alphas and it < 400:
         vf = solver.backup(model, grow_walks[it % len(grow_walks)], vf, append=True, belief_dominance_prune=False)
         it += 1
-    rows, actions = vf.alpha_vector_array, vf.actions
-    if len(vf) < n_alphas:                                # top up (not expected): perturbed copies keep the shape of the data
-        g = torch.Generator(device='cpu').manual_seed(7)
-        need = n_alphas - len(vf)
-        pick = torch.randint(0, len(vf), (need,), generator=g)
-        scale = 1.0 + 1e-3 * torch.rand((need, 1), generator=g, dtype=torch.float64)
-        rows = torch.cat([rows, rows[pick.to(rows.device)] * scale.to(rows.device)])
-        actions = np.concatenate([actions, actions[pick.numpy()]])
-    rows, actions = rows[:n_alphas].contiguous(), actions[:n_alphas]
-    vf = ValueFunction(model, rows, actions)
-    return solver, beliefs, vf, it
+    young = pad_to(vf, vf.alpha_vector_array, vf.actions)
+    info['young'] = {'provenance': f'{it} new-points backups over Perseus walks from the initial value function', 'growth_backups': it}
+
+    # ---- late: the engine's own FSVI 300 x 100 solve (the reference's published shape); rows of expansions >= 200
+    seed_all(0)
+    fsvi = FSVI_Solver(gamma=GAMMA, eps=1e-6)
+    vf_f, hist, summary = timed_solve(fsvi, model, expansions=300, max_belief_growth=100)
+    counts = hist.alpha_vector_counts                      # [initial, after backup 1, ...]
+    cut = min(200, len(counts) - 1)
+    n_late = len(vf_f) - counts[cut]                       # new rows are PREPENDED by every new-points backup: rows [0, n_late) are the late ones
+    if n_late < n_alphas:
+        n_late = min(len(vf_f), max(n_late, n_alphas))
+    idx = np.unique(np.linspace(0, n_late - 1, min(n_alphas, n_late)).astype(np.int64))
+    rows = vf_f.alpha_vector_array[torch.as_tensor(idx, device=vf_f.alpha_vector_array.device)]
+    late = pad_to(vf_f, rows, vf_f.actions[idx])
+    info['late'] = {'provenance': f'{len(idx)} alphas sampled evenly from the {n_late} rows that expansions >= {cut} of the engine\'s FSVI '
+                                  f'300x100 solve (seed 0) produced; final |V| = {len(vf_f)}', 'fsvi_solve': summary}
+    return solver, beliefs, {'young': young, 'late': late}, info
 
 
-def cpu_reference_sample(model, beliefs_host: np.ndarray, alphas_host: np.ndarray, n_sample: int, n_full: int):
+def make_dense(model, vf):
+    import torch
+    from pomdp_pbvi_exploration_b200 import ValueFunction
+    g = torch.Generator(device='cpu').manual_seed(11)
+    noise = (1e-3 * torch.rand(vf.alpha_vector_array.shape, generator=g, dtype=torch.float64) + 1e-6).to(vf.alpha_vector_array.device)
+    return ValueFunction(model, vf.alpha_vector_array + noise, vf.actions)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def oracle_backup_sample(reach, rto, rbar, gamma, beliefs_host: np.ndarray, alphas_host: np.ndarray, chunk: int = 512):
     """
-    The reference's backup arithmetic (NumPy restatement, oracle/pbvi_oracle.py) on a bounded sample: the Gamma projection
-    for ALL alphas (its cost does not depend on B) + the per-belief part for `n_sample` beliefs, extrapolated linearly in B
-    to the full step (rows are independent given V).  Returns (pairs_per_s_full_step, detail dict).
+    The reference's backup arithmetic (NumPy restatement, oracle/pbvi_oracle.py: same primitives, same order as src/pomdp.py:1485-1506)
+    on `beliefs_host`, in chunks of `chunk` rows (the reference itself needs belief chunks at this size: Gamma* is
+    8*B*A*O*S bytes).  Returns (outputs dict, timing dict): the Gamma projection is timed separately because its cost does not depend
+    on the number of beliefs.
     """
     from oracle import pbvi_oracle as orc
-    reach = model.reachable_states
-    rto = model.reachable_transitional_observation_table
-    rbar = model.expected_rewards_table
-    V = alphas_host.shape[0]
-    A, O, S = model.action_count, model.observation_count, model.state_count
+    A, O, S = rto.shape[1], rto.shape[2], rto.shape[0]
     t0 = time.perf_counter()
-    G = orc.gamma_projection(reach, rto, alphas_host, GAMMA)
+    G = orc.gamma_projection(reach, rto, alphas_host, gamma)
     t_gamma = time.perf_counter() - t0
+    outs = {k: [] for k in ('v_star', 'a_star', 'alpha', 'values', 'best', 'gap')}
     t0 = time.perf_counter()
-    for i0 in range(0, n_sample, 64):
-        b = beliefs_host[i0:min(n_sample, i0 + 64)]
+    t_extra = 0.0
+    for i0 in range(0, beliefs_host.shape[0], chunk):
+        b = beliefs_host[i0:i0 + chunk]
         scores = np.tensordot(b, G, (1, 3))
         v_star = np.argmax(scores, axis=3)
         best_per_o = G[np.arange(A)[None, :, None, None], np.arange(O)[None, None, :, None], v_star[:, :, :, None], np.arange(S)[None, None, None, :]]
@@ -191,16 +275,109 @@ def cpu_reference_sample(model, beliefs_host: np.ndarray, alphas_host: np.ndarra
         a_star = np.argmax(values, axis=1)
         rows = np.take_along_axis(alpha_a, a_star[:, None, None], axis=1)[:, 0, :]
         orc.dedup_rows(rows, a_star)
-    t_rows = time.perf_counter() - t0
-    t_full = t_gamma + t_rows * (n_full / n_sample)
-    return n_full * V / t_full, {'gamma_projection_s': round(t_gamma, 3), 'per_belief_part_s': round(t_rows, 3), 'sample_beliefs': n_sample,
-                                 'sample_pairs_per_s_raw': n_sample * V / (t_gamma + t_rows)}
+        te = time.perf_counter()                      # (not part of the reference's work: top-2 gaps for the parity contract)
+        if scores.shape[3] > 1:
+            top = np.partition(scores, scores.shape[3] - 2, axis=3)[..., -2:]
+            outs['best'].append(top[..., 1]); outs['gap'].append(top[..., 1] - top[..., 0])
+        else:
+            outs['best'].append(scores[..., 0]); outs['gap'].append(np.full(scores.shape[:3], np.inf))
+        for k, v in (('v_star', v_star), ('a_star', a_star), ('alpha', rows), ('values', values)):
+            outs[k].append(v)
+        t_extra += time.perf_counter() - te
+    t_rows = time.perf_counter() - t0 - t_extra
+    out = {k: np.concatenate(v) for k, v in outs.items()}
+    return out, {'gamma_projection_s': t_gamma, 'per_belief_part_s': t_rows, 'sample_beliefs': int(beliefs_host.shape[0]), 'chunk_rows': chunk}
+
+
+def extrapolate(timing: dict, n_full: int, n_alphas: int) -> dict:
+    """pairs/s of the full step from a timed sample: Gamma projection once + the per-belief part scaled linearly in B."""
+    n = timing['sample_beliefs']
+    t_full = timing['gamma_projection_s'] + timing['per_belief_part_s'] * (n_full / n)
+    t_sample = timing['gamma_projection_s'] + timing['per_belief_part_s']
+    return {'value': n_full * n_alphas / t_full, 'full_step_s_estimate': t_full, 'extrapolation_factor': n_full / n,
+            'sample_pairs_per_s_raw': n * n_alphas / t_sample, 'sample_s': t_sample}
+
+
+def parity_check(dev, host_model, gamma, sample_beliefs, vf, ref: dict, step_output=None) -> dict:
+    """
+    The engine (through the C ABI, `DeviceModel.backup`: select + assemble for every belief) against the oracle outputs `ref` on the same
+    beliefs and alphas.  Contract: v* / a* identical wherever the oracle's top-2 gap is decided; rows bit-identical where both chose the
+    same tuple (R = 1) / within 1e-9 (R > 1).  With `step_output` (the ValueFunction the timed step returned) every oracle row of a
+    decided belief must also occur, bytewise, in that output.
+    """
+    import torch
+    reach = host_model['reach']
+    alpha, act, vstar, value = [t.cpu().numpy() for t in dev.backup(sample_beliefs, vf.alpha_vector_array, gamma)]
+    scale = np.maximum(1.0, np.abs(ref['best']))
+    decided = ref['gap'] > GAP_TOL * scale
+    v_bad = int(np.sum(vstar[decided] != ref['v_star'][decided]))
+    vs = np.sort(ref['values'], axis=1)
+    agap = vs[:, -1] - vs[:, -2] if vs.shape[1] > 1 else np.full(vs.shape[0], np.inf)
+    adecided = agap > GAP_TOL * np.maximum(1.0, np.abs(vs[:, -1]))
+    a_bad = int(np.sum(act[adecided] != ref['a_star'][adecided]))
+    ours_sel = np.take_along_axis(vstar, act[:, None, None].astype(np.int64), axis=1)[:, 0, :]
+    ref_sel = np.take_along_axis(ref['v_star'], ref['a_star'][:, None, None], axis=1)[:, 0, :]
+    same = (act == ref['a_star']) & np.all(ours_sel == ref_sel, axis=1)
+    exact = reach.shape[2] == 1
+    if exact:
+        rows_equal = int(np.sum(np.all(alpha[same].view(np.uint64) == ref['alpha'][same].view(np.uint64), axis=1)))
+        max_rel = 0.0 if rows_equal == int(same.sum()) else float(np.max(np.abs(alpha[same] - ref['alpha'][same])))
+    else:
+        close = np.isclose(alpha[same], ref['alpha'][same], rtol=1e-9, atol=1e-12).all(axis=1)
+        rows_equal = int(close.sum())
+        max_rel = float(np.max(np.abs(alpha[same] - ref['alpha'][same]) / np.maximum(1e-300, np.abs(ref['alpha'][same])))) if same.any() else 0.0
+    out = {'beliefs': int(sample_beliefs.shape[0]), 'alphas': int(len(vf)), 'vstar_compared_decided': int(decided.sum()),
+           'vstar_mismatch_decided': v_bad, 'astar_compared_decided': int(adecided.sum()), 'astar_mismatch_decided': a_bad,
+           'rows_compared': int(same.sum()), 'rows_bitwise_equal' if exact else 'rows_within_1e-9': rows_equal, 'max_abs_row_diff': max_rel,
+           'gap_tolerance': GAP_TOL}
+    ok = v_bad == 0 and a_bad == 0 and rows_equal == int(same.sum())
+    if step_output is not None and exact:
+        # the oracle's rows of the decided beliefs must be rows of the timed step's value function: 128-bit keys, then bytes
+        want = ref['alpha'][same & adecided]
+        keys_out = step_output.row_hashes
+        index = {tuple(k): i for i, k in enumerate(keys_out.tolist())}
+        d_want = torch.as_tensor(want).to(dev.device)
+        keys_want = dev.row_hash(d_want).cpu().numpy().tolist()
+        pos = [index.get(tuple(k), -1) for k in keys_want]
+        found = [i for i, p in enumerate(pos) if p >= 0]
+        n_found = 0
+        if found:
+            flags = dev.rows_equal(d_want, np.array(found, dtype=np.int32), step_output.alpha_vector_array, np.array([pos[i] for i in found], dtype=np.int32))
+            n_found = int(flags.sum())
+        out['oracle_rows_looked_up_in_step_output'] = int(want.shape[0])
+        out['oracle_rows_found_bytewise_in_step_output'] = n_found
+        ok = ok and n_found == int(want.shape[0])
+    out['ok'] = bool(ok)
+    return out
+
+
+def host_tables(model) -> dict:
+    return {'reach': model.reachable_states, 'rto': model.reachable_transitional_observation_table, 'rbar': model.expected_rewards_table}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def workload_config(args, world, headline=None, density=None):
+    per_gpu = args.beliefs if args.scaling == 'weak' else -(-args.beliefs // world)
+    cfg = {'workload': f'olfactory_wrap S=22021 A=6 O=3 R=1 (BASELINE configs[2]): Perseus-walk beliefs B={per_gpu}/GPU x V={args.alphas} alphas, '
+                       f'full PBVI backup incl. dedup; value function: {headline or args.headline}',
+           'beliefs_per_gpu': per_gpu, 'beliefs_total': per_gpu * world, 'alphas': args.alphas, 'gamma': GAMMA,
+           'value_function': headline or args.headline,
+           'parallelism': f'belief-sharded x{world}' if world > 1 else 'single GPU',
+           'l2_policy': 'inputs larger than L2 (beliefs 1.76 GB, alphaT 0.18 GB per step)'}
+    if density:
+        cfg.update(density)
+    return cfg
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to the GPU box)."""
+    """
+    Reference arm: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to the GPU box) on the b200
+    arm's workload.  The value function is the b200 arm's (built by the engine when a GPU is present -- that construction is not
+    timed and nothing of the engine runs inside the timed region), each step = the whole backup arithmetic on a bounded sample of
+    the B beliefs in 512-row chunks; `value` extrapolates linearly in B to the full step (factor printed).
+    """
     rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return
     import torch
@@ -208,35 +385,72 @@ def run_reference(args):
     model = olfactory_wrap_model()
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    n_sample = 32
-    beliefs = perseus_walk_beliefs(model, n_sample, seed=0)
-    rng = np.random.default_rng(0)
-    # alpha set of the same shape as the b200 arm's (values do not change the reference's cost): Rbar rows + smooth random rows
-    alphas = np.concatenate([model.expected_rewards_table.T, rng.random((args.alphas - model.action_count, model.state_count)) * 0.1])
+    n_full = (args.beliefs if args.scaling == 'weak' else -(-args.beliefs // world)) * world
+    n_sample = min(n_full, 512 if args.steps + args.warmup <= 16 else 256)
+    built_by = 'numpy (no CUDA device): Rbar rows + smooth random rows'
+    density = None
+    if torch.cuda.is_available():
+        try:
+            torch.cuda.set_device(0)
+            _, beliefs_d, vfs, info = build_workload(model, n_sample, args.alphas, seed=0)
+            vf = vfs[args.headline] if args.headline != 'dense' else make_dense(model, vfs['late'])
+            alphas = vf.alpha_vector_array.cpu().numpy()
+            beliefs = beliefs_d.cpu().numpy()
+            density = {'alpha_density': float((alphas != 0).mean()), 'belief_density': float((beliefs != 0).mean())}
+            built_by = f'the b200 engine, untimed ({info.get(args.headline, info["late"])["provenance"]})'
+            model.device.close()
+            torch.cuda.empty_cache()
+        except Exception as e:                     # the reference arm must not depend on the engine
+            print(f'[reference arm] engine-built workload unavailable ({e}); using the numpy stand-in', file=sys.stderr)
+            beliefs = None
+    else:
+        beliefs = None
+    if beliefs is None:
+        beliefs = perseus_walk_beliefs(model, n_sample, seed=0)
+        rng = np.random.default_rng(0)
+        alphas = np.concatenate([model.expected_rewards_table.T, rng.random((args.alphas - model.action_count, model.state_count)) * 0.1])
+    tabs = host_tables(model)
     vals = []
     for step in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(model, beliefs, alphas, n_sample, args.beliefs)
+        _, timing = oracle_backup_sample(tabs['reach'], tabs['rto'], tabs['rbar'], GAMMA, beliefs, alphas, chunk=512)
         if step >= args.warmup:
-            vals.append((v, detail))
-    value = float(np.mean([v for v, _ in vals]))
-    detail = vals[-1][1]
-    t_step = args.beliefs * args.alphas / value
-    sample = (f'per step: Gamma projection for all {args.alphas} alphas + per-belief part on {n_sample} of {args.beliefs} beliefs, '
-              f'extrapolated linearly in B; NumPy/OpenBLAS, {cores} threads')
+            vals.append((extrapolate(timing, n_full, args.alphas), timing))
+    value = float(np.mean([v['value'] for v, _ in vals]))
+    ext, timing = vals[-1]
+    sample = (f'per step: Gamma projection for all {args.alphas} alphas + per-belief part on {n_sample} of {n_full} beliefs in 512-row chunks, '
+              f'extrapolated linearly in B (factor {n_full / n_sample:.1f}); NumPy/OpenBLAS, {cores} threads; alphas built by {built_by}')
     emit(({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, 1),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample, **detail},
+        'ms_per_step': float(np.mean([v['sample_s'] for v, _ in vals])) * 1e3, 'higher_is_better': True, 'scaling': args.scaling,
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, world, density=density),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'ms_per_step_is': 'the measured time of one SAMPLE step', **{k: v for k, v in ext.items() if k != 'value'}, **timing},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
 
-def workload_config(args, world):
-    return {'workload': f'olfactory_wrap S=22021 A=6 O=3 R=1 (BASELINE configs[2]): Perseus-walk beliefs B={args.beliefs}/GPU x V={args.alphas} alphas, '
-                        f'full PBVI backup incl. dedup', 'beliefs_per_gpu': args.beliefs, 'alphas': args.alphas, 'gamma': GAMMA,
-            'parallelism': f'belief-sharded x{world}' if world > 1 else 'single GPU',
-            'l2_policy': 'inputs larger than L2 (beliefs 1.76 GB, alphaT 0.18 GB per step)'}
+# ---------------------------------------------------------------------------------------------------------------------
+def time_device_steps(step_fn, dev, steps, warmup, barrier, sampler):
+    import torch
+    for _ in range(warmup):
+        out = step_fn()
+    dev.set_profiling(True)
+    barrier()
+    launches0 = dev.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    score_ms = []
+    sampler.begin()
+    ev0.record()
+    for _ in range(steps):
+        out = step_fn()
+        score_ms.append(dev.last_score_ms())       # the step has already synchronised (dedup reads counts back)
+    ev1.record()
+    barrier()
+    sampler.end()
+    stats = dev.last_stats()
+    return {'out': out, 'elapsed_ms': ev0.elapsed_time(ev1), 'score_ms': float(np.mean(score_ms)), 'launches': dev.launch_count - launches0,
+            'executed_flops': stats['executed_flops'], 'dense_flops': stats['dense_flops']}
 
 
 def run_b200(args):
@@ -249,181 +463,348 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    from pomdp_pbvi_exploration_b200 import BeliefSet, ValueFunction
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
     from pomdp_pbvi_exploration_b200.parallel import ShardedBackup
     from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model
 
+    legs = (args.legs.split(',') if args.legs else (['backup', 'solve', 'configs'] if world == 1 else ['backup', 'solve']))
     model = olfactory_wrap_model()
     dev = model.device
+    per_gpu = args.beliefs if args.scaling == 'weak' else -(-args.beliefs // world)
+    info = {}
     if args.load_workload:
-        from pomdp_pbvi_exploration_b200 import PBVI_Solver
         blob = torch.load(args.load_workload)
         solver = PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus')
         beliefs = blob['beliefs'].to(dev.device)
-        vf = ValueFunction(model, blob['alphas'].to(dev.device), blob['actions'].numpy())
-        grow_iters = int(blob['grow_iters'])
+        vfs = {k: ValueFunction(model, blob[k + '_alphas'].to(dev.device), blob[k + '_actions'].numpy()) for k in ('young', 'late')}
+        info = blob['info']
     else:
-        solver, beliefs, vf, grow_iters = build_workload(model, args.beliefs, args.alphas, seed=rank)
+        solver, beliefs, vfs, info = build_workload(model, per_gpu, args.alphas, seed=rank)
     if args.save_workload and rank == 0:
-        torch.save({'beliefs': beliefs.cpu(), 'alphas': vf.alpha_vector_array.cpu(), 'actions': torch.as_tensor(vf.actions), 'grow_iters': grow_iters},
+        torch.save({'beliefs': beliefs.cpu(), 'info': info,
+                    **{k + '_alphas': v.alpha_vector_array.cpu() for k, v in vfs.items()}, **{k + '_actions': torch.as_tensor(v.actions) for k, v in vfs.items()}},
                    args.save_workload)
-    B, V = beliefs.shape[0], len(vf)
+    vfs['dense'] = make_dense(model, vfs['late'])
+    info['dense'] = {'provenance': 'the late alphas plus a strictly positive perturbation (every alpha non-zero at every state)'}
+    B, V = beliefs.shape[0], len(vfs[args.headline])
     A, O, S = model.action_count, model.observation_count, model.state_count
     belief_set = BeliefSet(model, beliefs)
     sharded = ShardedBackup(solver, model) if world > 1 else None
     if sharded is not None:
         sharded.set_capacity(B)            # every rank backs up exactly B beliefs
 
-    def step_device():
-        if sharded is not None:
-            return sharded.backup(belief_set, vf, append=False)
-        return solver.backup(model, belief_set, vf, append=False, belief_dominance_prune=False)
+    def make_step(vf):
+        def step():
+            if sharded is not None:
+                return sharded.backup(belief_set, vf, append=False)
+            return solver.backup(model, belief_set, vf, append=False, belief_dominance_prune=False)
+        return step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -----------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()                     # started before the warm-up so that nvidia-smi is up when the timed regions run
-    for _ in range(args.warmup):
-        out = step_device()
-    dev.set_profiling(True)
-    barrier()
-    launches0 = dev.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    score_ms = []
-    sampler.begin()
-    ev0.record()
-    for _ in range(args.steps):
-        out = step_device()
-        score_ms.append(dev.last_score_ms())       # the step has already synchronised (dedup reads keys back)
-    ev1.record()
-    barrier()
-    sampler.end()
-    if args.trace_phases and sharded is not None:
-        sharded.trace = True
-        step_device()
-        sharded.trace = False
-        print(f'[rank {rank}] phases (ms): ' + json.dumps({k: round(v, 3) for k, v in sharded.last_phases.items()}), file=sys.stderr)
-    launches = dev.launch_count - launches0
-    elapsed_ms = ev0.elapsed_time(ev1)
-    stats = dev.last_stats()
-    n_new = len(out)
-
-    # ---- the same step against a DENSE value function (no alpha-side zeros to skip): same beliefs, same V count ------------
-    dense = None
-    if not args.no_dense_variant:
-        g = torch.Generator(device='cpu').manual_seed(11)
-        noise = (1e-3 * torch.rand(vf.alpha_vector_array.shape, generator=g, dtype=torch.float64) + 1e-6).to(dev.device)
-        vf_dense = ValueFunction(model, vf.alpha_vector_array + noise, vf.actions)
-        dsteps = max(2, args.steps // 2)
-        for _ in range(2):
-            solver.backup(model, belief_set, vf_dense, append=False, belief_dominance_prune=False)
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dscore = []
-        sampler.begin()
-        d0.record()
-        for _ in range(dsteps):
-            solver.backup(model, belief_set, vf_dense, append=False, belief_dominance_prune=False)
-            dscore.append(dev.last_score_ms())
-        d1.record()
-        barrier()
-        sampler.end()
-        dstats = dev.last_stats()
-        dms = d0.elapsed_time(d1) / dsteps
-        dense = {'what': 'same beliefs, the same alphas plus a strictly positive perturbation (every alpha non-zero at every state): only '
-                         'belief / observation zeros are left to skip; local backup only (no exchange at N > 1)',
-                 'value_per_gpu': float(B) * V / (dms * 1e-3), 'ms_per_step': dms, 'kernel_ms': float(np.mean(dscore)),
-                 'executed_flops_per_launch': dstats['executed_flops'],
-                 'executed_tflops': dstats['executed_flops'] / (float(np.mean(dscore)) * 1e-3) / 1e12}
-
-    clocks = sampler.stop()       # before the e2e leg: that one is PCIe-bound, the GPU idles through most of it
-
-    # ---- end to end from host buffers -----------------------------------------------------------------------------
-    h_beliefs = beliefs.cpu().pin_memory()
-    h_alphas = vf.alpha_vector_array.cpu().pin_memory()
-    h_actions = vf.actions.copy()
-
-    def step_e2e():
-        bs = BeliefSet(model, h_beliefs)                             # H2D
-        v_in = ValueFunction(model, h_alphas, h_actions)            # H2D (+ the constructor's byte-dedup)
-        if sharded is not None:
-            res = sharded.backup(bs, v_in, append=False)
-        else:
-            res = solver.backup(model, bs, v_in, append=False, belief_dominance_prune=False)
-        rows, acts = res.numpy(staged=True)                          # D2H into the pinned staging buffer
-        return rows, acts
-
-    e2e_steps = 0 if args.no_e2e else args.steps
-    for _ in range(0 if args.no_e2e else max(1, args.warmup // 2)):
-        rows, acts = step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    rows, acts = np.zeros((0, S)), np.zeros(0)
-    for _ in range(e2e_steps):
-        rows, acts = step_e2e()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) if e2e_steps else 0.0   # device clock; every step ends with the blocking D2H read
-    # bytes that actually crossed PCIe per step: the belief rows travel packed (bitmap + non-zero 4-double chunks, packed by host
-    # threads inside the timed region and rebuilt bytewise on the device), the alpha rows as they are
-    h2d_dense = int(h_beliefs.numel() * 8 + h_alphas.numel() * 8)
-    h2d = int(getattr(solver, 'last_h2d_bytes', h_beliefs.numel() * 8) + h_alphas.numel() * 8) if e2e_steps else h2d_dense
-    d2h = int(rows.size * 8 + acts.size * 8)
-
-    # ---- max over ranks ---------------------------------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, float(np.mean(score_ms))], dtype=torch.float64, device=dev.device)
+    def reduce_max(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device=dev.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, score_mean = [float(x) for x in t]
-    else:
-        score_mean = float(np.mean(score_ms))
+        return [float(x) for x in t]
 
-    if rank == 0:
+    line = None
+    results = {}
+    belief_density = float((beliefs != 0).double().mean())
+    if 'backup' in legs:
+        # ---- device-resident timing: the headline value function first, then the other two points --------------------
+        sampler = ClockSampler(local_rank)
+        sampler.start()                     # started before the warm-up so that nvidia-smi is up when the timed regions run
+        order = [args.headline] + [k for k in ('late', 'young', 'dense') if k != args.headline]
+        if args.only_point:
+            order = [args.only_point]
+        for name in order:
+            n_steps = args.steps if name == args.headline else max(3, args.steps // 2)
+            n_warm = args.warmup if name == args.headline else max(2, args.warmup // 2)
+            r = time_device_steps(make_step(vfs[name]), dev, n_steps, n_warm, barrier, sampler)
+            r['steps'] = n_steps
+            r['elapsed_ms'], r['score_ms'] = reduce_max([r['elapsed_ms'], r['score_ms']])
+            r['alpha_density'] = float((vfs[name].alpha_vector_array != 0).double().mean())
+            results[name] = r
+        if args.trace_phases and sharded is not None:
+            sharded.trace = True
+            make_step(vfs[args.headline])()
+            sharded.trace = False
+            print(f'[rank {rank}] phases (ms): ' + json.dumps({k: round(v, 3) for k, v in sharded.last_phases.items()}), file=sys.stderr)
+        clocks = sampler.stop()       # before the e2e leg: that one is PCIe-bound, the GPU idles through part of it
+        head = results[order[0]]
+        vf_head = vfs[order[0]]
+        out = head['out']
+
+        # ---- end to end from host buffers -----------------------------------------------------------------------------
+        h_beliefs = beliefs.cpu().pin_memory()
+        h_alphas = vf_head.alpha_vector_array.cpu().pin_memory()
+        h_actions = vf_head.actions.copy()
+
+        def step_e2e():
+            bs = BeliefSet(model, h_beliefs)                             # H2D
+            v_in = ValueFunction(model, h_alphas, h_actions)            # H2D (+ the constructor's byte-dedup)
+            if sharded is not None:
+                res = sharded.backup(bs, v_in, append=False)
+            else:
+                res = solver.backup(model, bs, v_in, append=False, belief_dominance_prune=False)
+            return res.numpy(staged=True)                                # D2H into the pinned staging buffer
+
+        e2e_steps = 0 if args.no_e2e else args.steps
+        for _ in range(0 if args.no_e2e else max(1, args.warmup // 2)):
+            rows, acts = step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rows, acts = np.zeros((0, S)), np.zeros(0)
+        for _ in range(e2e_steps):
+            rows, acts = step_e2e()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1) if e2e_steps else 0.0   # device clock; every step ends with the blocking D2H read
+        # bytes that actually crossed PCIe per step: the belief rows travel packed (bitmap + non-zero 4-double chunks, packed by host
+        # threads inside the timed region and rebuilt bytewise on the device), the alpha rows as they are
+        h2d_dense = int(h_beliefs.numel() * 8 + h_alphas.numel() * 8)
+        h2d = int(getattr(solver, 'last_h2d_bytes', h_beliefs.numel() * 8) + h_alphas.numel() * 8) if e2e_steps else h2d_dense
+        d2h = int(rows.size * 8 + acts.size * 8)
+        (e2e_ms,) = reduce_max([e2e_ms])
+
         units = float(B) * V * world
-        value = units * args.steps / (elapsed_ms * 1e-3)
-        e2e_value = units * args.steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None
-        algo_flops = 2.0 * A * O * S * B * V                  # per launch (per rank)
-        achieved = algo_flops / (score_mean * 1e-3) / 1e12
+        ms_step = head['elapsed_ms'] / head['steps']
+        algo_flops = 2.0 * A * O * S * B * V                  # per launch (per rank), dense count
+        exec_tflops = head['executed_flops'] / (head['score_ms'] * 1e-3) / 1e12
+        points = {}
+        for name, r in results.items():
+            ms = r['elapsed_ms'] / r['steps']
+            points[name] = {'value': float(B) * len(vfs[name]) * world / (ms * 1e-3), 'ms_per_step': ms, 'kernel_ms': r['score_ms'],
+                            'alpha_density': r['alpha_density'], 'executed_flops_per_launch': r['executed_flops'],
+                            'executed_over_algorithmic': r['executed_flops'] / algo_flops,
+                            'executed_tflops': r['executed_flops'] / (r['score_ms'] * 1e-3) / 1e12,
+                            'pipe_frac': r['executed_flops'] / (r['score_ms'] * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                            'new_alpha_rows': len(r['out']), 'provenance': info.get(name, {}).get('provenance')}
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(args, world),
+            'metric': METRIC, 'value': units / (ms_step * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': head['steps'], 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': workload_config(args, world, order[0], {'alpha_density': head['alpha_density'], 'belief_density': belief_density,
+                                                               'value_function_provenance': info.get(order[0], {}).get('provenance')}),
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
+            'e2e': {'value': units * args.steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
                     'host_input_bytes_per_step': h2d_dense, 'host_threads': min(32, os.cpu_count() or 1) if (e2e_steps and h2d < h2d_dense) else 1,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy(); sparse belief rows are packed by '
                            'host threads (pbvi_pack_rows_host) for the upload and unpacked on the device'},
-            'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (persistent block-sparse FP64 DMMA m8n8k4 GEMM + fused argmax)', 'achieved': achieved,
-                         'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': achieved / FP64_PEAK_TFLOPS,
-                         'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH if (B == 10000 and V == 1000) else None,
+            'gpu_launches': int(head['launches']),
+            'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (persistent block-sparse FP64 DMMA m8n8k4 GEMM + fused argmax)',
+                         'achieved': exec_tflops, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': exec_tflops / FP64_PEAK_TFLOPS,
+                         'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH.get(order[0]) if (B == 10000 and V == 1000) else None,
                          'peak_source': 'own FP64 DMMA microbenchmark on this pool (profiles/r01_fp64_pipe_microbench.txt); '
-                                        'MEASURED_PEAKS.json has no FP64 entry',
-                         'algorithmic_flops_per_launch': algo_flops, 'executed_flops_per_launch': stats['executed_flops'],
-                         'executed_over_algorithmic': stats['executed_flops'] / algo_flops,
-                         'note': 'frac uses ALGORITHMIC (dense) flops, so it exceeds 1 by the share of exact-zero work skipped (belief, '
-                                 'RTO and alpha-tile zeros; results are bit-identical to the dense computation); executed_tflops / peak '
-                                 'is the pipe utilisation',
-                         'executed_tflops': stats['executed_flops'] / (score_mean * 1e-3) / 1e12,
-                         'kernel_ms': score_mean, 'kernel_share_of_step': score_mean / (elapsed_ms / args.steps)},
-            'new_alpha_rows': n_new, 'value_function_growth_backups': grow_iters,
-            'dense_alpha_variant': dense,
+                                        'MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM reaches 35.5 on the same box)',
+                         'flops_counted': 'EXECUTED flops of the launch (2 * 16 beliefs * 64 alphas * 4 states per visited (chunk, row group, '
+                                          'column quarter), counted by the kernel); skipped terms are exact zeros',
+                         'executed_flops_per_launch': head['executed_flops'], 'algorithmic_flops_per_launch': algo_flops,
+                         'algorithmic_over_executed': algo_flops / max(head['executed_flops'], 1.0),
+                         'kernel_ms': head['score_ms'], 'kernel_share_of_step': head['score_ms'] / ms_step},
+            'value_function_points': points,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count()
-            n_sample = 128
-            v, detail = cpu_reference_sample(model, beliefs[:n_sample].cpu().numpy(), vf.alpha_vector_array.cpu().numpy(), n_sample, B)
-            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': f'Gamma projection for all {V} alphas + per-belief part on {n_sample} of {B} beliefs, extrapolated '
-                                              f'linearly in B; NumPy/OpenBLAS with {cores} threads', **detail}
+
+    # ---- parity sample + CPU baseline: the oracle on the headline alphas, for a sample of the timed beliefs (rank 0) -----------------
+    parity_failed = False
+    if 'backup' in legs and rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        n_sample = min(B, args.parity_beliefs or (512 if world == 1 else 128))
+        pick = np.unique(np.linspace(0, B - 1, n_sample).astype(np.int64))
+        sample_b = beliefs[torch.as_tensor(pick, device=dev.device)]
+        tabs = host_tables(model)
+        ref, timing = oracle_backup_sample(tabs['reach'], tabs['rto'], tabs['rbar'], GAMMA, sample_b.cpu().numpy(),
+                                           vf_head.alpha_vector_array.cpu().numpy(), chunk=512)
+        line['parity_sample'] = parity_check(dev, tabs, GAMMA, sample_b, vf_head, ref, step_output=out)
+        line['parity_sample']['what'] = (f'{len(pick)} of the {B} timed beliefs (evenly spaced), the headline value function; oracle = '
+                                         'oracle/pbvi_oracle.py (NumPy restatement of src/pomdp.py:1485-1506)')
+        parity_failed = not line['parity_sample']['ok']
+        if world == 1:
+            ext = extrapolate(timing, B, V)
+            line['cpu_baseline'] = {'value': ext['value'], 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': f'Gamma projection for all {V} alphas + per-belief part on {len(pick)} of {B} beliefs in 512-row chunks, '
+                                              f'extrapolated linearly in B (factor {ext["extrapolation_factor"]:.1f}); NumPy/OpenBLAS with {cores} threads; '
+                                              'the same alphas and beliefs as the timed step',
+                                    **{k: v for k, v in ext.items() if k != 'value'}, **timing}
+
+    # ---- whole solves ---------------------------------------------------------------------------------------------------------
+    if 'solve' in legs:
+        solve = {}
+        try:
+            solve = run_solve_leg(model, world, rank, info, reduce_max)
+        except Exception as e:          # the solve leg must not take the headline down with it
+            solve = {'error': f'{type(e).__name__}: {e}'}
+        if line is not None:
+            line['solve'] = solve
+        elif rank == 0:
+            line = {'metric': 'PBVI solve wall time', 'solve': solve, 'n_gpus': world}
+        if rank == 0 and line is not None and 'cpu_baseline' in line and 'error' not in solve:
+            cpu = line['cpu_baseline']['value']
+            for k, s in solve.items():
+                if isinstance(s, dict) and 'backup_pairs' in s:
+                    s['cpu_port_backup_s_estimate'] = s['backup_pairs'] / cpu
+                    s['cpu_port_estimate_note'] = ('backup pairs of this solve / the cpu_baseline pairs-per-second of this run (late value '
+                                                   'function, B = 10 000): an estimate of the reference CPU path\'s backup time alone')
+
+    if 'configs' in legs and world == 1 and rank == 0:
+        try:
+            line['configs'] = run_config_leg(args)
+        except Exception as e:
+            line['configs'] = {'error': f'{type(e).__name__}: {e}'}
+
+    if rank == 0 and line is not None:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit(3)
+
+
+def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
+    """
+    Whole solves of the olfactory model, device-synchronised wall clock, max over ranks:
+      fsvi_300x100           the reference's published shape (2983.5 s NumPy CPU, 204.9 s CuPy GPU: BASELINE.md section 1);
+      perseus_full_2x5000    PBVI_Solver('perseus').solve(expansions=2, max_belief_growth=5000, full_backup=True): every backup
+                             covers the whole belief set, 10 001 beliefs at the end (north_star: ">= 10k belief points").
+    At N > 1 the loop is sharded over the ranks (`solve(group=True)`).
+    """
+    from pomdp_pbvi_exploration_b200 import FSVI_Solver, PBVI_Solver
+    out = {}
+    shard = {'group': True} if world > 1 else {}
+    if world == 1 and 'late' in info and 'fsvi_solve' in info['late']:
+        s = dict(info['late']['fsvi_solve'])         # the workload's own solve (timed when it ran)
+    else:
+        seed_all(0)
+        _, _, s = timed_solve(FSVI_Solver(gamma=GAMMA, eps=1e-6), model, expansions=300, max_belief_growth=100, **shard)
+    s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
+    s['reference_published'] = {'numpy_cpu_s': 2983.5, 'cupy_gpu_s': 204.9, 'source': 'Olfactory_Alternation_Paper_Wrap.ipynb[43],[30] (BASELINE.md)'}
+    out['fsvi_300x100'] = s
+    seed_all(0)
+    _, _, s = timed_solve(PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus'), model, expansions=2, max_belief_growth=5000,
+                          full_backup=True, **shard)
+    s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
+    out['perseus_full_2x5000'] = s
+    out['n_gpus'] = world
+    out['note'] = ('expansions draw on the host RNG and are sequential in the belief (b_{t+1} depends on o_t): they run on rank 0 and are '
+                   'broadcast; backups and compute_change are sharded')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _time_backup(model, gamma, B, V, acts, reps):
+    import torch
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='ssea')
+    bs, vf = BeliefSet(model, B), ValueFunction(model, V, acts)
+    for _ in range(3):
+        out = solver.backup(model, bs, vf, append=False, belief_dominance_prune=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = solver.backup(model, bs, vf, append=False, belief_dominance_prune=False)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out, vf
+
+
+def _dirichlet_beliefs(rng, n, S, k):
+    B = np.zeros((n, S))
+    for i in range(n):
+        idx = rng.choice(S, min(k, S), replace=False)
+        B[i, idx] = rng.dirichlet(np.ones(len(idx)))
+    return B
+
+
+def _config_point(name, model, gamma, B, V, acts, reps, parity_rows):
+    """One backup shape of another model: time per backup (CUDA events), pairs/s, and a parity sample against the oracle."""
+    import torch
+    ms, out, vf = _time_backup(model, gamma, B, V, acts, reps)
+    S, A, O, R = model.state_count, model.action_count, model.observation_count, model.reachable_state_count
+    rec = {'config': name, 'S': S, 'A': A, 'O': O, 'R': R, 'B': int(B.shape[0]), 'V': len(vf), 'ms_per_backup': ms,
+           'pairs_per_s': B.shape[0] * len(vf) / (ms * 1e-3), 'new_alpha_rows': len(out),
+           'algorithmic_tflops': 2.0 * A * O * S * B.shape[0] * len(vf) / (ms * 1e-3) / 1e12}
+    if parity_rows:
+        tabs = host_tables(model)
+        pick = np.unique(np.linspace(0, B.shape[0] - 1, min(parity_rows, B.shape[0])).astype(np.int64))
+        sb = np.ascontiguousarray(B[pick])
+        t0 = time.perf_counter()
+        ref, timing = oracle_backup_sample(tabs['reach'], tabs['rto'], tabs['rbar'], gamma, sb, vf.alpha_vector_array.cpu().numpy(), chunk=256)
+        rec['parity_sample'] = parity_check(model.device, tabs, gamma, torch.as_tensor(sb).to(model.device.device), vf, ref,
+                                            step_output=out if R == 1 else None)
+        rec['cpu_oracle_pairs_per_s'] = extrapolate(timing, B.shape[0], len(vf))['value']
+    return rec
+
+
+def run_config_leg(args) -> dict:
+    """
+    The other BASELINE configs on one GPU, each point with a parity sample against the oracle:
+      configs[0] tiger (S2 A3 O2 R2): the PBVI-RA solve the reference runs on CPU + one backup shape;
+      configs[1] 4x4 grid (R = 15 dense and R = 1 no_loop) at B x V in {16, 256, 4096} x {4, 64, 1024};
+      configs[4] synthetic random sparse POMDPs; and the sea-robin size (S = 63 555, A = 16, O = 2), the reference's largest workload.
+    """
+    import torch
+    from pomdp_pbvi_exploration_b200 import Model, PBVI_Solver
+    from pomdp_pbvi_exploration_b200.recipes import sea_robin_model, synthetic_sparse_model, tiger_model
+    rng = np.random.default_rng(0)
+    points = []
+    # ---- configs[0]
+    model = tiger_model()
+    seed_all(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vf, hist = PBVI_Solver(0.95, eps=1e-6, expand_function='ra').solve(model, expansions=8, max_belief_growth=10, print_progress=False)
+    torch.cuda.synchronize()
+    tiger_solve = {'config': 'tiger PBVI-RA solve (expansions=8, max_belief_growth=10)', 'wall_s': time.perf_counter() - t0,
+                   'final_alphas': len(vf), 'final_beliefs': int(hist.beliefs_counts[-1]), 'backups': len(hist.backup_times)}
+    Bt = _dirichlet_beliefs(rng, 80, 2, 2)
+    Vt = np.array([[-100.0, 10.0], [10.0, -100.0], [-1.0, -1.0], [3.0, 5.0], [5.0, 3.0], [-20.0, 8.0], [8.0, -20.0], [0.0, 0.0], [1.0, 2.0]])
+    points.append(_config_point('tiger', model, 0.95, Bt, Vt, rng.integers(0, 3, len(Vt)), 50, 80))
+    # ---- configs[1]
+    for tag in ('grid4x4', 'grid4x4_noloop'):
+        m = dict(np.load(os.path.join(ROOT, 'tests', 'golden', f'model_{tag}.npz')))
+        S, A, O = m['rto'].shape[0], m['rto'].shape[1], m['rto'].shape[2]
+        model = Model(states=S, actions=A, observations=O, transitions=m['transition_table'], rewards=m['reward_table'],
+                      observation_table=m['obs_table'], start_probabilities=m['start'])
+        for nB in (16, 256, 4096):
+            for nV in (4, 64, 1024):
+                if tag == 'grid4x4_noloop' and (nB, nV) not in ((256, 64), (4096, 1024)):
+                    continue
+                B = np.concatenate([np.eye(16)[:min(16, nB)], _dirichlet_beliefs(rng, max(0, nB - 16), 16, 16)])
+                V = rng.random((nV, 16)) * 3
+                points.append(_config_point(f'{tag} (R={model.reachable_state_count})', model, float(m['gamma']), B, V, rng.integers(0, 4, nV), 20,
+                                            256 if nB * nV <= 4096 * 64 else 0))
+    # ---- configs[4] + sea-robin size
+    for S, A, O, R, parity in ((1000, 4, 2, 1, 256), (10000, 8, 4, 2, 128), (30000, 8, 4, 1, 0), (100000, 16, 8, 4, 0)):
+        model = synthetic_sparse_model(S, A, O, R, seed=1)
+        B = _dirichlet_beliefs(rng, 1024, S, 2048)
+        V = rng.random((256, S))
+        points.append(_config_point('synthetic_sparse', model, 0.95, B, V, rng.integers(0, A, 256), 5, parity))
+        model.device.close()
+        del model
+        torch.cuda.empty_cache()
+    model = sea_robin_model()
+    solver = PBVI_Solver(gamma=GAMMA, eps=1e-8, expand_function='perseus')
+    from pomdp_pbvi_exploration_b200 import Belief, ValueFunction
+    np.random.seed(4)
+    walks = [solver.expand_perseus(model, Belief(model), max_generation=100) for _ in range(10)]
+    vf = ValueFunction(model, model.expected_rewards_table.T, model.actions)
+    for w in walks[:6]:
+        vf = solver.backup(model, w, vf, append=True, belief_dominance_prune=False)
+    Bs = torch.cat([w.belief_array for w in walks]).cpu().numpy()
+    rec = _config_point('sea_robin (Sea_Robins_Swim_Walk.ipynb)', model, GAMMA, Bs, vf.alpha_vector_array.cpu().numpy(), vf.actions, 5, 48)
+    rec['gamma_bytes_the_reference_would_allocate'] = 8.0 * 16 * 2 * rec['V'] * 63555
+    points.append(rec)
+    bad = [p['config'] for p in points if 'parity_sample' in p and not p['parity_sample']['ok']]
+    return {'tiger_solve': tiger_solve, 'points': points, 'parity_failures': bad}
 
 
 _JSON_OUT = None

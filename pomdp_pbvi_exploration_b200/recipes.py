@@ -9,6 +9,7 @@ models are missing blobs (.MISSING_LARGE_BLOBS) -- not part of the hot path:
                            `Experiments/Olfactory Navigation/Olfactory_Alternation_Paper_Wrap.ipynb[3-15]`
                            (6 actions, 3 observations, deterministic moves => R=1).
 * `synthetic_sparse_model` the random sparse POMDP recipe of BASELINE.json configs[4].
+* `sea_robin_model`        the 63 555-state sea-robin tank POMDP (A = 16, O = 2), the reference's largest workload.
 """
 from __future__ import annotations
 
@@ -110,6 +111,40 @@ def olfactory_wrap_model(ground_map: np.ndarray | None = None, nose_map: np.ndar
     return Model(states=grid_labels, actions=['N', 'E', 'S', 'W', 'O_Ground', 'O_Air'],
                  observations=['nothing', 'something', 'goal'], reachable_states=reach, rewards=reward_func,
                  observation_table=obs, end_states=[goal], start_probabilities=start.ravel())
+
+
+def sea_robin_model(tank_size=(111, 142), swim_radius: float = 8.5, source_radius: float = 10.5) -> Model:
+    """
+    The sea-robin "walk + swim" tank POMDP of `Experiments/Sea Robins/Sea_Robins_Swim_Walk.ipynb[2-12]` -- the reference's largest
+    workload (S = 223 x 285 = 63 555, A = 16, O = 2, R = 1; its FSVI solve runs out of memory at |V| = 1364 because
+    Gamma = 8*A*O*V*S bytes = 22 GB).  State = agent position relative to the source on a toroidal grid of
+    (2*tank + 1); 4 walking moves (1 cell) that sense ('something' inside the source disc, else 'nothing') and 12 swimming
+    moves (the distinct lattice points at distance ~8.5: r in {0, 4}) that always observe 'nothing'; the end state is the centre.
+    """
+    tank = np.array(tank_size)
+    H, W = (tank * 2 + 1).tolist()
+    S = H * W
+    walking = [np.array([1, 0]), np.array([0, 1]), np.array([-1, 0]), np.array([0, -1])]
+    moves = []
+    for r in [0, 4]:
+        d = int(np.floor(np.sqrt(swim_radius ** 2 - r ** 2)))
+        moves += [np.array([-d, r]), np.array([d, r]), np.array([-d, -r]), np.array([d, -r]),
+                  np.array([r, -d]), np.array([r, d]), np.array([-r, -d]), np.array([-r, d])]
+    swimming = list({m.tobytes(): m for m in moves}.values())          # dict insertion order, like the notebook
+    all_moves = walking + swimming
+    A = len(all_moves)
+    xs, ys = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+    like = (((xs - tank[0]) ** 2 + (ys - tank[1]) ** 2) <= source_radius ** 2).astype(float).ravel()
+    reach = np.empty((S, A, 1), dtype=int)
+    for a, mv in enumerate(all_moves):
+        nx, ny = (xs + mv[0]) % H, (ys + mv[1]) % W
+        reach[:, a, 0] = (nx * W + ny).ravel()
+    obs = np.empty((S, A, 2))
+    obs[:, :4, 0], obs[:, :4, 1] = like[:, None], 1.0 - like[:, None]
+    obs[:, 4:, 0], obs[:, 4:, 1] = 0.0, 1.0
+    grid_labels = [[f's_{i}_{j}' for j in range(W)] for i in range(H)]
+    return Model(states=grid_labels, actions=[f'm_{int(m[0])}_{int(m[1])}' for m in all_moves], observations=['something', 'nothing'],
+                 reachable_states=reach, observation_table=obs, end_states=[int(W * (H - 1) / 2 + (W - 1) / 2)])
 
 
 def synthetic_sparse_model(S: int, A: int, O: int, R: int, seed: int = 0) -> Model:

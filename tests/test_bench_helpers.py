@@ -49,7 +49,33 @@ def test_workload_config_names_the_baseline_config():
     import bench
 
     class A:
-        beliefs, alphas = 10000, 1000
+        beliefs, alphas, scaling, headline = 10000, 1000, 'weak', 'late'
     cfg = bench.workload_config(A, 8)
     assert 'BASELINE configs[2]' in cfg['workload'] and cfg['parallelism'] == 'belief-sharded x8'
+    assert cfg['beliefs_per_gpu'] == 10000 and cfg['beliefs_total'] == 80000 and cfg['value_function'] == 'late'
     assert bench.workload_config(A, 1)['parallelism'] == 'single GPU'
+
+    class Strong(A):
+        beliefs, scaling = 50000, 'strong'
+    cfg = bench.workload_config(Strong, 8)
+    assert cfg['beliefs_per_gpu'] == 6250 and cfg['beliefs_total'] == 50000
+
+
+def test_oracle_sample_and_extrapolation_on_a_small_model():
+    """bench.py's oracle leg (the reference's arithmetic in 512-row chunks + the top-2 gaps of the parity contract) equals
+    oracle.backup on a golden model, and the extrapolation formula is the stated one."""
+    import numpy as np
+    import bench
+    from conftest import load_golden
+    from oracle import pbvi_oracle as orc
+    m, g = load_golden('model_grid4x4_noloop'), load_golden('backup_grid4x4_noloop')
+    reach = m['reach'].astype(np.int64)
+    out, timing = bench.oracle_backup_sample(reach, m['rto'], m['rbar'], float(m['gamma']), g['beliefs'], g['alphas'], chunk=7)
+    ref = orc.backup(reach, m['rto'], m['rbar'], float(m['gamma']), g['beliefs'], g['alphas'], return_scores=True)
+    assert np.array_equal(out['v_star'], ref['v_star']) and np.array_equal(out['a_star'], ref['a_star'])
+    assert np.array_equal(out['alpha'], ref['alpha'])
+    top = np.sort(ref['scores'], axis=3)
+    assert np.allclose(out['best'], top[..., -1]) and np.allclose(out['gap'], top[..., -1] - top[..., -2])
+    ext = bench.extrapolate({'gamma_projection_s': 2.0, 'per_belief_part_s': 3.0, 'sample_beliefs': 100}, 1000, 50)
+    assert ext['extrapolation_factor'] == 10.0 and abs(ext['full_step_s_estimate'] - 32.0) < 1e-12
+    assert abs(ext['value'] - 1000 * 50 / 32.0) < 1e-9 and abs(ext['sample_pairs_per_s_raw'] - 100 * 50 / 5.0) < 1e-9
