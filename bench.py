@@ -166,20 +166,25 @@ def timed_solve(solver, model, **kw):
         change_s[0] += time.perf_counter() - t
         return out
     solver.compute_change = timed_change
+    # units of a solve: every backup call processes (beliefs backed up) x (alphas of the value function it starts from)
+    pair_count = [0.0]
+    orig_backup = solver.backup
+
+    def counted_backup(model_, belief_set, value_function, *a, **k):
+        pair_count[0] += float(len(belief_set)) * len(value_function)
+        return orig_backup(model_, belief_set, value_function, *a, **k)
+    solver.backup = counted_backup
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     vf, hist = solver.solve(model, print_progress=False, **kw)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    solver.compute_change = orig_change
-    full = hist.expand_append
-    nb = hist.beliefs_counts[1:] if full else np.diff(hist.beliefs_counts)
-    # units of a solve: every backup call processes (beliefs backed up) x (alphas of the value function it starts from)
-    pairs = float(sum(int(b) * int(v) for b, v in zip(nb, hist.alpha_vector_counts[:-1])))
+    solver.compute_change, solver.backup = orig_change, orig_backup
+    st = getattr(solver, '_shard_state', None)
+    pairs = pair_count[0] + (st.stats.get('sharded_pairs', 0.0) if st is not None else 0.0)     # sharded backups: pairs of the WHOLE set
     out = dict(wall_s=wall, expand_s=float(sum(hist.expansion_times)), backup_s=float(sum(hist.backup_times)), change_s=change_s[0],
                expansions=len(hist.expansion_times), backups=len(hist.backup_times), final_alphas=len(vf), final_beliefs=int(hist.beliefs_counts[-1]),
                backup_pairs=pairs, backup_pairs_per_s=pairs / max(float(sum(hist.backup_times)), 1e-9))
-    st = getattr(solver, '_shard_state', None)
     if st is not None:
         out['sharding'] = dict(st.stats)
     return vf, hist, out
@@ -672,8 +677,10 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
     """
     Whole solves of the olfactory model, device-synchronised wall clock, max over ranks:
       fsvi_300x100           the reference's published shape (2983.5 s NumPy CPU, 204.9 s CuPy GPU: BASELINE.md section 1);
-      perseus_full_2x5000    PBVI_Solver('perseus').solve(expansions=2, max_belief_growth=5000, full_backup=True): every backup
-                             covers the whole belief set, 10 001 beliefs at the end (north_star: ">= 10k belief points").
+      perseus_full_10k       PBVI_Solver('perseus').solve(expansions=2, max_belief_growth=6000, full_backup=True, update_passes=15):
+                             the Perseus scheme -- a belief set collected by random walks (12 000 walk steps; > 10 000 distinct beliefs,
+                             north_star: ">= 10k belief points"), then repeated backups of the WHOLE set (`update_passes` is the
+                             reference's own parameter, src/pomdp.py:2172-2186), each followed by compute_change.
     At N > 1 the loop is sharded over the ranks (`solve(group=True)`).
     """
     from pomdp_pbvi_exploration_b200 import FSVI_Solver, PBVI_Solver
@@ -688,10 +695,10 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
     s['reference_published'] = {'numpy_cpu_s': 2983.5, 'cupy_gpu_s': 204.9, 'source': 'Olfactory_Alternation_Paper_Wrap.ipynb[43],[30] (BASELINE.md)'}
     out['fsvi_300x100'] = s
     seed_all(0)
-    _, _, s = timed_solve(PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus'), model, expansions=2, max_belief_growth=5000,
-                          full_backup=True, **shard)
+    _, _, s = timed_solve(PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus'), model, expansions=2, max_belief_growth=6000,
+                          full_backup=True, update_passes=15, **shard)
     s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
-    out['perseus_full_2x5000'] = s
+    out['perseus_full_10k'] = s
     out['n_gpus'] = world
     out['note'] = ('expansions draw on the host RNG and are sequential in the belief (b_{t+1} depends on o_t): they run on rank 0 and are '
                    'broadcast; backups and compute_change are sharded')

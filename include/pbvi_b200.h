@@ -112,6 +112,15 @@ PBVI_API int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const in
 PBVI_API int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const int32_t* h_observations,
                                     const uint8_t* h_reset, int n, double* d_out, void* stream);
 
+/* The Perseus random walk in belief space (PBVI_Solver.expand_perseus, src/pomdp.py:2040-2054): for i < n, a_i = h_actions[i] (drawn on the
+ * host, `np.random.choice(model.actions)`), o_i ~ P(o | b_i, a_i) drawn ON THE DEVICE from the host's uniform h_uniforms[i] exactly as
+ * `np.random.choice(observations, p=obs_prob)` does (cdf = cumsum(p) / cumsum(p)[-1]; searchsorted(cdf, u, 'right') -- that call
+ * consumes one `random_sample()`, so pre-drawing (a_i, u_i) in this order leaves the reference's RNG stream unchanged), and
+ * d_out[i] = b_{i+1} = update(b_i, a_i, o_i), b_0 = d_b0.  d_observations [n] (nullable) receives the o_i.  4n launches are
+ * enqueued and nothing is read back: the host-driven form pays two synchronisations per step. */
+PBVI_API int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const double* h_uniforms, int n,
+                               double* d_out, int32_t* d_observations, void* stream);
+
 /* Every successor of every belief (Belief.generate_successors, src/pomdp.py:424-438; the B*A*O loop of SSEA :1679 and
  * GER :1732): d_out [n][A][O][S], d_norm [n][A][O] (nullable).  Rows of impossible observations are NaN when normalised. */
 PBVI_API int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, void* stream);

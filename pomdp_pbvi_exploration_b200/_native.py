@@ -34,6 +34,7 @@ SIGNATURES = {
     'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
     'pbvi_belief_update': [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     'pbvi_belief_trajectory': [_P, _P, _P, _P, _P, c_int, _P, _P],
+    'pbvi_perseus_walk': [_P, _P, _P, _P, c_int, _P, _P, _P],
     'pbvi_belief_successors': [_P, _P, c_int, c_int, _P, _P, _P],
     'pbvi_observation_probabilities': [_P, _P, c_int, _P, _P],
     'pbvi_row_hash': [_P, _P, c_int, c_int, _P, _P],
@@ -248,6 +249,19 @@ class DeviceModel:
         self._call(self._lib.pbvi_belief_trajectory(self._h, _ptr(b), a.ctypes.data, o.ctypes.data, None if r is None else r.ctypes.data, n,
                                                     _ptr(out), self._stream))
         return out
+
+    def perseus_walk(self, b0: torch.Tensor, actions, uniforms, want_observations: bool = False):
+        """Random walk in belief space from b0: host-drawn actions and uniforms, observations drawn on the device (see
+        `pbvi_perseus_walk`).  Returns the n visited beliefs [n,S] (and the drawn observations [n] int32 when asked)."""
+        b = _f64(b0, self.device).reshape(-1)
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        n = a.shape[0]
+        assert u.shape == (n,) and b.shape[0] == self.S
+        out = torch.empty((n, self.S), dtype=torch.float64, device=self.device)
+        obs = torch.empty((n,), dtype=torch.int32, device=self.device) if want_observations else None
+        self._call(self._lib.pbvi_perseus_walk(self._h, _ptr(b), a.ctypes.data, u.ctypes.data, n, _ptr(out), _ptr(obs), self._stream))
+        return (out, obs) if want_observations else out
 
     def belief_successors(self, beliefs, normalise: bool = True):
         """All (a,o) successors: (succ [n,A,O,S], mass [n,A,O]); NaN rows for impossible observations when normalised."""

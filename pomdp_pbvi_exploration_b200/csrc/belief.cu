@@ -13,11 +13,28 @@ __global__ void __launch_bounds__(256) belief_project_kernel(const double* __res
                                                              const int32_t* __restrict__ observations, size_t beliefStride,
                                                              const int32_t* __restrict__ predPtr, const int32_t* __restrict__ predK,
                                                              const double* __restrict__ rtoK, int S, int R, int O,
-                                                             double* __restrict__ out, int aConst, int oConst) {
+                                                             double* __restrict__ out, int aConst, int oConst,
+                                                             const double* __restrict__ chooseP, double chooseU, int32_t* __restrict__ chosen) {
     const int i = blockIdx.y;
     const int sp = blockIdx.x * 256 + threadIdx.x;
+    int oPick = oConst;
+    if (chooseP) {
+        // the observation is DRAWN here (Perseus walk, src/pomdp.py:2045-2047): np.random.choice(observations, p=P(o|b,a)) is
+        // cdf = cumsum(p) (sequential adds); cdf /= cdf[-1]; searchsorted(cdf, u, side='right') with ONE uniform u, which the host
+        // drew in the reference's order.  Every thread repeats the O additions (same order => same doubles => same choice).
+        double tot = 0.0;
+        for (int o = 0; o < O; o++) tot = __dadd_rn(tot, chooseP[o]);
+        double run = 0.0;
+        int idx = 0;
+        for (int o = 0; o < O; o++) {
+            run = __dadd_rn(run, chooseP[o]);
+            if (__ddiv_rn(run, tot) <= chooseU) idx++;
+        }
+        oPick = min(idx, O - 1);
+        if (chosen && blockIdx.x == 0 && threadIdx.x == 0) *chosen = oPick;
+    }
     if (sp >= S) return;
-    const int a = actions ? actions[i] : aConst, o = observations ? observations[i] : oConst;
+    const int a = actions ? actions[i] : aConst, o = observations ? observations[i] : oPick;
     const size_t K = (size_t)S * R;
     const int32_t* ptr = predPtr + (size_t)a * (S + 1);
     const int32_t* pk = predK + (size_t)a * K;
@@ -184,7 +201,7 @@ static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t bel
         double* out = d_out + (size_t)i0 * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, 0, st>>>(d_beliefs + (size_t)i0 * beliefStride, d_actions + i0,
                                                                             d_observations + i0, beliefStride, m->predPtr, m->predK,
-                                                                            m->rtoK, m->S, m->R, m->O, out, 0, 0);
+                                                                            m->rtoK, m->S, m->R, m->O, out, 0, 0, nullptr, 0.0, nullptr);
         m->last_launches++;
         if (normalise && ni <= 4 && smem <= 48 * 1024) {
             // a few rows (one step of a Perseus walk, a single Belief.update): the multi-block form of the normaliser, row by row
@@ -238,11 +255,46 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
     for (int i = 0; i < n; i++) {
         double* out = d_out + (size_t)i * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
-                                                                           m->O, out, h_actions[i], h_observations[i]);
+                                                                           m->O, out, h_actions[i], h_observations[i], nullptr, 0.0, nullptr);
         pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
         pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
         m->last_launches += 3;
         src = (h_reset && h_reset[i]) ? d_b0 : out;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
+extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const double* h_uniforms, int n,
+                                 double* d_out, int32_t* d_observations, void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_b0 && h_actions && h_uniforms && d_out, "NULL pointer argument");
+    for (int i = 0; i < n; i++) PBVI_REQUIRE(h_actions[i] >= 0 && h_actions[i] < m->A, "action index out of range");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
+    PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
+    m->arena.reset();
+    PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
+    PBVI_TAKE(obsProb, double, (size_t)m->O);
+    const size_t K = (size_t)m->S * m->R;
+    const double* src = d_b0;
+    for (int i = 0; i < n; i++) {
+        const int a = h_actions[i];
+        double* out = d_out + (size_t)i * m->S;
+        // P(o | b, a): the blocks of observation_probability_kernel that belong to action a (same arithmetic as
+        // pbvi_observation_probabilities, so the walk equals the step-by-step host-driven one bit for bit)
+        observation_probability_kernel<<<dim3(m->O, 1), 256, 0, st>>>(src, m->rtoK + (size_t)a * m->O * K, m->S, m->R, m->O, obsProb);
+        belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
+                                                                           m->O, out, a, 0, obsProb, h_uniforms[i],
+                                                                           d_observations ? d_observations + i : nullptr);
+        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
+        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
+        m->last_launches += 4;
+        src = out;
     }
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;

@@ -364,7 +364,7 @@ class ShardedSolveState:
         self.n_local = 0
         self.n_global = 0
         self.max_owned = 0           # upper bound on any rank's number of owned rows
-        self.stats = {'broadcast_rows': 0, 'sharded_backups': 0, 'replicated_backups': 0}
+        self.stats = {'broadcast_rows': 0, 'sharded_backups': 0, 'replicated_backups': 0, 'sharded_pairs': 0.0}
 
     # ---- expansion on rank 0, rows broadcast ---------------------------------------------------------------------------
     def expand(self, model, belief_set, value_function, max_generation, **params):
@@ -421,6 +421,7 @@ class ShardedSolveState:
     def backup_full(self, value_function):
         """Backup over the whole belief set (full_backup=True flavours), sharded by ownership."""
         self.stats['sharded_backups'] += 1
+        self.stats['sharded_pairs'] += float(self.n_global) * len(value_function)
         return self.sb.backup(self.local_set, value_function, append=False, positions=self._pos[:self.n_local],
                               capacity=max(self.max_owned, 1))
 
@@ -432,6 +433,7 @@ class ShardedSolveState:
             self.stats['replicated_backups'] += 1
             return self.solver.backup(self.model, new_belief_set, value_function, append=True, belief_dominance_prune=False)
         self.stats['sharded_backups'] += 1
+        self.stats['sharded_pairs'] += float(n) * len(value_function)
         lo, hi = shard_bounds(n, self.world, self.rank)
         self.sb_new.set_capacity(-(-n // self.world))
         return self.sb_new.backup(BeliefSet(self.model, new_belief_set.belief_array[lo:hi]), value_function, append=True)

@@ -728,18 +728,22 @@ class PBVI_Solver:
         return self._trajectory(model, b0, mdp_policy, max_generation, eps_greedy)
 
     def expand_perseus(self, model: Model, b: Belief, max_generation: int = 10) -> BeliefSet:
-        """Random walk in belief space (reference src/pomdp.py:2010-2056): a uniform, o ~ P(o|b,a), b <- update(b,a,o)."""
+        """
+        Random walk in belief space (reference src/pomdp.py:2010-2056): a uniform, o ~ P(o|b,a), b <- update(b,a,o).
+        The host draws, per step and in the reference's order, the action (`np.random.choice(model.actions)`) and the ONE uniform
+        that `np.random.choice(observations, p=obs_prob)` consumes; the observation itself is picked on the device with NumPy's
+        rule (cumsum, normalise, searchsorted 'right'), so the whole walk is enqueued without a host round trip per step and the
+        legacy RNG stream advances exactly as in the reference.
+        """
         dev = model.device
-        rows = []
-        cur = b.values
-        for _ in range(max_generation):
-            a = int(np.random.choice(model.actions, size=1)[0])
-            obs_prob = dev.observation_probabilities(cur[None, :])[0, a].cpu().numpy()
-            o = int(np.random.choice(model.observations, size=1, p=obs_prob)[0])
-            out, _ = dev.belief_update(cur[None, :], [a], [o])
-            cur = out[0]
-            rows.append(cur)
-        return BeliefSet(model, torch.stack(rows))
+        n = int(max_generation)
+        if n <= 0:
+            return BeliefSet(model, torch.empty((0, model.state_count), dtype=torch.float64, device=dev.device))
+        acts, us = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.float64)
+        for i in range(n):
+            acts[i] = int(np.random.choice(model.actions, size=1)[0])
+            us[i] = np.random.random_sample()
+        return BeliefSet(model, dev.perseus_walk(b.values, acts, us))
 
     def expand(self, model: Model, belief_set: BeliefSet, max_generation: int, **function_specific_parameters) -> BeliefSet:
         """Dispatcher (reference src/pomdp.py:2059-2138): the strategy is matched by substring, e.g. 'ra', 'ssra', 'expand_ssra'."""

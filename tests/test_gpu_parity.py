@@ -528,3 +528,35 @@ def test_belief_trajectory_equals_chained_updates(torch_cuda, tag):
         cur = b0 if reset else nxt[0]
     chain = dev.belief_trajectory(b0, actions, observations, resets)
     assert torch.equal(chain, torch.stack(want))
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'grid4x4', 'olfactory_wrap'])
+def test_perseus_walk_equals_host_driven_steps(torch_cuda, tag):
+    """`pbvi_perseus_walk` (observations drawn on the device from host uniforms) == the step-by-step form of the reference's
+    expand_perseus (src/pomdp.py:2040-2054): P(o|b,a) read back, `np.random.choice(observations, p=...)` on the host, one update
+    -- same beliefs bit for bit, same observations, same state of the legacy RNG stream afterwards."""
+    dev, m, reach, _ = device_model(tag)
+    A, O = m['rto'].shape[1], m['rto'].shape[2]
+    n = 40
+    b0 = m['start']
+    np.random.seed(21)
+    cur = torch_cuda.as_tensor(b0).cuda()
+    want_rows, want_obs = [], []
+    for _ in range(n):
+        a = int(np.random.choice(np.arange(A), size=1)[0])
+        p = dev.observation_probabilities(cur[None, :])[0, a].cpu().numpy()
+        o = int(np.random.choice(np.arange(O), size=1, p=p)[0])
+        cur = dev.belief_update(cur[None, :], [a], [o])[0][0]
+        want_rows.append(cur.cpu().numpy())
+        want_obs.append(o)
+    tail_want = np.random.random_sample()
+    np.random.seed(21)
+    acts, us = np.empty(n, dtype=np.int32), np.empty(n)
+    for i in range(n):
+        acts[i] = int(np.random.choice(np.arange(A), size=1)[0])
+        us[i] = np.random.random_sample()
+    tail_got = np.random.random_sample()
+    rows, obs = dev.perseus_walk(b0, acts, us, want_observations=True)
+    assert tail_got == tail_want
+    assert np.array_equal(obs.cpu().numpy(), np.array(want_obs))
+    assert np.array_equal(rows.cpu().numpy(), np.stack(want_rows), equal_nan=True)
