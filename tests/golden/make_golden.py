@@ -364,6 +364,43 @@ def gen_simulations():
     save('simulations', **out)
 
 
+def gen_io():
+    """
+    On-disk formats (src/mdp.py:909-1036): files WRITTEN BY THE UNMODIFIED REFERENCE -- `ValueFunction.save` (csv, csv.gzip) and
+    `save_parquet` of a small value function (the reference's own backup of the 4x4 no_loop fixture) -- plus the one value-function
+    artefact the reference ships, gzip-compressed as its own `save(compress=True)` would (the loader keys on '.gzip' in the name).
+    """
+    import gzip
+    import shutil
+    print('[io]')
+    out_dir = os.path.join(HERE, 'io')
+    os.makedirs(out_dir, exist_ok=True)
+    with quiet():
+        m, s0 = ref.load_POMDP_file(os.path.join(EXAMPLES, '4x4.95-no_loop.POMDP'))
+    g = dict(np.load(os.path.join(HERE, 'backup_grid4x4_noloop.npz')))
+    vf = ref.ValueFunction(m, g['alphas'], g['alpha_actions'])
+    with quiet():
+        vf.save(path=out_dir, file_name='ref_saved_grid4x4_noloop.csv')
+        vf.save(path=out_dir, file_name='ref_saved_grid4x4_noloop_gz.csv', compress=True)
+        vf.save_parquet(path=out_dir, file_name='ref_saved_grid4x4_noloop.parquet')
+    # what the reference's own loaders return for its own files (pandas' default csv float parser is not round-trip exact: the
+    # reference's csv round trip moves some entries by one ulp; parquet is exact)
+    back_csv = ref.ValueFunction.load_from_file(os.path.join(out_dir, 'ref_saved_grid4x4_noloop.csv'), m)
+    back_gz = ref.ValueFunction.load_from_file(os.path.join(out_dir, 'ref_saved_grid4x4_noloop_gz.csv.gzip'), m)
+    back_pq = ref.ValueFunction.load_from_parquet(os.path.join(out_dir, 'ref_saved_grid4x4_noloop.parquet'), m)
+    assert np.array_equal(back_pq.alpha_vector_array, vf.alpha_vector_array)
+    assert np.array_equal(back_csv.alpha_vector_array, back_gz.alpha_vector_array)
+    print('  reference csv round trip: max |loaded - saved| =', np.max(np.abs(np.asarray(back_csv.alpha_vector_array) - np.asarray(vf.alpha_vector_array))))
+    save('io_grid4x4_noloop', alphas=np.asarray(vf.alpha_vector_array), actions=np.asarray(vf.actions, dtype=np.int64),
+         state_labels=np.array(m.state_labels), ref_loaded_csv_alphas=np.asarray(back_csv.alpha_vector_array),
+         ref_loaded_csv_actions=np.asarray(back_csv.actions, dtype=np.int64), ref_loaded_parquet_alphas=np.asarray(back_pq.alpha_vector_array),
+         ref_loaded_parquet_actions=np.asarray(back_pq.actions, dtype=np.int64))
+    with open(OLF_VF, 'rb') as f_in, gzip.GzipFile(os.path.join(out_dir, 'ref_20231113_182429_value_function.csv.gzip'), 'wb', mtime=0) as f_out:
+        shutil.copyfileobj(f_in, f_out)
+    for f in sorted(os.listdir(out_dir)):
+        print(f'  wrote io/{f} ({os.path.getsize(os.path.join(out_dir, f)) / 1e3:.1f} kB)')
+
+
 if __name__ == '__main__':
     want = sys.argv[1:] or ['']
     def on(tag):
@@ -384,3 +421,5 @@ if __name__ == '__main__':
         gen_olfactory()
     if on('simulations'):
         gen_simulations()
+    if on('io'):
+        gen_io()
