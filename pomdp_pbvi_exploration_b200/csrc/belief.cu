@@ -14,7 +14,8 @@ __global__ void __launch_bounds__(256) belief_project_kernel(const double* __res
                                                              const int32_t* __restrict__ predPtr, const int32_t* __restrict__ predK,
                                                              const double* __restrict__ rtoK, int S, int R, int O,
                                                              double* __restrict__ out, int aConst, int oConst,
-                                                             const double* __restrict__ chooseP, double chooseU, int32_t* __restrict__ chosen) {
+                                                             const double* __restrict__ chooseP, double chooseU, int32_t* __restrict__ chosen,
+                                                             int zTile) {
     const int i = blockIdx.y;
     const int sp = blockIdx.x * 256 + threadIdx.x;
     int oPick = oConst;
@@ -34,12 +35,14 @@ __global__ void __launch_bounds__(256) belief_project_kernel(const double* __res
         if (chosen && blockIdx.x == 0 && threadIdx.x == 0) *chosen = oPick;
     }
     if (sp >= S) return;
-    const int a = actions ? actions[i] : aConst, o = observations ? observations[i] : oPick;
+    // zTile > 0: row i is successor z = i % zTile (a = z / O, o = z % O) of belief i / zTile -- all successors of a belief chunk in one launch
+    const int a = zTile > 0 ? (i % zTile) / O : (actions ? actions[i] : aConst);
+    const int o = zTile > 0 ? (i % zTile) % O : (observations ? observations[i] : oPick);
     const size_t K = (size_t)S * R;
     const int32_t* ptr = predPtr + (size_t)a * (S + 1);
     const int32_t* pk = predK + (size_t)a * K;
     const double* rto = rtoK + ((size_t)a * O + o) * K;
-    const double* b = beliefs + (size_t)i * beliefStride;
+    const double* b = beliefs + (size_t)(zTile > 0 ? i / zTile : i) * beliefStride;
     double acc = 0.0;   // bincount starts every bin at +0.0 and adds in order
     const int end = ptr[sp + 1];
     for (int j = ptr[sp]; j < end; j++) {
@@ -201,7 +204,7 @@ static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t bel
         double* out = d_out + (size_t)i0 * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), ni), 256, 0, st>>>(d_beliefs + (size_t)i0 * beliefStride, d_actions + i0,
                                                                             d_observations + i0, beliefStride, m->predPtr, m->predK,
-                                                                            m->rtoK, m->S, m->R, m->O, out, 0, 0, nullptr, 0.0, nullptr);
+                                                                            m->rtoK, m->S, m->R, m->O, out, 0, 0, nullptr, 0.0, nullptr, 0);
         m->last_launches++;
         if (normalise && ni <= 4 && smem <= 48 * 1024) {
             // a few rows (one step of a Perseus walk, a single Belief.update): the multi-block form of the normaliser, row by row
@@ -255,7 +258,7 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
     for (int i = 0; i < n; i++) {
         double* out = d_out + (size_t)i * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
-                                                                           m->O, out, h_actions[i], h_observations[i], nullptr, 0.0, nullptr);
+                                                                           m->O, out, h_actions[i], h_observations[i], nullptr, 0.0, nullptr, 0);
         pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
         pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
         m->last_launches += 3;
@@ -290,7 +293,7 @@ extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_
         observation_probability_kernel<<<dim3(m->O, 1), 256, 0, st>>>(src, m->rtoK + (size_t)a * m->O * K, m->S, m->R, m->O, obsProb);
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
                                                                            m->O, out, a, 0, obsProb, h_uniforms[i],
-                                                                           d_observations ? d_observations + i : nullptr);
+                                                                           d_observations ? d_observations + i : nullptr, 0);
         pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
         pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
         m->last_launches += 4;
@@ -311,17 +314,22 @@ extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, in
     m->last_launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int nZ = m->nZ;
-    // (a, o) index vectors for one belief, reused for every belief (stride-0 source)
-    std::vector<int32_t> ha(nZ), ho(nZ);
-    for (int z = 0; z < nZ; z++) { ha[z] = z / m->O; ho[z] = z % m->O; }
-    PBVI_TAKE(d_a, int32_t, (size_t)nZ);
-    PBVI_TAKE(d_o, int32_t, (size_t)nZ);
-    PBVI_CUDA(cudaMemcpyAsync(d_a, ha.data(), nZ * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PBVI_CUDA(cudaMemcpyAsync(d_o, ho.data(), nZ * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PBVI_CUDA(cudaStreamSynchronize(st));   // ha / ho are stack-owned
-    for (int i = 0; i < n; i++)
-        PBVI_TRY(belief_update_impl(m, d_beliefs + (size_t)i * m->S, 0, d_a, d_o, nZ, normalise, d_out + (size_t)i * nZ * m->S,
-                                    d_norm ? d_norm + (size_t)i * nZ : nullptr, st));
+    const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
+    PBVI_REQUIRE(smem <= 200 * 1024, "state space too large for the pairwise-sum kernel");
+    // every successor of a slab of beliefs in ONE projection launch (row i = successor i % nZ of belief i / nZ) and one normaliser
+    // launch -- the per-belief host loop of the first version cost two launches per belief
+    const int slab = std::max(1, 65535 / nZ);
+    for (int i0 = 0; i0 < n; i0 += slab) {
+        const int nb = std::min(slab, n - i0), rows = nb * nZ;
+        double* out = d_out + (size_t)i0 * nZ * m->S;
+        belief_project_kernel<<<dim3(ceil_div(m->S, 256), rows), 256, 0, st>>>(d_beliefs + (size_t)i0 * m->S, nullptr, nullptr, (size_t)m->S,
+                                                                              m->predPtr, m->predK, m->rtoK, m->S, m->R, m->O, out, 0, 0,
+                                                                              nullptr, 0.0, nullptr, nZ);
+        pairwise_normalise_kernel<<<rows, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
+                                                          d_norm ? d_norm + (size_t)i0 * nZ : nullptr);
+        m->last_launches += 2;
+    }
+    PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
 }
 

@@ -357,34 +357,75 @@ __global__ void __launch_bounds__(128) row_min_kernel(const double* __restrict__
     out[qi] = best;
 }
 
-// out[j] = min_i || beliefs[i] - candidates[j] ||_2; block per candidate
-__global__ void __launch_bounds__(256) min_l2_kernel(const double* __restrict__ beliefs, int nB, const double* __restrict__ cands, int S,
-                                                     double* __restrict__ out) {
-    __shared__ double sh[8];
-    __shared__ double s_bc;
-    const double* c = cands + (size_t)blockIdx.x * S;
-    double best = INFINITY;
-    bool sawNan = false;
-    for (int i = 0; i < nB; i++) {
-        const double* b = beliefs + (size_t)i * S;
-        double part = 0.0;
-        for (int s = threadIdx.x; s < S; s += 256) { const double d = b[s] - c[s]; part = fma(d, d, part); }
+// out[j] = min_i || beliefs[i] - candidates[j] ||_2  (SSEA novelty, src/pomdp.py:1682-1686: the reference forms the whole
+// [B, B*A*O, S] difference tensor).  Tiled like a GEMM, with the reference's DIRECT arithmetic sum_s (b - c)^2 -- the expanded form
+// |b|^2 + |c|^2 - 2 b.c would cancel catastrophically exactly where the distance matters (successors close to the set).  A block owns
+// L2_TC candidates and walks all beliefs in tiles of L2_TB; state chunks of L2_TS go through shared memory; a thread accumulates a
+// 4 x 4 block of pair sums, so every shared-memory load feeds four subtract-multiply-adds.  np.min propagates NaN (the all-NaN
+// successor of an impossible observation): any NaN pair sum makes the candidate's result NaN.
+constexpr int L2_TC = 64, L2_TB = 64, L2_TS = 32;
+
+__global__ void __launch_bounds__(256) min_l2_tiled_kernel(const double* __restrict__ beliefs, int nB, const double* __restrict__ cands, int nC,
+                                                           int S, double* __restrict__ out) {
+    __shared__ double sc[L2_TS][L2_TC + 1];      // [state][candidate]: the four candidates of a thread are 16 apart (no bank conflicts)
+    __shared__ double sb[L2_TS][L2_TB + 1];
+    __shared__ double smin[16][L2_TC];
+    __shared__ int snan[L2_TC];
+    const int tid = threadIdx.x, tc = tid & 15, tb = tid >> 4;     // candidate lane / belief lane of the 16 x 16 thread grid
+    const int c0 = blockIdx.x * L2_TC;
+    double best[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    bool sawNan[4] = {false, false, false, false};
+    for (int b0 = 0; b0 < nB; b0 += L2_TB) {
+        double acc[4][4];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int w = 0; w < 8; w++) t += sh[w];
-            s_bc = t;
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+        for (int s0 = 0; s0 < S; s0 += L2_TS) {
+            __syncthreads();
+            // 64 rows x 32 states per tile, 256 threads: thread loads rows r = tid / 32 + 8 k at state tid % 32 (coalesced)
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = (tid >> 5) + 8 * k, sx = tid & 31, s = s0 + sx;
+                sc[sx][r] = (c0 + r < nC && s < S) ? cands[(size_t)(c0 + r) * S + s] : 0.0;
+                sb[sx][r] = (b0 + r < nB && s < S) ? beliefs[(size_t)(b0 + r) * S + s] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int sx = 0; sx < L2_TS; sx++) {
+                double cv[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { cv[i] = sc[sx][tc + 16 * i]; bv[i] = sb[sx][tb + 16 * i]; }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const double d = bv[j] - cv[i]; acc[i][j] = fma(d, d, acc[i][j]); }
+            }
         }
-        __syncthreads();
-        const double d2 = s_bc;
-        if (d2 != d2) sawNan = true;       // np.min propagates NaN
-        best = fmin(best, d2);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (b0 + tb + 16 * j < nB) {
+                    if (acc[i][j] != acc[i][j]) sawNan[i] = true;
+                    best[i] = fmin(best[i], acc[i][j]);
+                }
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = sawNan ? NAN : sqrt(best);
+    __syncthreads();
+    if (tid < L2_TC) snan[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        smin[tb][tc + 16 * i] = best[i];
+        if (sawNan[i]) snan[tc + 16 * i] = 1;
+    }
+    __syncthreads();
+    if (tid < L2_TC && c0 + tid < nC) {
+        double m = INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; k++) m = fmin(m, smin[k][tid]);
+        out[c0 + tid] = snan[tid] ? NAN : sqrt(m);
+    }
 }
 
 // GER error term of one successor (block per (b, z)): sum_s (alpha'[s] - alpha_b[s]) * (succ[s] - b[s]),
@@ -630,7 +671,7 @@ extern "C" int pbvi_min_l2_distance(pbvi_model* m, const double* d_beliefs, int 
     if (nC == 0) return PBVI_OK;
     PBVI_REQUIRE(d_beliefs && d_candidates && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    min_l2_kernel<<<nC, 256, 0, (cudaStream_t)stream>>>(d_beliefs, nB, d_candidates, m->S, d_out);
+    min_l2_tiled_kernel<<<ceil_div(nC, L2_TC), 256, 0, (cudaStream_t)stream>>>(d_beliefs, nB, d_candidates, nC, m->S, d_out);
     m->last_launches = 1;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;

@@ -560,3 +560,35 @@ def test_perseus_walk_equals_host_driven_steps(torch_cuda, tag):
     assert tail_got == tail_want
     assert np.array_equal(obs.cpu().numpy(), np.array(want_obs))
     assert np.array_equal(rows.cpu().numpy(), np.stack(want_rows), equal_nan=True)
+
+
+@pytest.mark.parametrize('tag,n_b,n_src', [('hallway', 70, 9), ('grid4x4', 300, 40), ('olfactory_wrap', 90, 6), ('tiger', 5, 5)])
+def test_min_l2_and_batched_successors_at_scale(torch_cuda, tag, n_b, n_src):
+    """SSEA ingredients beyond tiger (the reference's SSEA crashes there, so the ingredients are compared): all successors of
+    a belief chunk from ONE launch == per-belief updates of the oracle (bit-exact, NaN rows included), and the tiled distance kernel ==
+    the reference's diff / einsum / sqrt / min on the possible successors (tile edges: n_b, n_src, S not multiples of the tiles)."""
+    dev, m, reach, _ = device_model(tag)
+    g = load_golden('backup_' + tag)
+    rng = np.random.default_rng(5)
+    S = dev.S
+    B = g['beliefs']
+    if B.shape[0] < n_b:
+        extra = _sparse_beliefs(rng, n_b - B.shape[0], S, [S, max(1, S // 3), 2])
+        B = np.concatenate([B, extra])
+    B = np.ascontiguousarray(B[:n_b])
+    src = B[:n_src]
+    succ, mass = dev.belief_successors(src)
+    with np.errstate(all='ignore'):
+        want_succ = orc.all_successors(reach, m['rto'], src)
+    assert np.array_equal(succ.cpu().numpy(), want_succ, equal_nan=True)
+    possible = mass.cpu().numpy().reshape(-1) > 0
+    assert np.array_equal(possible, ~np.isnan(want_succ.reshape(-1, S)).any(axis=1))
+    cand = succ.reshape(-1, S)
+    got = dev.min_l2_distance(B, cand).cpu().numpy()
+    with np.errstate(all='ignore'):
+        want = orc.ssea_min_distances(B, want_succ).reshape(-1)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-13, equal_nan=True)
+    assert np.isnan(got[~possible]).all() and np.isfinite(got[possible]).all()
+    # successors that are already in the set are at distance exactly 0, as in the reference
+    in_set = dev.min_l2_distance(np.concatenate([B, want_succ.reshape(-1, S)[possible][:3]]), cand[torch_cuda.as_tensor(np.flatnonzero(possible)[:3]).cuda()])
+    assert np.all(in_set.cpu().numpy() == 0.0)
