@@ -41,7 +41,8 @@ typedef enum pbvi_status {
     PBVI_ERR_BAD_ARG = -1,
     PBVI_ERR_CUDA = -2,
     PBVI_ERR_OOM = -3,
-    PBVI_ERR_UNSUPPORTED = -4
+    PBVI_ERR_UNSUPPORTED = -4,
+    PBVI_ERR_NCCL = -5
 } pbvi_status;
 
 /* library version (major*100 + minor) and the message of the calling thread's last error */
@@ -203,6 +204,29 @@ PBVI_API int pbvi_min_l2_distance(pbvi_model* m, const double* d_beliefs, int nB
  * successor gained mass and r_min elsewhere; 0 for the NaN successor of an impossible observation. */
 PBVI_API int pbvi_ger_scores(pbvi_model* m, const double* d_beliefs, const double* d_alpha_b, const double* d_succ, int n,
                              double r_min, double r_max, double* d_eps, void* stream);
+
+/* ---- collectives of the belief-sharded path (north_star item 4; reference loop src/pomdp.py:2306-2389) -----------------------------------
+ * One process (or thread) per GPU, each with its own pbvi_model and one pbvi_comm.  NCCL is bound with dlopen("libnccl.so.2") on first
+ * use (PBVI_NCCL_LIB overrides the name); without it these calls return PBVI_ERR_UNSUPPORTED and everything else keeps working.
+ *   pbvi_comm_unique_id   rank 0 creates the 128-byte id and hands it to the other ranks by any host-side means
+ *   pbvi_comm_init        collective: every rank calls it with the same id
+ *   pbvi_allgather_tuples the exchange step after a local select: every rank contributes one block of block_rows rows of row_words
+ *                         int32 -- [header row (record count); records (a*, v*[a*, 0..O-1], first position, last position); padding] --
+ *                         and receives the `nranks` blocks in rank order, ready for pbvi_group_record_blocks; every rank then assembles
+ *                         the merged tuples itself (pbvi_backup_assemble), so alpha vectors cross NVLink as 4*(3+O) bytes, not 8*S
+ *   pbvi_allgather_rows   the literal form: n_rows rows of row_len doubles per rank (pad to a common n_rows)
+ *   pbvi_allreduce_max    in-place max over ranks of n doubles (the scalar of compute_change, src/pomdp.py:2165-2169)
+ *   pbvi_broadcast_rows   in-place broadcast of `count` doubles from `root` (rank-0 expansion: the new belief rows)
+ * All of them enqueue on `stream` and return without synchronising. */
+typedef struct pbvi_comm pbvi_comm;
+PBVI_API int pbvi_comm_unique_id(unsigned char* id128);
+PBVI_API int pbvi_comm_init(pbvi_model* m, const unsigned char* id128, int rank, int nranks, pbvi_comm** out);
+PBVI_API int pbvi_comm_destroy(pbvi_comm* c);
+PBVI_API int pbvi_comm_rank(const pbvi_comm* c, int* rank, int* nranks);
+PBVI_API int pbvi_allgather_tuples(pbvi_comm* c, const int32_t* d_block, int block_rows, int row_words, int32_t* d_gathered, void* stream);
+PBVI_API int pbvi_allgather_rows(pbvi_comm* c, const double* d_rows, int n_rows, int row_len, double* d_gathered, void* stream);
+PBVI_API int pbvi_allreduce_max(pbvi_comm* c, double* d_values, int n, void* stream);
+PBVI_API int pbvi_broadcast_rows(pbvi_comm* c, double* d_rows, size_t count, int root, void* stream);
 
 /* ---- instrumentation: flops actually issued by the last pbvi_backup_select / pbvi_max_values score launch, its grid size
  * and kernel launch count of the last call (for bench.py's roofline / gpu_launches accounting) */

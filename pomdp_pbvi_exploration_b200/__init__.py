@@ -17,7 +17,7 @@ _LAZY = {
     'Agent': 'simulation', 'Simulation': 'simulation', 'SimulationSet': 'simulation', 'SimulationHistory': 'simulation',
     'RewardSet': 'simulation',
     'load_POMDP_file': 'pomdp_file', 'save_POMDP_file': 'pomdp_file', 'parse_POMDP': 'pomdp_file',
-    'DeviceModel': '_native', 'ShardedBackup': 'parallel',
+    'DeviceModel': '_native', 'ShardedBackup': 'parallel', 'ShardedSolveState': 'parallel', 'NativeComm': 'parallel',
 }
 
 

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('PBVI_B200_LIB', os.path.join(_HERE, 'libpbvi_b200.so'))     # override: A/B builds of the same engine
 
-PBVI_OK, PBVI_ERR_BAD_ARG, PBVI_ERR_CUDA, PBVI_ERR_OOM, PBVI_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+PBVI_OK, PBVI_ERR_BAD_ARG, PBVI_ERR_CUDA, PBVI_ERR_OOM, PBVI_ERR_UNSUPPORTED, PBVI_ERR_NCCL = 0, -1, -2, -3, -4, -5
 
 # name -> argtypes; every function returns int except pbvi_last_error.  Kept in one table so that the CPU test-suite can
 # check the library exports exactly what include/pbvi_b200.h declares.
@@ -50,6 +50,14 @@ SIGNATURES = {
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_min_l2_distance': [_P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_ger_scores': [_P, _P, _P, _P, c_int, c_double, c_double, _P, _P],
+    'pbvi_comm_unique_id': [_P],
+    'pbvi_comm_init': [_P, _P, c_int, c_int, POINTER(c_void_p)],
+    'pbvi_comm_destroy': [_P],
+    'pbvi_comm_rank': [_P, POINTER(c_int), POINTER(c_int)],
+    'pbvi_allgather_tuples': [_P, _P, c_int, c_int, _P, _P],
+    'pbvi_allgather_rows': [_P, _P, c_int, c_int, _P, _P],
+    'pbvi_allreduce_max': [_P, _P, c_int, _P],
+    'pbvi_broadcast_rows': [_P, _P, ctypes.c_size_t, c_int, _P],
     'pbvi_last_stats': [_P, POINTER(c_double), POINTER(c_double), POINTER(c_int)],
     'pbvi_last_launches': [_P],
     'pbvi_set_profiling': [_P, c_int],

@@ -21,6 +21,80 @@ import torch.distributed as dist
 from .sets import group_by_key, unique_rows_first
 
 
+class NativeComm:
+    """
+    A process group backed by the LIBRARY'S OWN NCCL binding (`pbvi_comm_*` of include/pbvi_b200.h) instead of torch.distributed: the
+    collectives a host in any language would call.  Pass it wherever a `group` is accepted (`ShardedBackup`, `PBVI_Solver.solve`).
+    The 128-byte id comes from `NativeComm.unique_id()` on rank 0 and reaches the other ranks by any host-side channel.
+    """
+
+    def __init__(self, model, rank: int, world: int, unique_id: bytes):
+        import ctypes
+        from . import _native
+        self._lib = _native.load_library()
+        self._check = _native._check
+        self.device = model.device.device
+        self._rank, self._world = int(rank), int(world)
+        assert len(unique_id) == 128
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.pbvi_comm_init(model.device._h, buf, self._rank, self._world, ctypes.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes
+        from . import _native
+        buf = (ctypes.c_ubyte * 128)()
+        _native._check(_native.load_library().pbvi_comm_unique_id(buf))
+        return bytes(buf)
+
+    def close(self) -> None:
+        if getattr(self, '_h', None) is not None:
+            self._lib.pbvi_comm_destroy(self._h)
+            self._h = None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def all_gather(self, out: torch.Tensor, local: torch.Tensor) -> None:
+        assert out.is_cuda and local.is_cuda and out.is_contiguous() and out.dtype == local.dtype
+        local = local.contiguous()
+        if local.dtype == torch.float64:
+            self._check(self._lib.pbvi_allgather_rows(self._h, local.data_ptr(), 1, local.numel(), out.data_ptr(), self._stream()))
+        else:
+            words = local.numel() * local.element_size() // 4
+            assert local.numel() * local.element_size() % 4 == 0
+            self._check(self._lib.pbvi_allgather_tuples(self._h, local.data_ptr(), 1, words, out.data_ptr(), self._stream()))
+
+    def all_reduce(self, t: torch.Tensor, op) -> None:
+        """MAX / MIN of a small tensor of any numeric dtype, through the library's double-precision max."""
+        assert op in (dist.ReduceOp.MAX, dist.ReduceOp.MIN)
+        d = t.to(torch.float64)
+        if op == dist.ReduceOp.MIN:
+            d = -d
+        d = d.contiguous()
+        self._check(self._lib.pbvi_allreduce_max(self._h, d.data_ptr(), d.numel(), self._stream()))
+        t.copy_((-d if op == dist.ReduceOp.MIN else d).to(t.dtype))
+
+    def broadcast(self, t: torch.Tensor, src: int) -> None:
+        assert t.is_cuda and t.is_contiguous()
+        if t.dtype == torch.float64:
+            self._check(self._lib.pbvi_broadcast_rows(self._h, t.data_ptr(), t.numel(), int(src), self._stream()))
+        else:                                       # counts / indices: exact in float64 below 2^53
+            d = t.to(torch.float64).contiguous()
+            self._check(self._lib.pbvi_broadcast_rows(self._h, d.data_ptr(), d.numel(), int(src), self._stream()))
+            t.copy_(d.to(t.dtype))
+
+
+def group_size(group=None) -> int:
+    return group._world if isinstance(group, NativeComm) else dist.get_world_size(group)
+
+
+def group_rank(group=None) -> int:
+    return group._rank if isinstance(group, NativeComm) else dist.get_rank(group)
+
+
 def _host_backend(group=None) -> bool:
     """True when the group's collectives run on CPU tensors (gloo): device tensors are staged through the host.  Used by the
     tests that run two ranks of the real engine on ONE GPU (NCCL refuses two ranks per device)."""
@@ -28,8 +102,10 @@ def _host_backend(group=None) -> bool:
 
 
 def all_gather_rows(out: torch.Tensor, local: torch.Tensor, group=None) -> None:
-    """`all_gather_into_tensor` that also works for CUDA tensors over a gloo group (staged through the host)."""
-    if local.is_cuda and _host_backend(group):
+    """`all_gather_into_tensor` that also works for CUDA tensors over a gloo group (staged through the host) and over a NativeComm."""
+    if isinstance(group, NativeComm):
+        group.all_gather(out, local)
+    elif local.is_cuda and _host_backend(group):
         tmp = torch.empty(out.shape, dtype=out.dtype)
         dist.all_gather_into_tensor(tmp, local.cpu(), group=group)
         out.copy_(tmp)
@@ -38,7 +114,9 @@ def all_gather_rows(out: torch.Tensor, local: torch.Tensor, group=None) -> None:
 
 
 def all_reduce_(t: torch.Tensor, op, group=None) -> torch.Tensor:
-    if t.is_cuda and _host_backend(group):
+    if isinstance(group, NativeComm):
+        group.all_reduce(t, op)
+    elif t.is_cuda and _host_backend(group):
         tmp = t.cpu()
         dist.all_reduce(tmp, op=op, group=group)
         t.copy_(tmp)
@@ -49,6 +127,9 @@ def all_reduce_(t: torch.Tensor, op, group=None) -> torch.Tensor:
 
 def broadcast_(t: torch.Tensor, src: int, group=None) -> torch.Tensor:
     """Broadcast from GROUP rank `src`."""
+    if isinstance(group, NativeComm):
+        group.broadcast(t, src)
+        return t
     gsrc = dist.get_global_rank(group, src) if group is not None else src
     if t.is_cuda and _host_backend(group):
         tmp = t.cpu()
@@ -100,7 +181,7 @@ def exchange_new_rows(rows: torch.Tensor, actions: np.ndarray, hashes: np.ndarra
     its rows which lost to an earlier rank really equal the received copy (`rows_equal`), and the ranks agree on the outcome
     with a scalar all-reduce.  Returns (rows, actions, hashes, payload_bytes).
     """
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = group_size(group), group_rank(group)
     dev = rows.device
     n = rows.shape[0]
     counts_t = torch.empty((world,), dtype=torch.int64, device=dev)
@@ -183,7 +264,7 @@ def exchange_tuples(tuples, first, last, capacity: int, device, group=None, merg
     takes part in the same sequence of exchanges, so the block size guess is the same everywhere).
     Returns (tuples [U, 1+O], first [U], last [U]) of the whole belief set as int32 tensors on `device`.
     """
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = group_size(group), group_rank(group)
     device = torch.device(device)
     tuples = torch.as_tensor(tuples).to(device=device, dtype=torch.int32)
     first = torch.as_tensor(first).to(device=device, dtype=torch.int32)
@@ -255,8 +336,8 @@ class ShardedBackup:
         self.exchange = exchange        # 'tuples': all-gather the generating tuples, assemble everywhere; 'rows': all-gather the rows
         self._cap = (None, None)
         self._guess = [256]             # largest record count of this instance's previous exchange (sizes the next blocks)
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+        self.world = group_size(group)
+        self.rank = group_rank(group)
         self.last_payload_bytes = 0
         self.trace = False              # set True to record per-phase wall times (device-synchronised) in `last_phases`
         self.last_phases = {}
@@ -368,14 +449,18 @@ class ShardedSolveState:
 
     # ---- expansion on rank 0, rows broadcast ---------------------------------------------------------------------------
     def expand(self, model, belief_set, value_function, max_generation, **params):
+        import time
         from .belief import BeliefSet
         dev = model.device.device
-        head = torch.zeros((1,), dtype=torch.int64, device=dev)
+        t0 = time.perf_counter()
         new = None
         if self.rank == 0:
             new = self.solver.expand(model=model, belief_set=belief_set, value_function=value_function, max_generation=max_generation,
                                      **params)
-            head[0] = len(new)
+            head = torch.tensor([len(new)], dtype=torch.int64, device=dev)
+        else:
+            head = torch.zeros((1,), dtype=torch.int64, device=dev)
+        t1 = time.perf_counter()
         broadcast_(head, 0, self.group)
         n = int(head[0])
         if self.rank == 0:
@@ -385,12 +470,18 @@ class ShardedSolveState:
         if n:
             broadcast_(rows, 0, self.group)
         self.stats['broadcast_rows'] += n
-        return new if self.rank == 0 else BeliefSet(model, rows)
+        out = new if self.rank == 0 else BeliefSet(model, rows)
+        t2 = time.perf_counter()
+        self.stats['expand_rank0_s'] = self.stats.get('expand_rank0_s', 0.0) + (t1 - t0)
+        self.stats['expand_broadcast_s'] = self.stats.get('expand_broadcast_s', 0.0) + (t2 - t1)     # includes waiting for rank 0
+        return out
 
     # ---- ownership of the rows a union appended ---------------------------------------------------------------------------
     def absorb(self, belief_set) -> None:
         """Called after every `belief_set = belief_set.union(new)` (and once for the initial set): rows [n_global, len) are new."""
+        import time
         from .belief import BeliefSet
+        t0 = time.perf_counter()
         n_prev, n_now = self.n_global, len(belief_set)
         n_fresh = n_now - n_prev
         assert n_fresh >= 0, 'the belief set of a solve only grows'
@@ -416,6 +507,7 @@ class ShardedSolveState:
         if self.local_set is not None:
             grown._inherit(self.local_set, n0)
         self.local_set, self.n_local = grown, n1
+        self.stats['absorb_s'] = self.stats.get('absorb_s', 0.0) + (time.perf_counter() - t0)
 
     # ---- backups ------------------------------------------------------------------------------------------------------
     def backup_full(self, value_function):

@@ -599,8 +599,14 @@ class PBVI_Solver:
         to_generate = min(max_generation, len(belief_set))
         dists = []
         for i0, succ, mass in self._successors_chunked(model, belief_set):
-            d = dev.min_l2_distance(belief_set.belief_array, succ.reshape(-1, dev.S)).reshape(succ.shape[:3])
-            dists.append(d.cpu().numpy())
+            # one launch gave every successor of the chunk; only the possible ones (mass P(o|b,a) > 0, i.e. not 0/0 rows) are candidates
+            flat = succ.reshape(-1, dev.S)
+            possible = torch.nonzero(mass.reshape(-1) > 0)[:, 0]
+            d = torch.full((flat.shape[0],), float('-inf'), dtype=torch.float64, device=dev.device)
+            if possible.numel():
+                cand = flat if possible.numel() == flat.shape[0] else flat[possible]
+                d[possible] = dev.min_l2_distance(belief_set.belief_array, cand)
+            dists.append(d.reshape(succ.shape[:3]).cpu().numpy())
         dist = np.concatenate(dists, axis=0)
         dist = np.where(np.isnan(dist), -np.inf, dist)
         pick = np.argsort(dist, axis=None)[::-1][:to_generate]

@@ -21,12 +21,24 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     model = olfactory_wrap_model()
+    native = None
+    if '--native' in sys.argv:
+        # the library's own NCCL binding (pbvi_comm_*): the id travels over the torch group, every collective of the checks below
+        # then goes through the C ABI
+        from pomdp_pbvi_exploration_b200 import NativeComm
+        idt = torch.zeros((128,), dtype=torch.uint8, device='cuda')
+        if rank == 0:
+            idt = torch.tensor(list(NativeComm.unique_id()), dtype=torch.uint8, device='cuda')
+        dist.broadcast(idt, 0)
+        native = NativeComm(model, rank, world, bytes(idt.cpu().tolist()))
+        if rank == 0:
+            print('collectives: libpbvi_b200 NCCL binding (pbvi_comm_init / pbvi_allgather_tuples / pbvi_allreduce_max / pbvi_broadcast_rows)', flush=True)
     B = perseus_walk_beliefs(model, 1500, seed=5)                      # same beliefs on every rank (same seed)
     g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'backup_olfactory_wrap.npz')))
     vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
     solver = PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus')
     for mode, append in [('tuples', False), ('tuples', True), ('rows', False), ('rows', True)]:
-        sb = ShardedBackup(solver, model, exchange=mode)
+        sb = ShardedBackup(solver, model, group=native, exchange=mode)
         lo, hi = sb.bounds(B.shape[0])
         merged = sb.backup(BeliefSet(model, B[lo:hi]), vf, append=append)
         rows, actions = merged.numpy()
@@ -56,7 +68,7 @@ def main():
             random.seed(5 if (grp is None or rank == 0) else 1000 + rank)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            vf_s, hist = make().solve(model, print_progress=False, **kw, **({'group': True} if grp else {}))
+            vf_s, hist = make().solve(model, print_progress=False, **kw, **({'group': native if native is not None else True} if grp else {}))
             torch.cuda.synchronize()
             outs.append((vf_s.numpy(), hist.alpha_vector_counts, hist.beliefs_counts, hist.value_function_changes, time.perf_counter() - t0))
         (r1, a1), (r2, a2) = outs[0][0], outs[1][0]
