@@ -94,6 +94,17 @@ PBVI_API int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const d
 PBVI_API int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
                      double* h_out_alpha, int32_t* h_out_action, void* stream);
 
+/* pbvi_backup_small: the WHOLE `PBVI_Solver.backup(append=False)` of a small problem (tiger, 4x4 grids: BASELINE configs[0] / [1]) in one
+ * call -- one kernel (a block per belief: projections, v*, values, a*, the alpha row and its 128-bit key, all in shared memory), one
+ * copy back, the ValueFunction constructor's dict semantics on the host (src/mdp.py:668-669: position of the first occurrence, action
+ * of the last; key matches confirmed with memcmp) and a gather of the surviving rows.  d_out_rows has room for nB rows; the first
+ * *h_n_out are written (stream-ordered), h_out_actions [nB] / h_out_keys [nB][2] (nullable) receive their actions and row keys.
+ * Synchronises `stream` once.  pbvi_backup_small_eligible tells whether the sizes qualify (everything of one belief in shared memory,
+ * at most ~6e7 multiply-adds); otherwise PBVI_ERR_UNSUPPORTED: use pbvi_backup_select / pbvi_backup_assemble. */
+PBVI_API int pbvi_backup_small_eligible(const pbvi_model* m, int nB, int nV);
+PBVI_API int pbvi_backup_small(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                               double* d_out_rows, int32_t* h_out_actions, uint64_t* h_out_keys, int* h_n_out, void* stream);
+
 /* ---- maxima over a value function (src/pomdp.py:2165-2167 compute_change, :1639 SSGA, :1735 GER, :1393) ----
  * d_max[b] = max_v belief_b . alpha_v, d_arg[b] = its first index.  Either output may be NULL. */
 PBVI_API int pbvi_max_values(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV,

@@ -31,6 +31,8 @@ SIGNATURES = {
     'pbvi_backup_assemble': [_P, _P, c_int, c_double, _P, _P, c_int, _P, _P, _P],
     'pbvi_backup': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P, _P],
     'pbvi_backup_host': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P],
+    'pbvi_backup_small_eligible': [_P, c_int, c_int],
+    'pbvi_backup_small': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, POINTER(c_int), _P],
     'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
     'pbvi_belief_update': [_P, _P, _P, _P, c_int, c_int, _P, _P, _P],
     'pbvi_belief_trajectory': [_P, _P, _P, _P, _P, c_int, _P, _P],
@@ -211,6 +213,22 @@ class DeviceModel:
         self._call(self._lib.pbvi_backup(self._h, _ptr(b), nB, _ptr(al), nV, float(gamma), _ptr(out), _ptr(act), _ptr(vstar), _ptr(value),
                                      self._stream))
         return out, act, vstar, value
+
+    def backup_small_eligible(self, n_beliefs: int, n_alphas: int) -> bool:
+        return bool(self._lib.pbvi_backup_small_eligible(self._h, int(n_beliefs), int(n_alphas)))
+
+    def backup_small(self, beliefs: torch.Tensor, alphas: torch.Tensor, gamma: float):
+        """Whole backup of a small problem in one library call (see `pbvi_backup_small`): returns (rows [n,S] CUDA tensor,
+        actions [n] int64, row keys [n,2] int64) of the deduplicated new value function."""
+        b, al = self._beliefs(beliefs), self._beliefs(alphas)
+        nB = b.shape[0]
+        out = torch.empty((nB, self.S), dtype=torch.float64, device=self.device)
+        acts = np.empty((nB,), dtype=np.int32)
+        keys = np.empty((nB, 2), dtype=np.int64)
+        n = c_int()
+        self._call(self._lib.pbvi_backup_small(self._h, _ptr(b), nB, _ptr(al), al.shape[0], float(gamma), _ptr(out), acts.ctypes.data,
+                                               keys.ctypes.data, byref(n), self._stream))
+        return out[:n.value], acts[:n.value].astype(np.int64), keys[:n.value]
 
     def backup_host(self, beliefs: np.ndarray, alphas: np.ndarray, gamma: float, out_alpha: np.ndarray | None = None,
                     out_action: np.ndarray | None = None):

@@ -573,6 +573,133 @@ static void launch_assemble_grouped(pbvi_model* m, const double* d_alphas, int n
         d_alphas, d_actions, d_vsel, order, m->reachK, m->rtoK, m->rbarT, gamma, m->S, m->O, d_out, hacc, m->hashKeys, nonfinite, m->A, nV);
 }
 
+// =====================================================================================================================
+// Small-model path (tiger, 4x4 grids: BASELINE configs[0] / [1]).  The general pipeline above is ~20 launches and four host
+// synchronisations whatever the problem size -- 0.3 ms for a backup whose arithmetic takes microseconds.  Here ONE kernel does the whole
+// per-belief part, one block per belief, everything in shared memory:
+//   1. btilde[z][s'] = sum_{k: reach[a][k] = s'} RTO[a][o][k] * b[k / R]      (the un-normalised Belief.update, CSR over landing states)
+//   2. v*[z] = first argmax_v btilde[z] . alpha_v                             (warp per z, np.argmax semantics incl. NaN)
+//   3. value[a] = sum_s b[s] * alpha_a[s],  a* = first argmax_a               (alpha_a_entry: the reference's operation order)
+//   4. row = alpha_{a*}, its 128-bit key, a*
+// and pbvi_backup_small finishes the backup on the host side of the same call: rows, keys and actions come back in one copy, the
+// ValueFunction constructor's dict semantics (first position, last action; keys confirmed with memcmp) run on at most a few
+// thousand rows, and a gather kernel writes the surviving rows.  One synchronisation per backup.
+constexpr int SMALL_THREADS = 128;
+
+__global__ void __launch_bounds__(SMALL_THREADS) small_backup_kernel(const double* __restrict__ beliefs, const double* __restrict__ alphas,
+                                                                     const int32_t* __restrict__ reachK, const double* __restrict__ rtoK,
+                                                                     const double* __restrict__ rbarT, const int32_t* __restrict__ predPtr,
+                                                                     const int32_t* __restrict__ predK, double gamma, int S, int R, int A, int O,
+                                                                     int nV, double* __restrict__ rows, unsigned long long* __restrict__ keys,
+                                                                     int32_t* __restrict__ actions) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    const int nZ = A * O, K = S * R;
+    double* sb = reinterpret_cast<double*>(small_smem);            // [S]
+    double* sbt = sb + S;                                          // [nZ][S]
+    double* sval = sbt + (size_t)nZ * S;                           // [A]
+    int* svs = reinterpret_cast<int*>(sval + A);                   // [nZ]
+    __shared__ unsigned long long sh[2][SMALL_THREADS / 32];
+    __shared__ int s_bad, s_astar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const double* brow = beliefs + (size_t)b * S;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int s = tid; s < S; s += SMALL_THREADS) {
+        const double v = brow[s];
+        sb[s] = v;
+        if (!(fabs(v) <= 1.79769313486231570e308)) s_bad = 1;      // NaN / inf belief entry: every score is NaN in the reference
+    }
+    __syncthreads();
+    // 1. projections (bincount order, like belief_project_kernel)
+    for (int i = tid; i < nZ * S; i += SMALL_THREADS) {
+        const int z = i / S, sp = i - z * S, a = z / O;
+        const int32_t* ptr = predPtr + (size_t)a * (S + 1);
+        const int32_t* pk = predK + (size_t)a * K;
+        const double* rto = rtoK + (size_t)z * K;
+        double acc = 0.0;
+        for (int j = ptr[sp]; j < ptr[sp + 1]; j++) {
+            const int k = pk[j];
+            acc = __dadd_rn(acc, __dmul_rn(rto[k], sb[R == 1 ? k : k / R]));
+        }
+        sbt[i] = acc;
+    }
+    __syncthreads();
+    // 2. v*[z]: warp per z, lanes over v (ascending per lane), warp argmax with the lower index winning ties
+    const bool bad = s_bad != 0;
+    for (int z = warp; z < nZ; z += SMALL_THREADS / 32) {
+        const double* bt = sbt + (size_t)z * S;
+        double best = -INFINITY;
+        int bidx = ARG_NONE;
+        for (int v = lane; v < nV; v += 32) {
+            const double* al = alphas + (size_t)v * S;
+            double acc = 0.0;
+            for (int s = 0; s < S; s++) acc = fma(bt[s], al[s], acc);
+            argmax_append(best, bidx, acc, v);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+            argmax_combine(best, bidx, ov, oi);
+        }
+        if (lane == 0) svs[z] = bad ? 0 : min(max(bidx, 0), nV - 1);
+    }
+    __syncthreads();
+    // 3. value[a] and a*
+    for (int a = warp; a < A; a += SMALL_THREADS / 32) {
+        double part = 0.0;
+        for (int s = lane; s < S; s += 32)
+            part = fma(sb[s], alpha_a_entry(alphas, S, R, O, svs + a * O, reachK + (size_t)a * K, rtoK + (size_t)a * O * K, rbarT + (size_t)a * S,
+                                            gamma, s, false), part);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == 0) sval[a] = part;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double best = sval[0];
+        int idx = 0;
+        for (int a = 1; a < A && best == best; a++) {
+            const double v = sval[a];
+            if (v != v || v > best) { best = v; idx = a; }
+        }
+        s_astar = idx;
+        actions[b] = idx;
+    }
+    __syncthreads();
+    // 4. the row of a* and its key
+    const int a = s_astar;
+    unsigned long long h0 = 0, h1 = 0;
+    for (int s = tid; s < S; s += SMALL_THREADS) {
+        const double v = alpha_a_entry(alphas, S, R, O, svs + a * O, reachK + (size_t)a * K, rtoK + (size_t)a * O * K, rbarT + (size_t)a * S, gamma,
+                                       s, false);
+        rows[(size_t)b * S + s] = v;
+        const uint64_t w = (uint64_t)__double_as_longlong(v);
+        const uint4 k = row_key_words(s);
+        h0 += row_hash_term0(w, k);
+        h1 += row_hash_term1(w, k);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        h0 += __shfl_down_sync(0xffffffffu, h0, off);
+        h1 += __shfl_down_sync(0xffffffffu, h1, off);
+    }
+    if (lane == 0) { sh[0][warp] = h0; sh[1][warp] = h1; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long x = 0, y = 0;
+        for (int w = 0; w < SMALL_THREADS / 32; w++) { x += sh[0][w]; y += sh[1][w]; }
+        keys[(size_t)b * 2] = row_hash_final0(x, S);
+        keys[(size_t)b * 2 + 1] = row_hash_final1(y, S);
+    }
+}
+
+__global__ void __launch_bounds__(128) gather_rows_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int S,
+                                                          double* __restrict__ dst) {
+    const double* r = src + (size_t)idx[blockIdx.x] * S;
+    for (int s = threadIdx.x; s < S; s += 128) dst[(size_t)blockIdx.x * S + s] = r[s];
+}
+
 __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* __restrict__ h, int n, int rowLen) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -844,6 +971,96 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, d_out, (size_t)nB * S * sizeof(double), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaMemcpyAsync(h_out_action, d_act, (size_t)nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));
+    return PBVI_OK;
+}
+
+// Sizes the small path accepts: everything of one belief fits in shared memory and the per-belief arithmetic is short.
+static bool small_eligible(const pbvi_model* m, int nB, int nV) {
+    const double work = (double)nB * nV * m->nZ * m->S;
+    return m->S <= 1024 && (size_t)(1 + m->nZ) * m->S + m->A + m->nZ <= 5000 && (long long)nB * m->S <= 262144 && nV <= 4096 &&
+           nB <= 16384 && work <= 6e7;
+}
+
+extern "C" int pbvi_backup_small_eligible(const pbvi_model* m, int nB, int nV) {
+    return (m && nB > 0 && nV > 0 && small_eligible(m, nB, nV)) ? 1 : 0;
+}
+
+extern "C" int pbvi_backup_small(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double gamma,
+                                 double* d_out_rows, int32_t* h_out_actions, uint64_t* h_out_keys, int* h_n_out, void* stream) {
+    PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, gamma));
+    PBVI_REQUIRE(h_n_out != nullptr, "count output is required");
+    *h_n_out = 0;
+    m->last_launches = 0;
+    if (nB == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_out_rows && h_out_actions, "row / action outputs are required");
+    if (!small_eligible(m, nB, nV)) {
+        set_error("pbvi_backup_small: the problem is too large for the single-kernel path (use pbvi_backup_select / pbvi_backup_assemble)");
+        return PBVI_ERR_UNSUPPORTED;
+    }
+    PBVI_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = m->S;
+    m->arena.reset();
+    PBVI_TAKE(rowsAll, double, (size_t)nB * S);
+    PBVI_TAKE(keys, unsigned long long, (size_t)nB * 2);
+    PBVI_TAKE(acts, int32_t, (size_t)nB);
+    PBVI_TAKE(idx, int32_t, (size_t)nB);
+    // pinned staging of the handle: [rows | keys | actions | gather indices]
+    const size_t rowBytes = (size_t)nB * S * sizeof(double), keyBytes = (size_t)nB * 16, actBytes = (size_t)nB * 4;
+    const size_t need = rowBytes + keyBytes + 2 * actBytes;
+    if (m->h_stage_bytes < need) {
+        if (m->h_stage) cudaFreeHost(m->h_stage);
+        m->h_stage = nullptr;
+        m->h_stage_bytes = 0;
+        PBVI_CUDA(cudaHostAlloc(&m->h_stage, std::max<size_t>(need, 1 << 16), cudaHostAllocDefault));
+        m->h_stage_bytes = std::max<size_t>(need, 1 << 16);
+    }
+    char* hs = static_cast<char*>(m->h_stage);
+    double* hRows = reinterpret_cast<double*>(hs);
+    unsigned long long* hKeys = reinterpret_cast<unsigned long long*>(hs + rowBytes);
+    int32_t* hActs = reinterpret_cast<int32_t*>(hs + rowBytes + keyBytes);
+    int32_t* hIdx = hActs + nB;
+    const size_t smem = ((size_t)(1 + m->nZ) * S + m->A) * sizeof(double) + (size_t)m->nZ * sizeof(int);
+    small_backup_kernel<<<nB, SMALL_THREADS, smem, st>>>(d_beliefs, d_alphas, m->reachK, m->rtoK, m->rbarT, m->predPtr, m->predK, gamma, S, m->R,
+                                                         m->A, m->O, nV, rowsAll, keys, acts);
+    PBVI_CUDA(cudaGetLastError());
+    PBVI_CUDA(cudaMemcpyAsync(hRows, rowsAll, rowBytes, cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaMemcpyAsync(hKeys, keys, keyBytes, cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaMemcpyAsync(hActs, acts, actBytes, cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    // dict semantics of the ValueFunction constructor (src/mdp.py:668-669) over the nB rows: position of the first occurrence, action of
+    // the last; open addressing on the 128-bit key, every key match confirmed on the bytes
+    int T = 16;
+    while (T < 2 * nB) T <<= 1;
+    std::vector<int32_t> table((size_t)T, -1);
+    int nOut = 0;
+    for (int i = 0; i < nB; i++) {
+        const unsigned long long k0 = hKeys[(size_t)i * 2], k1 = hKeys[(size_t)i * 2 + 1];
+        uint32_t h = (uint32_t)(k0 ^ (k1 >> 17)) & (uint32_t)(T - 1);
+        for (;;) {
+            const int g = table[h];
+            if (g < 0) {
+                table[h] = nOut;
+                hIdx[nOut] = i;
+                h_out_actions[nOut] = hActs[i];
+                if (h_out_keys) { h_out_keys[(size_t)nOut * 2] = k0; h_out_keys[(size_t)nOut * 2 + 1] = k1; }
+                nOut++;
+                break;
+            }
+            const int f = hIdx[g];
+            if (hKeys[(size_t)f * 2] == k0 && hKeys[(size_t)f * 2 + 1] == k1 &&
+                std::memcmp(hRows + (size_t)f * S, hRows + (size_t)i * S, (size_t)S * sizeof(double)) == 0) {
+                h_out_actions[g] = hActs[i];                     // last action wins
+                break;
+            }
+            h = (h + 1) & (uint32_t)(T - 1);
+        }
+    }
+    PBVI_CUDA(cudaMemcpyAsync(idx, hIdx, (size_t)nOut * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<nOut, 128, 0, st>>>(rowsAll, idx, S, d_out_rows);
+    PBVI_CUDA(cudaGetLastError());
+    m->last_launches = 2;
+    *h_n_out = nOut;
     return PBVI_OK;
 }
 

@@ -245,6 +245,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
     m->arena.release();
+    if (m->h_stage) cudaFreeHost(m->h_stage);
     delete m;
     return PBVI_OK;
 }

@@ -142,6 +142,8 @@ struct pbvi_model {
     int nLeaves = 0, nNodes = 0;
 
     pbvi::Arena arena;
+    void* h_stage = nullptr;     // pinned host staging of pbvi_backup_small (grow-only)
+    size_t h_stage_bytes = 0;
     // instrumentation of the last select / max_values call
     unsigned long long* d_stats = nullptr;   // [1] live (tile, z, chunk, row group) quadruples visited by the score launch
     // sign information for the exact-zero shortcut of the value pass: with RTO, Rbar, every belief and every alpha >= 0 a sum

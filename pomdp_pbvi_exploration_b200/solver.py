@@ -340,8 +340,15 @@ class PBVI_Solver:
         Two beliefs that select the same (a*, v*[a*,:]) tuple produce the same bytes, so only the distinct tuples are
         assembled; the byte-dedup then runs over those rows (different tuples can still give identical rows).
         """
-        tuples, _, last = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune)
-        new_vf = self.rows_from_tuples(model, value_function, tuples, last)
+        dev = model.device
+        if (not belief_dominance_prune and self.SMALL_PATH and belief_set._device is not None and len(belief_set) > 0 and
+                dev.backup_small_eligible(len(belief_set), len(value_function))):
+            # tiger / 4x4-class problems: one kernel, one synchronisation (`pbvi_backup_small`) instead of the ~20-launch pipeline
+            rows, actions, keys = dev.backup_small(belief_set.belief_array, value_function.alpha_vector_array, self.gamma)
+            new_vf = ValueFunction(model, rows, actions, _trusted=True, _hashes=keys)
+        else:
+            tuples, _, last = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune)
+            new_vf = self.rows_from_tuples(model, value_function, tuples, last)
         if append:
             n_new = len(new_vf)
             new_vf.extend(value_function)
@@ -418,6 +425,7 @@ class PBVI_Solver:
             actions, rows, hashes = t[torch.as_tensor(own, device=dev.device), 0], rows[gf], keys[gf]
         return ValueFunction(model, rows, actions.cpu().numpy().astype(np.int64), _trusted=True, _hashes=hashes)
 
+    SMALL_PATH = True              # use the single-kernel backup where the sizes qualify (False: always the general pipeline)
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
     STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
     PACK_MAX_DENSITY = 0.6         # above this share of non-zero 4-double chunks the rows are uploaded as they are

@@ -280,3 +280,30 @@ def test_olfactory_fsvi_solve_and_backup_parity():
     urows, uacts = orc.extend_union(rows, acts, prev_rows, prev_actions)
     got_rows, got_actions = got.numpy()
     assert got_rows.shape == urows.shape and np.array_equal(got_actions, uacts) and np.array_equal(got_rows, urows)
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid'])
+def test_small_model_path_equals_general_pipeline(tag):
+    """`pbvi_backup_small` (one kernel + host dict over the rows, BASELINE configs[0] / [1]) returns the value function of the general
+    pipeline (select -> tuple grouping -> assemble -> byte-dedup): same rows bit for bit, same order, same actions, same row keys --
+    with and without append; and it is the path `PBVI_Solver.backup` actually takes for these sizes."""
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    model = fixture_model(tag)
+    g = load_golden('backup_' + tag)
+    gamma = float(load_golden('model_' + tag)['gamma'])
+    solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='ssra')
+    bs = BeliefSet(model, g['beliefs'])
+    vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
+    assert model.device.backup_small_eligible(len(bs), len(vf))
+    for append in (False, True):
+        solver.SMALL_PATH = True
+        calls = model.device.launch_count
+        small = solver.backup(model, bs, vf, append=append, belief_dominance_prune=False)
+        assert model.device.launch_count - calls == 2                    # the fused kernel + the gather
+        solver.SMALL_PATH = False
+        general = solver.backup(model, bs, vf, append=append, belief_dominance_prune=False)
+        a, b = small.numpy(), general.numpy()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(small.row_hashes, general.row_hashes)
+    # beyond the size limit the general pipeline runs
+    assert not model.device.backup_small_eligible(20000, 4096)
