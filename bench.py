@@ -436,6 +436,18 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def gpu_warm(device, seconds: float = 0.4) -> None:
+    """Keeps the GPU busy for a moment (plain torch matmuls): after seconds of idling behind a CPU-only phase the SM clocks are down, and
+    a launch-bound leg measured right then would be timed at idle clocks."""
+    import torch
+    a = torch.rand((2048, 2048), device=device)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            a = (a @ a).clamp_(0, 1)
+        torch.cuda.synchronize(device)
+
+
 def time_device_steps(step_fn, dev, steps, warmup, barrier, sampler):
     import torch
     for _ in range(warmup):
@@ -617,10 +629,25 @@ def run_b200(args):
             'value_function_points': points,
         }
 
+    # ---- whole solves ---------------------------------------------------------------------------------------------------------
+    if 'solve' in legs:
+        # (before the CPU oracle leg: several seconds of an idle GPU let its clocks drop, and a launch-bound solve that starts right
+        # after that runs several times slower until they are back up)
+        solve = {}
+        gpu_warm(dev.device)
+        try:
+            solve = run_solve_leg(model, world, rank, info, reduce_max)
+        except Exception as e:          # the solve leg must not take the headline down with it
+            solve = {'error': f'{type(e).__name__}: {e}'}
+        if line is not None:
+            line['solve'] = solve
+        elif rank == 0:
+            line = {'metric': 'PBVI solve wall time', 'solve': solve, 'n_gpus': world}
     # ---- parity sample + CPU baseline: the oracle on the headline alphas, for a sample of the timed beliefs (rank 0) -----------------
     parity_failed = False
     if 'backup' in legs and rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count()
+        prev_threads = torch.get_num_threads()
         torch.set_num_threads(cores)
         n_sample = min(B, args.parity_beliefs or (512 if world == 1 else 128))
         pick = np.unique(np.linspace(0, B - 1, n_sample).astype(np.int64))
@@ -639,19 +666,11 @@ def run_b200(args):
                                               f'extrapolated linearly in B (factor {ext["extrapolation_factor"]:.1f}); NumPy/OpenBLAS with {cores} threads; '
                                               'the same alphas and beliefs as the timed step',
                                     **{k: v for k, v in ext.items() if k != 'value'}, **timing}
+        torch.set_num_threads(prev_threads)
 
-    # ---- whole solves ---------------------------------------------------------------------------------------------------------
-    if 'solve' in legs:
-        solve = {}
-        try:
-            solve = run_solve_leg(model, world, rank, info, reduce_max)
-        except Exception as e:          # the solve leg must not take the headline down with it
-            solve = {'error': f'{type(e).__name__}: {e}'}
-        if line is not None:
-            line['solve'] = solve
-        elif rank == 0:
-            line = {'metric': 'PBVI solve wall time', 'solve': solve, 'n_gpus': world}
-        if rank == 0 and line is not None and 'cpu_baseline' in line and 'error' not in solve:
+    if 'solve' in legs and rank == 0 and line is not None and 'cpu_baseline' in line and 'error' not in line.get('solve', {'error': 1}):
+        solve = line['solve']
+        if True:
             cpu = line['cpu_baseline']['value']
             for k, s in solve.items():
                 if isinstance(s, dict) and 'backup_pairs' in s:
@@ -660,6 +679,7 @@ def run_b200(args):
                                                    'function, B = 10 000): an estimate of the reference CPU path\'s backup time alone')
 
     if 'configs' in legs and world == 1 and rank == 0:
+        gpu_warm(dev.device)
         try:
             line['configs'] = run_config_leg(args)
         except Exception as e:
@@ -811,7 +831,57 @@ def run_config_leg(args) -> dict:
     rec['gamma_bytes_the_reference_would_allocate'] = 8.0 * 16 * 2 * rec['V'] * 63555
     points.append(rec)
     bad = [p['config'] for p in points if 'parity_sample' in p and not p['parity_sample']['ok']]
-    return {'tiger_solve': tiger_solve, 'points': points, 'parity_failures': bad}
+    return {'tiger_solve': tiger_solve, 'points': points, 'parity_failures': bad, 'ssea_expansions': run_ssea_points(rng)}
+
+
+def run_ssea_points(rng) -> list:
+    """
+    SSEA expansions at scale (configs[1] names SSEA on the 4x4 grid; the reference's own expand_ssea crashes on every model that has an
+    impossible observation): all B*A*O successors from one launch, their distance to the belief set with the tiled
+    direct-difference kernel, the `max_generation` farthest kept.  Timed end to end (`PBVI_Solver.expand_ssea`), with the distances of a
+    sample of possible successors checked against the reference's formula (oracle.ssea_min_distances).
+    """
+    import torch
+    from oracle import pbvi_oracle as orc
+    from pomdp_pbvi_exploration_b200 import BeliefSet, Model, PBVI_Solver
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model
+    out = []
+    m = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'model_grid4x4.npz')))
+    grid = Model(states=16, actions=4, observations=2, transitions=m['transition_table'], rewards=m['reward_table'],
+                 observation_table=m['obs_table'], start_probabilities=m['start'])
+    olf = olfactory_wrap_model()
+    solver = PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='ssea')
+    np.random.seed(9)
+    cases = [('grid4x4 (R=15)', grid, np.concatenate([np.eye(16), _dirichlet_beliefs(rng, 4096 - 16, 16, 16)]), 100),
+             ('olfactory_wrap', olf, torch.cat([solver.expand_perseus(olf, __import__('pomdp_pbvi_exploration_b200').Belief(olf), 100).belief_array
+                                                for _ in range(10)]).cpu().numpy(), 100)]
+    for name, model, B, n_new in cases:
+        bs = BeliefSet(model, B)
+        dev = model.device
+        for _ in range(2):
+            new = solver.expand_ssea(model, bs, max_generation=n_new)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        new = solver.expand_ssea(model, bs, max_generation=n_new)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        # parity of the ingredients on a sample: successors of 4 beliefs, distances to the whole set
+        pick = np.unique(np.linspace(0, B.shape[0] - 1, 4).astype(np.int64))
+        succ, mass = dev.belief_successors(torch.as_tensor(B[pick]).to(dev.device))
+        tabs = host_tables(model)
+        with np.errstate(all='ignore'):
+            want_succ = orc.all_successors(tabs['reach'], tabs['rto'], B[pick])
+            ok_succ = bool(np.array_equal(succ.cpu().numpy(), want_succ, equal_nan=True))
+            possible = ~np.isnan(want_succ.reshape(-1, B.shape[1])).any(axis=1)
+            cand = want_succ.reshape(-1, B.shape[1])[possible]
+            want_d = np.array([np.sqrt(np.min(np.einsum('bs,bs->b', B - c, B - c))) for c in cand])
+        got_d = dev.min_l2_distance(bs.belief_array, torch.as_tensor(cand).to(dev.device)).cpu().numpy()
+        out.append({'config': name, 'S': model.state_count, 'B': int(B.shape[0]), 'candidates': int(B.shape[0] * model.action_count * model.observation_count),
+                    'max_generation': n_new, 'new_beliefs': len(new), 'expand_ssea_s': wall,
+                    'parity_sample': {'successor_rows_bitwise_equal': ok_succ, 'distances_checked': int(cand.shape[0]),
+                                      'max_rel_distance_error': float(np.max(np.abs(got_d - want_d) / np.maximum(want_d, 1e-300))) if cand.shape[0] else 0.0,
+                                      'ok': ok_succ and bool(np.allclose(got_d, want_d, rtol=1e-10, atol=1e-13))}})
+    return out
 
 
 _JSON_OUT = None
