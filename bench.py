@@ -231,6 +231,9 @@ def build_workload(model, n_beliefs: int, n_alphas: int, seed: int):
 
     # ---- late: the engine's own FSVI 300 x 100 solve (the reference's published shape); rows of expansions >= 200
     seed_all(0)
+    FSVI_Solver(gamma=GAMMA, eps=1e-6).solve(model, expansions=3, max_belief_growth=100, print_progress=False)    # one-time costs (arena, module load)
+    gpu_warm(model.device.device)
+    seed_all(0)
     fsvi = FSVI_Solver(gamma=GAMMA, eps=1e-6)
     vf_f, hist, summary = timed_solve(fsvi, model, expansions=300, max_belief_growth=100)
     counts = hist.alpha_vector_counts                      # [initial, after backup 1, ...]
@@ -709,11 +712,13 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
     if world == 1 and 'late' in info and 'fsvi_solve' in info['late']:
         s = dict(info['late']['fsvi_solve'])         # the workload's own solve (timed when it ran)
     else:
+        gpu_warm(model.device.device)
         seed_all(0)
         _, _, s = timed_solve(FSVI_Solver(gamma=GAMMA, eps=1e-6), model, expansions=300, max_belief_growth=100, **shard)
     s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
     s['reference_published'] = {'numpy_cpu_s': 2983.5, 'cupy_gpu_s': 204.9, 'source': 'Olfactory_Alternation_Paper_Wrap.ipynb[43],[30] (BASELINE.md)'}
     out['fsvi_300x100'] = s
+    gpu_warm(model.device.device)
     seed_all(0)
     _, _, s = timed_solve(PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='perseus'), model, expansions=2, max_belief_growth=6000,
                           full_backup=True, update_passes=15, **shard)

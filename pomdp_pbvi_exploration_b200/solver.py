@@ -754,8 +754,11 @@ class PBVI_Solver:
         if n <= 0:
             return BeliefSet(model, torch.empty((0, model.state_count), dtype=torch.float64, device=dev.device))
         acts, us = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.float64)
+        n_actions = len(model.actions)
         for i in range(n):
-            acts[i] = int(np.random.choice(model.actions, size=1)[0])
+            # `np.random.choice(model.actions, size=1)` draws its index with `randint(0, len, size=1)`: the same call, without choice's
+            # argument checks (half the host time of a long walk); `choice(observations, p=...)` consumes one `random_sample()`
+            acts[i] = int(model.actions[np.random.randint(0, n_actions, size=1)[0]])
             us[i] = np.random.random_sample()
         return BeliefSet(model, dev.perseus_walk(b.values, acts, us))
 

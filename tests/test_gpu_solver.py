@@ -288,9 +288,8 @@ def test_small_model_path_equals_general_pipeline(tag):
     pipeline (select -> tuple grouping -> assemble -> byte-dedup): same rows bit for bit, same order, same actions, same row keys --
     with and without append; and it is the path `PBVI_Solver.backup` actually takes for these sizes."""
     from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
-    model = fixture_model(tag)
+    model, gamma = fixture_model(tag)
     g = load_golden('backup_' + tag)
-    gamma = float(load_golden('model_' + tag)['gamma'])
     solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='ssra')
     bs = BeliefSet(model, g['beliefs'])
     vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
