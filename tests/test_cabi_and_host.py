@@ -69,6 +69,25 @@ def test_error_convention_without_a_device(lib_path):
         _native._check(rc)
 
 
+def test_comm_and_small_path_entry_points_reject_bad_arguments(lib_path):
+    """The multi-GPU collectives (pbvi_comm_*) and the small-model backup are part of the C ABI: exported, int status, bad-argument
+    errors without touching a device or NCCL."""
+    from pomdp_pbvi_exploration_b200 import _native
+    lib = _native.load_library()
+    h = ctypes.c_void_p()
+    buf = (ctypes.c_ubyte * 128)()
+    assert lib.pbvi_comm_init(None, buf, 0, 2, ctypes.byref(h)) == _native.PBVI_ERR_BAD_ARG and h.value is None
+    assert lib.pbvi_comm_rank(None, None, None) == _native.PBVI_ERR_BAD_ARG
+    assert lib.pbvi_comm_destroy(None) == _native.PBVI_OK
+    assert lib.pbvi_allgather_tuples(None, None, 4, 5, None, None) == _native.PBVI_ERR_BAD_ARG
+    assert lib.pbvi_allreduce_max(None, None, 1, None) == _native.PBVI_ERR_BAD_ARG
+    assert lib.pbvi_broadcast_rows(None, None, 0, 0, None) == _native.PBVI_ERR_BAD_ARG
+    assert lib.pbvi_backup_small_eligible(None, 10, 10) == 0
+    n = ctypes.c_int(7)
+    assert lib.pbvi_backup_small(None, None, 1, None, 1, 0.9, None, None, None, ctypes.byref(n), None) == _native.PBVI_ERR_BAD_ARG
+    assert lib.pbvi_perseus_walk(None, None, None, None, 3, None, None, None) == _native.PBVI_ERR_BAD_ARG
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'pomdp_pbvi_exploration_b200')
     for dirpath, _, files in os.walk(pkg):
