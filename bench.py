@@ -55,7 +55,7 @@ GAP_TOL = 1e-9                 # parity contract: indices identical wherever the
 FP64_PEAK_TFLOPS = 37.1        # DMMA m8n8k4 / m16n8k16 on this pool's B200, profiles/r01_fp64_pipe_microbench.txt
 # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (`ncu --set full`, profiles/), per workload point at the
 # default sizes (B = 10000, V = 1000); None = not captured
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {'young': 0.2346e9, 'late': None, 'dense': None}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {'young': 0.2400e9, 'late': 10.4627e9, 'dense': None}     # profiles/r02_score_kernel_{young,late}_ncu_summary.txt
 
 
 def parse_args():
