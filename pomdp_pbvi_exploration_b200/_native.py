@@ -50,6 +50,9 @@ SIGNATURES = {
     'pbvi_vi_sweep': [_P, _P, c_double, _P, _P, _P],
     'pbvi_prune_dominated': [_P, _P, c_int, _P, _P],
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
+    'pbvi_support_lists': [_P, _P, c_int, _P, _P, _P, _P, _P, _P],
+    'pbvi_sawtooth_lists': [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P],
+    'pbvi_hsvi_level': [_P, _P, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, c_int, _P, _P, _P, _P],
     'pbvi_min_l2_distance': [_P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_ger_scores': [_P, _P, _P, _P, c_int, c_double, c_double, _P, _P],
     'pbvi_comm_unique_id': [_P],
@@ -455,6 +458,35 @@ class DeviceModel:
         self._call(self._lib.pbvi_sawtooth(self._h, _ptr(c), _ptr(ubb) if ubb.shape[0] else None, _ptr(ubv) if ubb.shape[0] else None,
                                        ubb.shape[0], _ptr(q), q.shape[0], _ptr(out), self._stream))
         return out
+
+    def support_lists(self, rows: torch.Tensor, corner: torch.Tensor, idx: torch.Tensor, val: torch.Tensor, count: torch.Tensor,
+                      dot: torch.Tensor) -> None:
+        """Support lists (states / values of the positive entries, ELL layout with row pitch S) and row . corner of `rows` [n,S], written
+        into the given slices (idx int32 [n,S], val f64 [n,S], count int32 [n], dot f64 [n])."""
+        n = rows.shape[0]
+        assert rows.is_contiguous() and idx.is_contiguous() and val.is_contiguous() and idx.shape == (n, self.S) and val.shape == (n, self.S)
+        self._call(self._lib.pbvi_support_lists(self._h, _ptr(rows), n, _ptr(corner), _ptr(idx), _ptr(val), _ptr(count), _ptr(dot), self._stream))
+
+    def sawtooth_lists(self, corner, idx, val, count, dot, ub_values, n_ub: int, queries) -> torch.Tensor:
+        q = self._beliefs(queries)
+        out = torch.empty((q.shape[0],), dtype=torch.float64, device=self.device)
+        self._call(self._lib.pbvi_sawtooth_lists(self._h, _ptr(corner), _ptr(idx), _ptr(val), _ptr(count), _ptr(dot), _ptr(ub_values), int(n_ub),
+                                                 _ptr(q), q.shape[0], _ptr(out), self._stream))
+        return out
+
+    def hsvi_level(self, b: torch.Tensor, alphas: torch.Tensor, gamma: float, corner, idx, val, count, dot, ub_values, n_ub: int,
+                   stored_keys, stored_vals, n_stored: int, conv_term: float, may_continue: bool):
+        """One level of HSVI's exploration (`pbvi_hsvi_level`): returns (successors [A,O,S], masses [A,O], (best_a, best_o, Q, upper - lower),
+        (added, key0, key1, n_possible))."""
+        al = self._beliefs(alphas)
+        succ = torch.empty((self.A, self.O, self.S), dtype=torch.float64, device=self.device)
+        mass = torch.empty((self.A, self.O), dtype=torch.float64, device=self.device)
+        out = np.empty(8, dtype=np.float64)
+        cap = 0 if stored_keys is None else stored_keys.shape[0]
+        self._call(self._lib.pbvi_hsvi_level(self._h, _ptr(b), _ptr(al), al.shape[0], float(gamma), _ptr(corner), _ptr(idx), _ptr(val), _ptr(count),
+                                             _ptr(dot), _ptr(ub_values), int(n_ub), _ptr(stored_keys), _ptr(stored_vals), int(n_stored), int(cap),
+                                             float(conv_term), int(bool(may_continue)), _ptr(succ), _ptr(mass), out.ctypes.data, self._stream))
+        return succ, mass, out[:4], out[4:].view(np.int64)
 
     def min_l2_distance(self, beliefs, candidates) -> torch.Tensor:
         b, c = self._beliefs(beliefs), self._beliefs(candidates)

@@ -974,6 +974,12 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     return PBVI_OK;
 }
 
+namespace pbvi {
+int max_values_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max, int32_t* d_arg, cudaStream_t st) {
+    return score_argmax(m, d_beliefs, nB, d_alphas, nV, false, d_max, d_arg, st);
+}
+}  // namespace pbvi
+
 // Sizes the small path accepts: everything of one belief fits in shared memory and the per-belief arithmetic is short.
 static bool small_eligible(const pbvi_model* m, int nB, int nV) {
     const double work = (double)nB * nV * m->nZ * m->S;

@@ -303,16 +303,8 @@ extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_
     return PBVI_OK;
 }
 
-extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm,
-                                      void* stream) {
-    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
-    PBVI_REQUIRE(n >= 0, "n must be non-negative");
-    if (n == 0) return PBVI_OK;
-    PBVI_REQUIRE(d_beliefs && d_out, "NULL pointer argument");
-    PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
-    m->last_launches = 0;
-    cudaStream_t st = (cudaStream_t)stream;
+namespace pbvi {
+int belief_successors_impl(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, cudaStream_t st) {
     const int nZ = m->nZ;
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 200 * 1024, "state space too large for the pairwise-sum kernel");
@@ -331,6 +323,19 @@ extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, in
     }
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
+}
+}  // namespace pbvi
+
+extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm,
+                                      void* stream) {
+    PBVI_REQUIRE(m != nullptr, "model handle is NULL");
+    PBVI_REQUIRE(n >= 0, "n must be non-negative");
+    if (n == 0) return PBVI_OK;
+    PBVI_REQUIRE(d_beliefs && d_out, "NULL pointer argument");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    m->arena.reset();
+    m->last_launches = 0;
+    return belief_successors_impl(m, d_beliefs, n, normalise, d_out, d_norm, (cudaStream_t)stream);
 }
 
 extern "C" int pbvi_observation_probabilities(pbvi_model* m, const double* d_beliefs, int n, double* d_out, void* stream) {

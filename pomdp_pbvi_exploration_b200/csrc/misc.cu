@@ -455,6 +455,13 @@ __global__ void __launch_bounds__(256) ger_eps_kernel(const double* __restrict__
     }
 }
 
+int row_hash_launch(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, cudaStream_t st) {
+    row_hash_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_hash);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
 int configure_misc_kernels() {
     PBVI_CUDA(cudaFuncSetAttribute(sawtooth_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)((sizeof(double) + sizeof(int)) * SAW_RANGE + sizeof(double) * SAW_Q_SLAB)));

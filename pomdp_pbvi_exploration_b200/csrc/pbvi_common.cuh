@@ -166,6 +166,10 @@ namespace pbvi {
 int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st);
 // per-device function attributes (dynamic shared memory opt-ins) of each translation unit; pbvi_model_create calls them with the
 // handle's device current, so a second handle on another GPU of the same process is configured too
+// building blocks shared across translation units (none of them resets the arena: the calling entry point does)
+int belief_successors_impl(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, cudaStream_t st);
+int row_hash_launch(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, cudaStream_t st);
+int max_values_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max, int32_t* d_arg, cudaStream_t st);
 int configure_backup_kernels();
 int configure_belief_kernels();
 int configure_misc_kernels();

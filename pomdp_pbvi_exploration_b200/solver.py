@@ -121,20 +121,48 @@ class VI_Solver:
 class BeliefValueMapping:
     """
     HSVI's upper bound: (belief, value) pairs interpolated with the sawtooth rule over the corner values of an MDP
-    solution (reference src/pomdp.py:786-895).  The stored arrays are refreshed by `update()` only, as in the
-    reference.  Divergence (documented): the ratio min_s b(s)/b_i(s) runs over the support of b_i
-    -- the reference's formula takes 0/0 = NaN on sparse beliefs, which disables its own HSVI outside tiger-class models;
-    on strictly positive beliefs the two agree.
+    solution (reference src/pomdp.py:786-895).  The arrays the interpolation runs over are refreshed by `update()` only (and built
+    lazily on first use), as in the reference; a belief that is already stored returns its stored value.  Divergence (documented,
+    SURVEY.md section 4): the ratio min_s b(s)/b_i(s) runs over the support of b_i -- the reference's formula takes 0/0 = NaN on
+    sparse beliefs, which disables its own HSVI outside tiger-class models; on strictly positive beliefs the two agree.
+
+    Device state: the stored beliefs live in one growing row store with their 128-bit keys and values next to them, and -- for
+    the rows the interpolation covers -- as SUPPORT LISTS (`pbvi_support_lists`: states / values of the positive entries and
+    b_i . corner), built once per row, so that a level of the exploration (`pbvi_hsvi_level`) touches nnz instead of S entries per
+    stored belief and needs no host round trip for the lookups.
     """
 
     def __init__(self, model: Model, corner_belief_values: ValueFunction) -> None:
         self.model = model
         self.corner_belief_values = corner_belief_values
-        self.corner_values = torch.max(corner_belief_values.alpha_vector_array, dim=0).values
+        self.corner_values = torch.max(corner_belief_values.alpha_vector_array, dim=0).values.contiguous()
         self.beliefs = []
         self.belief_value_mapping = {}
-        self._belief_array = None
-        self._value_array = None
+        self._cap = 0
+        self._rows = self._keys_dev = self._vals_dev = None
+        self._idx = self._val = self._count = self._dot = None
+        self._n_listed = 0          # rows that have support lists
+        self._n_ub = None           # rows the interpolation covers (None: arrays not built yet -- built lazily on first use)
+
+    # ---- storage ------------------------------------------------------------------------------------------------------
+    def _reserve(self, n: int) -> None:
+        if n <= self._cap:
+            return
+        dev, S = self.model.device.device, self.model.state_count
+        cap = max(64, 2 * n)
+        def grown(old, shape, dtype):
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            if old is not None and len(self.beliefs):
+                t[:old.shape[0]] = old
+            return t
+        self._rows = grown(self._rows, (cap, S), torch.float64)
+        self._keys_dev = grown(self._keys_dev, (cap, 2), torch.int64)
+        self._vals_dev = grown(self._vals_dev, (cap,), torch.float64)
+        self._idx = grown(self._idx, (cap, S), torch.int32)
+        self._val = grown(self._val, (cap, S), torch.float64)
+        self._count = grown(self._count, (cap,), torch.int32)
+        self._dot = grown(self._dot, (cap,), torch.float64)
+        self._cap = cap
 
     def _key(self, b: Belief):
         k = b.__dict__.get('_row_key')
@@ -142,32 +170,56 @@ class BeliefValueMapping:
             k = b._row_key = tuple(self.model.device.row_hash(b.values[None, :]).cpu().numpy()[0].tolist())
         return k
 
+    def _append(self, b: Belief, key: tuple, v: float, on_device: bool) -> None:
+        """Bookkeeping of one new pair; `on_device`: the level kernel already wrote the key and the value."""
+        n = len(self.beliefs)
+        self._reserve(n + 1)
+        self._rows[n] = b.values
+        if not on_device:
+            self._keys_dev[n] = torch.tensor(key, dtype=torch.int64)
+            self._vals_dev[n] = float(v)
+        self.beliefs.append(b)
+        self.belief_value_mapping[key] = v
+
     def add(self, b: Belief, v: float) -> None:
         """Adds (belief, value) unless the belief is already stored (reference :838-850).  Identity is the 128-bit row key."""
         k = self._key(b)
         if k not in self.belief_value_mapping:
-            self.beliefs.append(b)
-            self.belief_value_mapping[k] = v
+            self._append(b, k, v, on_device=False)
+
+    def _cover(self, n: int) -> None:
+        """Makes the interpolation arrays cover the first n stored beliefs (support lists for the rows that lack them)."""
+        if n > self._n_listed:
+            lo = self._n_listed
+            self.model.device.support_lists(self._rows[lo:n], self.corner_values, self._idx[lo:n], self._val[lo:n], self._count[lo:n],
+                                            self._dot[lo:n])
+            self._n_listed = n
+        self._n_ub = n
 
     @property
     def belief_array(self) -> torch.Tensor:
-        if self._belief_array is None:
-            self._belief_array = torch.stack([b.values for b in self.beliefs])
-        return self._belief_array
+        if self._n_ub is None:
+            self._cover(len(self.beliefs))
+        return self._rows[:self._n_ub]
 
     @property
     def value_array(self) -> torch.Tensor:
-        if self._value_array is None:
-            self._value_array = torch.as_tensor(list(self.belief_value_mapping.values()), dtype=torch.float64,
-                                                device=self.model.device.device)
-        return self._value_array
+        if self._n_ub is None:
+            self._cover(len(self.beliefs))
+        return self._vals_dev[:self._n_ub]
 
     def update(self) -> None:
         if len(self.beliefs) == 0:
             return
-        self._belief_array = torch.stack([b.values for b in self.beliefs])
-        self._value_array = torch.as_tensor(list(self.belief_value_mapping.values()), dtype=torch.float64,
-                                            device=self.model.device.device)
+        self._cover(len(self.beliefs))
+
+    def _arrays(self):
+        """(idx, val, count, dot, values, n_ub) of the interpolation, built lazily like the reference's array properties."""
+        if len(self.beliefs) == 0:
+            return None, None, None, None, None, 0
+        if self._n_ub is None:
+            self._cover(len(self.beliefs))
+        return self._idx, self._val, self._count, self._dot, self._vals_dev, self._n_ub
 
     def evaluate_rows(self, rows: torch.Tensor) -> np.ndarray:
         """
@@ -178,12 +230,8 @@ class BeliefValueMapping:
         dev = self.model.device
         n = rows.shape[0]
         keys = dev.row_hash(rows).cpu().numpy().tolist()
-        if len(self.beliefs) == 0:
-            ub_b = torch.empty((0, dev.S), dtype=torch.float64, device=dev.device)
-            ub_v = torch.empty((0,), dtype=torch.float64, device=dev.device)
-        else:
-            ub_b, ub_v = self.belief_array, self.value_array
-        out = dev.sawtooth(self.corner_values, ub_b, ub_v, rows).cpu().numpy()
+        idx, val, count, dot, vals, n_ub = self._arrays()
+        out = dev.sawtooth_lists(self.corner_values, idx, val, count, dot, vals, n_ub, rows).cpu().numpy()
         for i in range(n):
             hit = self.belief_value_mapping.get(tuple(keys[i]))
             if hit is not None:
@@ -657,50 +705,39 @@ class PBVI_Solver:
 
     def _expand_hsvi_list(self, model: Model, b: Belief, value_function: ValueFunction, upper_bound_belief_value_map: BeliefValueMapping,
                           conv_term: Union[float, None], max_generation: int) -> list:
+        """The recursion of the reference unrolled: one `pbvi_hsvi_level` call (one synchronisation) per level; the beliefs come out
+        in the recursion's order (deepest first)."""
         dev = model.device
+        ub = upper_bound_belief_value_map
         if conv_term is None:
             conv_term = self.eps
-        conv_term /= self.gamma
-        A, O = model.action_count, model.observation_count
-        # one level = a handful of launches: all A*O successors with their masses P(o|b,a), their upper bounds, b . Rbar
-        succ, mass = dev.belief_successors(b.values[None, :])
-        succ, probs = succ[0], mass[0].cpu().numpy()                                          # [A,O,S], [A,O]
-        possible = probs > 0
-        upper = np.zeros((A, O))
-        if possible.any():
-            idx = np.flatnonzero(possible.reshape(-1))
-            upper.reshape(-1)[idx] = upper_bound_belief_value_map.evaluate_rows(succ.reshape(A * O, -1)[torch.as_tensor(idx, device=dev.device)])
-        if getattr(model, '_rbar_device', None) is None:
-            model._rbar_device = torch.as_tensor(np.ascontiguousarray(model.expected_rewards_table.T), dtype=torch.float64).to(dev.device)
-        rb = torch.mv(model._rbar_device, b.values).cpu().numpy()
-        max_qv, best_a = -np.inf, -1
-        for a in model.actions:
-            b_prob_val = 0
-            for o in model.observations:
-                if possible[a, o]:
-                    b_prob_val += probs[a, o] * upper[a, o]
-            qva = float(rb[a] + self.gamma * b_prob_val)
-            if qva > max_qv:
-                max_qv, best_a = qva, a
-        lower = dev.max_values(succ[best_a], value_function.alpha_vector_array)[0].cpu().numpy()
-        max_o_val, best_v_diff, next_b = -np.inf, -np.inf, b
-        for o in model.observations:
-            if not possible[best_a, o]:
-                continue
-            v_diff = upper[best_a, o] - lower[o]
-            o_val = probs[best_a, o] * v_diff
-            if o_val > max_o_val:
-                max_o_val, best_v_diff = o_val, v_diff
-                next_b = succ[best_a, o]
-        if next_b is not b:
+        chosen = []
+        V = value_function.alpha_vector_array
+        while True:
+            conv_term /= self.gamma
+            idx, val, count, dot, vals, n_ub = ub._arrays()
+            n_stored = len(ub.beliefs)
+            ub._reserve(n_stored + 1)
+            may_continue = max_generation > 1
+            succ, mass, res, meta = dev.hsvi_level(b.values, V, self.gamma, ub.corner_values, idx, val, count, dot, vals, n_ub,
+                                                   ub._keys_dev, ub._vals_dev, n_stored, conv_term, may_continue)
+            best_a, best_o, max_qv, best_v_diff = int(res[0]), int(res[1]), float(res[2]), float(res[3])
             # own storage for the chosen successor: a view would keep the whole [A,O,S] successor block of every level alive
-            next_b = Belief._from_device(model, next_b.clone())
-        if best_v_diff < conv_term or max_generation <= 1:
-            return [next_b]
-        upper_bound_belief_value_map.add(b, max_qv)
-        new_belief_list = self._expand_hsvi_list(model, next_b, value_function, upper_bound_belief_value_map, conv_term, max_generation - 1)
-        new_belief_list.append(next_b)
-        return new_belief_list
+            next_b = b if best_o < 0 else Belief._from_device(model, succ[best_a, best_o].clone())
+            if best_v_diff < conv_term or not may_continue:
+                chosen.append(next_b)
+                break
+            key = (int(meta[1]), int(meta[2]))
+            b._row_key = key
+            if int(meta[0]):
+                ub._append(b, key, max_qv, on_device=True)
+            elif key not in ub.belief_value_mapping:
+                ub._append(b, key, max_qv, on_device=False)          # (stored arrays were full: host-side append)
+            chosen.append(next_b)
+            b = next_b
+            max_generation -= 1
+        chosen.reverse()
+        return chosen
 
     def _trajectory(self, model: Model, b0: Belief, mdp_policy: ValueFunction, max_generation: int, eps_greedy=None) -> BeliefSet:
         """

@@ -306,3 +306,73 @@ def test_small_model_path_equals_general_pipeline(tag):
         assert np.array_equal(small.row_hashes, general.row_hashes)
     # beyond the size limit the general pipeline runs
     assert not model.device.backup_small_eligible(20000, 4096)
+
+
+@pytest.mark.parametrize('ppu,n_store', [(6, 0), (6, 7), (8, 40)])
+def test_hsvi_level_equals_host_driven_level(ppu, n_store):
+    """`pbvi_hsvi_level` (one call, one synchronisation) == the level of the reference's expand_hsvi (src/pomdp.py:1803-1855) driven
+    from the host with the separate kernels: successors, upper bounds (stored value for stored beliefs, else the sawtooth over the arrays
+    as of the last update), Q-values, lower bounds, the (a, o) choice, and the append of (b, Q) to the stored pairs."""
+    import torch
+    from pomdp_pbvi_exploration_b200 import Belief, BeliefSet, BeliefValueMapping, FSVI_Solver, PBVI_Solver, VI_Solver
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model
+    model = olfactory_wrap_model(points_per_unit=ppu)
+    dev = model.device
+    gamma = 0.99
+    mdp, _ = VI_Solver(gamma=gamma, eps=1e-6).solve(model, print_progress=False)
+    seed_all(2)
+    vf, _ = FSVI_Solver(gamma=gamma, eps=1e-6, mdp_policy=mdp).solve(model, expansions=4, max_belief_growth=15, print_progress=False)
+    solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='hsvi')
+    walk = solver.expand_perseus(model, Belief(model), max_generation=max(n_store, 1) + 6)
+    ub = BeliefValueMapping(model, mdp)
+    rng = np.random.default_rng(0)
+    for i in range(n_store):
+        ub.add(walk.belief_at(i), float(rng.random() * 0.5))
+    if n_store:
+        ub.update()
+        ub.add(walk.belief_at(n_store), 0.123)                  # stored after the update: known by key, not part of the interpolation arrays
+    for j, b in enumerate([Belief(model), walk.belief_at(n_store + 2), walk.belief_at(max(n_store - 1, 0))]):
+        # ---- host-driven level
+        succ, mass = dev.belief_successors(b.values[None, :])
+        succ, probs = succ[0], mass[0].cpu().numpy()
+        A, O = probs.shape
+        possible = probs > 0
+        n_ub = 0 if ub._n_ub is None else ub._n_ub
+        saw = dev.sawtooth(ub.corner_values, ub._rows[:n_ub] if n_ub else np.zeros((0, model.state_count)), ub._vals_dev[:n_ub] if n_ub else np.zeros(0),
+                           succ.reshape(A * O, -1)).cpu().numpy().reshape(A, O)
+        keys = dev.row_hash(succ.reshape(A * O, -1)).cpu().numpy().reshape(A, O, 2)
+        upper = saw.copy()
+        for a in range(A):
+            for o in range(O):
+                hit = ub.belief_value_mapping.get(tuple(keys[a, o].tolist()))
+                if hit is not None:
+                    upper[a, o] = hit
+        rb = model.expected_rewards_table.T @ b.values_host
+        q = np.array([rb[a] + gamma * sum(probs[a, o] * upper[a, o] for o in range(O) if possible[a, o]) for a in range(A)])
+        best_a = int(np.argmax(q))
+        lower = dev.max_values(succ[best_a], vf.alpha_vector_array)[0].cpu().numpy()
+        o_vals = [probs[best_a, o] * (upper[best_a, o] - lower[o]) if possible[best_a, o] else -np.inf for o in range(O)]
+        best_o = int(np.argmax(o_vals))
+        # ---- the fused level
+        idx, val, count, dot, vals, n_cover = ub._arrays()
+        n_before = len(ub.beliefs)
+        ub._reserve(n_before + 1)
+        s2, m2, res, meta = dev.hsvi_level(b.values, vf.alpha_vector_array, gamma, ub.corner_values, idx, val, count, dot, vals, n_cover,
+                                           ub._keys_dev, ub._vals_dev, n_before, conv_term=-1.0, may_continue=True)
+        assert torch.equal(s2.reshape(-1), succ.reshape(-1)) or np.array_equal(s2.cpu().numpy(), succ.cpu().numpy(), equal_nan=True)
+        assert np.array_equal(m2.cpu().numpy(), probs)
+        assert (int(res[0]), int(res[1])) == (best_a, best_o)
+        assert res[2] == pytest.approx(q[best_a], rel=1e-12, abs=1e-14)
+        assert res[3] == pytest.approx(upper[best_a, best_o] - lower[best_o], rel=1e-9, abs=1e-12)
+        assert int(meta[3]) == int(possible.sum())
+        key_b = tuple(dev.row_hash(b.values[None, :]).cpu().numpy()[0].tolist())
+        assert (int(meta[1]), int(meta[2])) == key_b
+        already = key_b in ub.belief_value_mapping
+        assert int(meta[0]) == (0 if already else 1)
+        if not already:                                            # the kernel appended (key, Q) at index n_before
+            assert tuple(ub._keys_dev[n_before].cpu().tolist()) == key_b and float(ub._vals_dev[n_before]) == res[2]
+            ub._append(b, key_b, float(res[2]), on_device=True)
+        # sawtooth over support lists == the dense-row kernel, bit for bit
+        if n_cover:
+            lists = dev.sawtooth_lists(ub.corner_values, idx, val, count, dot, vals, n_cover, succ.reshape(A * O, -1)).cpu().numpy()
+            assert np.array_equal(lists, saw.reshape(-1), equal_nan=True)
