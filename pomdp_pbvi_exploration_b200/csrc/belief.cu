@@ -108,8 +108,10 @@ __global__ void __launch_bounds__(256) pairwise_normalise_kernel(double* __restr
 // model, the whole cost of an FSVI expansion).  pairwise_leaf_kernel spreads the leaf sums over ceil(nLeaves / 32) blocks,
 // pairwise_finish_kernel walks the (tiny) combine tree in every block and divides that block's slice.  Same additions in the
 // same order: bit-identical to pairwise_normalise_kernel.
-__global__ void __launch_bounds__(256) pairwise_leaf_kernel(const double* __restrict__ row, const int2* __restrict__ leaves, int nLeaves,
-                                                            double* __restrict__ leafSums) {
+__global__ void __launch_bounds__(256) pairwise_leaf_kernel(const double* __restrict__ rows, int S, const int2* __restrict__ leaves, int nLeaves,
+                                                            double* __restrict__ leafSumsAll) {
+    const double* row = rows + (size_t)blockIdx.y * S;             // blockIdx.y: row (a few rows at a time: grid.y <= 64)
+    double* leafSums = leafSumsAll + (size_t)blockIdx.y * nLeaves;
     const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
     const int l = blockIdx.x * 32 + grp;
     const bool valid = l < nLeaves;
@@ -134,10 +136,13 @@ __global__ void __launch_bounds__(256) pairwise_leaf_kernel(const double* __rest
 
 constexpr int FINISH_SLICE = 2048;   // elements divided per block
 
-__global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict__ row, int S, const double* __restrict__ leafSums, int nLeaves,
-                                                              const int2* __restrict__ nodes, int nNodes, double* __restrict__ norm) {
+__global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict__ rows, int S, const double* __restrict__ leafSumsAll, int nLeaves,
+                                                              const int2* __restrict__ nodes, int nNodes, double* __restrict__ normAll, int normalise) {
     extern __shared__ double s_sum[];   // [nLeaves] leaf sums, then [nNodes] node sums
     __shared__ double s_total;
+    double* row = rows + (size_t)blockIdx.y * S;
+    const double* leafSums = leafSumsAll + (size_t)blockIdx.y * nLeaves;
+    double* norm = normAll ? normAll + blockIdx.y : nullptr;
     for (int l = threadIdx.x; l < nLeaves; l += 256) s_sum[l] = leafSums[l];
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(256) pairwise_finish_kernel(double* __restrict
         if (norm && blockIdx.x == 0) *norm = s_total;
     }
     __syncthreads();
+    if (!normalise) return;
     const double tot = s_total;
     const int s1 = min(S, (int)(blockIdx.x + 1) * FINISH_SLICE);
     for (int s = blockIdx.x * FINISH_SLICE + threadIdx.x; s < s1; s += 256) row[s] = row[s] / tot;   // 0/0 = NaN, as in the reference
@@ -192,6 +198,22 @@ int configure_belief_kernels() {
 }
 }  // namespace pbvi
 
+namespace pbvi {
+constexpr int PAIRWISE_SPLIT_ROWS = 64;
+// multi-block pairwise normaliser over n <= PAIRWISE_SPLIT_ROWS rows (leaf sums spread over blocks, then per-slice finish): same
+// additions in the same order as pairwise_normalise_kernel
+static int pairwise_split_launch(pbvi_model* m, double* rows, int n, int normalise, double* d_norm, cudaStream_t st) {
+    const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
+    double* leafSums = m->arena.take<double>((size_t)m->nLeaves * n);
+    if (!leafSums) return PBVI_ERR_OOM;
+    pairwise_leaf_kernel<<<dim3(ceil_div(m->nLeaves, 32), n), 256, 0, st>>>(rows, m->S, m->pwLeaves, m->nLeaves, leafSums);
+    pairwise_finish_kernel<<<dim3(ceil_div(m->S, FINISH_SLICE), n), 256, smem, st>>>(rows, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes,
+                                                                                      d_norm, normalise);
+    m->last_launches += 2;
+    return PBVI_OK;
+}
+}  // namespace pbvi
+
 using namespace pbvi;
 
 // belief_stride: doubles between consecutive source beliefs (S for one belief per (a,o) pair, 0 to update one belief n ways)
@@ -206,16 +228,10 @@ static int belief_update_impl(pbvi_model* m, const double* d_beliefs, size_t bel
                                                                             d_observations + i0, beliefStride, m->predPtr, m->predK,
                                                                             m->rtoK, m->S, m->R, m->O, out, 0, 0, nullptr, 0.0, nullptr, 0);
         m->last_launches++;
-        if (normalise && ni <= 4 && smem <= 48 * 1024) {
-            // a few rows (one step of a Perseus walk, a single Belief.update): the multi-block form of the normaliser, row by row
-            double* leafSums = m->arena.take<double>((size_t)m->nLeaves);
-            if (!leafSums) return PBVI_ERR_OOM;
-            for (int r = 0; r < ni; r++) {
-                pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out + (size_t)r * m->S, m->pwLeaves, m->nLeaves, leafSums);
-                pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out + (size_t)r * m->S, m->S, leafSums, m->nLeaves,
-                                                                                        m->pwNodes, m->nNodes, d_norm ? d_norm + i0 + r : nullptr);
-                m->last_launches += 2;
-            }
+        if ((normalise || d_norm) && ni <= PAIRWISE_SPLIT_ROWS && smem <= 48 * 1024) {
+            // a few rows (one step of a walk, a single Belief.update, the successors of one belief): the multi-block form of the
+            // normaliser -- with one block per row a handful of SMs would walk ~170 leaves and S divisions each
+            PBVI_TRY(pairwise_split_launch(m, out, ni, normalise, d_norm ? d_norm + i0 : nullptr, st));
         } else if (normalise || d_norm) {
             pairwise_normalise_kernel<<<ni, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
                                                             d_norm ? d_norm + i0 : nullptr);
@@ -259,8 +275,8 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
         double* out = d_out + (size_t)i * m->S;
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
                                                                            m->O, out, h_actions[i], h_observations[i], nullptr, 0.0, nullptr, 0);
-        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
-        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
+        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->S, m->pwLeaves, m->nLeaves, leafSums);
+        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr, 1);
         m->last_launches += 3;
         src = (h_reset && h_reset[i]) ? d_b0 : out;
     }
@@ -294,8 +310,8 @@ extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), 1), 256, 0, st>>>(src, nullptr, nullptr, 0, m->predPtr, m->predK, m->rtoK, m->S, m->R,
                                                                            m->O, out, a, 0, obsProb, h_uniforms[i],
                                                                            d_observations ? d_observations + i : nullptr, 0);
-        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->pwLeaves, m->nLeaves, leafSums);
-        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr);
+        pairwise_leaf_kernel<<<ceil_div(m->nLeaves, 32), 256, 0, st>>>(out, m->S, m->pwLeaves, m->nLeaves, leafSums);
+        pairwise_finish_kernel<<<ceil_div(m->S, FINISH_SLICE), 256, smem, st>>>(out, m->S, leafSums, m->nLeaves, m->pwNodes, m->nNodes, nullptr, 1);
         m->last_launches += 4;
         src = out;
     }
@@ -317,6 +333,11 @@ int belief_successors_impl(pbvi_model* m, const double* d_beliefs, int n, int no
         belief_project_kernel<<<dim3(ceil_div(m->S, 256), rows), 256, 0, st>>>(d_beliefs + (size_t)i0 * m->S, nullptr, nullptr, (size_t)m->S,
                                                                               m->predPtr, m->predK, m->rtoK, m->S, m->R, m->O, out, 0, 0,
                                                                               nullptr, 0.0, nullptr, nZ);
+        if (rows <= PAIRWISE_SPLIT_ROWS && smem <= 48 * 1024) {
+            m->last_launches++;
+            PBVI_TRY(pairwise_split_launch(m, out, rows, normalise, d_norm ? d_norm + (size_t)i0 * nZ : nullptr, st));
+            continue;
+        }
         pairwise_normalise_kernel<<<rows, 256, smem, st>>>(out, m->S, m->pwLeaves, m->nLeaves, m->pwNodes, m->nNodes, normalise,
                                                           d_norm ? d_norm + (size_t)i0 * nZ : nullptr);
         m->last_launches += 2;

@@ -63,8 +63,10 @@ constexpr int SAW_QT = 8;
 __global__ void __launch_bounds__(256) sawtooth_lists_kernel(const int32_t* __restrict__ idx, const double* __restrict__ val,
                                                              const int32_t* __restrict__ count, const double* __restrict__ dot,
                                                              const double* __restrict__ ubV, int nUb, const double* __restrict__ queries, int nQ,
-                                                             int S, const double* __restrict__ v0, double* __restrict__ terms) {
+                                                             int S, const double* __restrict__ v0, const double* __restrict__ qMass,
+                                                             double* __restrict__ terms) {
     __shared__ double sh[8][SAW_QT];
+    __shared__ unsigned s_hit;
     const int i = blockIdx.x;
     const int32_t* li = idx + (size_t)i * S;
     const double* lv = val + (size_t)i * S;
@@ -72,14 +74,40 @@ __global__ void __launch_bounds__(256) sawtooth_lists_kernel(const int32_t* __re
     const double scale = ubV[i] - dot[i];
     for (int q0 = 0; q0 < nQ; q0 += SAW_QT) {
         double r[SAW_QT];
+        unsigned live = 0u;                       // queries of the tile that exist and (qMass given) have positive mass: NaN rows are skipped
 #pragma unroll
-        for (int k = 0; k < SAW_QT; k++) r[k] = INFINITY;
-        for (int j = threadIdx.x; j < cnt; j += 256) {
-            const int s = li[j];
-            const double b = lv[j];
+        for (int k = 0; k < SAW_QT; k++) {
+            r[k] = INFINITY;
+            if (q0 + k < nQ && (!qMass || qMass[q0 + k] > 0.0)) live |= 1u << k;
+        }
+        // Queries and stored beliefs are non-negative, so a ratio of 0 is the floor of the minimum: once every query of the tile has
+        // hit a state of the support where it is zero -- the rule: two beliefs of a 22 021-state model rarely nest -- the rest of the list
+        // cannot change the result.  (A NaN query, the 0/0 successor of an impossible observation, never reaches 0 and walks the whole
+        // list unless the caller passes the masses, which mark it as not live.)  s_hit collects, per query of the tile, "some thread holds a 0".
+        if (threadIdx.x == 0) s_hit = 0u;
+        __syncthreads();
+        const unsigned full = (1u << SAW_QT) - 1u;
+        for (int j0 = 0; j0 < cnt; j0 += 256 * 4) {
 #pragma unroll
-            for (int k = 0; k < SAW_QT; k++)
-                if (q0 + k < nQ) r[k] = fmin(r[k], queries[(size_t)(q0 + k) * S + s] / b);
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u * 256 + threadIdx.x;
+                if (j < cnt) {
+                    const int s = li[j];
+                    const double b = lv[j];
+#pragma unroll
+                    for (int k = 0; k < SAW_QT; k++)
+                        if ((live >> k) & 1u) r[k] = fmin(r[k], queries[(size_t)(q0 + k) * S + s] / b);
+                }
+            }
+            unsigned hit = ~live & full;
+#pragma unroll
+            for (int k = 0; k < SAW_QT; k++) hit |= (r[k] == 0.0) ? (1u << k) : 0u;
+            hit = __reduce_or_sync(0xffffffffu, hit);
+            if ((threadIdx.x & 31) == 0 && hit) atomicOr(&s_hit, hit);
+            __syncthreads();
+            const bool done = s_hit == full;
+            __syncthreads();
+            if (done) break;
         }
 #pragma unroll
         for (int k = 0; k < SAW_QT; k++) {
@@ -138,6 +166,73 @@ __global__ void __launch_bounds__(256) reward_dot_kernel(const double* __restric
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
     if (lane == 0) rb[a] = part;
+}
+
+// scores[j][v] = rows[j] . alphas[v] for a FEW rows (the A*O successors of one belief) against all alphas, straight from the row-major
+// alphas: block = 8 alphas x 8 rows, thread t owns the states t, t + 256, ... (coalesced loads of both operands), 64 accumulators, fixed
+// reduction tree.  The score kernel would run this shape on two SMs (one z, one belief tile: a tile walks its ~1400 pipeline stages
+// alone, 0.7 ms); here V / 8 * ceil(n / 8) blocks share the work.  few_rows_max_kernel then takes max_v per row (np.max semantics: NaN wins).
+constexpr int FR_A = 8, FR_B = 8;
+
+__global__ void __launch_bounds__(256) few_rows_scores_kernel(const double* __restrict__ rows, int n, const double* __restrict__ alphas, int nV, int S,
+                                                              double* __restrict__ scores) {
+    __shared__ double sh[8][FR_A * FR_B];
+    const int v0 = blockIdx.x * FR_A, j0 = blockIdx.y * FR_B;
+    double acc[FR_A][FR_B];
+#pragma unroll
+    for (int a = 0; a < FR_A; a++)
+#pragma unroll
+        for (int b = 0; b < FR_B; b++) acc[a][b] = 0.0;
+    for (int s = threadIdx.x; s < S; s += 256) {
+        double av[FR_A], bv[FR_B];
+#pragma unroll
+        for (int a = 0; a < FR_A; a++) av[a] = (v0 + a < nV) ? alphas[(size_t)(v0 + a) * S + s] : 0.0;
+#pragma unroll
+        for (int b = 0; b < FR_B; b++) bv[b] = (j0 + b < n) ? rows[(size_t)(j0 + b) * S + s] : 0.0;
+#pragma unroll
+        for (int a = 0; a < FR_A; a++)
+#pragma unroll
+            for (int b = 0; b < FR_B; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < FR_A; a++)
+#pragma unroll
+        for (int b = 0; b < FR_B; b++) {
+            double x = acc[a][b];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][a * FR_B + b] = x;
+        }
+    __syncthreads();
+    if (threadIdx.x < FR_A * FR_B) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w][threadIdx.x];
+        const int a = threadIdx.x / FR_B, b = threadIdx.x % FR_B;
+        if (v0 + a < nV && j0 + b < n) scores[(size_t)(j0 + b) * nV + v0 + a] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) few_rows_max_kernel(const double* __restrict__ scores, int nV, double* __restrict__ out) {
+    __shared__ double sh[8];
+    __shared__ int snan;
+    const double* r = scores + (size_t)blockIdx.x * nV;
+    if (threadIdx.x == 0) snan = 0;
+    __syncthreads();
+    double m = -INFINITY;
+    for (int v = threadIdx.x; v < nV; v += 256) {
+        const double x = r[v];
+        if (x != x) snan = 1;
+        m = fmax(m, x);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = -INFINITY;
+        for (int w = 0; w < 8; w++) t = fmax(t, sh[w]);
+        out[blockIdx.x] = snan ? __longlong_as_double(0x7ff8000000000000ll) : t;
+    }
 }
 
 struct HsviOut {
@@ -220,13 +315,13 @@ extern "C" int pbvi_support_lists(pbvi_model* m, const double* d_rows, int n, co
 namespace pbvi {
 // upper bounds of n_q query rows over the stored beliefs given as support lists; scratch from the arena (no reset here)
 static int sawtooth_lists_impl(pbvi_model* m, const double* d_corner, const int32_t* d_idx, const double* d_val, const int32_t* d_count,
-                               const double* d_dot, const double* d_ub_values, int n_ub, const double* d_queries, int n_q, double* d_out,
-                               cudaStream_t st) {
+                               const double* d_dot, const double* d_ub_values, int n_ub, const double* d_queries, int n_q,
+                               const double* d_query_mass, double* d_out, cudaStream_t st) {
     PBVI_TAKE(terms, double, (size_t)n_q * (n_ub + 1));
     PBVI_TAKE(v0, double, (size_t)n_q);
     sawtooth_v0_terms_kernel<<<n_q, 256, 0, st>>>(d_corner, d_queries, m->S, n_ub, v0, terms);
     if (n_ub > 0)
-        sawtooth_lists_kernel<<<n_ub, 256, 0, st>>>(d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_queries, n_q, m->S, v0, terms);
+        sawtooth_lists_kernel<<<n_ub, 256, 0, st>>>(d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_queries, n_q, m->S, v0, d_query_mass, terms);
     row_min_lists_kernel<<<ceil_div(n_q, 128), 128, 0, st>>>(terms, n_q, n_ub + 1, d_out);
     m->last_launches += 3;
     PBVI_CUDA(cudaGetLastError());
@@ -244,7 +339,7 @@ extern "C" int pbvi_sawtooth_lists(pbvi_model* m, const double* d_corner, const 
     PBVI_CUDA(cudaSetDevice(m->device));
     m->arena.reset();
     m->last_launches = 0;
-    return sawtooth_lists_impl(m, d_corner, d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_queries, n_q, d_out, (cudaStream_t)stream);
+    return sawtooth_lists_impl(m, d_corner, d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_queries, n_q, nullptr, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d_alphas, int nV, double gamma, const double* d_corner,
@@ -270,10 +365,13 @@ extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d
     PBVI_TRY(belief_successors_impl(m, d_b, 1, 1, d_succ, d_mass, st));
     PBVI_TRY(row_hash_launch(m, d_succ, nZ, S, reinterpret_cast<uint64_t*>(keys), st));
     PBVI_TRY(row_hash_launch(m, d_b, 1, S, reinterpret_cast<uint64_t*>(keys + (size_t)nZ * 2), st));
-    PBVI_TRY(sawtooth_lists_impl(m, d_corner, d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_succ, nZ, upper, st));
+    PBVI_TRY(sawtooth_lists_impl(m, d_corner, d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_succ, nZ, d_mass, upper, st));
     reward_dot_kernel<<<ceil_div(m->A * 32, 256), 256, 0, st>>>(d_b, m->rbarNzPtr, m->rbarNzIdx, m->rbarNzVal, m->A, rb);
     m->last_launches++;
-    PBVI_TRY(max_values_impl(m, d_succ, nZ, d_alphas, nV, lower, nullptr, st));
+    PBVI_TAKE(scores, double, (size_t)nZ * nV);
+    few_rows_scores_kernel<<<dim3(ceil_div(nV, FR_A), ceil_div(nZ, FR_B)), 256, 0, st>>>(d_succ, nZ, d_alphas, nV, S, scores);
+    few_rows_max_kernel<<<nZ, 256, 0, st>>>(scores, nV, lower);
+    m->last_launches += 2;
     hsvi_choose_kernel<<<1, 256, (size_t)nZ * sizeof(double), st>>>(d_mass, upper, lower, keys, keys + (size_t)nZ * 2, rb,
                                                                     reinterpret_cast<unsigned long long*>(d_stored_keys), d_stored_vals, n_stored,
                                                                     stored_capacity, m->A, m->O, gamma, conv_term, may_continue, outDev);

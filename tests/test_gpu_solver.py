@@ -302,8 +302,14 @@ def test_small_model_path_equals_general_pipeline(tag):
         solver.SMALL_PATH = False
         general = solver.backup(model, bs, vf, append=append, belief_dominance_prune=False)
         a, b = small.numpy(), general.numpy()
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-        assert np.array_equal(small.row_hashes, general.row_hashes)
+        assert a[0].shape == b[0].shape and np.array_equal(a[1], b[1])
+        if model.reachable_state_count == 1:
+            assert np.array_equal(a[0], b[0]) and np.array_equal(small.row_hashes, general.row_hashes)
+        else:
+            # R > 1: the general pipeline skips zero-probability terms of the r-sum, the fused kernel adds them as +-0.0; a sum that is
+            # zero can differ in the sign of the zero (the reference's einsum order is not reproducible for R > 1 either)
+            np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=0.0)
+            assert np.array_equal(np.abs(a[0]), np.abs(b[0])), float(np.max(np.abs(a[0] - b[0])))
     # beyond the size limit the general pipeline runs
     assert not model.device.backup_small_eligible(20000, 4096)
 

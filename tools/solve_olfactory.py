@@ -1,7 +1,7 @@
 """
 Full solves of the 22021-state olfactory POMDP in the as-published shapes:
     FSVI, 300 expansions x 100 beliefs, gamma 0.99, eps 1e-6   (reference: 2983.5 s NumPy CPU, 204.9 s CuPy GPU)
-    python tools/solve_olfactory.py [flavour] [expansions] [growth]
+    python tools/solve_olfactory.py [flavour] [expansions] [growth] [full] [update_passes]
 Prints the reference-format summary plus wall time split into expand / backup / change / other.
 """
 import json
@@ -45,12 +45,14 @@ def main():
     solver.compute_change = timed_change
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    kw = dict(full_backup=True) if flavour == 'perseus' and len(sys.argv) > 4 else {}
+    kw = dict(full_backup=True) if len(sys.argv) > 4 and sys.argv[4] == 'full' else {}
+    if len(sys.argv) > 5:
+        kw['update_passes'] = int(sys.argv[5])
     vf, hist = solver.solve(model, expansions=expansions, max_belief_growth=growth, print_progress=False, **kw)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     print(hist.summary)
-    pairs = sum(b * v for b, v in zip(np.diff(hist.beliefs_counts) if not hist.expand_append else hist.beliefs_counts[1:], hist.alpha_vector_counts[:-1]))
+    pairs = sum(b * v for b, v in zip(np.diff(hist.beliefs_counts) if not hist.expand_append else hist.beliefs_counts[1:], hist.alpha_vector_counts[:-1])) if 'update_passes' not in kw else 0
     out = dict(flavour=flavour, expansions=len(hist.expansion_times), growth=growth, wall_s=wall, expand_s=sum(hist.expansion_times),
                backup_s=sum(hist.backup_times), change_s=change_s[0], final_alphas=len(vf), final_beliefs=hist.beliefs_counts[-1],
                backup_pairs=float(pairs), backup_pairs_per_s=float(pairs) / max(sum(hist.backup_times), 1e-9),
