@@ -704,6 +704,9 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
                              the Perseus scheme -- a belief set collected by random walks (12 000 walk steps; > 10 000 distinct beliefs,
                              north_star: ">= 10k belief points"), then repeated backups of the WHOLE set (`update_passes` is the
                              reference's own parameter, src/pomdp.py:2172-2186), each followed by compute_change.
+      pbvi_full_backup_fsvi_200x100  classic PBVI: PBVI_Solver('fsvi').solve(expansions=200, max_belief_growth=100, full_backup=True) -- FSVI
+                             exploration, but EVERY expansion backs up the whole belief set (8 437 beliefs at the end, 2.5e9 pairs): the
+                             solve whose time is in the phases that shard.
     At N > 1 the loop is sharded over the ranks (`solve(group=True)`).
     """
     from pomdp_pbvi_exploration_b200 import FSVI_Solver, PBVI_Solver
@@ -724,6 +727,12 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
                           full_backup=True, update_passes=15, **shard)
     s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
     out['perseus_full_10k'] = s
+    gpu_warm(model.device.device)
+    seed_all(0)
+    _, _, s = timed_solve(PBVI_Solver(gamma=GAMMA, eps=1e-6, expand_function='fsvi'), model, expansions=200, max_belief_growth=100,
+                          full_backup=True, **shard)
+    s['wall_s'], s['expand_s'], s['backup_s'], s['change_s'] = reduce_max([s['wall_s'], s['expand_s'], s['backup_s'], s['change_s']])
+    out['pbvi_full_backup_fsvi_200x100'] = s
     out['n_gpus'] = world
     out['note'] = ('expansions draw on the host RNG and are sequential in the belief (b_{t+1} depends on o_t): they run on rank 0 and are '
                    'broadcast; backups and compute_change are sharded')

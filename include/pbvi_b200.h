@@ -215,19 +215,20 @@ PBVI_API int pbvi_sawtooth_lists(pbvi_model* m, const double* d_corner, const in
                                  void* stream);
 
 /* ---- one level of HSVI's exploration (PBVI_Solver.expand_hsvi, src/pomdp.py:1803-1855) in one call, one synchronisation ---------------
- * For the belief d_b: all A*O successors (d_succ [A][O][S], NaN rows for impossible observations) and masses P(o|b,a) (d_mass [A][O]);
+ * For the belief d_b: all A*O successors (d_succ [A][O][S], NaN rows for impossible observations) and masses P(o|b,a) (d_mass [A][O]; both
+ * nullable: scratch is used when the caller does not want them);
  * their upper bounds -- the stored value when the successor's 128-bit key is among d_stored_keys [n_stored][2] (:884-885), else the
  * sawtooth over the n_ub stored beliefs of the support lists (the arrays as of the last BeliefValueMapping.update, :866-871) --;
  * Q(a) = b.Rbar[:,a] + gamma * sum_o P(o|b,a) * upper(a,o) and a = its first argmax (:1807-1821); max_v alpha_v . successor as the lower
  * bound; o = first argmax of P(o|b,a) * (upper - lower) (:1826-1842); observations of probability zero are skipped.  When may_continue
  * != 0, upper - lower >= conv_term and key(b) is not stored yet, (key(b), Q(a)) is appended at index n_stored of the stored arrays
- * (:1849).  h_out8 receives {best_a, best_o, Q(a), upper - lower} as doubles followed by {added, key0(b), key1(b), #possible (a,o)} as
+ * (:1849).  d_next [S] (nullable) receives the chosen successor update(b, a, o) -- b itself when no observation is possible.  h_out8 receives {best_a, best_o, Q(a), upper - lower} as doubles followed by {added, key0(b), key1(b), #possible (a,o)} as
  * int64.  Synchronises `stream`. */
 PBVI_API int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d_alphas, int nV, double gamma, const double* d_corner,
                              const int32_t* d_idx, const double* d_val, const int32_t* d_count, const double* d_dot,
                              const double* d_ub_values, int n_ub, uint64_t* d_stored_keys, double* d_stored_vals, int n_stored,
-                             int stored_capacity, double conv_term, int may_continue, double* d_succ, double* d_mass, double* h_out8,
-                             void* stream);
+                             int stored_capacity, double conv_term, int may_continue, double* d_next, double* d_succ, double* d_mass,
+                             double* h_out8, void* stream);
 
 /* ---- SSEA novelty score (src/pomdp.py:1682-1686) --------------------------------------------------
  * d_out[j] = min_i || d_beliefs[i] - d_candidates[j] ||_2 */

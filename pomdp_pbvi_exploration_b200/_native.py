@@ -52,7 +52,7 @@ SIGNATURES = {
     'pbvi_sawtooth': [_P, _P, _P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_support_lists': [_P, _P, c_int, _P, _P, _P, _P, _P, _P],
     'pbvi_sawtooth_lists': [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P],
-    'pbvi_hsvi_level': [_P, _P, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, c_int, _P, _P, _P, _P],
+    'pbvi_hsvi_level': [_P, _P, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_double, c_int, _P, _P, _P, _P, _P],
     'pbvi_min_l2_distance': [_P, _P, c_int, _P, c_int, _P, _P],
     'pbvi_ger_scores': [_P, _P, _P, _P, c_int, c_double, c_double, _P, _P],
     'pbvi_comm_unique_id': [_P],
@@ -475,17 +475,21 @@ class DeviceModel:
         return out
 
     def hsvi_level(self, b: torch.Tensor, alphas: torch.Tensor, gamma: float, corner, idx, val, count, dot, ub_values, n_ub: int,
-                   stored_keys, stored_vals, n_stored: int, conv_term: float, may_continue: bool):
-        """One level of HSVI's exploration (`pbvi_hsvi_level`): returns (successors [A,O,S], masses [A,O], (best_a, best_o, Q, upper - lower),
-        (added, key0, key1, n_possible))."""
-        al = self._beliefs(alphas)
-        succ = torch.empty((self.A, self.O, self.S), dtype=torch.float64, device=self.device)
-        mass = torch.empty((self.A, self.O), dtype=torch.float64, device=self.device)
+                   stored_keys, stored_vals, n_stored: int, conv_term: float, may_continue: bool, next_out: torch.Tensor | None = None,
+                   want_successors: bool = True):
+        """One level of HSVI's exploration (`pbvi_hsvi_level`): returns (successors [A,O,S] | None, masses [A,O] | None,
+        (best_a, best_o, Q, upper - lower), (added, key0, key1, n_possible)); the chosen successor is written into `next_out` [S]."""
+        al = alphas if (isinstance(alphas, torch.Tensor) and alphas.is_cuda and alphas.is_contiguous() and alphas.dtype == torch.float64) else self._beliefs(alphas)
+        succ = mass = None
+        if want_successors:
+            succ = torch.empty((self.A, self.O, self.S), dtype=torch.float64, device=self.device)
+            mass = torch.empty((self.A, self.O), dtype=torch.float64, device=self.device)
         out = np.empty(8, dtype=np.float64)
         cap = 0 if stored_keys is None else stored_keys.shape[0]
         self._call(self._lib.pbvi_hsvi_level(self._h, _ptr(b), _ptr(al), al.shape[0], float(gamma), _ptr(corner), _ptr(idx), _ptr(val), _ptr(count),
                                              _ptr(dot), _ptr(ub_values), int(n_ub), _ptr(stored_keys), _ptr(stored_vals), int(n_stored), int(cap),
-                                             float(conv_term), int(bool(may_continue)), _ptr(succ), _ptr(mass), out.ctypes.data, self._stream))
+                                             float(conv_term), int(bool(may_continue)), _ptr(next_out), _ptr(succ), _ptr(mass), out.ctypes.data,
+                                             self._stream))
         return succ, mass, out[:4], out[4:].view(np.int64)
 
     def min_l2_distance(self, beliefs, candidates) -> torch.Tensor:

@@ -295,6 +295,15 @@ __global__ void __launch_bounds__(256) hsvi_choose_kernel(const double* __restri
     out->added = added; out->key0 = (long long)b0; out->key1 = (long long)b1; out->n_possible = nPossible;
 }
 
+// next[s] = the chosen successor (b itself when no observation is possible), picked with the indices the choose kernel left on the device
+__global__ void __launch_bounds__(256) hsvi_take_next_kernel(const double* __restrict__ succ, const double* __restrict__ b, const HsviOut* __restrict__ res,
+                                                             int O, int S, double* __restrict__ next) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= S) return;
+    const int a = (int)res->best_a, o = (int)res->best_o;
+    next[s] = (a >= 0 && o >= 0) ? succ[((size_t)a * O + o) * S + s] : b[s];
+}
+
 }  // namespace pbvi
 
 using namespace pbvi;
@@ -345,10 +354,10 @@ extern "C" int pbvi_sawtooth_lists(pbvi_model* m, const double* d_corner, const 
 extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d_alphas, int nV, double gamma, const double* d_corner,
                                const int32_t* d_idx, const double* d_val, const int32_t* d_count, const double* d_dot,
                                const double* d_ub_values, int n_ub, uint64_t* d_stored_keys, double* d_stored_vals, int n_stored,
-                               int stored_capacity, double conv_term, int may_continue, double* d_succ, double* d_mass, double* h_out8,
-                               void* stream) {
+                               int stored_capacity, double conv_term, int may_continue, double* d_next, double* d_succ, double* d_mass,
+                               double* h_out8, void* stream) {
     PBVI_REQUIRE(m != nullptr, "model handle is NULL");
-    PBVI_REQUIRE(d_b && d_alphas && d_corner && d_succ && d_mass && h_out8, "NULL pointer argument");
+    PBVI_REQUIRE(d_b && d_alphas && d_corner && h_out8, "NULL pointer argument");
     PBVI_REQUIRE(nV > 0 && n_ub >= 0 && n_stored >= 0 && stored_capacity >= n_stored, "bad counts");
     PBVI_REQUIRE(n_ub == 0 || (d_idx && d_val && d_count && d_dot && d_ub_values), "support lists are required when n_ub > 0");
     PBVI_REQUIRE(n_stored == 0 || stored_capacity == 0 || (d_stored_keys && d_stored_vals), "stored key / value arrays are required");
@@ -362,6 +371,8 @@ extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d
     PBVI_TAKE(lower, double, (size_t)nZ);
     PBVI_TAKE(rb, double, (size_t)m->A);
     PBVI_TAKE(outDev, HsviOut, 1);
+    if (!d_succ) { d_succ = m->arena.take<double>((size_t)nZ * S); if (!d_succ) return PBVI_ERR_OOM; }     // the caller does not want the block
+    if (!d_mass) { d_mass = m->arena.take<double>((size_t)nZ); if (!d_mass) return PBVI_ERR_OOM; }
     PBVI_TRY(belief_successors_impl(m, d_b, 1, 1, d_succ, d_mass, st));
     PBVI_TRY(row_hash_launch(m, d_succ, nZ, S, reinterpret_cast<uint64_t*>(keys), st));
     PBVI_TRY(row_hash_launch(m, d_b, 1, S, reinterpret_cast<uint64_t*>(keys + (size_t)nZ * 2), st));
@@ -376,6 +387,10 @@ extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d
                                                                     reinterpret_cast<unsigned long long*>(d_stored_keys), d_stored_vals, n_stored,
                                                                     stored_capacity, m->A, m->O, gamma, conv_term, may_continue, outDev);
     m->last_launches++;
+    if (d_next) {
+        hsvi_take_next_kernel<<<ceil_div(S, 256), 256, 0, st>>>(d_succ, d_b, outDev, m->O, S, d_next);
+        m->last_launches++;
+    }
     PBVI_CUDA(cudaGetLastError());
     PBVI_CUDA(cudaMemcpyAsync(h_out8, outDev, sizeof(HsviOut), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));

@@ -712,18 +712,22 @@ class PBVI_Solver:
         if conv_term is None:
             conv_term = self.eps
         chosen = []
-        V = value_function.alpha_vector_array
+        V = value_function.alpha_vector_array.contiguous()
+        # the chosen successors of all levels land in one buffer, written by the level call itself (no allocation, no copy per level)
+        chain = torch.empty((max(int(max_generation), 1), model.state_count), dtype=torch.float64, device=dev.device)
+        level = 0
         while True:
             conv_term /= self.gamma
             idx, val, count, dot, vals, n_ub = ub._arrays()
             n_stored = len(ub.beliefs)
             ub._reserve(n_stored + 1)
             may_continue = max_generation > 1
-            succ, mass, res, meta = dev.hsvi_level(b.values, V, self.gamma, ub.corner_values, idx, val, count, dot, vals, n_ub,
-                                                   ub._keys_dev, ub._vals_dev, n_stored, conv_term, may_continue)
+            _, _, res, meta = dev.hsvi_level(b.values, V, self.gamma, ub.corner_values, idx, val, count, dot, vals, n_ub,
+                                             ub._keys_dev, ub._vals_dev, n_stored, conv_term, may_continue, next_out=chain[level],
+                                             want_successors=False)
             best_a, best_o, max_qv, best_v_diff = int(res[0]), int(res[1]), float(res[2]), float(res[3])
-            # own storage for the chosen successor: a view would keep the whole [A,O,S] successor block of every level alive
-            next_b = b if best_o < 0 else Belief._from_device(model, succ[best_a, best_o].clone())
+            next_b = b if best_o < 0 else Belief._from_device(model, chain[level])
+            level += 1
             if best_v_diff < conv_term or not may_continue:
                 chosen.append(next_b)
                 break

@@ -306,10 +306,10 @@ def test_small_model_path_equals_general_pipeline(tag):
         if model.reachable_state_count == 1:
             assert np.array_equal(a[0], b[0]) and np.array_equal(small.row_hashes, general.row_hashes)
         else:
-            # R > 1: the general pipeline skips zero-probability terms of the r-sum, the fused kernel adds them as +-0.0; a sum that is
-            # zero can differ in the sign of the zero (the reference's einsum order is not reproducible for R > 1 either)
-            np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=0.0)
-            assert np.array_equal(np.abs(a[0]), np.abs(b[0])), float(np.max(np.abs(a[0] - b[0])))
+            # R > 1: the reference's own value functions hold rows that differ by an ulp (its einsum r-order is not reproducible,
+            # SURVEY 8a); the two pipelines sum the scores in different orders and may resolve such a near-tie to either twin, so the
+            # rows agree to the last few bits, not bytewise (contract: 1e-9)
+            np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-15)
     # beyond the size limit the general pipeline runs
     assert not model.device.backup_small_eligible(20000, 4096)
 
@@ -363,8 +363,10 @@ def test_hsvi_level_equals_host_driven_level(ppu, n_store):
         idx, val, count, dot, vals, n_cover = ub._arrays()
         n_before = len(ub.beliefs)
         ub._reserve(n_before + 1)
+        nxt = torch.empty((model.state_count,), dtype=torch.float64, device=dev.device)
         s2, m2, res, meta = dev.hsvi_level(b.values, vf.alpha_vector_array, gamma, ub.corner_values, idx, val, count, dot, vals, n_cover,
-                                           ub._keys_dev, ub._vals_dev, n_before, conv_term=-1.0, may_continue=True)
+                                           ub._keys_dev, ub._vals_dev, n_before, conv_term=-1.0, may_continue=True, next_out=nxt)
+        assert torch.equal(nxt, succ[best_a, best_o])
         assert torch.equal(s2.reshape(-1), succ.reshape(-1)) or np.array_equal(s2.cpu().numpy(), succ.cpu().numpy(), equal_nan=True)
         assert np.array_equal(m2.cpu().numpy(), probs)
         assert (int(res[0]), int(res[1])) == (best_a, best_o)

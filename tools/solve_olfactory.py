@@ -26,7 +26,8 @@ def main():
     model.device                                   # create the handle outside the timed region (the reference times solve() only)
     np.random.seed(0)
     random.seed(0)
-    if flavour == 'fsvi':
+    full = len(sys.argv) > 4 and sys.argv[4] == 'full'
+    if flavour == 'fsvi' and not full:
         solver = FSVI_Solver(gamma=0.99, eps=1e-6)
     elif flavour == 'hsvi':
         solver = HSVI_Solver(gamma=0.99, eps=1e-6)
@@ -48,7 +49,12 @@ def main():
     kw = dict(full_backup=True) if len(sys.argv) > 4 and sys.argv[4] == 'full' else {}
     if len(sys.argv) > 5:
         kw['update_passes'] = int(sys.argv[5])
+    if os.environ.get('PBVI_CPROFILE'):
+        import cProfile, pstats, io
+        pr = cProfile.Profile(); pr.enable()
     vf, hist = solver.solve(model, expansions=expansions, max_belief_growth=growth, print_progress=False, **kw)
+    if os.environ.get('PBVI_CPROFILE'):
+        pr.disable(); st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats('tottime').print_stats(22); print(st.getvalue()[:5000])
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     print(hist.summary)
