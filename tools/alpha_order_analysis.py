@@ -3,6 +3,10 @@ How much alpha-side work would a better COLUMN ORDER of the value function save?
 quarter) when no alpha of the quarter is non-zero on the states the chunk lands on; which alphas share a quarter is just their order.
 Proxy: live (chunk, quarter) cells of the alpha pattern itself (identity landing), for several orderings of the late value function.
     python tools/alpha_order_analysis.py
+Result (round 2): on the late value function the proxy drops from 42.9 % (identity) to 30.1 % (sorted by the first non-zero state; a greedy
+union clustering: 28.6 %) -- but the flops the score kernel actually executes only fell by 6 % when the select path sorted its columns that
+way (7.43e11 -> 6.98e11; kernel 22.5 -> 21.7 ms), because most of the alpha cells that disappear lie where the beliefs are zero anyway, and
+the two extra passes over the alphas cost 0.5 ms per call (young value function: 3.5 -> 4.1 ms per step).  The re-ordering was dropped.
 """
 import os
 import sys
