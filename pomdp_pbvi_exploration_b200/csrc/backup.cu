@@ -17,13 +17,10 @@
 //                             reference's operation order, no FMA contraction, 128-bit row keys accumulated on the way
 #include <algorithm>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "score_kernel.cuh"
 
 namespace pbvi {
 
-constexpr int REORDER_MIN_BELIEFS = 512;               // select / max_values calls with at least this many beliefs re-order the alpha columns
 constexpr int MASK_COLS = 256;                         // states per belief_mask_kernel block
 constexpr int MASK_SLABS = MASK_COLS / 32;             // 32-state slabs (one warp load per row)
 constexpr int MASK_CHUNKS = MASK_COLS / KC;            // chunks per block
@@ -31,16 +28,14 @@ static_assert(NRG == 4 && RG == 16 && 32 % KC == 0 && MASK_SLABS % 2 == 0, "beli
 static_assert(BN == 256 && NCW == 4, "alpha_row_mask_kernel: four 64-column quarters per alpha tile");
 
 // ---- alphas [V][S] -> alphaT [S][Vp], zero in the pad columns ---------------------------------------------------
-//      colOrig (nullable): column j holds alpha colOrig[j] (columns re-ordered by support, see alpha_first_nz_kernel)
-__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out,
-                                                        const int32_t* __restrict__ colOrig) {
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, int V, int S, int Vp, double* __restrict__ out) {
     __shared__ double tile[32][33];
     const int v0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int v = v0 + ty + j * 8, s = s0 + tx;
-        tile[ty + j * 8][tx] = (v < V && s < S) ? in[(size_t)(colOrig ? colOrig[v] : v) * S + s] : 0.0;
+        tile[ty + j * 8][tx] = (v < V && s < S) ? in[(size_t)v * S + s] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -50,86 +45,12 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
     }
 }
 
-int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st, const int32_t* colOrig) {
+int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st) {
     dim3 grid(ceil_div(Vp, 32), ceil_div(m->S, 32));
-    transpose_kernel<<<grid, 256, 0, st>>>(d_alphas, nV, m->S, Vp, d_alphaT, colOrig);
+    transpose_kernel<<<grid, 256, 0, st>>>(d_alphas, nV, m->S, Vp, d_alphaT);
     m->last_launches++;
     PBVI_CUDA(cudaGetLastError());
     return PBVI_OK;
-}
-
-// ---- column order of the value function.  The score kernel skips a (chunk, 64-alpha column quarter) when NO alpha of the quarter is
-//      non-zero on the states the chunk lands on -- which alphas share a quarter is only a matter of their order.  Alpha vectors of a
-//      goal-reward model are blobs around the goal whose extent grows with the backup that produced them; sorted by the FIRST state at
-//      which they are non-zero, alphas with similar supports become neighbours (late value function of the bench: live (chunk, quarter)
-//      cells 42.9 % -> 30.1 %; a greedy union clustering reaches 28.6 %: tools/alpha_order_analysis.py).  Young value functions are
-//      already well ordered by construction (consecutive backups of one walk), so BOTH orders are scored exactly -- live cells at chunk
-//      granularity, one pass over the alphas each -- and the better one is taken, on the device.  The dot products do not depend on the
-//      column order (same terms, same order along the states), so every score, hence v*, is bit-identical; the fused argmax reports
-//      original indices and breaks ties on them (score_kernel.cuh).
-__global__ void __launch_bounds__(256) alpha_first_nz_kernel(const double* __restrict__ alphas, int V, int S, uint32_t* __restrict__ firstNz,
-                                                             int32_t* __restrict__ iota) {
-    const int v = blockIdx.x;
-    const double* row = alphas + (size_t)v * S;
-    int found = S;
-    for (int s0 = 0; s0 < S; s0 += 256) {
-        const int s = s0 + threadIdx.x;
-        const bool nz = s < S && row[s] != 0.0;
-        if (__syncthreads_or(nz)) {
-            // some thread of this slab holds the first non-zero: block minimum over the slab
-            __shared__ int smin;
-            if (threadIdx.x == 0) smin = S;
-            __syncthreads();
-            if (nz) atomicMin(&smin, s);
-            __syncthreads();
-            found = smin;
-            break;
-        }
-    }
-    if (threadIdx.x == 0) { firstNz[v] = (uint32_t)found; iota[v] = v; }
-}
-
-// live (4-state chunk, 64-alpha quarter) cells of the alpha pattern in a given column order; block = one quarter x a slab of 2048 states
-__global__ void __launch_bounds__(256) alpha_live_cells_kernel(const double* __restrict__ alphas, const int32_t* __restrict__ order, int V, int S,
-                                                               unsigned long long* __restrict__ cells) {
-    const int q = blockIdx.x, s0 = blockIdx.y * 2048;
-    bool live[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) live[u] = false;
-    for (int j = 0; j < 64; j++) {
-        const int col = q * 64 + j;
-        if (col >= V) break;
-        const double* row = alphas + (size_t)(order ? order[col] : col) * S;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int s = s0 + u * 256 + threadIdx.x;
-            live[u] |= s < S && row[s] != 0.0;
-        }
-    }
-    int n = 0;
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-        // a chunk = 4 consecutive states = 4 consecutive lanes
-        const unsigned bal = __ballot_sync(0xffffffffu, live[u]);
-        if ((threadIdx.x & 3) == 0) n += ((bal >> (threadIdx.x & 31)) & 0xFu) ? 1 : 0;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(cells, (unsigned long long)n);
-}
-
-// colOrig = the sorted order if it has fewer live cells than the given order, else the identity
-__global__ void __launch_bounds__(256) alpha_pick_order_kernel(const int32_t* __restrict__ sorted, const unsigned long long* __restrict__ cells, int V,
-                                                               int Vp, int32_t* __restrict__ colOrig) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= Vp) return;
-    const bool useSorted = cells[1] < cells[0];
-    colOrig[j] = j < V ? (useSorted ? sorted[j] : j) : j;
-}
-
-__global__ void __launch_bounds__(256) iota_kernel(int32_t* __restrict__ out, int n) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j < n) out[j] = j;
 }
 
 // ---- bits[mt][c]: bit g set iff some belief of row group g of tile mt is non-zero on chunk c.  The same pass writes
@@ -278,7 +199,10 @@ __global__ void __launch_bounds__(256) combine_tiles_kernel(const double* __rest
     if (i >= n) return;
     double best = pval[i];
     int idx = pidx[i];
-    for (int t = 1; t < nNt; t++) argmax_combine(best, idx, pval[(size_t)t * n + i], pidx[(size_t)t * n + i]);     // indices are ORIGINAL alpha indices
+    for (int t = 1; t < nNt; t++) {
+        const int id = pidx[(size_t)t * n + i];
+        if (id != ARG_NONE) argmax_append(best, idx, pval[(size_t)t * n + i], id);
+    }
     if (rowBad[i / (size_t)nZ]) { best = __longlong_as_double(0x7ff8000000000000ll); idx = 0; }
     if (outVal) outVal[i] = best;
     if (outIdx) outIdx[i] = min(max(idx, 0), nV - 1);
@@ -817,31 +741,8 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
 
     // S + 1 rows: row S is all zero.  The pad states of the last pipeline stage (S is rounded up to whole stages) gather THAT row, so
     // their contribution is 0 * 0 whatever the alphas hold (a pad that re-read a real row would turn an infinite alpha into NaN).
-    // column order (see alpha_first_nz_kernel): worth two extra passes over the alphas only when there is enough belief-side work
-    PBVI_TAKE(colOrig, int32_t, (size_t)Vp);
-    if (nB >= REORDER_MIN_BELIEFS && nV > 64) {
-        PBVI_TAKE(firstNz, uint32_t, (size_t)nV);
-        PBVI_TAKE(firstNzSorted, uint32_t, (size_t)nV);
-        PBVI_TAKE(iota, int32_t, (size_t)nV);
-        PBVI_TAKE(sorted, int32_t, (size_t)nV);
-        PBVI_TAKE(cells, unsigned long long, 2);
-        size_t sortBytes = 0;
-        PBVI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, firstNz, firstNzSorted, iota, sorted, nV, 0, 32, st));
-        PBVI_TAKE(sortTemp, char, sortBytes);
-        PBVI_CUDA(cudaMemsetAsync(cells, 0, 2 * sizeof(unsigned long long), st));
-        alpha_first_nz_kernel<<<nV, 256, 0, st>>>(d_alphas, nV, S, firstNz, iota);
-        PBVI_CUDA(cub::DeviceRadixSort::SortPairs(sortTemp, sortBytes, firstNz, firstNzSorted, iota, sorted, nV, 0, 32, st));   // stable: ties keep the original order
-        const dim3 lg(ceil_div(nV, 64), ceil_div(S, 2048));
-        alpha_live_cells_kernel<<<lg, 256, 0, st>>>(d_alphas, nullptr, nV, S, cells);
-        alpha_live_cells_kernel<<<lg, 256, 0, st>>>(d_alphas, sorted, nV, S, cells + 1);
-        alpha_pick_order_kernel<<<ceil_div(Vp, 256), 256, 0, st>>>(sorted, cells, nV, Vp, colOrig);
-        m->last_launches += 5;
-    } else {
-        iota_kernel<<<ceil_div(Vp, 256), 256, 0, st>>>(colOrig, Vp);
-        m->last_launches++;
-    }
     PBVI_TAKE(alphaT, double, (size_t)(S + 1) * Vp);
-    PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st, colOrig));
+    PBVI_TRY(transpose_alphas(m, d_alphas, nV, Vp, alphaT, st));
     PBVI_CUDA(cudaMemsetAsync(alphaT + (size_t)S * Vp, 0, (size_t)Vp * sizeof(double), st));
 
     PBVI_TAKE(bits, uint8_t, (size_t)nMt * nC);
@@ -885,7 +786,7 @@ static int score_argmax(pbvi_model* m, const double* d_beliefs, int nB, const do
 
     if (m->profile) PBVI_CUDA(cudaEventRecord(m->evScore0, st));
     ScoreParams p{};
-    p.beliefsP = beliefsP; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats; p.colOrig = colOrig;
+    p.beliefsP = beliefsP; p.lists = lists; p.listCount = counts; p.pval = pval; p.pidx = pidx; p.stats = m->d_stats;
     p.nB = nB; p.S = S; p.Sp = m->Sp; p.V = nV; p.Vp = Vp; p.nChunks = nC; p.nStages = nC / SUB; p.nZ = nZ; p.O = m->O;
     if (!backup) {
         p.bmat = alphaT; p.zStrideB = 0; p.zOrder = nullptr;

@@ -163,7 +163,7 @@ struct pbvi_model {
 
 namespace pbvi {
 // implemented in backup.cu, used by other translation units
-int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st, const int32_t* colOrig = nullptr);
+int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, double* d_alphaT, cudaStream_t st);
 // per-device function attributes (dynamic shared memory opt-ins) of each translation unit; pbvi_model_create calls them with the
 // handle's device current, so a second handle on another GPU of the same process is configured too
 // building blocks shared across translation units (none of them resets the arena: the calling entry point does)

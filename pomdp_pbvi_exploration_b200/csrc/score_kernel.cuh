@@ -71,8 +71,6 @@ struct ScoreParams {
     const uint2* lists;        // [nMt][nZ][nNt][nStages]  (stage index, flags): flags byte h = live row groups | live column quarters << 4 of chunk h
     const int32_t* listCount;  // [nMt][nZ][nNt]
     const int32_t* zOrder;     // [nzLaunch] z of queue position zi, heavy first (nullptr: identity)
-    const int32_t* colOrig;    // [Vp] original alpha index of column j of bmat (the columns may be re-ordered so that alphas with similar
-                               // supports share a column quarter; the argmax reports ORIGINAL indices and breaks ties on them)
     double* pval;              // [nNt * NCW][nB][nZ]  partial maxima per 64-column quarter, ascending columns
     int32_t* pidx;             // [nNt * NCW][nB][nZ]
     int* tileCounter;          // zeroed before the launch: next tile of the queue
@@ -308,7 +306,7 @@ __global__ void __launch_bounds__(SCORE_THREADS_TOTAL, 1) score_kernel(const Sco
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
                             const int col = cbase + n * 8 + j;
-                            if (col < p.V) argmax_combine(best, bidx, acc[i][n][j], p.colOrig[col]);
+                            if (col < p.V) argmax_append(best, bidx, acc[i][n][j], col);
                             acc[i][n][j] = 0.0;
                         }
 #pragma unroll
