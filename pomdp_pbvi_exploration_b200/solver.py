@@ -799,7 +799,7 @@ class PBVI_Solver:
         for i in range(n):
             # `np.random.choice(model.actions, size=1)` draws its index with `randint(0, len, size=1)`: the same call, without choice's
             # argument checks (half the host time of a long walk); `choice(observations, p=...)` consumes one `random_sample()`
-            acts[i] = int(model.actions[np.random.randint(0, n_actions, size=1)[0]])
+            acts[i] = int(model.actions[np.random.randint(0, n_actions)])
             us[i] = np.random.random_sample()
         return BeliefSet(model, dev.perseus_walk(b.values, acts, us))
 
