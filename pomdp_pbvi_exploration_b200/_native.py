@@ -218,20 +218,28 @@ class DeviceModel:
         return out, act, vstar, value
 
     def backup_small_eligible(self, n_beliefs: int, n_alphas: int) -> bool:
-        return bool(self._lib.pbvi_backup_small_eligible(self._h, int(n_beliefs), int(n_alphas)))
+        """Mirror of the library's size rule (`pbvi_backup_small_eligible`), kept on the host: this path is about microseconds."""
+        S, nZ = self.S, self.A * self.O
+        return (0 < n_beliefs <= 16384 and 0 < n_alphas <= 4096 and S <= 1024 and (1 + nZ) * S + self.A + nZ <= 5000 and
+                n_beliefs * S <= 262144 and float(n_beliefs) * n_alphas * nZ * S <= 6e7)
 
     def backup_small(self, beliefs: torch.Tensor, alphas: torch.Tensor, gamma: float):
         """Whole backup of a small problem in one library call (see `pbvi_backup_small`): returns (rows [n,S] CUDA tensor,
         actions [n] int64, row keys [n,2] int64) of the deduplicated new value function."""
-        b, al = self._beliefs(beliefs), self._beliefs(alphas)
+        def ready(t):
+            return isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.is_contiguous()
+        b = beliefs if ready(beliefs) else self._beliefs(beliefs)
+        al = alphas if ready(alphas) else self._beliefs(alphas)
         nB = b.shape[0]
         out = torch.empty((nB, self.S), dtype=torch.float64, device=self.device)
         acts = np.empty((nB,), dtype=np.int32)
         keys = np.empty((nB, 2), dtype=np.int64)
         n = c_int()
-        self._call(self._lib.pbvi_backup_small(self._h, _ptr(b), nB, _ptr(al), al.shape[0], float(gamma), _ptr(out), acts.ctypes.data,
-                                               keys.ctypes.data, byref(n), self._stream))
-        return out[:n.value], acts[:n.value].astype(np.int64), keys[:n.value]
+        _check(self._lib.pbvi_backup_small(self._h, b.data_ptr(), nB, al.data_ptr(), al.shape[0], float(gamma), out.data_ptr(), acts.ctypes.data,
+                                           keys.ctypes.data, byref(n), self._stream))
+        self.launch_count += 2                                   # the fused kernel + the gather
+        k = n.value
+        return out[:k], acts[:k].astype(np.int64), keys[:k]
 
     def backup_host(self, beliefs: np.ndarray, alphas: np.ndarray, gamma: float, out_alpha: np.ndarray | None = None,
                     out_action: np.ndarray | None = None):

@@ -384,3 +384,13 @@ def test_hsvi_level_equals_host_driven_level(ppu, n_store):
         if n_cover:
             lists = dev.sawtooth_lists(ub.corner_values, idx, val, count, dot, vals, n_cover, succ.reshape(A * O, -1)).cpu().numpy()
             assert np.array_equal(lists, saw.reshape(-1), equal_nan=True)
+
+
+def test_small_path_size_rule_matches_the_library():
+    """`DeviceModel.backup_small_eligible` is a host mirror of `pbvi_backup_small_eligible` (saves a library call on a path that is
+    about microseconds): the two must agree."""
+    for tag in ('tiger', 'grid4x4', 'hallway', 'olfactory_wrap'):
+        model, _ = fixture_model(tag)
+        dev = model.device
+        for nB, nV in [(1, 1), (80, 9), (256, 64), (4096, 4), (4096, 1024), (16384, 1), (16385, 1), (10, 4096), (10, 4097), (100000, 3)]:
+            assert dev.backup_small_eligible(nB, nV) == bool(dev._lib.pbvi_backup_small_eligible(dev._h, nB, nV)), (tag, nB, nV)
