@@ -1007,12 +1007,14 @@ extern "C" int pbvi_backup_small(pbvi_model* m, const double* d_beliefs, int nB,
     cudaStream_t st = (cudaStream_t)stream;
     const int S = m->S;
     m->arena.reset();
-    PBVI_TAKE(rowsAll, double, (size_t)nB * S);
-    PBVI_TAKE(keys, unsigned long long, (size_t)nB * 2);
-    PBVI_TAKE(acts, int32_t, (size_t)nB);
-    PBVI_TAKE(idx, int32_t, (size_t)nB);
-    // pinned staging of the handle: [rows | keys | actions | gather indices]
+    // one device block [rows | keys | actions] so that a single copy brings everything back; pinned staging of the handle:
+    // [rows | keys | actions | gather indices]
     const size_t rowBytes = (size_t)nB * S * sizeof(double), keyBytes = (size_t)nB * 16, actBytes = (size_t)nB * 4;
+    PBVI_TAKE(blob, char, rowBytes + keyBytes + actBytes);
+    double* rowsAll = reinterpret_cast<double*>(blob);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(blob + rowBytes);
+    int32_t* acts = reinterpret_cast<int32_t*>(blob + rowBytes + keyBytes);
+    PBVI_TAKE(idx, int32_t, (size_t)nB);
     const size_t need = rowBytes + keyBytes + 2 * actBytes;
     if (m->h_stage_bytes < need) {
         if (m->h_stage) cudaFreeHost(m->h_stage);
@@ -1030,9 +1032,7 @@ extern "C" int pbvi_backup_small(pbvi_model* m, const double* d_beliefs, int nB,
     small_backup_kernel<<<nB, SMALL_THREADS, smem, st>>>(d_beliefs, d_alphas, m->reachK, m->rtoK, m->rbarT, m->predPtr, m->predK, gamma, S, m->R,
                                                          m->A, m->O, nV, rowsAll, keys, acts);
     PBVI_CUDA(cudaGetLastError());
-    PBVI_CUDA(cudaMemcpyAsync(hRows, rowsAll, rowBytes, cudaMemcpyDeviceToHost, st));
-    PBVI_CUDA(cudaMemcpyAsync(hKeys, keys, keyBytes, cudaMemcpyDeviceToHost, st));
-    PBVI_CUDA(cudaMemcpyAsync(hActs, acts, actBytes, cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaMemcpyAsync(hs, blob, rowBytes + keyBytes + actBytes, cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));
     // dict semantics of the ValueFunction constructor (src/mdp.py:668-669) over the nB rows: position of the first occurrence, action of
     // the last; open addressing on the 128-bit key, every key match confirmed on the bytes
