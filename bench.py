@@ -146,6 +146,24 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """The CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave NumPy's OpenBLAS (the
+    reference's tensordot) single-threaded; threadpoolctl raises the limit at run time.  Returns the BLAS thread count in effect."""
+    cores = os.cpu_count() or 1
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        blas = [i['num_threads'] for i in threadpool_info() if i.get('user_api') == 'blas']
+        return max(blas) if blas else cores
+    except Exception:
+        return cores
+
+
 def seed_all(seed: int) -> None:
     np.random.seed(seed)
     random.seed(seed)
@@ -391,8 +409,7 @@ def run_reference(args):
     import torch
     from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs
     model = olfactory_wrap_model()
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    cores = use_all_host_threads()
     n_full = (args.beliefs if args.scaling == 'weak' else -(-args.beliefs // world)) * world
     n_sample = min(n_full, 512 if args.steps + args.warmup <= 16 else 256)
     built_by = 'numpy (no CUDA device): Rbar rows + smooth random rows'
@@ -649,9 +666,8 @@ def run_b200(args):
     # ---- parity sample + CPU baseline: the oracle on the headline alphas, for a sample of the timed beliefs (rank 0) -----------------
     parity_failed = False
     if 'backup' in legs and rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count()
         prev_threads = torch.get_num_threads()
-        torch.set_num_threads(cores)
+        cores = use_all_host_threads()
         n_sample = min(B, args.parity_beliefs or (512 if world == 1 else 128))
         pick = np.unique(np.linspace(0, B - 1, n_sample).astype(np.int64))
         sample_b = beliefs[torch.as_tensor(pick, device=dev.device)]
