@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument('--alphas', type=int, default=1000)
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--headline', default='late', choices=['late', 'young', 'dense'])
-    ap.add_argument('--legs', default=None, help='comma list of backup,solve,configs (default: all three at N = 1, backup,solve at N > 1)')
+    ap.add_argument('--legs', default=None, help='comma list of backup,solve,configs (default: all three; at N > 1 the config leg runs a sharded subset)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the oracle run (no parity_sample / cpu_baseline)')
     ap.add_argument('--parity-beliefs', type=int, default=None, help='beliefs of the oracle sample (default 512 at N = 1, 128 at N > 1)')
     ap.add_argument('--trace-phases', action='store_true', help='N > 1: print the phase times of the last sharded step to stderr')
@@ -504,7 +504,7 @@ def run_b200(args):
     from pomdp_pbvi_exploration_b200.parallel import ShardedBackup
     from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model
 
-    legs = (args.legs.split(',') if args.legs else (['backup', 'solve', 'configs'] if world == 1 else ['backup', 'solve']))
+    legs = args.legs.split(',') if args.legs else ['backup', 'solve', 'configs']
     model = olfactory_wrap_model()
     dev = model.device
     per_gpu = args.beliefs if args.scaling == 'weak' else -(-args.beliefs // world)
@@ -703,6 +703,11 @@ def run_b200(args):
             line['configs'] = run_config_leg(args)
         except Exception as e:
             line['configs'] = {'error': f'{type(e).__name__}: {e}'}
+    elif 'configs' in legs and world > 1:
+        gpu_warm(dev.device)
+        cfg = run_config_leg_sharded(world, rank)          # every rank takes part (collectives); rank 0 keeps the records
+        if rank == 0 and line is not None:
+            line['configs'] = cfg
 
     if rank == 0 and line is not None:
         emit(line)
@@ -756,21 +761,40 @@ def run_solve_leg(model, world, rank, info, reduce_max) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def _time_backup(model, gamma, B, V, acts, reps):
+def _time_backup(model, gamma, B, V, acts, reps, world=1):
+    """ms per `PBVI_Solver.backup` of the belief set B (CUDA events).  world > 1: the SAME belief set sharded over the ranks (strong
+    scaling: contiguous row blocks, tuple exchange), time = max over ranks."""
     import torch
     from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
     solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='ssea')
-    bs, vf = BeliefSet(model, B), ValueFunction(model, V, acts)
+    vf = ValueFunction(model, V, acts)
+    if world > 1:
+        import torch.distributed as dist
+        from pomdp_pbvi_exploration_b200.parallel import ShardedBackup
+        sb = ShardedBackup(solver, model)
+        lo, hi = sb.bounds(B.shape[0])
+        bs = BeliefSet(model, np.ascontiguousarray(B[lo:hi]) if hi > lo else torch.empty((0, B.shape[1]), dtype=torch.float64, device=model.device.device))
+        step = lambda: sb.backup(bs, vf, append=False)
+    else:
+        bs = BeliefSet(model, B)
+        step = lambda: solver.backup(model, bs, vf, append=False, belief_dominance_prune=False)
     for _ in range(3):
-        out = solver.backup(model, bs, vf, append=False, belief_dominance_prune=False)
+        out = step()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        out = solver.backup(model, bs, vf, append=False, belief_dominance_prune=False)
+        out = step()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps, out, vf
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=model.device.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms, out, vf
 
 
 def _dirichlet_beliefs(rng, n, S, k):
@@ -781,10 +805,12 @@ def _dirichlet_beliefs(rng, n, S, k):
     return B
 
 
-def _config_point(name, model, gamma, B, V, acts, reps, parity_rows):
+def _config_point(name, model, gamma, B, V, acts, reps, parity_rows, world=1, rank=0):
     """One backup shape of another model: time per backup (CUDA events), pairs/s, and a parity sample against the oracle."""
     import torch
-    ms, out, vf = _time_backup(model, gamma, B, V, acts, reps)
+    ms, out, vf = _time_backup(model, gamma, B, V, acts, reps, world)
+    if rank != 0:
+        return None
     S, A, O, R = model.state_count, model.action_count, model.observation_count, model.reachable_state_count
     rec = {'config': name, 'S': S, 'A': A, 'O': O, 'R': R, 'B': int(B.shape[0]), 'V': len(vf), 'ms_per_backup': ms,
            'pairs_per_s': B.shape[0] * len(vf) / (ms * 1e-3), 'new_alpha_rows': len(out),
@@ -862,6 +888,53 @@ def run_config_leg(args) -> dict:
     points.append(rec)
     bad = [p['config'] for p in points if 'parity_sample' in p and not p['parity_sample']['ok']]
     return {'tiger_solve': tiger_solve, 'points': points, 'parity_failures': bad, 'ssea_expansions': run_ssea_points(rng)}
+
+
+def run_config_leg_sharded(world: int, rank: int) -> dict:
+    """The other BASELINE configs at N > 1: the same belief sets as at N = 1, SHARDED over the ranks (strong scaling).  tiger and the 4x4
+    grid are launch- and latency-bound (a few microseconds of arithmetic): more GPUs only add the exchange, and the numbers say so."""
+    import torch
+    from pomdp_pbvi_exploration_b200 import Belief, Model, PBVI_Solver, ValueFunction
+    from pomdp_pbvi_exploration_b200.recipes import sea_robin_model, synthetic_sparse_model, tiger_model
+    rng = np.random.default_rng(0)                       # same inputs on every rank
+    points = []
+    try:
+        model = tiger_model()
+        Bt = _dirichlet_beliefs(rng, 80, 2, 2)
+        Vt = np.array([[-100.0, 10.0], [10.0, -100.0], [-1.0, -1.0], [3.0, 5.0], [5.0, 3.0], [-20.0, 8.0], [8.0, -20.0], [0.0, 0.0], [1.0, 2.0]])
+        points.append(_config_point('tiger', model, 0.95, Bt, Vt, rng.integers(0, 3, len(Vt)), 20, 80, world, rank))
+        for tag in ('grid4x4', 'grid4x4_noloop'):
+            m = dict(np.load(os.path.join(ROOT, 'tests', 'golden', f'model_{tag}.npz')))
+            model = Model(states=16, actions=4, observations=2, transitions=m['transition_table'], rewards=m['reward_table'],
+                          observation_table=m['obs_table'], start_probabilities=m['start'])
+            B = np.concatenate([np.eye(16), _dirichlet_beliefs(rng, 4096 - 16, 16, 16)])
+            V = rng.random((1024, 16)) * 3
+            points.append(_config_point(f'{tag} (R={model.reachable_state_count})', model, float(m['gamma']), B, V, rng.integers(0, 4, 1024), 10, 64,
+                                        world, rank))
+        for S, A, O, R, parity in ((10000, 8, 4, 2, 64), (30000, 8, 4, 1, 0)):
+            model = synthetic_sparse_model(S, A, O, R, seed=1)
+            B = _dirichlet_beliefs(rng, 1024, S, 2048)
+            V = rng.random((256, S))
+            points.append(_config_point('synthetic_sparse', model, 0.95, B, V, rng.integers(0, A, 256), 5, parity, world, rank))
+            model.device.close()
+            del model
+            torch.cuda.empty_cache()
+        model = sea_robin_model()
+        solver = PBVI_Solver(gamma=GAMMA, eps=1e-8, expand_function='perseus')
+        np.random.seed(4)
+        walks = [solver.expand_perseus(model, Belief(model), max_generation=100) for _ in range(10)]
+        vf = ValueFunction(model, model.expected_rewards_table.T, model.actions)
+        for w in walks[:6]:
+            vf = solver.backup(model, w, vf, append=True, belief_dominance_prune=False)
+        Bs = torch.cat([w.belief_array for w in walks]).cpu().numpy()
+        points.append(_config_point('sea_robin (Sea_Robins_Swim_Walk.ipynb)', model, GAMMA, Bs, vf.alpha_vector_array.cpu().numpy(), vf.actions, 5, 48,
+                                    world, rank))
+    except Exception as e:                                # (a rank that fails here would leave the others in a collective: report and stop)
+        return {'error': f'{type(e).__name__}: {e}', 'points': [p for p in points if p]}
+    points = [p for p in points if p]
+    bad = [p['config'] for p in points if 'parity_sample' in p and not p['parity_sample']['ok']]
+    return {'points': points, 'parity_failures': bad, 'n_gpus': world,
+            'note': 'the N = 1 belief sets sharded over the ranks (strong scaling), time = max over ranks'}
 
 
 def run_ssea_points(rng) -> list:
