@@ -16,7 +16,9 @@
  *     is the opaque model handle, which owns the device copy of the model tables and a grow-only scratch arena.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls enqueue work on it and
  *     return without synchronising unless stated otherwise.
- *   - a handle is not re-entrant: one host thread per handle (one process per GPU under torchrun).
+ *   - a handle is not re-entrant: one host thread per handle (one process per GPU under torchrun).  Its scratch is reused by
+ *     consecutive calls in stream order; a call issued on a different stream than the previous one on the same handle first waits, on
+ *     the device, for the work that call enqueued (so switching streams is safe, overlapping two calls of one handle is not possible).
  */
 #ifndef PBVI_B200_H
 #define PBVI_B200_H

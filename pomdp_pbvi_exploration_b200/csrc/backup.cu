@@ -876,7 +876,7 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
     constexpr int G = 8, SPT = 2;
     if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024 &&
         ((long long)n + (long long)m->A * (G - 1)) / G + 1 <= 65535) {            // grid.y of the grouped kernel
-        m->arena.reset();
+        PBVI_TRY(enter_call(m, st));
         const int nPad = ceil_div(n + m->A * (G - 1), G) * G;
         PBVI_TAKE(order, int32_t, (size_t)nPad);
         PBVI_CUDA(cudaMemsetAsync(order, 0xFF, (size_t)nPad * sizeof(int32_t), st));
@@ -916,7 +916,7 @@ extern "C" int pbvi_backup_select(pbvi_model* m, const double* d_beliefs, int nB
     PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, gamma));
     PBVI_REQUIRE(nB == 0 || d_vstar != nullptr, "v_star output is required");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return select_impl(m, d_beliefs, nB, d_alphas, nV, gamma, d_vstar, d_value, d_astar, (cudaStream_t)stream);
 }
@@ -928,6 +928,7 @@ extern "C" int pbvi_backup_assemble(pbvi_model* m, const double* d_alphas, int n
     if (n == 0) return PBVI_OK;
     PBVI_REQUIRE(d_alphas && d_actions && d_vsel && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return assemble_impl(m, d_alphas, nV, gamma, d_actions, d_vsel, (size_t)m->O, 0, n, d_out, d_hash, (cudaStream_t)stream);
 }
@@ -938,7 +939,7 @@ extern "C" int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const
     if (nB == 0) return PBVI_OK;
     PBVI_REQUIRE(d_out_alpha && d_out_action, "alpha / action outputs are required");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!d_out_vstar) {
@@ -955,7 +956,7 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     if (nB == 0) return PBVI_OK;
     PBVI_REQUIRE(h_out_alpha && h_out_action, "alpha / action outputs are required");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t S = m->S;
@@ -1006,7 +1007,7 @@ extern "C" int pbvi_backup_small(pbvi_model* m, const double* d_beliefs, int nB,
     PBVI_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int S = m->S;
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     // one device block [rows | keys | actions] so that a single copy brings everything back; pinned staging of the handle:
     // [rows | keys | actions | gather indices]
     const size_t rowBytes = (size_t)nB * S * sizeof(double), keyBytes = (size_t)nB * 16, actBytes = (size_t)nB * 4;
@@ -1075,7 +1076,7 @@ extern "C" int pbvi_max_values(pbvi_model* m, const double* d_beliefs, int nB, c
     PBVI_TRY(check_backup_args(m, d_beliefs, nB, d_alphas, nV, 1.0));
     if (nB == 0) return PBVI_OK;
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return score_argmax(m, d_beliefs, nB, d_alphas, nV, false, d_max, d_arg, (cudaStream_t)stream);
 }

@@ -249,7 +249,7 @@ extern "C" int pbvi_belief_update(pbvi_model* m, const double* d_beliefs, const 
     if (n == 0) return PBVI_OK;
     PBVI_REQUIRE(d_beliefs && d_actions && d_observations && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return belief_update_impl(m, d_beliefs, (size_t)m->S, d_actions, d_observations, n, normalise, d_out, d_norm, (cudaStream_t)stream);
 }
@@ -268,7 +268,7 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
     const double* src = d_b0;
     for (int i = 0; i < n; i++) {
@@ -296,7 +296,7 @@ extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
     PBVI_TAKE(obsProb, double, (size_t)m->O);
     const size_t K = (size_t)m->S * m->R;
@@ -354,7 +354,7 @@ extern "C" int pbvi_belief_successors(pbvi_model* m, const double* d_beliefs, in
     if (n == 0) return PBVI_OK;
     PBVI_REQUIRE(d_beliefs && d_out, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return belief_successors_impl(m, d_beliefs, n, normalise, d_out, d_norm, (cudaStream_t)stream);
 }

@@ -346,7 +346,7 @@ extern "C" int pbvi_sawtooth_lists(pbvi_model* m, const double* d_corner, const 
     if (n_q == 0) return PBVI_OK;
     PBVI_REQUIRE(d_corner && d_queries && d_out && (n_ub == 0 || (d_idx && d_val && d_count && d_dot && d_ub_values)), "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     return sawtooth_lists_impl(m, d_corner, d_idx, d_val, d_count, d_dot, d_ub_values, n_ub, d_queries, n_q, nullptr, d_out, (cudaStream_t)stream);
 }
@@ -363,7 +363,7 @@ extern "C" int pbvi_hsvi_level(pbvi_model* m, const double* d_b, const double* d
     PBVI_REQUIRE(n_stored == 0 || stored_capacity == 0 || (d_stored_keys && d_stored_vals), "stored key / value arrays are required");
     PBVI_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     const int nZ = m->nZ, S = m->S;
     PBVI_TAKE(keys, unsigned long long, (size_t)(nZ + 1) * 2);          // successors, then b itself

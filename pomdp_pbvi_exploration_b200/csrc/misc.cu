@@ -529,7 +529,7 @@ extern "C" int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int
     cudaStream_t st = (cudaStream_t)stream;
     int T = 64;
     while (T < 2 * n) T <<= 1;
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(rep, int32_t, (size_t)T);
     PBVI_TAKE(gfirst, int32_t, (size_t)T);
     PBVI_TAKE(glast, unsigned long long, (size_t)T);
@@ -563,7 +563,7 @@ extern "C" int pbvi_group_record_blocks(pbvi_model* m, const int32_t* d_blocks, 
     cudaStream_t st = (cudaStream_t)stream;
     int T = 64;
     while (T < 2 * n) T <<= 1;
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(rep, int32_t, (size_t)T);
     PBVI_TAKE(gfirst, unsigned long long, (size_t)T);
     PBVI_TAKE(glast, unsigned long long, (size_t)T);
@@ -601,7 +601,7 @@ extern "C" int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, i
     PBVI_REQUIRE(d_rows && d_first && d_inverse, "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(mismatch, int32_t, 1);
     PBVI_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int32_t), st));
     group_confirm_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_first, d_inverse, mismatch);
@@ -648,7 +648,7 @@ extern "C" int pbvi_sawtooth(pbvi_model* m, const double* d_corner, const double
     if (n_q == 0) return PBVI_OK;
     PBVI_REQUIRE(d_corner && d_queries && d_out && (n_ub == 0 || (d_ub_beliefs && d_ub_values)), "NULL pointer argument");
     PBVI_CUDA(cudaSetDevice(m->device));
-    m->arena.reset();
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(terms, double, (size_t)n_q * (n_ub + 1));
     // column n_ub of `terms` holds v0_q itself (the corner term of the minimum); the stored-belief blocks read it from there
     PBVI_TAKE(v0, double, (size_t)n_q);

@@ -83,6 +83,18 @@ static int build_pairwise(int off, int n, std::vector<int2>& leaves, std::vector
     return (int)nodes.size() - 1;
 }
 
+int enter_call(pbvi_model* m, cudaStream_t st) {
+    if (m->has_last_stream && m->last_stream != st) {
+        if (!m->evGuard) PBVI_CUDA(cudaEventCreateWithFlags(&m->evGuard, cudaEventDisableTiming));
+        PBVI_CUDA(cudaEventRecord(m->evGuard, m->last_stream));
+        PBVI_CUDA(cudaStreamWaitEvent(st, m->evGuard, 0));
+    }
+    m->last_stream = st;
+    m->has_last_stream = true;
+    m->arena.reset();
+    return PBVI_OK;
+}
+
 template <typename T>
 static int upload(T** dst, const std::vector<T>& src) {
     PBVI_CUDA(cudaMalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T)));
@@ -244,6 +256,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->d_stats);
     cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
+    if (m->evGuard) cudaEventDestroy(m->evGuard);
     m->arena.release();
     if (m->h_stage) cudaFreeHost(m->h_stage);
     delete m;

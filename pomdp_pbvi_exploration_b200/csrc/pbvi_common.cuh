@@ -142,6 +142,11 @@ struct pbvi_model {
     int nLeaves = 0, nNodes = 0;
 
     pbvi::Arena arena;
+    // stream guard: the scratch arena, the sign flags and the tile counter are reused by consecutive calls IN STREAM ORDER; a call that
+    // arrives on another stream than its predecessor first waits (on the device) for everything the predecessor enqueued
+    cudaStream_t last_stream = nullptr;
+    bool has_last_stream = false;
+    cudaEvent_t evGuard = nullptr;
     void* h_stage = nullptr;     // pinned host staging of pbvi_backup_small (grow-only)
     size_t h_stage_bytes = 0;
     // instrumentation of the last select / max_values call
@@ -170,6 +175,8 @@ int transpose_alphas(pbvi_model* m, const double* d_alphas, int nV, int Vp, doub
 int belief_successors_impl(pbvi_model* m, const double* d_beliefs, int n, int normalise, double* d_out, double* d_norm, cudaStream_t st);
 int row_hash_launch(pbvi_model* m, const double* d_rows, int n, int row_len, uint64_t* d_hash, cudaStream_t st);
 int max_values_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max, int32_t* d_arg, cudaStream_t st);
+// start of an API call that uses the handle's scratch: stream guard (see pbvi_model::last_stream) + arena rewind
+int enter_call(pbvi_model* m, cudaStream_t st);
 int configure_backup_kernels();
 int configure_belief_kernels();
 int configure_misc_kernels();

@@ -592,3 +592,29 @@ def test_min_l2_and_batched_successors_at_scale(torch_cuda, tag, n_b, n_src):
     # successors that are already in the set are at distance exactly 0, as in the reference
     in_set = dev.min_l2_distance(np.concatenate([B, want_succ.reshape(-1, S)[possible][:3]]), cand[torch_cuda.as_tensor(np.flatnonzero(possible)[:3]).cuda()])
     assert np.all(in_set.cpu().numpy() == 0.0)
+
+
+def test_calls_on_two_streams_of_one_handle_are_ordered(torch_cuda):
+    """A handle's scratch (arena, sign flags, tile counter) is reused in stream order; a call that arrives on another stream than its
+    predecessor waits on the device for the predecessor's work (pbvi_model::last_stream), so alternating streams gives the results of a
+    single stream."""
+    torch = torch_cuda
+    dev, m, reach, _ = device_model('olfactory_wrap')
+    g = load_golden('backup_olfactory_wrap')
+    B = torch.as_tensor(g['beliefs']).cuda()
+    V = torch.as_tensor(g['alphas']).cuda()
+    gamma = float(m['gamma'])
+    want = [t.clone() for t in dev.backup_select(B, V, gamma)]
+    want_mx = dev.max_values(B, V)[0].clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            outs.append(dev.backup_select(B, V, gamma) if i % 3 else (dev.max_values(B, V)[0],))
+    torch.cuda.synchronize()
+    for o in outs:
+        if len(o) == 1:
+            assert torch.equal(o[0], want_mx)
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(o, want) if a is not None)
