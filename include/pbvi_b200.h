@@ -270,6 +270,10 @@ PBVI_API int pbvi_broadcast_rows(pbvi_comm* c, double* d_rows, size_t count, int
  * and kernel launch count of the last call (for bench.py's roofline / gpu_launches accounting) */
 PBVI_API int pbvi_last_stats(const pbvi_model* m, double* executed_flops, double* dense_flops, int* launches);
 
+/* engine options (A/B runs, tests): "chain_kernel" = 1 (default) runs pbvi_belief_trajectory / pbvi_perseus_walk as ONE persistent launch
+ * when a belief fits in shared memory, 0 = one launch per step-kernel.  Both give the same bytes. */
+PBVI_API int pbvi_set_option(pbvi_model* m, const char* name, int value);
+
 /* kernels launched by the last API call on this handle (host-side counter, no synchronisation) */
 PBVI_API int pbvi_last_launches(const pbvi_model* m);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     'pbvi_broadcast_rows': [_P, _P, ctypes.c_size_t, c_int, _P],
     'pbvi_last_stats': [_P, POINTER(c_double), POINTER(c_double), POINTER(c_int)],
     'pbvi_last_launches': [_P],
+    'pbvi_set_option': [_P, c_char_p, c_int],
     'pbvi_set_profiling': [_P, c_int],
     'pbvi_last_score_ms': [_P, POINTER(ctypes.c_float)],
 }
@@ -525,6 +526,9 @@ class DeviceModel:
         view = buf[:n].view(t.shape)
         view.copy_(t)
         return view.numpy()
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(self._lib.pbvi_set_option(self._h, name.encode(), int(value)))
 
     def set_profiling(self, enable: bool) -> None:
         _check(self._lib.pbvi_set_profiling(self._h, int(enable)))

@@ -192,8 +192,181 @@ __global__ void __launch_bounds__(256) observation_probability_kernel(const doub
 }  // namespace pbvi
 
 namespace pbvi {
+constexpr size_t CHAIN_SMEM_MAX = 220 * 1024;
+
+// ---- a whole CHAIN of belief updates in ONE launch (the FSVI trajectory, the Perseus walk): one block of 1024 threads keeps the
+//      current belief in shared memory and runs the steps back to back, so a step costs a dozen block barriers instead of three or
+//      four dependent kernel launches (the multi-launch chain is bound by the launch rate: ~6 us per launch from the host, ~25 us
+//      per step).  Every phase repeats the arithmetic of the separate kernels bit for bit:
+//        observation draw   P(o|b,a) with observation_probability_kernel's summation shape (256 "virtual threads" per observation:
+//                           fma over s = t, t + 256, ..., warp shuffle tree, 8 warp partials in order), then NumPy's choice rule;
+//        projection         bincount order over the predecessors of every landing state (belief_project_kernel);
+//        normaliser         NumPy's pairwise sum: 8-lane leaf sums (pairwise_leaf_kernel), then the combine tree level by level
+//                           (same additions, same association), then one division per state.
+//      A step flagged `reset` continues from b0 (FSVI: end state reached).  Used when a belief fits in shared memory (S <= ~26 000).
+constexpr int CHAIN_THREADS = 1024;
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const double* __restrict__ b0, const int32_t* __restrict__ actions,
+                                                                        const int32_t* __restrict__ observations, const double* __restrict__ uniforms,
+                                                                        const uint8_t* __restrict__ resets, int n, const int32_t* __restrict__ predPtr,
+                                                                        const int32_t* __restrict__ predK, const double* __restrict__ rtoK, int S, int R,
+                                                                        int O, const int2* __restrict__ leaves, int nLeaves,
+                                                                        const int2* __restrict__ nodes, int nNodes,
+                                                                        const int32_t* __restrict__ levelNodes, const int32_t* __restrict__ levelPtr,
+                                                                        int nLevels, double* __restrict__ out, int32_t* __restrict__ chosenOut) {
+    extern __shared__ double chain_smem[];
+    double* sb = chain_smem;                     // [S] current belief
+    double* s_sum = sb + S;                      // [nLeaves] leaf sums, then [nNodes] node sums
+    __shared__ double s_part[4][8];              // warp partials of up to four observation sums at a time
+    __shared__ double s_p[32];                   // P(o | b, a)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const size_t K = (size_t)S * R;
+    for (int s = tid; s < S; s += CHAIN_THREADS) sb[s] = b0[s];
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+        const int a = actions[i];
+        int o = observations ? observations[i] : -1;
+        if (o < 0) {
+            // ---- P(o | b, a) for every o, four observations at a time (thread group g = tid / 256 takes observation o0 + g)
+            for (int o0 = 0; o0 < O; o0 += 4) {
+                const int g = tid >> 8, t = tid & 255, oo = o0 + g;
+                double part = 0.0;
+                if (oo < O) {
+                    const double* rto = rtoK + ((size_t)a * O + oo) * K;
+                    for (int s = t; s < S; s += 256) {
+                        const double bs = sb[s];
+                        if (bs != 0.0)
+                            for (int r = 0; r < R; r++) part = fma(rto[(size_t)s * R + r], bs, part);
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+                if (lane == 0) s_part[g][t >> 5] = part;
+                __syncthreads();
+                if (tid < 4 && o0 + tid < O) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) tot += s_part[tid][w];
+                    s_p[o0 + tid] = tot;
+                }
+                __syncthreads();
+            }
+            // np.random.choice(observations, p=P): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
+            const double u = uniforms[i];
+            double tot = 0.0;
+            for (int x = 0; x < O; x++) tot = __dadd_rn(tot, s_p[x]);
+            double run = 0.0;
+            int idx = 0;
+            for (int x = 0; x < O; x++) {
+                run = __dadd_rn(run, s_p[x]);
+                if (__ddiv_rn(run, tot) <= u) idx++;
+            }
+            o = min(idx, O - 1);
+        }
+        if (tid == 0 && chosenOut) chosenOut[i] = o;
+        // ---- projection (bincount order) into the output row
+        double* row = out + (size_t)i * S;
+        {
+            const int32_t* ptr = predPtr + (size_t)a * (S + 1);
+            const int32_t* pk = predK + (size_t)a * K;
+            const double* rto = rtoK + ((size_t)a * O + o) * K;
+            for (int sp = tid; sp < S; sp += CHAIN_THREADS) {
+                double acc = 0.0;
+                const int end = ptr[sp + 1];
+                for (int j = ptr[sp]; j < end; j++) {
+                    const int k = pk[j];
+                    acc = __dadd_rn(acc, __dmul_rn(rto[k], sb[R == 1 ? k : k / R]));
+                }
+                row[sp] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- leaf sums: 8 lanes per leaf, NumPy's accumulators r[0..7] + the fixed 3-level tree + the < 8 trailing elements
+        for (int q0 = 0; q0 < nLeaves * 8; q0 += CHAIN_THREADS) {            // uniform trip count: the shuffles need whole warps
+            const int q = q0 + tid, l = q >> 3, j = q & 7;
+            const bool valid = l < nLeaves;
+            const int off = valid ? leaves[l].x : 0, len = valid ? leaves[l].y : 0;
+            const double* av = row + off;
+            const int lim = len - (len % 8);
+            double r = (len >= 8) ? av[j] : 0.0;
+            for (int x = 8; x < lim; x += 8) r = __dadd_rn(r, av[x + j]);
+            const double p2 = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));
+            const double q2 = __dadd_rn(p2, __shfl_down_sync(0xffffffffu, p2, 2, 8));
+            double res = __dadd_rn(q2, __shfl_down_sync(0xffffffffu, q2, 4, 8));
+            if (valid && j == 0) {
+                if (len < 8) {
+                    res = 0.0;
+                    for (int x = 0; x < len; x++) res = __dadd_rn(res, av[x]);
+                } else {
+                    for (int x = lim; x < len; x++) res = __dadd_rn(res, av[x]);
+                }
+                s_sum[l] = res;
+            }
+        }
+        __syncthreads();
+        // ---- the combine tree, level by level
+        double* nsum = s_sum + nLeaves;
+        for (int lev = 0; lev < nLevels; lev++) {
+            for (int x = levelPtr[lev] + tid; x < levelPtr[lev + 1]; x += CHAIN_THREADS) {
+                const int j = levelNodes[x];
+                const int l = nodes[j].x, r = nodes[j].y;
+                nsum[j] = __dadd_rn(l < 0 ? s_sum[~l] : nsum[l], r < 0 ? s_sum[~r] : nsum[r]);
+            }
+            __syncthreads();
+        }
+        const double tot = nNodes ? nsum[nNodes - 1] : s_sum[0];
+        // ---- normalise; the next step starts from this row, or from b0 again after a reset
+        const bool reset = resets && resets[i];
+        for (int sp = tid; sp < S; sp += CHAIN_THREADS) {
+            const double v = row[sp] / tot;                               // 0/0 = NaN for an impossible observation, as in the reference
+            row[sp] = v;
+            sb[sp] = reset ? b0[sp] : v;
+        }
+        __syncthreads();
+    }
+}
+
 int configure_belief_kernels() {
     PBVI_CUDA(cudaFuncSetAttribute(pairwise_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PBVI_CUDA(cudaFuncSetAttribute(belief_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
+    return PBVI_OK;
+}
+
+// one-launch chain when a belief (+ the pairwise-sum scratch) fits in shared memory
+static bool chain_fits(const pbvi_model* m) {
+    return ((size_t)m->S + m->nLeaves + m->nNodes) * sizeof(double) <= CHAIN_SMEM_MAX && m->O <= 32;
+}
+
+// steps given in HOST arrays (observations < 0 / NULL: drawn on the device from h_uniforms); uploads them and launches the chain
+static int launch_chain(pbvi_model* m, const double* d_b0, const int32_t* h_actions, const int32_t* h_observations, const double* h_uniforms,
+                        const uint8_t* h_resets, int n, double* d_out, int32_t* d_chosen, cudaStream_t st) {
+    PBVI_TAKE(dA, int32_t, (size_t)n);
+    PBVI_CUDA(cudaMemcpyAsync(dA, h_actions, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int32_t* dO = nullptr;
+    double* dU = nullptr;
+    uint8_t* dR = nullptr;
+    if (h_observations) {
+        dO = m->arena.take<int32_t>((size_t)n);
+        if (!dO) return PBVI_ERR_OOM;
+        PBVI_CUDA(cudaMemcpyAsync(dO, h_observations, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    if (h_uniforms) {
+        dU = m->arena.take<double>((size_t)n);
+        if (!dU) return PBVI_ERR_OOM;
+        PBVI_CUDA(cudaMemcpyAsync(dU, h_uniforms, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (h_resets) {
+        dR = m->arena.take<uint8_t>((size_t)n);
+        if (!dR) return PBVI_ERR_OOM;
+        PBVI_CUDA(cudaMemcpyAsync(dR, h_resets, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    const size_t smem = ((size_t)m->S + m->nLeaves + m->nNodes) * sizeof(double);
+    belief_chain_kernel<<<1, CHAIN_THREADS, smem, st>>>(d_b0, dA, dO, dU, dR, n, m->predPtr, m->predK, m->rtoK, m->S, m->R, m->O, m->pwLeaves,
+                                                        m->nLeaves, m->pwNodes, m->nNodes, m->pwLevelNodes, m->pwLevelPtr, m->nLevels, d_out,
+                                                        d_chosen);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    // the host arrays are pageable: the copies above were staged synchronously by the runtime, so the caller may reuse them on return
     return PBVI_OK;
 }
 }  // namespace pbvi
@@ -269,6 +442,7 @@ extern "C" int pbvi_belief_trajectory(pbvi_model* m, const double* d_b0, const i
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
     PBVI_TRY(enter_call(m, (cudaStream_t)stream));
+    if (chain_fits(m) && !m->no_chain_kernel) return launch_chain(m, d_b0, h_actions, h_observations, nullptr, h_reset, n, d_out, nullptr, st);
     PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
     const double* src = d_b0;
     for (int i = 0; i < n; i++) {
@@ -297,6 +471,7 @@ extern "C" int pbvi_perseus_walk(pbvi_model* m, const double* d_b0, const int32_
     const size_t smem = (size_t)(m->nLeaves + m->nNodes) * sizeof(double);
     PBVI_REQUIRE(smem <= 48 * 1024, "state space too large for the chained pairwise-sum kernel");
     PBVI_TRY(enter_call(m, (cudaStream_t)stream));
+    if (chain_fits(m) && !m->no_chain_kernel) return launch_chain(m, d_b0, h_actions, nullptr, h_uniforms, nullptr, n, d_out, d_observations, st);
     PBVI_TAKE(leafSums, double, (size_t)m->nLeaves);         // reused by every step (stream order)
     PBVI_TAKE(obsProb, double, (size_t)m->O);
     const size_t K = (size_t)m->S * m->R;

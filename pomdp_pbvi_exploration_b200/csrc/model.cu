@@ -229,6 +229,22 @@ extern "C" int pbvi_model_create(int S, int A, int O, int R, const int64_t* h_re
     up(&m->zMask, zMask); up(&m->zOrder, zOrder);
     up(&m->predPtr, predPtr); up(&m->predK, predK);
     up(&m->pwLeaves, leaves); up(&m->pwNodes, nodes);
+    {   // the combine tree by levels (a node's level = 1 + the deeper child's; leaves are level 0): nodes of one level are independent
+        std::vector<int> level(nodes.size(), 0);
+        int maxLevel = 0;
+        for (size_t j = 0; j < nodes.size(); j++) {      // post-order: children precede their parent
+            const int l = nodes[j].x < 0 ? 0 : level[nodes[j].x], r = nodes[j].y < 0 ? 0 : level[nodes[j].y];
+            level[j] = 1 + std::max(l, r);
+            maxLevel = std::max(maxLevel, level[j]);
+        }
+        std::vector<int32_t> levelNodes, levelPtr(1, 0);
+        for (int lev = 1; lev <= maxLevel; lev++) {
+            for (size_t j = 0; j < nodes.size(); j++) if (level[j] == lev) levelNodes.push_back((int32_t)j);
+            levelPtr.push_back((int32_t)levelNodes.size());
+        }
+        m->nLevels = maxLevel;
+        up(&m->pwLevelNodes, levelNodes); up(&m->pwLevelPtr, levelPtr);
+    }
     std::vector<uint4> hashKeys((size_t)S);
     for (int s = 0; s < S; s++) hashKeys[s] = row_key_words(s);
     up(&m->hashKeys, hashKeys);
@@ -253,6 +269,7 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->rbarNzPtr); cudaFree(m->rbarNzIdx); cudaFree(m->rbarNzVal);
     cudaFree(m->reachP); cudaFree(m->rtoP); cudaFree(m->zMask); cudaFree(m->zOrder);
     cudaFree(m->predPtr); cudaFree(m->predK); cudaFree(m->pwLeaves); cudaFree(m->pwNodes); cudaFree(m->hashKeys);
+    cudaFree(m->pwLevelNodes); cudaFree(m->pwLevelPtr);
     cudaFree(m->d_stats);
     cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
@@ -273,6 +290,13 @@ extern "C" int pbvi_model_dims(const pbvi_model* m, int* S, int* A, int* O, int*
 }
 
 extern "C" int pbvi_last_launches(const pbvi_model* m) { return m ? m->last_launches : 0; }
+
+extern "C" int pbvi_set_option(pbvi_model* m, const char* name, int value) {
+    PBVI_REQUIRE(m != nullptr && name != nullptr, "NULL argument");
+    if (std::strcmp(name, "chain_kernel") == 0) { m->no_chain_kernel = value == 0; return PBVI_OK; }
+    set_error("bad argument: unknown option '%s'", name);
+    return PBVI_ERR_BAD_ARG;
+}
 
 extern "C" int pbvi_set_profiling(pbvi_model* m, int enable) {
     PBVI_REQUIRE(m != nullptr, "model handle is NULL");

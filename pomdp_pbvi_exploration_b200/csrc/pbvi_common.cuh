@@ -138,6 +138,10 @@ struct pbvi_model {
     // NumPy pairwise-sum tree over a length-S row
     int2* pwLeaves = nullptr;    // [nLeaves] (offset, length)
     int2* pwNodes = nullptr;     // [nNodes]  (left, right); child >= 0: node id, < 0: leaf ~id; root is the last node
+    int32_t* pwLevelNodes = nullptr;   // [nNodes] node ids grouped by tree level (children always in an earlier level)
+    int32_t* pwLevelPtr = nullptr;     // [nLevels + 1]
+    int nLevels = 0;
+    bool no_chain_kernel = false;      // pbvi_set_option("chain_kernel", 0): belief chains as one launch per step-kernel (tests, A/B)
     uint4* hashKeys = nullptr;   // [S] row_key_words(s): position keys of the 128-bit row key
     int nLeaves = 0, nNodes = 0;
 

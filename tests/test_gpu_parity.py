@@ -618,3 +618,44 @@ def test_calls_on_two_streams_of_one_handle_are_ordered(torch_cuda):
             assert torch.equal(o[0], want_mx)
         else:
             assert all(torch.equal(a, b) for a, b in zip(o, want) if a is not None)
+
+
+@pytest.mark.parametrize('tag', ['tiger', 'grid4x4', 'hallway', 'olfactory_wrap'])
+def test_chain_kernel_equals_multi_launch_chain(torch_cuda, tag):
+    """The persistent one-launch chain (belief_chain_kernel: belief in shared memory, a dozen block barriers per step) == the
+    multi-launch chain (one projection / leaf-sum / finish launch per step), bit for bit: FSVI trajectories with resets and with an
+    impossible observation (NaN rows), Perseus walks with the observations drawn on the device."""
+    dev, m, reach, _ = device_model(tag)
+    A, O = m['rto'].shape[1], m['rto'].shape[2]
+    rng = np.random.default_rng(8)
+    n = 57
+    b0 = m['start']
+    acts = rng.integers(0, A, n).astype(np.int32)
+    us = rng.random(n)
+    # observations that are possible along the way (from a device walk), plus resets
+    dev.set_option('chain_kernel', 0)
+    walk0, obs0 = dev.perseus_walk(b0, acts, us, want_observations=True)
+    resets = (rng.random(n) < 0.1)
+    traj0 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts, obs0.cpu().numpy(), resets)
+    launches_multi = dev._lib.pbvi_last_launches(dev._h)
+    dev.set_option('chain_kernel', 1)
+    walk1, obs1 = dev.perseus_walk(b0, acts, us, want_observations=True)
+    assert dev._lib.pbvi_last_launches(dev._h) == 1
+    traj1 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts, obs0.cpu().numpy(), resets)
+    assert dev._lib.pbvi_last_launches(dev._h) == 1 and launches_multi == 3 * n
+    assert torch_cuda.equal(obs0, obs1)
+    assert np.array_equal(walk0.cpu().numpy(), walk1.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(traj0.cpu().numpy(), traj1.cpu().numpy(), equal_nan=True)
+    # an impossible observation somewhere in the chain: NaN from there on, in both forms
+    bad_obs = obs0.cpu().numpy().copy()
+    out = orc.all_successors(reach, m['rto'], np.asarray(b0)[None, :])[0]
+    impossible = [(a, o) for a in range(A) for o in range(O) if np.isnan(out[a, o]).all()]
+    if impossible:
+        acts2 = acts.copy()
+        acts2[0], bad_obs[0] = impossible[0]
+        dev.set_option('chain_kernel', 0)
+        t0 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts2, bad_obs, None)
+        dev.set_option('chain_kernel', 1)
+        t1 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts2, bad_obs, None)
+        assert np.isnan(t1.cpu().numpy()[0]).all()
+        assert np.array_equal(t0.cpu().numpy(), t1.cpu().numpy(), equal_nan=True)
