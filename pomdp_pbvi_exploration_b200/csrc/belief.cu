@@ -232,11 +232,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const do
                 const int g = tid >> 8, t = tid & 255, oo = o0 + g;
                 double part = 0.0;
                 if (oo < O) {
+                    // (observation_probability_kernel skips bs == 0; fma(x, 0, part) == part for the finite x of a model table, so
+                    // the unconditional form gives the same bits and lets the loads of consecutive iterations overlap -- one block
+                    // has nothing else to hide their latency with)
                     const double* rto = rtoK + ((size_t)a * O + oo) * K;
-                    for (int s = t; s < S; s += 256) {
-                        const double bs = sb[s];
-                        if (bs != 0.0)
+                    if (R == 1) {
+#pragma unroll 8
+                        for (int s = t; s < S; s += 256) part = fma(rto[s], sb[s], part);
+                    } else {
+                        for (int s = t; s < S; s += 256) {
+                            const double bs = sb[s];
                             for (int r = 0; r < R; r++) part = fma(rto[(size_t)s * R + r], bs, part);
+                        }
                     }
                 }
 #pragma unroll
@@ -270,14 +277,32 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const do
             const int32_t* ptr = predPtr + (size_t)a * (S + 1);
             const int32_t* pk = predK + (size_t)a * K;
             const double* rto = rtoK + ((size_t)a * O + o) * K;
-            for (int sp = tid; sp < S; sp += CHAIN_THREADS) {
-                double acc = 0.0;
-                const int end = ptr[sp + 1];
-                for (int j = ptr[sp]; j < end; j++) {
-                    const int k = pk[j];
-                    acc = __dadd_rn(acc, __dmul_rn(rto[k], sb[R == 1 ? k : k / R]));
+            // four landing states per thread at a time: their predecessor chains are independent, so their loads overlap
+            constexpr int PU = 4;
+            for (int sp0 = tid; sp0 < S; sp0 += PU * CHAIN_THREADS) {
+                int beg[PU], len[PU], longest = 0;
+                double acc[PU];
+#pragma unroll
+                for (int u = 0; u < PU; u++) {
+                    const int sp = sp0 + u * CHAIN_THREADS;
+                    beg[u] = sp < S ? ptr[sp] : 0;
+                    len[u] = sp < S ? ptr[sp + 1] - beg[u] : 0;
+                    longest = max(longest, len[u]);
+                    acc[u] = 0.0;
                 }
-                row[sp] = acc;
+                for (int x = 0; x < longest; x++) {
+#pragma unroll
+                    for (int u = 0; u < PU; u++)
+                        if (x < len[u]) {
+                            const int k = pk[beg[u] + x];
+                            acc[u] = __dadd_rn(acc[u], __dmul_rn(rto[k], sb[R == 1 ? k : k / R]));
+                        }
+                }
+#pragma unroll
+                for (int u = 0; u < PU; u++) {
+                    const int sp = sp0 + u * CHAIN_THREADS;
+                    if (sp < S) row[sp] = acc[u];
+                }
             }
         }
         __syncthreads();
@@ -288,8 +313,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const do
             const int off = valid ? leaves[l].x : 0, len = valid ? leaves[l].y : 0;
             const double* av = row + off;
             const int lim = len - (len % 8);
-            double r = (len >= 8) ? av[j] : 0.0;
-            for (int x = 8; x < lim; x += 8) r = __dadd_rn(r, av[x + j]);
+            // a leaf has at most 128 elements = 16 per lane: load them all first (independent), then add in NumPy's order
+            double ev[16];
+#pragma unroll
+            for (int x = 0; x < 16; x++) ev[x] = (x * 8 < lim) ? av[x * 8 + j] : 0.0;
+            double r = (len >= 8) ? ev[0] : 0.0;
+#pragma unroll
+            for (int x = 1; x < 16; x++)
+                if (x * 8 < lim) r = __dadd_rn(r, ev[x]);
             const double p2 = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));
             const double q2 = __dadd_rn(p2, __shfl_down_sync(0xffffffffu, p2, 2, 8));
             double res = __dadd_rn(q2, __shfl_down_sync(0xffffffffu, q2, 4, 8));
@@ -317,6 +348,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const do
         const double tot = nNodes ? nsum[nNodes - 1] : s_sum[0];
         // ---- normalise; the next step starts from this row, or from b0 again after a reset
         const bool reset = resets && resets[i];
+#pragma unroll 4
         for (int sp = tid; sp < S; sp += CHAIN_THREADS) {
             const double v = row[sp] / tot;                               // 0/0 = NaN for an impossible observation, as in the reference
             row[sp] = v;
