@@ -476,7 +476,6 @@ class PBVI_Solver:
     SMALL_PATH = True              # use the single-kernel backup where the sizes qualify (False: always the general pipeline)
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
     STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
-    STREAM_LAST_CHUNK = 384        # the tail is halved down to about this many rows
     PACK_MAX_DENSITY = 0.6         # above this share of non-zero 4-double chunks the rows are uploaded as they are
 
     def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor, want_value: bool = True):
@@ -496,21 +495,11 @@ class PBVI_Solver:
         vstar = torch.empty((nB, dev.A, dev.O), dtype=torch.int32, device=dev.device)
         value = torch.empty((nB, dev.A), dtype=torch.float64, device=dev.device) if want_value else None
         astar = torch.empty((nB,), dtype=torch.int32, device=dev.device)
-        # Chunk plan: a small first chunk (the score kernel starts early), large middle chunks (each launch fills the SMs for many
-        # waves), and a TAPERED tail -- the packers and the kernels run at about the same rows per millisecond, so the step ends one
-        # chunk's worth of compute after the last slab is packed: the last chunk should be small (halving down to ~STREAM_LAST_CHUNK).
         bounds, lo = [], 0
         while lo < nB:
-            rest = nB - lo
-            if lo == 0:
-                take = self.STREAM_FIRST_CHUNK
-            elif rest > self.STREAM_CHUNK + self.STREAM_LAST_CHUNK:
-                take = self.STREAM_CHUNK
-            elif rest > 2 * self.STREAM_LAST_CHUNK:
-                take = -(-(rest // 2) // 64) * 64
-            else:
-                take = rest
-            hi = min(nB, lo + take)
+            hi = min(nB, lo + (self.STREAM_FIRST_CHUNK if lo == 0 else self.STREAM_CHUNK))
+            if nB - hi < self.STREAM_FIRST_CHUNK:
+                hi = nB
             bounds.append((lo, hi))
             lo = hi
         compute = torch.cuda.current_stream(dev.device)
