@@ -29,20 +29,25 @@ void* Arena::take_bytes(size_t bytes) {
             return p;
         }
     }
-    // geometric growth: a new chunk at least doubles the arena, so a solve whose value function grows every iteration
-    // (alphaT, partial argmax buffers) re-allocates O(log) times instead of at every size step
+    // geometric growth: a new chunk is at least TWICE the arena so far, so that it alone can hold the whole next call of a solve whose
+    // value function grows a little every iteration (alphaT, partial argmax buffers): the arena re-allocates O(log) times, and the
+    // consolidation below usually only frees the outgrown chunks instead of allocating again
     size_t total = 0;
     for (auto& c : chunks) total += c.cap;
-    size_t cap = std::max(bytes, std::max(total, size_t(64) << 20));
+    size_t cap = std::max(bytes, std::max(2 * total, size_t(64) << 20));
     char* p = nullptr;
     if (cudaMalloc(&p, cap) != cudaSuccess) {
         cudaGetLastError();
-        if (cap == bytes || cudaMalloc(&p, bytes) != cudaSuccess) {
+        cap = std::max(bytes, total);
+        if (cudaMalloc(&p, cap) != cudaSuccess) {
             cudaGetLastError();
-            set_error("out of device memory: scratch arena could not grow by %zu bytes", bytes);
-            return nullptr;
+            if (cap == bytes || cudaMalloc(&p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("out of device memory: scratch arena could not grow by %zu bytes", bytes);
+                return nullptr;
+            }
+            cap = bytes;
         }
-        cap = bytes;
     }
     chunks.push_back({p, cap, bytes});
     return p;
@@ -52,12 +57,25 @@ void* Arena::take_bytes(size_t bytes) {
 // with the work that may still be using the old chunks).
 void Arena::reset() {
     if (chunks.size() > 1) {
-        size_t total = 0;
-        for (auto& c : chunks) total += c.cap;
-        release();
-        char* p = nullptr;
-        if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back({p, total, 0});
-        else cudaGetLastError();
+        size_t total = 0, used = 0, best = 0;
+        for (size_t i = 0; i < chunks.size(); i++) {
+            total += chunks[i].cap;
+            used += padded(chunks[i].off);
+            if (chunks[i].cap > chunks[best].cap) best = i;
+        }
+        if (chunks[best].cap >= used + (used >> 3)) {
+            // the largest chunk alone holds what the previous call needed (with 12 % to spare): free the others, allocate nothing
+            Chunk keep = chunks[best];
+            for (size_t i = 0; i < chunks.size(); i++)
+                if (i != best) cudaFree(chunks[i].base);
+            chunks.clear();
+            chunks.push_back(keep);
+        } else {
+            release();
+            char* p = nullptr;
+            if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back({p, total, 0});
+            else cudaGetLastError();
+        }
     }
     for (auto& c : chunks) c.off = 0;
 }
