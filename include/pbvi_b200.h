@@ -270,8 +270,9 @@ PBVI_API int pbvi_broadcast_rows(pbvi_comm* c, double* d_rows, size_t count, int
  * and kernel launch count of the last call (for bench.py's roofline / gpu_launches accounting) */
 PBVI_API int pbvi_last_stats(const pbvi_model* m, double* executed_flops, double* dense_flops, int* launches);
 
-/* engine options (A/B runs, tests): "chain_kernel" = 1 (default) runs pbvi_belief_trajectory / pbvi_perseus_walk as ONE persistent launch
- * when a belief fits in shared memory, 0 = one launch per step-kernel.  Both give the same bytes. */
+/* engine options (A/B runs, tests): "chain_kernel" = 2 (default) runs pbvi_belief_trajectory / pbvi_perseus_walk as ONE persistent launch
+ * on a thread-block cluster of 8 blocks when a belief fits in shared memory, 1 = the same in one block, 0 = one launch per step-kernel.
+ * All three give the same bytes (olfactory model: 20 / 37 / 62 us per step of a Perseus walk). */
 PBVI_API int pbvi_set_option(pbvi_model* m, const char* name, int value);
 
 /* kernels launched by the last API call on this handle (host-side counter, no synchronisation) */

@@ -358,9 +358,155 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_kernel(const do
     }
 }
 
+// ---- the same chain on a thread-block CLUSTER of 8 CTAs (8 SMs): every CTA keeps a full copy of the current belief in its shared memory
+//      (the projection gathers predecessors from anywhere), owns one eighth of the states for the projection and the division and every
+//      eighth leaf of the pairwise sum, and the CTAs meet at four cluster barriers per step; rows, leaf sums and the observation
+//      probabilities cross CTAs through global memory (L2; read with ld.cg).  Same arithmetic, same association: bitwise the other two
+//      forms.  pbvi_set_option("chain_kernel", 2).
+constexpr int CHAIN_CLUSTER = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) belief_chain_cluster_kernel(
+    const double* __restrict__ b0, const int32_t* __restrict__ actions, const int32_t* __restrict__ observations,
+    const double* __restrict__ uniforms, const uint8_t* __restrict__ resets, int n, const int32_t* __restrict__ predPtr,
+    const int32_t* __restrict__ predK, const double* __restrict__ rtoK, int S, int R, int O, const int2* __restrict__ leaves, int nLeaves,
+    const int2* __restrict__ nodes, int nNodes, const int32_t* __restrict__ levelNodes, const int32_t* __restrict__ levelPtr, int nLevels,
+    double* out, int32_t* __restrict__ chosenOut, double* leafSumsG, double* obsG) {
+    extern __shared__ double chain_smem[];
+    double* sb = chain_smem;                     // [S] current belief (full copy per CTA)
+    double* s_sum = sb + S;                      // [nLeaves] leaf sums, then [nNodes] node sums
+    __shared__ double s_part[8];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int rank = (int)cluster_cta_rank();
+    const size_t K = (size_t)S * R;
+    const int per = (S + CHAIN_CLUSTER - 1) / CHAIN_CLUSTER, lo = min(S, rank * per), hi = min(S, lo + per);
+    for (int s = tid; s < S; s += CHAIN_THREADS) sb[s] = b0[s];
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+        const int a = actions[i];
+        int o = observations ? observations[i] : -1;
+        if (o < 0) {
+            // P(o | b, a): CTA r takes the observations r, r + 8, ...; 256 threads with observation_probability_kernel's summation shape
+            for (int oo = rank; oo < O; oo += CHAIN_CLUSTER) {
+                double part = 0.0;
+                if (tid < 256) {
+                    const double* rto = rtoK + ((size_t)a * O + oo) * K;
+                    if (R == 1) {
+#pragma unroll 8
+                        for (int s = tid; s < S; s += 256) part = fma(rto[s], sb[s], part);
+                    } else {
+                        for (int s = tid; s < S; s += 256) {
+                            const double bs = sb[s];
+                            for (int r = 0; r < R; r++) part = fma(rto[(size_t)s * R + r], bs, part);
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+                    if (lane == 0) s_part[tid >> 5] = part;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) tot += s_part[w];
+                    obsG[oo] = tot;
+                }
+                __syncthreads();
+            }
+            cluster_sync_all();
+            const double u = uniforms[i];
+            double tot = 0.0;
+            for (int x = 0; x < O; x++) tot = __dadd_rn(tot, __ldcg(obsG + x));
+            double run = 0.0;
+            int idx = 0;
+            for (int x = 0; x < O; x++) {
+                run = __dadd_rn(run, __ldcg(obsG + x));
+                if (__ddiv_rn(run, tot) <= u) idx++;
+            }
+            o = min(idx, O - 1);
+        }
+        if (rank == 0 && tid == 0 && chosenOut) chosenOut[i] = o;
+        // ---- projection of this CTA's slice (bincount order)
+        double* row = out + (size_t)i * S;
+        {
+            const int32_t* ptr = predPtr + (size_t)a * (S + 1);
+            const int32_t* pk = predK + (size_t)a * K;
+            const double* rto = rtoK + ((size_t)a * O + o) * K;
+            for (int sp = lo + tid; sp < hi; sp += CHAIN_THREADS) {
+                double acc = 0.0;
+                const int end = ptr[sp + 1];
+                for (int j = ptr[sp]; j < end; j++) {
+                    const int k = pk[j];
+                    acc = __dadd_rn(acc, __dmul_rn(rto[k], sb[R == 1 ? k : k / R]));
+                }
+                row[sp] = acc;
+            }
+        }
+        cluster_sync_all();
+        // ---- leaf sums of the leaves rank, rank + 8, ...: 8 lanes per leaf
+        for (int q0 = 0; q0 * CHAIN_CLUSTER < nLeaves * 8; q0 += CHAIN_THREADS) {        // uniform trip count over the cluster
+            const int q = q0 + tid, l = rank + CHAIN_CLUSTER * (q >> 3), j = q & 7;
+            const bool valid = l < nLeaves;
+            const int off = valid ? leaves[l].x : 0, len = valid ? leaves[l].y : 0;
+            const double* av = row + off;
+            const int lim = len - (len % 8);
+            double ev[16];
+#pragma unroll
+            for (int x = 0; x < 16; x++) ev[x] = (x * 8 < lim) ? __ldcg(av + x * 8 + j) : 0.0;
+            double r = (len >= 8) ? ev[0] : 0.0;
+#pragma unroll
+            for (int x = 1; x < 16; x++)
+                if (x * 8 < lim) r = __dadd_rn(r, ev[x]);
+            const double p2 = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1, 8));
+            const double q2 = __dadd_rn(p2, __shfl_down_sync(0xffffffffu, p2, 2, 8));
+            double res = __dadd_rn(q2, __shfl_down_sync(0xffffffffu, q2, 4, 8));
+            if (valid && j == 0) {
+                if (len < 8) {
+                    res = 0.0;
+                    for (int x = 0; x < len; x++) res = __dadd_rn(res, __ldcg(av + x));
+                } else {
+                    for (int x = lim; x < len; x++) res = __dadd_rn(res, __ldcg(av + x));
+                }
+                leafSumsG[l] = res;
+            }
+        }
+        cluster_sync_all();
+        // ---- the combine tree, level by level, redundantly in every CTA
+        for (int l = tid; l < nLeaves; l += CHAIN_THREADS) s_sum[l] = __ldcg(leafSumsG + l);
+        __syncthreads();
+        double* nsum = s_sum + nLeaves;
+        for (int lev = 0; lev < nLevels; lev++) {
+            for (int x = levelPtr[lev] + tid; x < levelPtr[lev + 1]; x += CHAIN_THREADS) {
+                const int j = levelNodes[x];
+                const int l = nodes[j].x, r = nodes[j].y;
+                nsum[j] = __dadd_rn(l < 0 ? s_sum[~l] : nsum[l], r < 0 ? s_sum[~r] : nsum[r]);
+            }
+            __syncthreads();
+        }
+        const double tot = nNodes ? nsum[nNodes - 1] : s_sum[0];
+        // ---- division of this CTA's slice, then every CTA reloads the whole row (or b0 after a reset)
+        for (int sp = lo + tid; sp < hi; sp += CHAIN_THREADS) row[sp] = __ldcg(row + sp) / tot;
+        cluster_sync_all();
+        const bool reset = resets && resets[i];
+#pragma unroll 4
+        for (int s = tid; s < S; s += CHAIN_THREADS) sb[s] = reset ? b0[s] : __ldcg(row + s);
+        __syncthreads();
+    }
+}
+
 int configure_belief_kernels() {
     PBVI_CUDA(cudaFuncSetAttribute(pairwise_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PBVI_CUDA(cudaFuncSetAttribute(belief_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
+    PBVI_CUDA(cudaFuncSetAttribute(belief_chain_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
     return PBVI_OK;
 }
 
@@ -393,6 +539,33 @@ static int launch_chain(pbvi_model* m, const double* d_b0, const int32_t* h_acti
         PBVI_CUDA(cudaMemcpyAsync(dR, h_resets, (size_t)n, cudaMemcpyHostToDevice, st));
     }
     const size_t smem = ((size_t)m->S + m->nLeaves + m->nNodes) * sizeof(double);
+    if (m->chain_mode == 2) {
+        PBVI_TAKE(leafSumsG, double, (size_t)m->nLeaves);
+        PBVI_TAKE(obsG, double, 32);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CHAIN_CLUSTER);
+        cfg.blockDim = dim3(CHAIN_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CHAIN_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, belief_chain_cluster_kernel, d_b0, (const int32_t*)dA, (const int32_t*)dO, (const double*)dU,
+                                                 (const uint8_t*)dR, n, (const int32_t*)m->predPtr, (const int32_t*)m->predK, (const double*)m->rtoK,
+                                                 m->S, m->R, m->O, (const int2*)m->pwLeaves, m->nLeaves, (const int2*)m->pwNodes, m->nNodes,
+                                                 (const int32_t*)m->pwLevelNodes, (const int32_t*)m->pwLevelPtr, m->nLevels, d_out, d_chosen,
+                                                 leafSumsG, obsG);
+        if (e == cudaSuccess) {
+            m->last_launches++;
+            return PBVI_OK;
+        }
+        cudaGetLastError();                 // no room for an 8-block cluster with this much shared memory (partitioned device): one block
+        m->chain_mode = 1;
+    }
     belief_chain_kernel<<<1, CHAIN_THREADS, smem, st>>>(d_b0, dA, dO, dU, dR, n, m->predPtr, m->predK, m->rtoK, m->S, m->R, m->O, m->pwLeaves,
                                                         m->nLeaves, m->pwNodes, m->nNodes, m->pwLevelNodes, m->pwLevelPtr, m->nLevels, d_out,
                                                         d_chosen);

@@ -311,7 +311,7 @@ extern "C" int pbvi_last_launches(const pbvi_model* m) { return m ? m->last_laun
 
 extern "C" int pbvi_set_option(pbvi_model* m, const char* name, int value) {
     PBVI_REQUIRE(m != nullptr && name != nullptr, "NULL argument");
-    if (std::strcmp(name, "chain_kernel") == 0) { m->no_chain_kernel = value == 0; return PBVI_OK; }
+    if (std::strcmp(name, "chain_kernel") == 0) { m->no_chain_kernel = value == 0; m->chain_mode = value == 1 ? 1 : 2; return PBVI_OK; }
     set_error("bad argument: unknown option '%s'", name);
     return PBVI_ERR_BAD_ARG;
 }

@@ -142,6 +142,7 @@ struct pbvi_model {
     int32_t* pwLevelPtr = nullptr;     // [nLevels + 1]
     int nLevels = 0;
     bool no_chain_kernel = false;      // pbvi_set_option("chain_kernel", 0): belief chains as one launch per step-kernel (tests, A/B)
+    int chain_mode = 2;                // 2 (default): a cluster of 8 blocks; 1: one persistent block (pbvi_set_option("chain_kernel", ...))
     uint4* hashKeys = nullptr;   // [S] row_key_words(s): position keys of the 128-bit row key
     int nLeaves = 0, nNodes = 0;
 

@@ -638,7 +638,7 @@ def test_chain_kernel_equals_multi_launch_chain(torch_cuda, tag):
     resets = (rng.random(n) < 0.1)
     traj0 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts, obs0.cpu().numpy(), resets)
     launches_multi = dev._lib.pbvi_last_launches(dev._h)
-    dev.set_option('chain_kernel', 1)
+    dev.set_option('chain_kernel', 1)                 # one persistent block
     walk1, obs1 = dev.perseus_walk(b0, acts, us, want_observations=True)
     assert dev._lib.pbvi_last_launches(dev._h) == 1
     traj1 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts, obs0.cpu().numpy(), resets)
@@ -646,6 +646,13 @@ def test_chain_kernel_equals_multi_launch_chain(torch_cuda, tag):
     assert torch_cuda.equal(obs0, obs1)
     assert np.array_equal(walk0.cpu().numpy(), walk1.cpu().numpy(), equal_nan=True)
     assert np.array_equal(traj0.cpu().numpy(), traj1.cpu().numpy(), equal_nan=True)
+    # the cluster form (8 blocks, four cluster barriers per step)
+    dev.set_option('chain_kernel', 2)
+    walk2, obs2 = dev.perseus_walk(b0, acts, us, want_observations=True)
+    traj2 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts, obs0.cpu().numpy(), resets)
+    assert torch_cuda.equal(obs0, obs2)
+    assert np.array_equal(walk0.cpu().numpy(), walk2.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(traj0.cpu().numpy(), traj2.cpu().numpy(), equal_nan=True)
     # an impossible observation somewhere in the chain: NaN from there on, in both forms
     bad_obs = obs0.cpu().numpy().copy()
     out = orc.all_successors(reach, m['rto'], np.asarray(b0)[None, :])[0]
@@ -655,7 +662,7 @@ def test_chain_kernel_equals_multi_launch_chain(torch_cuda, tag):
         acts2[0], bad_obs[0] = impossible[0]
         dev.set_option('chain_kernel', 0)
         t0 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts2, bad_obs, None)
-        dev.set_option('chain_kernel', 1)
+        dev.set_option('chain_kernel', 2)
         t1 = dev.belief_trajectory(torch_cuda.as_tensor(b0).cuda(), acts2, bad_obs, None)
         assert np.isnan(t1.cpu().numpy()[0]).all()
         assert np.array_equal(t0.cpu().numpy(), t1.cpu().numpy(), equal_nan=True)
