@@ -2,12 +2,12 @@
 # A/B timing of engine builds on the same box and the same saved workload: tools/ab_bench.sh lib1.so lib2.so ...
 # (libraries built with PBVI_B200_LIB=... PBVI_B200_DEFS=... python -m pomdp_pbvi_exploration_b200.build --force)
 set -u
-python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-dense-variant --save-workload /tmp/ab_wl.pt > /dev/null 2>&1
+python bench.py --steps 2 --warmup 1 --legs backup --no-e2e --no-cpu-baseline --save-workload /tmp/ab_wl.pt > /dev/null 2>&1
 for rep in 1 2; do
   for lib in "$@"; do
-    PBVI_B200_LIB=$(realpath "$lib") python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --load-workload /tmp/ab_wl.pt 2>/dev/null | python -c "
+    PBVI_B200_LIB=$(realpath "$lib") python bench.py --steps 20 --warmup 3 --legs backup --no-e2e --no-cpu-baseline --load-workload /tmp/ab_wl.pt 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']; dv=d['dense_alpha_variant']
+d=json.loads(sys.stdin.read()); r=d['roofline']; dv=d['value_function_points']['dense']; r['executed_tflops']=r['achieved']
 print('$lib rep$rep step %.3f ms score %.3f ms %.1f TF | dense step %.2f ms score %.2f ms %.1f TF' % (d['ms_per_step'], r['kernel_ms'], r['executed_tflops'], dv['ms_per_step'], dv['kernel_ms'], dv['executed_tflops']))"
   done
 done

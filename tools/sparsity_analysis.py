@@ -22,7 +22,8 @@ def main():
         blob = torch.load(sys.argv[1])
         beliefs, alphas = blob['beliefs'].to(dev), blob['alphas'].to(dev)
     else:
-        _, beliefs, vf, _ = bench.build_workload(model, 10000, 1000, seed=0)
+        _, beliefs, vfs, _ = bench.build_workload(model, 10000, 1000, seed=0)
+        vf = vfs[os.environ.get('PBVI_VF', 'young')]           # 'young' (round 1's analysis) or 'late'
         alphas = vf.alpha_vector_array
     B, S = beliefs.shape
     V = alphas.shape[0]

@@ -27,7 +27,8 @@ def main():
     model = olfactory_wrap_model()
     dev = model.device
     nB = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
-    solver, beliefs, vf, _ = bench.build_workload(model, nB, 1000, seed=0)
+    solver, beliefs, vfs, _ = bench.build_workload(model, nB, 1000, seed=0)
+    vf = vfs[os.environ.get('PBVI_VF', 'late')]
     bs = BeliefSet(model, beliefs)
     V = vf.alpha_vector_array
     _, t = timed(lambda: dev.backup_select(beliefs, V, 0.99)); print(f'backup_select (kernels)      {t:8.3f} ms')
