@@ -873,7 +873,13 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
     PBVI_CUDA(cudaMemsetAsync(nonfinite, gammaBad, sizeof(int), st));
     nonfinite_scan_kernel<<<m->sm_count * 8, 256, 0, st>>>(d_alphas, (size_t)nV * m->S, nonfinite);
     m->last_launches++;
-    constexpr int G = 8, SPT = 2;
+#ifndef PBVI_ASM_G
+#define PBVI_ASM_G 8
+#endif
+#ifndef PBVI_ASM_SPT
+#define PBVI_ASM_SPT 2
+#endif
+    constexpr int G = PBVI_ASM_G, SPT = PBVI_ASM_SPT;      // tuples per block / states per thread of the grouped assemble kernel (A/B builds)
     if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024 &&
         ((long long)n + (long long)m->A * (G - 1)) / G + 1 <= 65535) {            // grid.y of the grouped kernel
         PBVI_TRY(enter_call(m, st));
