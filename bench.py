@@ -632,9 +632,10 @@ def run_b200(args):
             'clocks': clocks,
             'e2e': {'value': units * args.steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
-                    'host_input_bytes_per_step': h2d_dense, 'host_threads': min(32, os.cpu_count() or 1) if (e2e_steps and h2d < h2d_dense) else 1,
+                    'host_input_bytes_per_step': h2d_dense, 'host_threads': (dev.__dict__.get('_pack') or {}).get('pool')._max_workers if (e2e_steps and h2d < h2d_dense) else 1,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy(); sparse belief rows are packed by '
-                           'host threads (pbvi_pack_rows_host) for the upload and unpacked on the device'},
+                           'host threads (pbvi_pack_slabs_host) for the upload and unpacked on the device; the alpha rows known before the last '
+                           'chunk of beliefs is scored are read back beside that kernel'},
             'gpu_launches': int(head['launches']),
             'roofline': {'bound': 'tensor', 'kernel': 'score_kernel<GATHER> (persistent block-sparse FP64 DMMA m8n8k4 GEMM + fused argmax)',
                          'achieved': exec_tflops, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': exec_tflops / FP64_PEAK_TFLOPS,

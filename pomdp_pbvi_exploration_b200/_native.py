@@ -401,12 +401,15 @@ class DeviceModel:
 
     # ---- packed upload of host-resident rows: persistent staging + packer threads --------------------------------------------
     PACK_SLAB = 64                 # rows packed by one host task (small: the first chunk is ready after a few milliseconds)
+    PACK_THREADS = None            # packer threads (None: one per host core but one -- the threads that issue copies and kernels need a core --, at most 32)
+    PACK_MAX_DENSITY = 0.6         # above this share of non-zero 4-double chunks the rows are uploaded as they are
 
     def start_pack(self, host: torch.Tensor):
         """
         Starts packing the pinned host rows [n,L] on the packer threads and returns a job handle (or None when the staging
         buffers are in use by another pending job).  Called when a host-resident BeliefSet is created, so that the host work
-        overlaps whatever the caller does before the backup; `PBVI_Solver._select_streamed` consumes the job.
+        overlaps whatever the caller does before the backup (the upload of the value function, for one);
+        `PBVI_Solver._select_streamed` consumes the job: it ships the packed slabs (`_PackJob.shipped`) and unpacks them.
         """
         import os
         import weakref
@@ -421,25 +424,29 @@ class DeviceModel:
             return None
         for f in (st or {}).get('futures') or ():  # packers of an abandoned job may still be writing the staging buffers
             f.result()
-        if st is None or st['key'] != (n, L):
-            if st is not None and st['copies_done'] is not None:
-                st['copies_done'].synchronize()    # copy-stream writes into the old device staging must land before it is released
+        if st is not None and st['job'] is not None and st['job']() is None:
+            st['stream'].synchronize()             # a job dropped without `close()`: no event marks the end of its copies
+        if st is not None and st['copies_done'] is not None:
+            st['copies_done'].synchronize()        # the copies of the previous job may still be reading the pinned staging
+        workers = self.PACK_THREADS or max(1, min(32, (os.cpu_count() or 2) - 1))
+        if st is None or st['key'] != (n, L) or st['pool']._max_workers != workers:
             n_c, W = self.pack_geometry(L)
             SL = self.PACK_SLAB
             n_slabs = -(-n // SL)
             region = SL * n_c * 4 + 4              # doubles per slab: worst case + the packer's one-chunk slack
-            pool = st['pool'] if st is not None else ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
+            pool = st['pool'] if st is not None and st['pool']._max_workers == workers else ThreadPoolExecutor(max_workers=workers)
+            stream = st['stream'] if st is not None else torch.cuda.Stream(device=self.device)
             st = self._pack = {
-                'key': (n, L), 'n_c': n_c, 'W': W, 'SL': SL, 'n_slabs': n_slabs, 'region': region, 'pool': pool, 'job': None, 'copies_done': None,
-                'futures': None, 'alive': None,
+                'key': (n, L), 'n_c': n_c, 'W': W, 'SL': SL, 'n_slabs': n_slabs, 'region': region, 'pool': pool, 'stream': stream, 'job': None,
+                'copies_done': None, 'futures': None, 'alive': None,
                 'h_bm': torch.empty((n, W), dtype=torch.int32).pin_memory(),
                 'h_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32).pin_memory(),
                 'h_pk': torch.empty((n_slabs * region,), dtype=torch.float64).pin_memory(),
                 'd_bm': torch.empty((n, W), dtype=torch.int32, device=self.device),
                 'd_rs': torch.empty((n_slabs, SL + 1), dtype=torch.int32, device=self.device),
                 'd_pk': torch.empty((n_slabs * region,), dtype=torch.float64, device=self.device)}
-        if st['copies_done'] is not None:
-            st['copies_done'].synchronize()        # the copies of the previous job may still be reading the pinned staging
+        # the unpack kernels of the previous job (the caller's stream waited for each of them) read the device staging the new copies overwrite
+        st['stream'].wait_stream(torch.cuda.current_stream(self.device))
         job = _PackJob(self, st, host)
         # the staging dict keeps what the packer threads touch alive for as long as they may run
         st['job'], st['futures'], st['alive'] = weakref.ref(job), job.futures, (job.totals, host)
@@ -517,15 +524,59 @@ class DeviceModel:
         self._call(self._lib.pbvi_ger_scores(self._h, _ptr(b), _ptr(al), _ptr(sc), n, float(r_min), float(r_max), _ptr(eps), self._stream))
         return eps
 
+    def _staging_buffer(self, n: int) -> torch.Tensor:
+        """Grow-only pinned staging of the read-backs; every new use invalidates the views handed out before (`_staging_token`)."""
+        buf = getattr(self, '_staging', None)
+        want = max(n, getattr(self, '_staging_want', 0), 1 << 20)
+        if buf is None or buf.numel() < n:
+            buf = self._staging = torch.empty((want,), dtype=torch.float64).pin_memory()
+        self._staging_token = getattr(self, '_staging_token', 0) + 1
+        return buf
+
     def to_host_staged(self, t: torch.Tensor) -> np.ndarray:
         """Device -> host through a grow-only pinned staging buffer; returns a NumPy view valid until the next call."""
         n = t.numel()
-        buf = getattr(self, '_staging', None)
-        if buf is None or buf.numel() < n:
-            buf = self._staging = torch.empty((max(n, 1 << 20),), dtype=torch.float64).pin_memory()
-        view = buf[:n].view(t.shape)
+        view = self._staging_buffer(n)[:n].view(t.shape)
         view.copy_(t)
         return view.numpy()
+
+    def mirror_begin(self, rows: torch.Tensor) -> dict:
+        """
+        Starts reading `rows` [n,L] (complete on the current stream) back into the pinned staging on the read-back stream and returns
+        a handle for `mirror_finish`.  The streamed backup uses it for the alpha rows it can assemble before its last chunk of beliefs
+        is selected: their device->host copy then runs beside the score kernel instead of after it (the link is full duplex).
+        """
+        n = rows.numel()
+        buf = self._staging_buffer(max(2 * n, n + 512 * rows.shape[1]))     # room for the rows the last chunk may add
+        stream = getattr(self, '_readback_stream', None)
+        if stream is None:
+            stream = self._readback_stream = torch.cuda.Stream(device=self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(stream):
+            buf[:n].view(rows.shape).copy_(rows, non_blocking=True)
+        return {'buf': buf, 'token': self._staging_token, 'rows': rows.shape[0], 'L': rows.shape[1], 'stream': stream, 'keep': rows}
+
+    def mirror_finish(self, mirror: dict, tail: torch.Tensor | None):
+        """
+        Appends `tail` [m,L] (complete on the current stream; None: nothing to add) to the read-back started by `mirror_begin`.
+        Returns (NumPy view of all rows, CUDA event behind the copies, staging token), or None when the staging was re-used in
+        between or is too small (the next one is allocated larger; the caller reads the rows back the plain way).
+        """
+        n0, L = mirror['rows'], mirror['L']
+        m = 0 if tail is None else tail.shape[0]
+        buf, stream = mirror['buf'], mirror['stream']
+        if mirror['token'] != getattr(self, '_staging_token', 0):
+            return None
+        if (n0 + m) * L > buf.numel():
+            self._staging_want = 2 * (n0 + m) * L
+            return None
+        if m:
+            stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(stream):
+                buf[n0 * L:(n0 + m) * L].view(m, L).copy_(tail, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+        return buf[:(n0 + m) * L].view(n0 + m, L).numpy(), done, mirror['token']
 
     def set_option(self, name: str, value: int) -> None:
         _check(self._lib.pbvi_set_option(self._h, name.encode(), int(value)))
@@ -545,19 +596,32 @@ class DeviceModel:
 
 
 class _PackJob:
-    """Slabs of host rows being packed by the packer threads; `result(i)` = number of chunks of slab i (waits until it is packed).
-    Every thread makes ONE library call (slabs t, t + T, t + 2T, ... in a C loop, GIL released throughout) and publishes a
-    slab's chunk count as its last store, so finished slabs are shipped without any thread having to return to Python."""
+    """
+    Packed upload of host rows in flight.  The packer threads each make ONE library call (slabs t, t + T, t + 2T, ... in a C loop, GIL
+    released throughout) and publish a slab's chunk count as their last store; `result(i)` = number of chunks of slab i (waits until it
+    is packed).  `shipped(rows)` follows the packers slab by slab, enqueues the copies [chunks of every slab | bitmaps | row offsets]
+    of the ship units up to `rows` on the upload stream and returns the CUDA event behind them; the consumer makes its stream wait on
+    it and unpacks.  A ship unit is one round of the packer threads (T slabs, at most SHIP_SLABS), so the first one is complete after
+    ONE slab time.  (A feeder thread that ships while the caller is still busy elsewhere was measured: no gain, the link is taken by
+    the value function's upload until the caller is back; tools/e2e_timeline.py.)
+    """
+    SHIP_SLABS = 16
 
     def __init__(self, dev: 'DeviceModel', st: dict, host: torch.Tensor):
         self.st, self.host, self.consumed = st, host, False
         n, L = host.shape
+        self.n = n
         self.totals = np.full((st['n_slabs'],), -1, dtype=np.int64)
         lib, pool = dev._lib, st['pool']
         T = max(1, min(pool._max_workers, st['n_slabs']))
+        self.ship_rows = st['SL'] * min(T, self.SHIP_SLABS)
         args = (host.data_ptr(), n, L, st['SL'])
         tail = (st['h_bm'].data_ptr(), st['h_rs'].data_ptr(), st['h_pk'].data_ptr(), st['region'], self.totals.ctypes.data)
         self.futures = [pool.submit(lib.pbvi_pack_slabs_host, *args, t, T, *tail) for t in range(T)]
+        self.max_density = dev.PACK_MAX_DENSITY
+        self.events = [None] * (-(-n // self.ship_rows))     # CUDA event behind the copies of ship unit u
+        self.units_shipped = 0
+        self.h2d_bytes = 0
 
     def result(self, i: int) -> int:
         import time
@@ -568,3 +632,38 @@ class _PackJob:
             if v == -2 or all(f.done() for f in self.futures) and int(self.totals[i]) < 0:
                 raise PBVIError('packing the host rows failed')
             time.sleep(2e-5)
+
+    def is_packed(self) -> bool:
+        """Sparse enough to travel packed (decided on the first slab)?  False: nothing is shipped, the caller copies the rows."""
+        st = self.st
+        return self.result(0) <= self.max_density * min(st['SL'], self.n) * st['n_c']
+
+    def shipped(self, rows: int):
+        """CUDA event behind the copies of the first `rows` rows (ships every unit up to there that is not on its way yet)."""
+        st, n = self.st, self.n
+        SL, region, W, stream = st['SL'], st['region'], st['W'], st['stream']
+        units = -(-rows // self.ship_rows)
+        with torch.cuda.stream(stream):
+            while self.units_shipped < units:
+                u = self.units_shipped
+                lo, hi = u * self.ship_rows, min(n, (u + 1) * self.ship_rows)
+                s0, s1 = lo // SL, -(-hi // SL)
+                for i in range(s0, s1):
+                    total = self.result(i)                               # the packers run ahead of the copies
+                    st['d_pk'][i * region:i * region + total * 4].copy_(st['h_pk'][i * region:i * region + total * 4], non_blocking=True)
+                    self.h2d_bytes += total * 32
+                st['d_bm'][lo:hi].copy_(st['h_bm'][lo:hi], non_blocking=True)
+                st['d_rs'][s0:s1].copy_(st['h_rs'][s0:s1], non_blocking=True)
+                self.h2d_bytes += (hi - lo) * W * 4 + (s1 - s0) * (SL + 1) * 4
+                self.events[u] = torch.cuda.Event(enable_timing=True)
+                self.events[u].record(stream)
+                self.units_shipped = u + 1
+        return self.events[units - 1]
+
+    def close(self) -> None:
+        """The consumer is done with the job (or never used it): the staging buffers become free once the enqueued copies have run."""
+        if not self.consumed:
+            self.consumed = True
+            done = torch.cuda.Event()
+            done.record(self.st['stream'])
+            self.st['copies_done'] = done

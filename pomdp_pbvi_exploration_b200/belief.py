@@ -176,7 +176,7 @@ class BeliefSet:
         if self._device is None:
             job = self.__dict__.pop('_pack_job', None)
             if job is not None:
-                job.consumed = True                 # plain upload: the packed form is not used (the staging buffers become free)
+                job.close()                         # plain upload: the packed form is not used (the staging buffers become free)
             self._device = _to_device(self.model, self._host)
         return self._device
 

@@ -52,6 +52,9 @@ __attribute__((target("avx2"))) int64_t pack_row_avx2(const uint64_t* row, int r
         int c = w * 32;
         const int cv = c1 < fullC ? c1 : fullC;
         for (; c < cv; c++) {
+            // one software prefetch per cache line, 2 KB ahead: on its hardware prefetcher alone (it stops at every 4 KB page) a core
+            // scans 5.6 GB/s, with this 9-10 -- the packers of a 16-core host go from 90 to 156 GB/s (tools/e2e_timeline.py)
+            if (!(c & 1)) _mm_prefetch(reinterpret_cast<const char*>(row + (size_t)c * PACK) + 2048, _MM_HINT_T0);
             const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(row + (size_t)c * PACK));
             const int live = !_mm256_testz_si256(v, v);
             _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + cnt * PACK), v);     // overwritten by the next live chunk if dead

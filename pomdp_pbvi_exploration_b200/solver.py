@@ -420,8 +420,11 @@ class PBVI_Solver:
             return torch.zeros((0, 1 + dev.O), dtype=torch.int32, device=dev.device), z, z
         # value[b][a] itself is only read by the dominance filter; without it a* alone is asked for and beliefs with a single
         # possible winner skip the exact reference-order sum
+        self._early = early = None
         if belief_set._device is None and nB >= 2 * self.STREAM_FIRST_CHUNK:
-            vstar, value, astar = self._select_streamed(model, belief_set, V, want_value=belief_dominance_prune)
+            if self.EARLY_ROWS and not belief_dominance_prune:
+                early = {}
+            vstar, value, astar = self._select_streamed(model, belief_set, V, want_value=belief_dominance_prune, early=early)
         else:
             vstar, value, astar = dev.backup_select(belief_set.belief_array, V, self.gamma, want_value=belief_dominance_prune)
         B = belief_set.belief_array
@@ -434,7 +437,14 @@ class PBVI_Solver:
             keep = value[ar, astar.long()] > best_old
             keys = keys[torch.nonzero(keep)[:, 0]]
         first, last, _ = dev.group_keys(keys)
-        return keys[first.long()], first, last
+        tuples = keys[first.long()]
+        if early:
+            # first-occurrence order: the tuples of the rows selected before the last chunk are a prefix of all tuples
+            u1 = early['tuples'].shape[0]
+            if tuples.shape[0] >= u1 and torch.equal(tuples[:u1], early['tuples']):
+                early['token'] = tuples
+                self._early = early
+        return tuples, first, last
 
     def select_tuples(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
         """`select_tuples_device` as host int64 arrays (tuples [u, 1+O], first [u], last [u])."""
@@ -455,10 +465,23 @@ class PBVI_Solver:
         if n == 0:
             return ValueFunction(model, torch.empty((0, dev.S), dtype=torch.float64, device=dev.device), np.zeros(0, dtype=np.int64))
         rank = torch.as_tensor(last).to(device=dev.device, dtype=torch.int32)
-        rows, keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, t[:, 0], t[:, 1:], with_hash=True)
+        early, self._early = self.__dict__.get('_early'), None
+        mirror = tail = None
+        if early is not None and early.get('token') is tuples:
+            # streamed backup: the rows of the first tuples were assembled (and their read-back started) before the last chunk of
+            # beliefs was selected -- same kernel, same bytes; only the tuples that chunk added are assembled now
+            u1 = early['tuples'].shape[0]
+            rows, keys, mirror = early['rows'], early['keys'], early['mirror']
+            if n > u1:
+                tail, tail_keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, t[u1:, 0], t[u1:, 1:], with_hash=True)
+                rows, keys = torch.cat([rows, tail], dim=0), torch.cat([keys, tail_keys], dim=0)
+        else:
+            rows, keys = dev.backup_assemble(value_function.alpha_vector_array, self.gamma, t[:, 0], t[:, 1:], with_hash=True)
         gfirst, owner, inverse = dev.group_keys(keys, rank=rank, want_inverse=True)
         if gfirst.shape[0] == n:
             actions, hashes = t[:, 0], keys
+            if mirror is not None:
+                mirror = dev.mirror_finish(mirror, tail)
         elif dev.confirm_groups(rows, gfirst, inverse):
             gf = gfirst.long()
             actions, rows, hashes = t[owner.long(), 0], rows[gf], keys[gf]
@@ -471,23 +494,48 @@ class PBVI_Solver:
             own[ginv[order[ends]]] = order[ends]
             gf = torch.as_tensor(first_h, device=dev.device)
             actions, rows, hashes = t[torch.as_tensor(own, device=dev.device), 0], rows[gf], keys[gf]
-        return ValueFunction(model, rows, actions.cpu().numpy().astype(np.int64), _trusted=True, _hashes=hashes)
+        out = ValueFunction(model, rows, actions.cpu().numpy().astype(np.int64), _trusted=True, _hashes=hashes)
+        if mirror is not None and gfirst.shape[0] == n:
+            out._mirror = mirror          # `numpy(staged=True)` returns this host copy (already on its way) instead of reading the rows back
+        return out
 
     SMALL_PATH = True              # use the single-kernel backup where the sizes qualify (False: always the general pipeline)
     STREAM_FIRST_CHUNK = 1024      # rows of the first host->device chunk (small, so the score kernel starts early)
-    STREAM_CHUNK = 3072            # rows of the following chunks (large, so each launch fills the 148 SMs for many waves)
-    PACK_MAX_DENSITY = 0.6         # above this share of non-zero 4-double chunks the rows are uploaded as they are
+    STREAM_CHUNK = 3072            # rows of the later chunks (large, so each launch fills the 148 SMs for many waves); the plan doubles up to it
+    EARLY_ROWS = True              # streamed backup: assemble + read back the rows known before the last chunk while that chunk is scored
+    EARLY_MIN_TUPLES = 64
 
-    def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor, want_value: bool = True):
+    def _chunk_plan(self, nB: int, unit: int = 1) -> list:
+        """Row ranges of the streamed select: STREAM_FIRST_CHUNK rows, then doubling up to STREAM_CHUNK, all multiples of `unit`."""
+        first = max(1, self.STREAM_FIRST_CHUNK // unit) * unit
+        cap = max(first, int(round(self.STREAM_CHUNK / unit)) * unit)
+        bounds, lo, size = [], 0, first
+        while lo < nB:
+            hi = min(nB, lo + size)
+            if nB - hi < first:                       # a tail shorter than the first chunk joins the last one
+                hi = nB
+            bounds.append((lo, hi))
+            lo, size = hi, min(cap, 2 * size)
+        return bounds
+
+    def _select_streamed(self, model: Model, belief_set: BeliefSet, V: torch.Tensor, want_value: bool = True, early: dict | None = None):
         """
         Select step for a belief set that still lives in (pinned) host memory: the rows are uploaded in chunks on a
         copy stream while the compute stream runs `pbvi_backup_select` on the chunks that have landed (rows are
         independent given V), so the PCIe transfer hides behind the score kernel instead of preceding it.
 
         Sparse rows travel packed: host threads turn slabs of rows into [bitmap | non-zero 4-double chunks]
-        (`pbvi_pack_rows_host`), only that crosses the bus and `pbvi_unpack_rows` rebuilds the dense rows in HBM, byte for
-        byte.  The packers run ahead of the copies, the copies ahead of the kernels.  `last_h2d_bytes` = bytes copied.
+        (`pbvi_pack_slabs_host`; started when the host-resident BeliefSet was created, `DeviceModel.start_pack`), only that
+        crosses the bus and `pbvi_unpack_rows` rebuilds the dense rows in HBM, byte for byte, on a stream of its own -- beside the
+        score kernel of the previous chunk.  The packers run ahead of the copies, the copies ahead of the kernels.
+        `last_h2d_bytes` = bytes copied.
+
+        `early` (a dict to fill, or None): before the LAST chunk is selected, the distinct tuples of the rows selected so far are
+        grouped, their alpha rows assembled and the device->host copy of those rows started (`DeviceModel.mirror_begin`) -- the
+        link is full duplex and the score kernel of the last chunk hides the copy.  The grouping synchronises on the chunks before the
+        last one; the last chunk's upload and unpack are enqueued before that, its select right after.
         """
+        import time
         dev = model.device
         host = belief_set._host
         nB, S = host.shape
@@ -495,57 +543,73 @@ class PBVI_Solver:
         vstar = torch.empty((nB, dev.A, dev.O), dtype=torch.int32, device=dev.device)
         value = torch.empty((nB, dev.A), dtype=torch.float64, device=dev.device) if want_value else None
         astar = torch.empty((nB,), dtype=torch.int32, device=dev.device)
-        bounds, lo = [], 0
-        while lo < nB:
-            hi = min(nB, lo + (self.STREAM_FIRST_CHUNK if lo == 0 else self.STREAM_CHUNK))
-            if nB - hi < self.STREAM_FIRST_CHUNK:
-                hi = nB
-            bounds.append((lo, hi))
-            lo = hi
         compute = torch.cuda.current_stream(dev.device)
-        copy = getattr(self, '_copy_stream', None)
-        if copy is None:
-            copy = self._copy_stream = torch.cuda.Stream(device=dev.device)
-        copy.wait_stream(compute)                       # `full` and the staging buffers must be free before the copies touch them
+        trace = self.__dict__.get('stream_trace')       # tools/e2e_timeline.py: a list to fill with per-chunk events (None: no tracing)
 
-        # the packers were started when the host-resident BeliefSet was created (`DeviceModel.start_pack`); start them now otherwise
-        job = belief_set.__dict__.pop('_pack_job', None) or dev.start_pack(host)
-        packed = False
-        if job is not None:
-            st = job.st
-            SL, region, n_c = st['SL'], st['region'], st['n_c']
-            packed = job.result(0) <= self.PACK_MAX_DENSITY * min(SL, nB) * n_c
-        self.last_h2d_bytes = 0
-        for lo, hi in bounds:
-            with torch.cuda.stream(copy):
-                if packed:
-                    s0, s1 = lo // SL, -(-hi // SL)
-                    for i in range(s0, s1):
-                        total = job.result(i)                                        # the packers run ahead of the copies
-                        st['d_pk'][i * region:i * region + total * 4].copy_(st['h_pk'][i * region:i * region + total * 4], non_blocking=True)
-                        self.last_h2d_bytes += total * 32
-                    st['d_bm'][lo:hi].copy_(st['h_bm'][lo:hi], non_blocking=True)
-                    st['d_rs'][s0:s1].copy_(st['h_rs'][s0:s1], non_blocking=True)
-                    self.last_h2d_bytes += (hi - lo) * st['W'] * 4 + (s1 - s0) * (SL + 1) * 4
-                else:
-                    full[lo:hi].copy_(host[lo:hi], non_blocking=True)
-                    self.last_h2d_bytes += (hi - lo) * S * 8
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            compute.wait_event(ev)                      # the kernels of this chunk are enqueued while later slabs are still being packed
-            if packed:
-                dev.unpack_rows(st['d_bm'][lo:hi], st['d_rs'][s0:s1], st['d_pk'][s0 * region:], full[lo:hi], slab_rows=SL, region_chunks=region // 4)
+        def select(lo, hi, landed):
             v, val, a = dev.backup_select(full[lo:hi], V, self.gamma, want_value=want_value)
             vstar[lo:hi], astar[lo:hi] = v, a
             if want_value:
                 value[lo:hi] = val
-        if job is not None:
-            job.consumed = True
-            done = torch.cuda.Event()
-            done.record(copy)
-            job.st['copies_done'] = done
+            if trace is not None:
+                done_ev = torch.cuda.Event(enable_timing=True)
+                done_ev.record(compute)
+                trace.append({'rows': (lo, hi), 'enqueued_host_s': time.perf_counter(), 'copied': landed, 'selected': done_ev})
+
+        # the upload was started when the host-resident BeliefSet was created (`DeviceModel.start_pack`); start it now otherwise
+        job = belief_set.__dict__.pop('_pack_job', None) or dev.start_pack(host)
+        if job is not None and job.is_packed():
+            st = job.st
+            SL, region = st['SL'], st['region']
+            unpack = st.get('unpack_stream')            # the rows are rebuilt beside the score kernel of the previous chunk, not before this one's
+            if unpack is None:
+                unpack = st['unpack_stream'] = torch.cuda.Stream(device=dev.device)
+            unpack.wait_stream(compute)                 # `full` must be allocated before the unpack kernels touch it
+            plan = self._chunk_plan(nB, job.ship_rows)
+            for lo, hi in plan:
+                ev = job.shipped(hi)                    # waits for the packers slab by slab and enqueues the copies
+                s0, s1 = lo // SL, -(-hi // SL)
+                with torch.cuda.stream(unpack):
+                    unpack.wait_event(ev)
+                    dev.unpack_rows(st['d_bm'][lo:hi], st['d_rs'][s0:s1], st['d_pk'][s0 * region:], full[lo:hi], slab_rows=SL, region_chunks=region // 4)
+                    rebuilt = torch.cuda.Event(enable_timing=trace is not None)
+                    rebuilt.record(unpack)
+                if early is not None and len(plan) >= 3 and hi == nB:
+                    self._early_rows(dev, V, vstar, astar, lo, early)
+                compute.wait_event(rebuilt)
+                select(lo, hi, rebuilt)
+            job.close()
+            self.last_h2d_bytes = job.h2d_bytes
+        else:
+            # rows as they are, chunk by chunk (dense belief sets; several ranks per host: the packers would compete for its memory)
+            if job is not None:
+                job.close()
+            copy = getattr(self, '_copy_stream', None)
+            if copy is None:
+                copy = self._copy_stream = torch.cuda.Stream(device=dev.device)
+            copy.wait_stream(compute)                   # `full` must be allocated before the copies touch it
+            self.last_h2d_bytes = 0
+            for lo, hi in self._chunk_plan(nB):
+                with torch.cuda.stream(copy):
+                    full[lo:hi].copy_(host[lo:hi], non_blocking=True)
+                    self.last_h2d_bytes += (hi - lo) * S * 8
+                    ev = torch.cuda.Event(enable_timing=trace is not None)
+                    ev.record(copy)
+                compute.wait_event(ev)
+                select(lo, hi, ev)
         belief_set._device = full
         return vstar, value, astar
+
+    def _early_rows(self, dev, V: torch.Tensor, vstar: torch.Tensor, astar: torch.Tensor, n_done: int, early: dict) -> None:
+        """Distinct tuples of the first `n_done` beliefs (selected, in stream order) -> their alpha rows -> read-back started."""
+        ar = torch.arange(n_done, device=dev.device)
+        keys = torch.cat([astar[:n_done, None], vstar[ar, astar[:n_done].long()]], dim=1)
+        first, _, _ = dev.group_keys(keys)              # synchronises: the chunks before the last one are done
+        if first.shape[0] < self.EARLY_MIN_TUPLES:
+            return
+        t = keys[first.long()]
+        rows, hk = dev.backup_assemble(V, self.gamma, t[:, 0], t[:, 1:], with_hash=True)
+        early.update(tuples=t, rows=rows, keys=hk, mirror=dev.mirror_begin(rows))
 
     # ------------------------------------------------------------------------------------------------------------
     def compute_change(self, value_function: ValueFunction, new_value_function: ValueFunction, belief_set: BeliefSet) -> float:

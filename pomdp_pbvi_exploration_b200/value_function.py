@@ -117,6 +117,10 @@ class ValueFunction:
         PCIe speed without a fresh pageable allocation per call.
         """
         if staged:
+            mirror = self.__dict__.get('_mirror')       # the streamed backup read the rows back while it was still computing
+            if mirror is not None and mirror[0].shape[0] == len(self) and mirror[2] == getattr(self.model.device, '_staging_token', 0):
+                mirror[1].synchronize()
+                return mirror[0], self._actions.copy()
             return self.model.device.to_host_staged(self._array), self._actions.copy()
         return self._array.cpu().numpy(), self._actions.copy()
 
@@ -179,6 +183,7 @@ class ValueFunction:
         self._buf, self._buf_start, self._buf_front = buf if buf is not None else (None, None, None)
         self._vector_list = None
         self._pruning_level = 1
+        self._mirror = None
         self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
 
     def append(self, alpha_vector: AlphaVector) -> None:
@@ -190,6 +195,7 @@ class ValueFunction:
         self._actions = np.append(self._actions, alpha_vector.action)
         self._hashes = None
         self._vector_list = None
+        self._mirror = None
         self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
         self._buf = None
 
@@ -219,6 +225,7 @@ class ValueFunction:
             self._actions = self._actions[idx]
             self._hashes = None if self._hashes is None else self.row_hashes[idx]
             self._vector_list = None
+            self._mirror = None
             self.uid, self.parent_uid, self.n_new = next(_UID), None, 0
             self._buf = None
         self._pruning_level = level

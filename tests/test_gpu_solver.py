@@ -225,6 +225,36 @@ def test_streamed_host_beliefs_equal_device_resident():
     assert torch.equal(host_set.belief_array.cpu(), torch.as_tensor(B))
 
 
+def test_streamed_backup_reads_early_rows_back_while_the_last_chunk_is_scored():
+    """Three or more chunks: the tuples known before the last chunk are assembled and their rows read back early (`mirror_begin`),
+    the last chunk adds the rest; value function, actions and the host copy equal the device-resident backup, byte for byte."""
+    import torch
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs
+    model = olfactory_wrap_model()
+    g = load_golden('backup_olfactory_wrap')
+    B = perseus_walk_beliefs(model, 3100, seed=5)
+    vf = ValueFunction(model, g['alphas'], g['alpha_actions'])
+    solver = PBVI_Solver(gamma=0.99, eps=1e-6, expand_function='perseus')
+    solver.STREAM_FIRST_CHUNK, solver.STREAM_CHUNK, solver.EARLY_MIN_TUPLES = 256, 512, 1
+    want = solver.backup(model, BeliefSet(model, B), vf, append=False, belief_dominance_prune=False)
+    r0, a0 = want.numpy()
+    for rep in range(2):                       # the second pass re-uses the staging buffers of the first
+        host_set = BeliefSet(model, torch.as_tensor(B).pin_memory())
+        got = solver.backup(model, host_set, vf, append=False, belief_dominance_prune=False)
+        assert got.__dict__.get('_mirror') is not None, 'the early read-back was not used'
+        r1, a1 = got.numpy(staged=True)
+        assert np.array_equal(r0, r1) and np.array_equal(a0, a1)
+        assert np.array_equal(got.numpy()[0], r0)
+        assert torch.equal(host_set.belief_array.cpu(), torch.as_tensor(B))
+    # a staged read of something else in between invalidates the mirror: the rows are read back the plain way
+    host_set = BeliefSet(model, torch.as_tensor(B).pin_memory())
+    got = solver.backup(model, host_set, vf, append=False, belief_dominance_prune=False)
+    vf.numpy(staged=True)
+    r2, a2 = got.numpy(staged=True)
+    assert np.array_equal(r0, r2) and np.array_equal(a0, a2)
+
+
 def test_streamed_dense_host_beliefs_take_the_plain_upload():
     """Dense rows are not worth packing: the streamed select falls back to plain chunked copies (same results, bytes counted)."""
     import torch

@@ -55,7 +55,7 @@ def main():
     job = dev.start_pack(h_b)
     for f in job.futures:
         f.result()
-    job.consumed = True
+    job.close()
     print(f'packers alone ({len(job.futures)} threads) {(time.perf_counter() - t0) * 1e3:7.2f} ms')
     t0 = time.perf_counter(); x = h_b.cuda(non_blocking=True); torch.cuda.synchronize()
     print(f'plain pinned H2D of the dense beliefs {(time.perf_counter() - t0) * 1e3:7.2f} ms ({h_b.numel() * 8 / 1e9 / (time.perf_counter() - t0):.1f} GB/s)')
