@@ -7,7 +7,7 @@ for rep in 1 2; do
   for lib in "$@"; do
     PBVI_B200_LIB=$(realpath "$lib") python bench.py --steps 20 --warmup 3 --legs backup --no-e2e --no-cpu-baseline --load-workload /tmp/ab_wl.pt 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']; dv=d['value_function_points']['dense']; r['executed_tflops']=r['achieved']
-print('$lib rep$rep step %.3f ms score %.3f ms %.1f TF | dense step %.2f ms score %.2f ms %.1f TF' % (d['ms_per_step'], r['kernel_ms'], r['executed_tflops'], dv['ms_per_step'], dv['kernel_ms'], dv['executed_tflops']))"
+d=json.loads(sys.stdin.read()); p=d['value_function_points']
+print('$lib rep$rep ' + ' | '.join('%s step %.3f ms score %.3f ms %.2f TF (%.3g executed)' % (k, v['ms_per_step'], v['kernel_ms'], v['executed_tflops'], v['executed_flops_per_launch']) for k, v in p.items()))"
   done
 done
