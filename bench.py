@@ -592,7 +592,7 @@ def run_b200(args):
             return res.numpy(staged=True)                                # D2H into the pinned staging buffer
 
         e2e_steps = 0 if args.no_e2e else args.steps
-        for _ in range(0 if args.no_e2e else max(1, args.warmup // 2)):
+        for _ in range(0 if args.no_e2e else args.warmup):
             rows, acts = step_e2e()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -395,7 +395,7 @@ class PBVI_Solver:
             rows, actions, keys = dev.backup_small(belief_set.belief_array, value_function.alpha_vector_array, self.gamma)
             new_vf = ValueFunction(model, rows, actions, _trusted=True, _hashes=keys)
         else:
-            tuples, _, last = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune)
+            tuples, _, last = self.select_tuples_device(model, belief_set, value_function, belief_dominance_prune, early_rows=True)
             new_vf = self.rows_from_tuples(model, value_function, tuples, last)
         if append:
             n_new = len(new_vf)
@@ -404,13 +404,16 @@ class PBVI_Solver:
             new_vf.parent_uid, new_vf.n_new = value_function.uid, n_new
         return new_vf
 
-    def select_tuples_device(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False):
+    def select_tuples_device(self, model: Model, belief_set: BeliefSet, value_function: ValueFunction, belief_dominance_prune: bool = False,
+                             early_rows: bool = False):
         """
         First half of the backup: for every belief the tuple (a*, v*[a*, 0..O-1]) that generates its alpha row, reduced to the
         DISTINCT tuples in order of first occurrence -- on the device (`pbvi_group_keys`), nothing but the count comes back.
         Returns CUDA int32 tensors (tuples [u, 1+O], first [u], last [u]) where first / last are the positions (in this belief
         set, after the optional dominance filter) of the first / last belief that chose the tuple.  A tuple is 4*(1+O) bytes,
-        the row it generates 8*S: the sharded backup exchanges these.
+        the row it generates 8*S: the sharded backup exchanges these.  `early_rows`: the caller will hand the returned tuples to
+        `rows_from_tuples` as they are (the single-process backup), so a streamed select may assemble and read back the rows of the
+        tuples it knows before its last chunk (`_select_streamed`).
         """
         dev = model.device
         V = value_function.alpha_vector_array
@@ -422,7 +425,7 @@ class PBVI_Solver:
         # possible winner skip the exact reference-order sum
         self._early = early = None
         if belief_set._device is None and nB >= 2 * self.STREAM_FIRST_CHUNK:
-            if self.EARLY_ROWS and not belief_dominance_prune:
+            if early_rows and self.EARLY_ROWS and not belief_dominance_prune:
                 early = {}
             vstar, value, astar = self._select_streamed(model, belief_set, V, want_value=belief_dominance_prune, early=early)
         else:
