@@ -130,6 +130,27 @@ def test_unique_rows_first_packed_and_wide():
         assert np.array_equal(keys[first][inverse], keys)
 
 
+@pytest.mark.parametrize('unit', [1, 64, 448, 960, 1024])
+def test_streamed_chunk_plan_covers_the_rows_in_order(unit):
+    """Chunk plan of the streamed (host-buffer) select: contiguous, in order, every boundary but the last a multiple of the ship unit,
+    sizes double from the first chunk up to the cap, and a tail shorter than the first chunk joins its predecessor."""
+    from pomdp_pbvi_exploration_b200.solver import PBVI_Solver
+    s = PBVI_Solver(expand_function='perseus')
+    for n in (1, 63, 2048, 2100, 2500, 4000, 6250, 10000, 50000):
+        plan = s._chunk_plan(n, unit)
+        assert plan[0][0] == 0 and plan[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+        assert all(lo < hi for lo, hi in plan)
+        assert all(hi % unit == 0 for _, hi in plan[:-1])
+        first = max(1, s.STREAM_FIRST_CHUNK // unit) * unit
+        cap = max(first, int(round(s.STREAM_CHUNK / unit)) * unit)
+        sizes = [hi - lo for lo, hi in plan]
+        assert all(x <= cap for x in sizes[:-1]) and sizes[-1] < cap + first
+        assert all(b in (min(cap, 2 * a), n - sum(sizes[:i + 1])) or i + 2 == len(sizes) for i, (a, b) in enumerate(zip(sizes, sizes[1:])))
+        if len(plan) > 1:
+            assert sizes[0] == first and sizes[-1] >= first
+
+
 def test_shard_bounds_cover_rows_contiguously():
     from pomdp_pbvi_exploration_b200.parallel import shard_bounds
     for n in [0, 1, 7, 8, 9, 50000]:

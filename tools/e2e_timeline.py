@@ -97,19 +97,23 @@ def main():
     solver, beliefs, vfs, _ = bench.build_workload(model, 10000, 1000, seed=0)
     h_b = beliefs.cpu().pin_memory()
     link_rates(dev, h_b)
-    for th in (8, 15, 16):
+    for th in (15,):
         packers_alone(dev, h_b, th)
     type(dev).PACK_THREADS = None
     for name in ('late', 'young'):
         vf = vfs[name]
         h_a = vf.alpha_vector_array.cpu().pin_memory()
         acts = vf.actions.copy()
-        for early, threads in ((True, 15), (False, 15), (True, 14), (True, 16), (True, 15)):
-            if name == 'young' and threads != 15:
+        for early, warm in ((True, False), (True, True), (False, True), (True, True)):
+            if name == 'young' and not early:
                 continue
-            type(dev).PACK_THREADS, type(solver).EARLY_ROWS = threads, early
-            print(f'{name} V, {threads} packer threads, early rows {early}:')
-            e2e(model, solver, h_b, h_a, acts)
+            type(solver).EARLY_ROWS = early
+            print(f'{name} V, early rows {early}, GPU kept busy for 0.5 s right before the steps: {warm}:')
+            if warm:
+                bench.gpu_warm(dev.device, 0.5)
+            else:
+                time.sleep(2.0)                   # an idle GPU drops its clocks
+            e2e(model, solver, h_b, h_a, acts, steps=8)
         type(solver).EARLY_ROWS = True
         type(dev).PACK_THREADS = None
         os.environ['LOCAL_WORLD_SIZE'] = '2'          # start_pack declines: the rows travel as they are
