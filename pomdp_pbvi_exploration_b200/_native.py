@@ -527,6 +527,9 @@ class DeviceModel:
 
     def _staging_buffer(self, n: int) -> torch.Tensor:
         """Grow-only pinned staging of the read-backs; every new use invalidates the views handed out before (`_staging_token`)."""
+        stream = getattr(self, '_readback_stream', None)
+        if stream is not None:
+            stream.synchronize()                    # an abandoned mirror may still be writing the staging
         buf = getattr(self, '_staging', None)
         want = max(n, getattr(self, '_staging_want', 0), 1 << 20)
         if buf is None or buf.numel() < n:

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "pbvi_common.cuh"
 
@@ -32,8 +33,10 @@ struct NcclApi {
 };
 
 NcclApi g_nccl;
+std::mutex g_nccl_mutex;        // one thread per GPU is a supported way to drive the library: the binding is resolved once
 
 int load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.lib) return PBVI_OK;
     const char* env = std::getenv("PBVI_NCCL_LIB");
     const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
