@@ -92,7 +92,9 @@ PBVI_API int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const d
                 double* d_out_alpha, int32_t* d_out_action, int32_t* d_out_vstar, double* d_out_value, void* stream);
 
 /* Same with HOST buffers: copies inputs to the device, runs pbvi_backup, copies alpha rows and actions back and
- * synchronises.  This is the end-to-end entry point a CPU-resident caller (the reference's NumPy path) would use. */
+ * synchronises.  This is the end-to-end entry point a CPU-resident caller (the reference's NumPy path) would use.  The beliefs are
+ * processed in chunks of 2048 rows through a two-deep pipeline (upload of chunk k + 1 | kernels of chunk k | download of chunk k - 1),
+ * so with pinned (page-locked) buffers the call is bound by the PCIe link, not by link + kernels + link; pageable buffers work, unoverlapped. */
 PBVI_API int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
                      double* h_out_alpha, int32_t* h_out_action, void* stream);
 

@@ -292,6 +292,13 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     cudaFree(m->d_signs);
     if (m->evScore0) { cudaEventDestroy(m->evScore0); cudaEventDestroy(m->evScore1); }
     if (m->evGuard) cudaEventDestroy(m->evGuard);
+    if (m->hostIn) cudaStreamDestroy(m->hostIn);
+    if (m->hostOut) cudaStreamDestroy(m->hostOut);
+    for (int i = 0; i < 2; i++) {
+        if (m->evIn[i]) cudaEventDestroy(m->evIn[i]);
+        if (m->evDone[i]) cudaEventDestroy(m->evDone[i]);
+        if (m->evOut[i]) cudaEventDestroy(m->evOut[i]);
+    }
     m->arena.release();
     if (m->h_stage) cudaFreeHost(m->h_stage);
     delete m;

@@ -67,6 +67,14 @@ struct Arena {
     std::vector<Chunk> chunks;
     void* take_bytes(size_t bytes);     // nullptr (and the error string set) when the device is out of memory
     void reset();
+    // scratch of a sub-step of one call: everything taken after mark() is handed back by rewind() (the kernels that used it precede the
+    // next user in stream order)
+    struct Mark { size_t chunks, off; };
+    Mark mark() const { return Mark{chunks.size(), chunks.empty() ? 0 : chunks.back().off}; }
+    void rewind(const Mark& k) {
+        for (size_t i = k.chunks; i < chunks.size(); i++) chunks[i].off = 0;
+        if (k.chunks > 0 && k.chunks <= chunks.size()) chunks[k.chunks - 1].off = k.off;
+    }
     void release();
     template <typename T> T* take(size_t n) { return reinterpret_cast<T*>(take_bytes(n * sizeof(T))); }
     static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
@@ -169,6 +177,9 @@ struct pbvi_model {
     bool profile = false;
     bool score_timed = false;
     cudaEvent_t evScore0 = nullptr, evScore1 = nullptr;
+    // pbvi_backup_host: upload / download streams and the events of its two-deep chunk pipeline (created on first use)
+    cudaStream_t hostIn = nullptr, hostOut = nullptr;
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
 };
 
 namespace pbvi {

@@ -105,6 +105,36 @@ def test_backup_golden(torch_cuda, tag):
     assert torch_cuda.equal(keys, dev.row_hash(rows_t)) and np.array_equal(rows_t.cpu().numpy(), alpha)
 
 
+@pytest.mark.parametrize('pinned', [False, True])
+def test_backup_host_chunk_pipeline_equals_device_backup(torch_cuda, pinned):
+    """`pbvi_backup_host` walks the beliefs in chunks of 2048 rows through a two-deep upload | kernels | download pipeline: 5000 beliefs
+    = three chunks (the third re-uses the staging of the first), pageable and pinned host buffers, two calls in a row on one handle;
+    alpha rows and actions equal the device entry point's, byte for byte."""
+    import ctypes
+    from pomdp_pbvi_exploration_b200.recipes import synthetic_sparse_model
+    torch = torch_cuda
+    model = synthetic_sparse_model(700, 4, 3, 1, seed=11)
+    dev = model.device
+    rng = np.random.default_rng(5)
+    B = _sparse_beliefs(rng, 5000, 700, (3, 40, 200))
+    V = rng.random((70, 700)) * (rng.random((70, 700)) < 0.4)
+    want_rows, want_act, _, _ = dev.backup(B, V, 0.95)
+    want_rows, want_act = want_rows.cpu().numpy(), want_act.cpu().numpy()
+    hb, hv = torch.as_tensor(B), torch.as_tensor(V)
+    out, act = torch.empty((5000, 700), dtype=torch.float64), torch.empty((5000,), dtype=torch.int32)
+    if pinned:
+        hb, hv, out, act = hb.pin_memory(), hv.pin_memory(), out.pin_memory(), act.pin_memory()
+    for rep in range(2):
+        out.fill_(-1.0)
+        rc = dev._lib.pbvi_backup_host(dev._h, hb.data_ptr(), 5000, hv.data_ptr(), 70, ctypes.c_double(0.95), out.data_ptr(), act.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        assert np.array_equal(out.numpy(), want_rows) and np.array_equal(act.numpy(), want_act)
+    # the arena is handed back to the next call intact: a plain device backup right after gives the same rows again
+    again, _, _, _ = dev.backup(B[:300], V, 0.95)
+    assert np.array_equal(again.cpu().numpy(), want_rows[:300])
+
+
 def _sparse_beliefs(rng, n, S, ks):
     B = np.zeros((n, S))
     for i in range(n):
