@@ -98,6 +98,17 @@ PBVI_API int pbvi_backup(pbvi_model* m, const double* d_beliefs, int nB, const d
 PBVI_API int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
                      double* h_out_alpha, int32_t* h_out_action, void* stream);
 
+/* The reference's whole `PBVI_Solver.backup` (src/pomdp.py:1447-1524 with belief_dominance_prune = False, append = False) from host
+ * buffers in one call -- including what `ValueFunction(model, alpha_vectors, best_actions)` does to the rows (src/mdp.py:668-669: one
+ * entry per distinct row, position of the first occurrence, action of the last).  Chunked upload behind the select kernels as in
+ * pbvi_backup_host; then the distinct generating tuples (a*, v*[a*, :]) in order of first occurrence, one alpha row per tuple, the
+ * byte-dedup of those rows on 128-bit keys (every match confirmed bytewise), and only the surviving rows are copied back:
+ * h_out_alpha [*h_n_out][S], h_out_action [*h_n_out].  out_capacity = rows the output buffers hold (nB always suffices); if the result
+ * has more, *h_n_out is set and PBVI_ERR_BAD_ARG returned.  PBVI_ERR_UNSUPPORTED: two different rows shared a key (never observed) --
+ * call pbvi_backup_host and de-duplicate on the host.  Synchronises. */
+PBVI_API int pbvi_backup_host_unique(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
+                            double* h_out_alpha, int out_capacity, int32_t* h_out_action, int* h_n_out, void* stream);
+
 /* pbvi_backup_small: the WHOLE `PBVI_Solver.backup(append=False)` of a small problem (tiger, 4x4 grids: BASELINE configs[0] / [1]) in one
  * call -- one kernel (a block per belief: projections, v*, values, a*, the alpha row and its 128-bit key, all in shared memory), one
  * copy back, the ValueFunction constructor's dict semantics on the host (src/mdp.py:668-669: position of the first occurrence, action

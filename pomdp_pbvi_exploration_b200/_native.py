@@ -31,6 +31,7 @@ SIGNATURES = {
     'pbvi_backup_assemble': [_P, _P, c_int, c_double, _P, _P, c_int, _P, _P, _P],
     'pbvi_backup': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, _P, _P],
     'pbvi_backup_host': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P],
+    'pbvi_backup_host_unique': [_P, _P, c_int, _P, c_int, c_double, _P, c_int, _P, POINTER(c_int), _P],
     'pbvi_backup_small_eligible': [_P, c_int, c_int],
     'pbvi_backup_small': [_P, _P, c_int, _P, c_int, c_double, _P, _P, _P, POINTER(c_int), _P],
     'pbvi_max_values': [_P, _P, c_int, _P, c_int, _P, _P, _P],
@@ -255,6 +256,19 @@ class DeviceModel:
         self._call(self._lib.pbvi_backup_host(self._h, b.ctypes.data, nB, al.ctypes.data, nV, float(gamma), out_alpha.ctypes.data,
                                           out_action.ctypes.data, self._stream))
         return out_alpha, out_action
+
+    def backup_host_unique(self, beliefs: np.ndarray, alphas: np.ndarray, gamma: float):
+        """The reference's whole backup from host arrays in one library call (`pbvi_backup_host_unique`): (rows [n,S], actions [n]) of
+        the de-duplicated new value function, rows in order of first occurrence."""
+        b = np.ascontiguousarray(beliefs, dtype=np.float64)
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        nB, nV = b.shape[0], al.shape[0]
+        out_alpha = np.empty((nB, self.S), dtype=np.float64)
+        out_action = np.empty((nB,), dtype=np.int32)
+        n = c_int()
+        self._call(self._lib.pbvi_backup_host_unique(self._h, b.ctypes.data, nB, al.ctypes.data, nV, float(gamma), out_alpha.ctypes.data, nB,
+                                                 out_action.ctypes.data, byref(n), self._stream))
+        return out_alpha[:n.value], out_action[:n.value]
 
     def max_values(self, beliefs, alphas):
         """(max_v b.alpha_v, first argmax) -- reference src/pomdp.py:2165, 1639, 1735."""

@@ -709,6 +709,33 @@ __global__ void __launch_bounds__(256) hash_finalise_kernel(unsigned long long* 
 
 // =====================================================================================================================
 // Function attributes are per device: called by pbvi_model_create for the handle's device (current when called).
+// ---- pbvi_backup_host_unique: the tuple (a*, v*[a*, :]) of every belief as a group key, and the tuples / actions of the chosen groups
+__global__ void __launch_bounds__(256) tuple_keys_kernel(const int32_t* __restrict__ vstar, const int32_t* __restrict__ astar, int n, int A,
+                                                         int O, uint32_t* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = min(max(astar[i], 0), A - 1);
+    keys[(size_t)i * (1 + O)] = (uint32_t)a;
+    for (int o = 0; o < O; o++) keys[(size_t)i * (1 + O) + 1 + o] = (uint32_t)vstar[((size_t)i * A + a) * O + o];
+}
+
+__global__ void __launch_bounds__(256) tuple_take_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ first,
+                                                         const int32_t* __restrict__ last, int u, int O, int32_t* __restrict__ actions,
+                                                         int32_t* __restrict__ vsel, int32_t* __restrict__ rank) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= u) return;
+    const uint32_t* k = keys + (size_t)first[g] * (1 + O);
+    actions[g] = (int32_t)k[0];
+    for (int o = 0; o < O; o++) vsel[(size_t)g * O + o] = (int32_t)k[1 + o];
+    rank[g] = last[g];
+}
+
+__global__ void __launch_bounds__(256) take_int_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int n,
+                                                       int32_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
 int configure_backup_kernels() {
     PBVI_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
     PBVI_CUDA(cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCORE_SMEM));
@@ -882,7 +909,6 @@ static int assemble_impl(pbvi_model* m, const double* d_alphas, int nV, double g
     constexpr int G = PBVI_ASM_G, SPT = PBVI_ASM_SPT;      // tuples per block / states per thread of the grouped assemble kernel (A/B builds)
     if (m->R == 1 && m->O <= 4 && !perAction && n >= 4 * G && (size_t)m->A * sizeof(int) <= 48 * 1024 &&
         ((long long)n + (long long)m->A * (G - 1)) / G + 1 <= 65535) {            // grid.y of the grouped kernel
-        PBVI_TRY(enter_call(m, st));
         const int nPad = ceil_div(n + m->A * (G - 1), G) * G;
         PBVI_TAKE(order, int32_t, (size_t)nPad);
         PBVI_CUDA(cudaMemsetAsync(order, 0xFF, (size_t)nPad * sizeof(int32_t), st));
@@ -969,6 +995,10 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     if (nB == 0) return PBVI_OK;
     PBVI_REQUIRE(h_out_alpha && h_out_action, "alpha / action outputs are required");
     PBVI_CUDA(cudaSetDevice(m->device));
+    if (m->hostIn) {      // a previous host call that returned early (an error) may have left copies in flight on the side streams
+        PBVI_CUDA(cudaStreamSynchronize(m->hostIn));
+        PBVI_CUDA(cudaStreamSynchronize(m->hostOut));
+    }
     PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     m->last_launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1022,6 +1052,126 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     PBVI_CUDA(cudaMemcpyAsync(h_out_action, d_act, (size_t)nB * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));
     PBVI_CUDA(cudaStreamSynchronize(m->hostOut));
+    PBVI_CUDA(cudaStreamSynchronize(m->hostIn));
+    return PBVI_OK;
+}
+
+// The reference's whole PBVI_Solver.backup (src/pomdp.py:1447-1524, belief_dominance_prune = False) from host buffers in one call:
+// chunked upload behind the select kernels as in pbvi_backup_host, then -- what the reference does with ValueFunction(model, rows,
+// actions) on the host, one `tobytes()` per row (src/mdp.py:668-669) -- the distinct generating tuples in order of first occurrence,
+// their alpha rows (assembled once per tuple, keys accumulated on the way), the byte-dedup of those rows (first position, action of
+// the tuple whose last belief comes latest; every key match confirmed bytewise), and only the surviving rows travel back.
+extern "C" int pbvi_backup_host_unique(pbvi_model* m, const double* h_beliefs, int nB, const double* h_alphas, int nV, double gamma,
+                                       double* h_out_alpha, int out_capacity, int32_t* h_out_action, int* h_n_out, void* stream) {
+    PBVI_TRY(check_backup_args(m, h_beliefs, nB, h_alphas, nV, gamma));
+    PBVI_REQUIRE(h_n_out != nullptr, "row count output is required");
+    *h_n_out = 0;
+    if (nB == 0) return PBVI_OK;
+    PBVI_REQUIRE(h_out_alpha && h_out_action && out_capacity > 0, "alpha / action outputs with room for out_capacity > 0 rows are required");
+    PBVI_CUDA(cudaSetDevice(m->device));
+    if (m->hostIn) {      // a previous host call that returned early (an error) may have left copies in flight on the side streams
+        PBVI_CUDA(cudaStreamSynchronize(m->hostIn));
+        PBVI_CUDA(cudaStreamSynchronize(m->hostOut));
+    }
+    PBVI_TRY(enter_call(m, (cudaStream_t)stream));
+    m->last_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!m->hostIn) {
+        PBVI_CUDA(cudaStreamCreateWithFlags(&m->hostIn, cudaStreamNonBlocking));
+        PBVI_CUDA(cudaStreamCreateWithFlags(&m->hostOut, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            PBVI_CUDA(cudaEventCreateWithFlags(&m->evIn[i], cudaEventDisableTiming));
+            PBVI_CUDA(cudaEventCreateWithFlags(&m->evDone[i], cudaEventDisableTiming));
+            PBVI_CUDA(cudaEventCreateWithFlags(&m->evOut[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t S = m->S;
+    const int O = m->O, W = 1 + O;
+    const int rows = std::min(nB, HOST_CHUNK_ROWS);
+    PBVI_TAKE(d_a, double, (size_t)nV * S);
+    PBVI_TAKE(d_act, int32_t, (size_t)nB);
+    PBVI_TAKE(d_vs, int32_t, (size_t)nB * m->nZ);
+    PBVI_TAKE(keys, uint32_t, (size_t)nB * W);
+    PBVI_TAKE(first, int32_t, (size_t)nB);
+    PBVI_TAKE(last, int32_t, (size_t)nB);
+    double* d_b[2];
+    for (int i = 0; i < 2; i++) {
+        d_b[i] = m->arena.take<double>((size_t)rows * S);
+        if (!d_b[i]) return PBVI_ERR_OOM;
+    }
+    PBVI_CUDA(cudaEventRecord(m->evDone[0], st));
+    PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[0], 0));          // the staging is scratch of this call (see pbvi_backup_host)
+    PBVI_CUDA(cudaMemcpyAsync(d_a, h_alphas, (size_t)nV * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    const pbvi::Arena::Mark mark = m->arena.mark();
+    int launches = 0;
+    for (int lo = 0, k = 0; lo < nB; lo += rows, k++) {
+        const int n = std::min(rows, nB - lo), b = k & 1;
+        if (k >= 2) PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[b], 0));        // chunk k - 2 has read d_b[b]
+        PBVI_CUDA(cudaMemcpyAsync(d_b[b], h_beliefs + (size_t)lo * S, (size_t)n * S * sizeof(double), cudaMemcpyHostToDevice, m->hostIn));
+        PBVI_CUDA(cudaEventRecord(m->evIn[b], m->hostIn));
+        PBVI_CUDA(cudaStreamWaitEvent(st, m->evIn[b], 0));
+        m->arena.rewind(mark);
+        m->last_launches = 0;
+        PBVI_TRY(select_impl(m, d_b[b], n, d_a, nV, gamma, d_vs + (size_t)lo * m->nZ, nullptr, d_act + lo, st));
+        launches += m->last_launches;
+        PBVI_CUDA(cudaEventRecord(m->evDone[b], st));
+    }
+    m->arena.rewind(mark);
+    m->last_launches = 0;
+    // distinct tuples, in order of first occurrence
+    tuple_keys_kernel<<<ceil_div(nB, 256), 256, 0, st>>>(d_vs, d_act, nB, m->A, O, keys);
+    int32_t* d_count = nullptr;
+    PBVI_TRY(group_keys_impl(m, keys, nB, W, nullptr, first, last, nullptr, &d_count, st));
+    int32_t u = 0;
+    PBVI_CUDA(cudaMemcpyAsync(&u, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    PBVI_REQUIRE(u > 0 && u <= nB, "tuple grouping failed");
+    PBVI_TAKE(t_act, int32_t, (size_t)u);
+    PBVI_TAKE(t_vsel, int32_t, (size_t)u * O);
+    PBVI_TAKE(t_rank, int32_t, (size_t)u);
+    tuple_take_kernel<<<ceil_div(u, 256), 256, 0, st>>>(keys, first, last, u, O, t_act, t_vsel, t_rank);
+    PBVI_TAKE(d_rows, double, (size_t)u * S);
+    PBVI_TAKE(d_hash, uint64_t, (size_t)u * 2);
+    PBVI_TRY(assemble_impl(m, d_a, nV, gamma, t_act, t_vsel, (size_t)O, 0, u, d_rows, d_hash, st));
+    // byte-dedup of the rows: groups on the 128-bit keys, owner = the tuple whose last belief comes latest
+    PBVI_TAKE(gfirst, int32_t, (size_t)u);
+    PBVI_TAKE(owner, int32_t, (size_t)u);
+    PBVI_TAKE(inverse, int32_t, (size_t)u);
+    PBVI_TRY(group_keys_impl(m, reinterpret_cast<const uint32_t*>(d_hash), u, 4, t_rank, gfirst, owner, inverse, &d_count, st));
+    int32_t r = 0;
+    PBVI_CUDA(cudaMemcpyAsync(&r, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
+    PBVI_REQUIRE(r > 0 && r <= u, "row grouping failed");
+    *h_n_out = (int)r;
+    m->last_launches += launches + 2;
+    if (r > out_capacity) {
+        set_error("the backup has %d distinct alpha rows, the output buffers have room for %d", (int)r, out_capacity);
+        return PBVI_ERR_BAD_ARG;
+    }
+    const double* out_rows = d_rows;
+    const int32_t* out_act = t_act;
+    if (r < u) {
+        PBVI_TAKE(mismatch, int32_t, 1);
+        PBVI_TRY(confirm_groups_launch(m, d_rows, u, (int)S, gfirst, inverse, mismatch, st));
+        int32_t bad = 0;
+        PBVI_CUDA(cudaMemcpyAsync(&bad, mismatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PBVI_CUDA(cudaStreamSynchronize(st));
+        if (bad) {          // two different rows with one 128-bit key (never observed): the caller falls back to pbvi_backup_host + its own dedup
+            set_error("128-bit row keys collided for different alpha rows; use pbvi_backup_host and de-duplicate on the host");
+            return PBVI_ERR_UNSUPPORTED;
+        }
+        PBVI_TAKE(kept, double, (size_t)r * S);
+        PBVI_TAKE(kept_act, int32_t, (size_t)r);
+        gather_rows_kernel<<<r, 128, 0, st>>>(d_rows, gfirst, (int)S, kept);
+        take_int_kernel<<<ceil_div(r, 256), 256, 0, st>>>(t_act, owner, r, kept_act);
+        m->last_launches += 2;
+        out_rows = kept;
+        out_act = kept_act;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, out_rows, (size_t)r * S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaMemcpyAsync(h_out_action, out_act, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PBVI_CUDA(cudaStreamSynchronize(st));
     PBVI_CUDA(cudaStreamSynchronize(m->hostIn));
     return PBVI_OK;
 }

@@ -516,6 +516,43 @@ extern "C" int pbvi_rows_equal(pbvi_model* m, const double* d_rows_a, const int3
     return PBVI_OK;
 }
 
+namespace pbvi {
+// First-occurrence grouping of n records of `words` 32-bit words (see pbvi_group_keys); scratch from the arena, nothing read back:
+// *d_count_out points at the group count on the device.
+int group_keys_impl(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first, int32_t* d_last,
+                    int32_t* d_inverse, int32_t** d_count_out, cudaStream_t st) {
+    int T = 64;
+    while (T < 2 * n) T <<= 1;
+    PBVI_TAKE(rep, int32_t, (size_t)T);
+    PBVI_TAKE(gfirst, int32_t, (size_t)T);
+    PBVI_TAKE(glast, unsigned long long, (size_t)T);
+    PBVI_TAKE(slotOf, int32_t, (size_t)n);
+    PBVI_TAKE(groupOfSlot, int32_t, (size_t)T);
+    PBVI_TAKE(count, int32_t, 1);
+    group_init_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, glast, T);
+    group_insert_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_keys, n, words, d_rank, T, rep, gfirst, glast, slotOf);
+    group_compact_kernel<<<1, 1024, 0, st>>>(slotOf, gfirst, glast, n, groupOfSlot, d_first, d_last, count);
+    m->last_launches += 3;
+    if (d_inverse) {
+        group_inverse_kernel<<<ceil_div(n, 256), 256, 0, st>>>(slotOf, groupOfSlot, n, d_inverse);
+        m->last_launches++;
+    }
+    PBVI_CUDA(cudaGetLastError());
+    *d_count_out = count;
+    return PBVI_OK;
+}
+
+// mismatch[0] != 0 afterwards iff some row differs bytewise from the first row of its group
+int confirm_groups_launch(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first, const int32_t* d_inverse,
+                          int32_t* d_mismatch, cudaStream_t st) {
+    PBVI_CUDA(cudaMemsetAsync(d_mismatch, 0, sizeof(int32_t), st));
+    group_confirm_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_first, d_inverse, d_mismatch);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+}  // namespace pbvi
+
 extern "C" int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first,
                                int32_t* d_last, int32_t* d_inverse, int* h_count, void* stream) {
     PBVI_REQUIRE(m != nullptr, "model handle is NULL");
@@ -527,24 +564,9 @@ extern "C" int pbvi_group_keys(pbvi_model* m, const uint32_t* d_keys, int n, int
     PBVI_REQUIRE(n <= (1 << 29), "too many records");
     PBVI_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int T = 64;
-    while (T < 2 * n) T <<= 1;
     PBVI_TRY(enter_call(m, (cudaStream_t)stream));
-    PBVI_TAKE(rep, int32_t, (size_t)T);
-    PBVI_TAKE(gfirst, int32_t, (size_t)T);
-    PBVI_TAKE(glast, unsigned long long, (size_t)T);
-    PBVI_TAKE(slotOf, int32_t, (size_t)n);
-    PBVI_TAKE(groupOfSlot, int32_t, (size_t)T);
-    PBVI_TAKE(count, int32_t, 1);
-    group_init_kernel<<<ceil_div(T, 256), 256, 0, st>>>(rep, gfirst, glast, T);
-    group_insert_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_keys, n, words, d_rank, T, rep, gfirst, glast, slotOf);
-    group_compact_kernel<<<1, 1024, 0, st>>>(slotOf, gfirst, glast, n, groupOfSlot, d_first, d_last, count);
-    m->last_launches = 3;
-    if (d_inverse) {
-        group_inverse_kernel<<<ceil_div(n, 256), 256, 0, st>>>(slotOf, groupOfSlot, n, d_inverse);
-        m->last_launches++;
-    }
-    PBVI_CUDA(cudaGetLastError());
+    int32_t* count = nullptr;
+    PBVI_TRY(group_keys_impl(m, d_keys, n, words, d_rank, d_first, d_last, d_inverse, &count, st));
     int32_t c = 0;
     PBVI_CUDA(cudaMemcpyAsync(&c, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));
@@ -603,10 +625,7 @@ extern "C" int pbvi_confirm_groups(pbvi_model* m, const double* d_rows, int n, i
     cudaStream_t st = (cudaStream_t)stream;
     PBVI_TRY(enter_call(m, (cudaStream_t)stream));
     PBVI_TAKE(mismatch, int32_t, 1);
-    PBVI_CUDA(cudaMemsetAsync(mismatch, 0, sizeof(int32_t), st));
-    group_confirm_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(d_rows), row_len, d_first, d_inverse, mismatch);
-    m->last_launches = 1;
-    PBVI_CUDA(cudaGetLastError());
+    PBVI_TRY(confirm_groups_launch(m, d_rows, n, row_len, d_first, d_inverse, mismatch, st));
     int32_t bad = 0;
     PBVI_CUDA(cudaMemcpyAsync(&bad, mismatch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PBVI_CUDA(cudaStreamSynchronize(st));

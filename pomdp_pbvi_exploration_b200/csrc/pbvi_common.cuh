@@ -193,6 +193,10 @@ int row_hash_launch(pbvi_model* m, const double* d_rows, int n, int row_len, uin
 int max_values_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max, int32_t* d_arg, cudaStream_t st);
 // start of an API call that uses the handle's scratch: stream guard (see pbvi_model::last_stream) + arena rewind
 int enter_call(pbvi_model* m, cudaStream_t st);
+int group_keys_impl(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first, int32_t* d_last,
+                    int32_t* d_inverse, int32_t** d_count_out, cudaStream_t st);
+int confirm_groups_launch(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first, const int32_t* d_inverse,
+                          int32_t* d_mismatch, cudaStream_t st);
 int configure_backup_kernels();
 int configure_belief_kernels();
 int configure_misc_kernels();

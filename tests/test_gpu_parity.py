@@ -135,6 +135,56 @@ def test_backup_host_chunk_pipeline_equals_device_backup(torch_cuda, pinned):
     assert np.array_equal(again.cpu().numpy(), want_rows[:300])
 
 
+@pytest.mark.parametrize('case', ['synthetic', 'tiger', 'olfactory_wrap'])
+def test_backup_host_unique_equals_the_solver_backup(torch_cuda, case):
+    """`pbvi_backup_host_unique` -- the reference's whole backup from host buffers in ONE library call, ValueFunction-constructor dedup
+    included -- returns the rows and actions of `PBVI_Solver.backup(append=False, belief_dominance_prune=False)`, in the same order,
+    byte for byte (three chunks of beliefs on the synthetic model; tiger has R = 2 and many tuples per row)."""
+    from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
+    from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs, synthetic_sparse_model
+    rng = np.random.default_rng(21)
+    if case == 'synthetic':
+        model, gamma = synthetic_sparse_model(700, 4, 3, 1, seed=11), 0.95
+        B = _sparse_beliefs(rng, 5000, 700, (1, 2, 3, 40))
+        B[100:140] = B[0]                                   # repeated beliefs: repeated tuples
+        V, acts = rng.random((70, 700)) * (rng.random((70, 700)) < 0.4), rng.integers(0, 4, 70)
+    elif case == 'tiger':
+        g = load_golden('backup_tiger')
+        dev, mm, _, _ = device_model('tiger')
+        B, V, gamma = g['beliefs'], g['alphas'], float(mm['gamma'])
+        rows, acts_out = dev.backup_host_unique(B, V, gamma)
+        alpha, act, _, _ = dev.backup(B, V, gamma)
+        alpha, act = alpha.cpu().numpy(), act.cpu().numpy()
+        table = {}
+        for i in range(alpha.shape[0]):                     # the reference's dict comprehension: first position, last action
+            k = alpha[i].tobytes()
+            table[k] = (table[k][0] if k in table else i, act[i])
+        want_rows = np.stack([alpha[p] for p, _ in table.values()])
+        want_acts = np.array([a for _, a in table.values()])
+        assert np.array_equal(rows, want_rows) and np.array_equal(acts_out, want_acts)
+        return
+    else:
+        model, gamma = olfactory_wrap_model(), 0.99
+        g = load_golden('backup_olfactory_wrap')
+        B = perseus_walk_beliefs(model, 2300, seed=2)
+        V, acts = g['alphas'], g['alpha_actions']
+    vf = ValueFunction(model, V, acts)
+    solver = PBVI_Solver(gamma=gamma, eps=1e-6, expand_function='perseus')
+    want = solver.backup(model, BeliefSet(model, B), vf, append=False, belief_dominance_prune=False)
+    want_rows, want_acts = want.numpy()
+    rows, acts_out = model.device.backup_host_unique(B, vf.alpha_vector_array.cpu().numpy(), gamma)
+    assert rows.shape == want_rows.shape and np.array_equal(rows, want_rows) and np.array_equal(acts_out, want_acts)
+    # too little room: the count comes back with the error
+    import ctypes
+    n = ctypes.c_int()
+    small = np.empty((1, model.state_count))
+    a1 = np.empty(1, dtype=np.int32)
+    Bc, Vc = np.ascontiguousarray(B), np.ascontiguousarray(vf.alpha_vector_array.cpu().numpy())
+    rc = model.device._lib.pbvi_backup_host_unique(model.device._h, Bc.ctypes.data, Bc.shape[0], Vc.ctypes.data, Vc.shape[0], gamma,
+                                                   small.ctypes.data, 1, a1.ctypes.data, ctypes.byref(n), None)
+    assert (rc != 0) == (want_rows.shape[0] > 1) and n.value == want_rows.shape[0]
+
+
 def _sparse_beliefs(rng, n, S, ks):
     B = np.zeros((n, S))
     for i in range(n):

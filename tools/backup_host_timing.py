@@ -50,6 +50,21 @@ def main():
     m = np.array(ts[1:]).mean(0)
     print(f'one after the other: upload {m[0]:.1f} + pbvi_backup {m[1]:.1f} + download {m[2]:.1f} = {m[3]:.1f} ms')
     print('rows equal:', bool(torch.equal(out, rows.cpu())), 'actions equal:', bool(torch.equal(act, a.cpu())))
+    # the whole backup (dedup included) in one call: only the distinct rows come back
+    n = ctypes.c_int()
+    ts = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = dev._lib.pbvi_backup_host_unique(dev._h, hb.data_ptr(), nB, hv.data_ptr(), V.shape[0], ctypes.c_double(0.99), out.data_ptr(), nB,
+                                              act.data_ptr(), ctypes.byref(n), st)
+        ts.append((time.perf_counter() - t0) * 1e3)
+        assert rc == 0
+    from pomdp_pbvi_exploration_b200 import BeliefSet
+    want = solver.backup(model, BeliefSet(model, beliefs), vfs['late'], append=False, belief_dominance_prune=False)
+    wr, wa = want.numpy()
+    print(f'pbvi_backup_host_unique: {[round(t, 1) for t in ts]} ms per call, {n.value} rows; equal to PBVI_Solver.backup: '
+          f'{bool(np.array_equal(out[:n.value].numpy(), wr) and np.array_equal(act[:n.value].numpy(), wa))}')
 
 
 if __name__ == '__main__':
