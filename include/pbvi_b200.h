@@ -100,8 +100,10 @@ PBVI_API int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, co
 
 /* The reference's whole `PBVI_Solver.backup` (src/pomdp.py:1447-1524 with belief_dominance_prune = False, append = False) from host
  * buffers in one call -- including what `ValueFunction(model, alpha_vectors, best_actions)` does to the rows (src/mdp.py:668-669: one
- * entry per distinct row, position of the first occurrence, action of the last).  Chunked upload behind the select kernels as in
- * pbvi_backup_host; then the distinct generating tuples (a*, v*[a*, :]) in order of first occurrence, one alpha row per tuple, the
+ * entry per distinct row, position of the first occurrence, action of the last).  Sparse belief sets of 2048 rows or more travel
+ * packed (the library's own host threads pack slabs of rows into pinned staging, pbvi_unpack_rows rebuilds them in HBM behind the
+ * copies: the belief buffer may be pageable), others through the chunked upload of pbvi_backup_host; pageable alpha / output buffers
+ * pass through pinned staging.  Then the distinct generating tuples (a*, v*[a*, :]) in order of first occurrence, one alpha row per tuple, the
  * byte-dedup of those rows on 128-bit keys (every match confirmed bytewise), and only the surviving rows are copied back:
  * h_out_alpha [*h_n_out][S], h_out_action [*h_n_out].  out_capacity = rows the output buffers hold (nB always suffices); if the result
  * has more, *h_n_out is set and PBVI_ERR_BAD_ARG returned.  PBVI_ERR_UNSUPPORTED: two different rows shared a key (never observed) --

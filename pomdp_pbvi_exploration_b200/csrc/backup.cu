@@ -16,6 +16,7 @@
 //   action_order_kernel + assemble_grouped_kernel (R = 1) / assemble_kernel   alpha_a rows for (action, v*[O]) tuples in the
 //                             reference's operation order, no FMA contraction, 128-bit row keys accumulated on the way
 #include <algorithm>
+#include <thread>
 
 #include "score_kernel.cuh"
 
@@ -1056,6 +1057,159 @@ extern "C" int pbvi_backup_host(pbvi_model* m, const double* h_beliefs, int nB, 
     return PBVI_OK;
 }
 
+// ---- pageable host buffers (NumPy arrays) ------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from / to pageable memory is staged by the driver at a fraction of the link rate and blocks the calling thread, which
+// the packed pipeline needs for shipping slabs.  Pageable alphas / output rows go through the handle's own pinned staging instead,
+// moved by a few host threads (a core copies ~8 GB/s; the 176 MB of the bench's alphas take 3 ms on 15 threads).
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+static void* io_staging(pbvi_model* m, size_t bytes) {
+    if (m->h_io_bytes < bytes) {
+        if (m->h_io) cudaFreeHost(m->h_io);
+        m->h_io = nullptr;
+        m->h_io_bytes = 0;
+        if (cudaHostAlloc(&m->h_io, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            m->h_io = nullptr;
+            return nullptr;
+        }
+        m->h_io_bytes = bytes;
+    }
+    return m->h_io;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)(hw > 1 ? hw - 1 : 1), (size_t)32, bytes >> 22}));   // >= 4 MB per thread
+    if (T == 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t slice = ((bytes / T) + 63) & ~size_t(63);
+    for (int t = 0; t < T; t++) {
+        const size_t lo = std::min(bytes, (size_t)t * slice), hi = std::min(bytes, lo + slice);
+        if (hi > lo) th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// ---- upload + select of a host-resident belief set, PACKED transport (the C form of PBVI_Solver._select_streamed) --------------------
+// Sparse belief rows cross the link as [bitmap over 4-double chunks | the non-zero chunks]: host threads pack slabs of 64 rows into
+// the handle's pinned staging (pbvi_pack_slabs_host), this thread ships every finished slab on the upload stream, pbvi_unpack_rows
+// rebuilds the dense rows in HBM on a second stream and the select kernels follow chunk by chunk on the caller's stream.  The
+// caller's belief buffer is only ever read by the host cores, so it may be pageable (a NumPy array) at no cost -- the dense pipeline
+// needs page-locked rows to overlap anything.  *packed = false (nothing done): the rows are too dense (or too few) to be worth it.
+constexpr int PACK_SLAB_ROWS = 64;
+constexpr double PACK_MAX_DENSITY = 0.6;
+
+static int host_select_packed(pbvi_model* m, const double* h_beliefs, int nB, const double* d_a, int nV, double gamma, int32_t* d_vs,
+                              int32_t* d_act, cudaStream_t st, int* launches, bool* packed) {
+    *packed = false;
+    const int S = m->S, SL = PACK_SLAB_ROWS;
+    const int nC = (S + 3) / 4, W = (nC + 31) / 32;
+    if (nB < 2048) return PBVI_OK;
+    {   // density of the first rows, at chunk granularity
+        const int probe = std::min(nB, 8);
+        long long live = 0;
+        for (int i = 0; i < probe; i++)
+            for (int c = 0; c < nC; c++) {
+                bool nz = false;
+                for (int j = 4 * c; j < std::min(S, 4 * c + 4) && !nz; j++) {
+                    uint64_t w;
+                    std::memcpy(&w, h_beliefs + (size_t)i * S + j, sizeof(w));
+                    nz = w != 0;
+                }
+                live += nz ? 1 : 0;
+            }
+        if ((double)live > PACK_MAX_DENSITY * (double)probe * nC) return PBVI_OK;
+    }
+    const int n_slabs = ceil_div(nB, SL);
+    const size_t region = (size_t)SL * nC * 4 + 4;                 // doubles per slab: worst case + the packer's one-chunk slack
+    auto up256 = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t bmBytes = up256((size_t)nB * W * 4), rsBytes = up256((size_t)n_slabs * (SL + 1) * 4), pkBytes = up256((size_t)n_slabs * region * 8),
+                 totBytes = up256((size_t)n_slabs * 8);
+    const size_t need = bmBytes + rsBytes + pkBytes + totBytes;
+    if (m->h_pack_bytes < need) {
+        if (m->h_pack) cudaFreeHost(m->h_pack);
+        m->h_pack = nullptr;
+        m->h_pack_bytes = 0;
+        if (cudaHostAlloc(&m->h_pack, need, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            m->h_pack = nullptr;
+            return PBVI_OK;                                      // no pinned memory for the staging: the dense pipeline does the job
+        }
+        m->h_pack_bytes = need;
+    }
+    char* hp = static_cast<char*>(m->h_pack);
+    uint32_t* h_bm = reinterpret_cast<uint32_t*>(hp);
+    int32_t* h_rs = reinterpret_cast<int32_t*>(hp + bmBytes);
+    double* h_pk = reinterpret_cast<double*>(hp + bmBytes + rsBytes);
+    int64_t* h_tot = reinterpret_cast<int64_t*>(hp + bmBytes + rsBytes + pkBytes);
+    for (int i = 0; i < n_slabs; i++) h_tot[i] = -1;
+    PBVI_TAKE(d_bm, uint32_t, (size_t)nB * W);
+    PBVI_TAKE(d_rs, int32_t, (size_t)n_slabs * (SL + 1));
+    PBVI_TAKE(d_pk, double, (size_t)n_slabs * region);
+    PBVI_TAKE(d_full, double, (size_t)nB * S);
+    // the staging above is scratch of this call: the side streams may touch it only after what the caller's stream held before
+    PBVI_CUDA(cudaEventRecord(m->evDone[0], st));
+    PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[0], 0));
+    PBVI_CUDA(cudaStreamWaitEvent(m->hostOut, m->evDone[0], 0));
+
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = std::max(1, std::min({32, (int)(hw > 1 ? hw - 1 : 1), n_slabs}));     // one core stays with this thread
+    std::vector<std::thread> packers;
+    packers.reserve(T);
+    for (int t = 0; t < T; t++)
+        packers.emplace_back([=] { pbvi_pack_slabs_host(h_beliefs, nB, S, SL, t, T, h_bm, h_rs, h_pk, (int64_t)region, h_tot); });
+    auto join_all = [&] { for (auto& th : packers) if (th.joinable()) th.join(); };
+
+    const int unit = SL * std::min(T, 16);                          // one round of the packers: ready after ONE slab time
+    const pbvi::Arena::Mark mark = m->arena.mark();
+    int rc = PBVI_OK, shipped = 0;                                  // slabs whose copies are enqueued
+    int lo = 0, size = unit;
+    while (lo < nB && rc == PBVI_OK) {
+        int hi = std::min(nB, lo + size);
+        if (nB - hi < unit) hi = nB;                                // a tail shorter than one unit joins the last chunk
+        const int s1 = ceil_div(hi, SL);
+        for (; shipped < s1 && rc == PBVI_OK; shipped++) {
+            int64_t total;
+            unsigned spins = 0;
+            while ((total = __atomic_load_n(&h_tot[shipped], __ATOMIC_ACQUIRE)) == -1)
+                if (++spins % 64 == 0) std::this_thread::yield();
+            if (total < 0) { set_error("packing the host rows failed"); rc = PBVI_ERR_BAD_ARG; break; }
+            if (total > 0 && cudaMemcpyAsync(d_pk + (size_t)shipped * region, h_pk + (size_t)shipped * region, (size_t)total * 32,
+                                             cudaMemcpyHostToDevice, m->hostIn) != cudaSuccess) { set_error("cudaMemcpyAsync failed"); rc = PBVI_ERR_CUDA; }
+        }
+        if (rc != PBVI_OK) break;
+        const int s0 = lo / SL;
+        bool ok = cudaMemcpyAsync(d_bm + (size_t)lo * W, h_bm + (size_t)lo * W, (size_t)(hi - lo) * W * 4, cudaMemcpyHostToDevice, m->hostIn) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(d_rs + (size_t)s0 * (SL + 1), h_rs + (size_t)s0 * (SL + 1), (size_t)(s1 - s0) * (SL + 1) * 4, cudaMemcpyHostToDevice,
+                                   m->hostIn) == cudaSuccess;
+        ok = ok && cudaEventRecord(m->evIn[0], m->hostIn) == cudaSuccess && cudaStreamWaitEvent(m->hostOut, m->evIn[0], 0) == cudaSuccess;
+        if (!ok) { set_error("CUDA error while shipping packed rows: %s", cudaGetErrorString(cudaGetLastError())); rc = PBVI_ERR_CUDA; break; }
+        m->last_launches = 0;
+        rc = unpack_rows_launch(m, d_bm + (size_t)lo * W, d_rs + (size_t)s0 * (SL + 1), d_pk + (size_t)s0 * region, hi - lo, S, SL,
+                                (long long)(region / 4), d_full + (size_t)lo * S, m->hostOut);
+        if (rc != PBVI_OK) break;
+        ok = cudaEventRecord(m->evOut[0], m->hostOut) == cudaSuccess && cudaStreamWaitEvent(st, m->evOut[0], 0) == cudaSuccess;
+        if (!ok) { set_error("CUDA error: %s", cudaGetErrorString(cudaGetLastError())); rc = PBVI_ERR_CUDA; break; }
+        m->arena.rewind(mark);
+        rc = select_impl(m, d_full + (size_t)lo * S, hi - lo, d_a, nV, gamma, d_vs + (size_t)lo * m->nZ, nullptr, d_act + lo, st);
+        *launches += m->last_launches;
+        lo = hi;
+        size = std::min(3 * unit, 2 * size);
+    }
+    join_all();
+    m->arena.rewind(mark);
+    if (rc == PBVI_OK) *packed = true;
+    return rc;
+}
+
 // The reference's whole PBVI_Solver.backup (src/pomdp.py:1447-1524, belief_dominance_prune = False) from host buffers in one call:
 // chunked upload behind the select kernels as in pbvi_backup_host, then -- what the reference does with ValueFunction(model, rows,
 // actions) on the host, one `tobytes()` per row (src/mdp.py:668-669) -- the distinct generating tuples in order of first occurrence,
@@ -1094,27 +1248,41 @@ extern "C" int pbvi_backup_host_unique(pbvi_model* m, const double* h_beliefs, i
     PBVI_TAKE(keys, uint32_t, (size_t)nB * W);
     PBVI_TAKE(first, int32_t, (size_t)nB);
     PBVI_TAKE(last, int32_t, (size_t)nB);
-    double* d_b[2];
-    for (int i = 0; i < 2; i++) {
-        d_b[i] = m->arena.take<double>((size_t)rows * S);
-        if (!d_b[i]) return PBVI_ERR_OOM;
+    {   // alphas: straight from page-locked memory, through the pinned staging otherwise
+        const size_t bytes = (size_t)nV * S * sizeof(double);
+        const void* src = h_alphas;
+        if (bytes >= (size_t(8) << 20) && !host_pointer_is_pinned(h_alphas)) {
+            void* stage = io_staging(m, bytes);
+            if (stage) { parallel_memcpy(stage, h_alphas, bytes); src = stage; }
+        }
+        PBVI_CUDA(cudaMemcpyAsync(d_a, src, bytes, cudaMemcpyHostToDevice, st));
     }
-    PBVI_CUDA(cudaEventRecord(m->evDone[0], st));
-    PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[0], 0));          // the staging is scratch of this call (see pbvi_backup_host)
-    PBVI_CUDA(cudaMemcpyAsync(d_a, h_alphas, (size_t)nV * S * sizeof(double), cudaMemcpyHostToDevice, st));
-    const pbvi::Arena::Mark mark = m->arena.mark();
     int launches = 0;
-    for (int lo = 0, k = 0; lo < nB; lo += rows, k++) {
-        const int n = std::min(rows, nB - lo), b = k & 1;
-        if (k >= 2) PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[b], 0));        // chunk k - 2 has read d_b[b]
-        PBVI_CUDA(cudaMemcpyAsync(d_b[b], h_beliefs + (size_t)lo * S, (size_t)n * S * sizeof(double), cudaMemcpyHostToDevice, m->hostIn));
-        PBVI_CUDA(cudaEventRecord(m->evIn[b], m->hostIn));
-        PBVI_CUDA(cudaStreamWaitEvent(st, m->evIn[b], 0));
-        m->arena.rewind(mark);
-        m->last_launches = 0;
-        PBVI_TRY(select_impl(m, d_b[b], n, d_a, nV, gamma, d_vs + (size_t)lo * m->nZ, nullptr, d_act + lo, st));
-        launches += m->last_launches;
-        PBVI_CUDA(cudaEventRecord(m->evDone[b], st));
+    bool packed = false;
+    PBVI_TRY(host_select_packed(m, h_beliefs, nB, d_a, nV, gamma, d_vs, d_act, st, &launches, &packed));
+    const pbvi::Arena::Mark mark = m->arena.mark();
+    if (!packed) {
+        // dense rows (or a small set): the two-deep chunk pipeline of pbvi_backup_host, upload of chunk k + 1 behind the kernels of chunk k
+        double* d_b[2];
+        for (int i = 0; i < 2; i++) {
+            d_b[i] = m->arena.take<double>((size_t)rows * S);
+            if (!d_b[i]) return PBVI_ERR_OOM;
+        }
+        const pbvi::Arena::Mark inner = m->arena.mark();
+        PBVI_CUDA(cudaEventRecord(m->evDone[0], st));
+        PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[0], 0));      // the staging is scratch of this call (see pbvi_backup_host)
+        for (int lo = 0, k = 0; lo < nB; lo += rows, k++) {
+            const int n = std::min(rows, nB - lo), b = k & 1;
+            if (k >= 2) PBVI_CUDA(cudaStreamWaitEvent(m->hostIn, m->evDone[b], 0));    // chunk k - 2 has read d_b[b]
+            PBVI_CUDA(cudaMemcpyAsync(d_b[b], h_beliefs + (size_t)lo * S, (size_t)n * S * sizeof(double), cudaMemcpyHostToDevice, m->hostIn));
+            PBVI_CUDA(cudaEventRecord(m->evIn[b], m->hostIn));
+            PBVI_CUDA(cudaStreamWaitEvent(st, m->evIn[b], 0));
+            m->arena.rewind(inner);
+            m->last_launches = 0;
+            PBVI_TRY(select_impl(m, d_b[b], n, d_a, nV, gamma, d_vs + (size_t)lo * m->nZ, nullptr, d_act + lo, st));
+            launches += m->last_launches;
+            PBVI_CUDA(cudaEventRecord(m->evDone[b], st));
+        }
     }
     m->arena.rewind(mark);
     m->last_launches = 0;
@@ -1169,9 +1337,14 @@ extern "C" int pbvi_backup_host_unique(pbvi_model* m, const double* h_beliefs, i
         out_act = kept_act;
     }
     PBVI_CUDA(cudaGetLastError());
-    PBVI_CUDA(cudaMemcpyAsync(h_out_alpha, out_rows, (size_t)r * S * sizeof(double), cudaMemcpyDeviceToHost, st));
-    PBVI_CUDA(cudaMemcpyAsync(h_out_action, out_act, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PBVI_CUDA(cudaStreamSynchronize(st));
+    {   // rows: straight into page-locked memory, through the pinned staging otherwise (the alphas left it long ago)
+        const size_t bytes = (size_t)r * S * sizeof(double);
+        void* stage = (bytes >= (size_t(8) << 20) && !host_pointer_is_pinned(h_out_alpha)) ? io_staging(m, bytes) : nullptr;
+        PBVI_CUDA(cudaMemcpyAsync(stage ? stage : (void*)h_out_alpha, out_rows, bytes, cudaMemcpyDeviceToHost, st));
+        PBVI_CUDA(cudaMemcpyAsync(h_out_action, out_act, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PBVI_CUDA(cudaStreamSynchronize(st));
+        if (stage) parallel_memcpy(h_out_alpha, stage, bytes);
+    }
     PBVI_CUDA(cudaStreamSynchronize(m->hostIn));
     return PBVI_OK;
 }

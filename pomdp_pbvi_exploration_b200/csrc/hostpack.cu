@@ -40,6 +40,16 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const uint32_t* __rest
     }
 }
 
+int unpack_rows_launch(pbvi_model* m, const uint32_t* d_bitmap, const int32_t* d_row_start, const double* d_packed, int n, int row_len,
+                       int slab_rows, long long region_chunks, double* d_out, cudaStream_t st) {
+    if (n <= 0) return PBVI_OK;
+    const int nC = (row_len + PACK - 1) / PACK, W = (nC + 31) / 32;
+    unpack_rows_kernel<<<ceil_div(n, 8), 256, 0, st>>>(d_bitmap, d_row_start, d_packed, n, row_len, W, slab_rows, region_chunks, d_out);
+    m->last_launches++;
+    PBVI_CUDA(cudaGetLastError());
+    return PBVI_OK;
+}
+
 }  // namespace pbvi
 
 using namespace pbvi;

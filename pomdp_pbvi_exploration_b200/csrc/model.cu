@@ -301,6 +301,8 @@ extern "C" int pbvi_model_destroy(pbvi_model* m) {
     }
     m->arena.release();
     if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_pack) cudaFreeHost(m->h_pack);
+    if (m->h_io) cudaFreeHost(m->h_io);
     delete m;
     return PBVI_OK;
 }

@@ -180,6 +180,10 @@ struct pbvi_model {
     // pbvi_backup_host: upload / download streams and the events of its two-deep chunk pipeline (created on first use)
     cudaStream_t hostIn = nullptr, hostOut = nullptr;
     cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evOut[2] = {nullptr, nullptr};
+    void* h_pack = nullptr;      // pinned staging of the packed belief upload of pbvi_backup_host_unique (grow-only)
+    size_t h_pack_bytes = 0;
+    void* h_io = nullptr;        // pinned staging for pageable alpha / output buffers of the same call (grow-only)
+    size_t h_io_bytes = 0;
 };
 
 namespace pbvi {
@@ -193,6 +197,8 @@ int row_hash_launch(pbvi_model* m, const double* d_rows, int n, int row_len, uin
 int max_values_impl(pbvi_model* m, const double* d_beliefs, int nB, const double* d_alphas, int nV, double* d_max, int32_t* d_arg, cudaStream_t st);
 // start of an API call that uses the handle's scratch: stream guard (see pbvi_model::last_stream) + arena rewind
 int enter_call(pbvi_model* m, cudaStream_t st);
+int unpack_rows_launch(pbvi_model* m, const uint32_t* d_bitmap, const int32_t* d_row_start, const double* d_packed, int n, int row_len,
+                       int slab_rows, long long region_chunks, double* d_out, cudaStream_t st);
 int group_keys_impl(pbvi_model* m, const uint32_t* d_keys, int n, int words, const int32_t* d_rank, int32_t* d_first, int32_t* d_last,
                     int32_t* d_inverse, int32_t** d_count_out, cudaStream_t st);
 int confirm_groups_launch(pbvi_model* m, const double* d_rows, int n, int row_len, const int32_t* d_first, const int32_t* d_inverse,

@@ -135,11 +135,12 @@ def test_backup_host_chunk_pipeline_equals_device_backup(torch_cuda, pinned):
     assert np.array_equal(again.cpu().numpy(), want_rows[:300])
 
 
-@pytest.mark.parametrize('case', ['synthetic', 'tiger', 'olfactory_wrap'])
+@pytest.mark.parametrize('case', ['synthetic', 'synthetic_dense', 'tiger', 'olfactory_wrap'])
 def test_backup_host_unique_equals_the_solver_backup(torch_cuda, case):
     """`pbvi_backup_host_unique` -- the reference's whole backup from host buffers in ONE library call, ValueFunction-constructor dedup
     included -- returns the rows and actions of `PBVI_Solver.backup(append=False, belief_dominance_prune=False)`, in the same order,
-    byte for byte (three chunks of beliefs on the synthetic model; tiger has R = 2 and many tuples per row)."""
+    byte for byte.  Sparse sets of 2048 rows or more travel packed (host threads + unpack kernel: `synthetic`, `olfactory_wrap`), dense
+    or small ones through the chunked dense pipeline (`synthetic_dense`: three chunks; tiger: R = 2, many tuples per row)."""
     from pomdp_pbvi_exploration_b200 import BeliefSet, PBVI_Solver, ValueFunction
     from pomdp_pbvi_exploration_b200.recipes import olfactory_wrap_model, perseus_walk_beliefs, synthetic_sparse_model
     rng = np.random.default_rng(21)
@@ -148,6 +149,11 @@ def test_backup_host_unique_equals_the_solver_backup(torch_cuda, case):
         B = _sparse_beliefs(rng, 5000, 700, (1, 2, 3, 40))
         B[100:140] = B[0]                                   # repeated beliefs: repeated tuples
         V, acts = rng.random((70, 700)) * (rng.random((70, 700)) < 0.4), rng.integers(0, 4, 70)
+    elif case == 'synthetic_dense':
+        model, gamma = synthetic_sparse_model(700, 4, 3, 1, seed=11), 0.95
+        B = rng.dirichlet(np.ones(700), size=4300)
+        B[7] = B[4200]
+        V, acts = rng.random((70, 700)), rng.integers(0, 4, 70)
     elif case == 'tiger':
         g = load_golden('backup_tiger')
         dev, mm, _, _ = device_model('tiger')

@@ -60,6 +60,16 @@ def main():
                                               act.data_ptr(), ctypes.byref(n), st)
         ts.append((time.perf_counter() - t0) * 1e3)
         assert rc == 0
+    pb, pv = beliefs.cpu().numpy(), V.cpu().numpy()            # pageable arrays: what a NumPy host holds
+    po, pa = np.empty((nB, dev.S)), np.empty(nB, dtype=np.int32)
+    tp = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        rc = dev._lib.pbvi_backup_host_unique(dev._h, pb.ctypes.data, nB, pv.ctypes.data, V.shape[0], ctypes.c_double(0.99), po.ctypes.data, nB,
+                                              pa.ctypes.data, ctypes.byref(n), st)
+        tp.append((time.perf_counter() - t0) * 1e3)
+        assert rc == 0
+    print(f'pbvi_backup_host_unique from pageable NumPy arrays: {[round(t, 1) for t in tp]} ms per call')
     from pomdp_pbvi_exploration_b200 import BeliefSet
     want = solver.backup(model, BeliefSet(model, beliefs), vfs['late'], append=False, belief_dominance_prune=False)
     wr, wa = want.numpy()
