@@ -609,6 +609,32 @@ def run_b200(args):
         h2d = int(getattr(solver, 'last_h2d_bytes', h_beliefs.numel() * 8) + h_alphas.numel() * 8) if e2e_steps else h2d_dense
         d2h = int(rows.size * 8 + acts.size * 8)
         (e2e_ms,) = reduce_max([e2e_ms])
+        # the same backup through the C ABI alone (what a non-Python host binds): one pbvi_backup_host_unique call,
+        # from page-locked buffers and from plain (pageable) NumPy arrays; its rows must be the step's rows
+        c_abi = None
+        if e2e_steps and world == 1:
+            import ctypes
+            n_out = ctypes.c_int()
+            cap = int(min(B, 4 * rows.shape[0] + 64))
+            st = torch.cuda.current_stream().cuda_stream
+            o_rows, o_act = torch.empty((cap, S), dtype=torch.float64).pin_memory(), torch.empty((cap,), dtype=torch.int32).pin_memory()
+            p_b, p_a = h_beliefs.numpy().copy(), h_alphas.numpy().copy()
+            p_rows, p_act = np.empty((cap, S)), np.empty(cap, dtype=np.int32)
+
+            def call(b_ptr, a_ptr, r_ptr, act_ptr):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rc = dev._lib.pbvi_backup_host_unique(dev._h, b_ptr, B, a_ptr, V, ctypes.c_double(GAMMA), r_ptr, cap, act_ptr, ctypes.byref(n_out), st)
+                assert rc == 0, dev._lib.pbvi_last_error()
+                return (time.perf_counter() - t0) * 1e3
+            pinned_ms = [call(h_beliefs.data_ptr(), h_alphas.data_ptr(), o_rows.data_ptr(), o_act.data_ptr()) for _ in range(5)][2:]
+            pageable_ms = [call(p_b.ctypes.data, p_a.ctypes.data, p_rows.ctypes.data, p_act.ctypes.data) for _ in range(5)][2:]
+            c_abi = {'entry': 'pbvi_backup_host_unique (whole backup incl. the ValueFunction-constructor dedup, host buffers in and out)',
+                     'ms_per_call_pinned': float(np.mean(pinned_ms)), 'ms_per_call_pageable_numpy': float(np.mean(pageable_ms)),
+                     'rows': int(n_out.value),
+                     'rows_equal_step_output': bool(n_out.value == rows.shape[0] and np.array_equal(p_rows[:n_out.value], rows)
+                                                    and np.array_equal(o_rows[:n_out.value].numpy(), rows)
+                                                    and np.array_equal(p_act[:n_out.value], np.asarray(acts)))}
 
         units = float(B) * V * world
         ms_step = head['elapsed_ms'] / head['steps']
@@ -632,7 +658,7 @@ def run_b200(args):
             'clocks': clocks,
             'e2e': {'value': units * args.steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': (e2e_ms / args.steps) if e2e_ms > 0 else None,
-                    'host_input_bytes_per_step': h2d_dense, 'host_threads': (dev.__dict__.get('_pack') or {}).get('pool')._max_workers if (e2e_steps and h2d < h2d_dense) else 1,
+                    'c_abi': c_abi, 'host_input_bytes_per_step': h2d_dense, 'host_threads': (dev.__dict__.get('_pack') or {}).get('pool')._max_workers if (e2e_steps and h2d < h2d_dense) else 1,
                     'api': 'BeliefSet(host) + ValueFunction(host) -> PBVI_Solver.backup -> ValueFunction.numpy(); sparse belief rows are packed by '
                            'host threads (pbvi_pack_slabs_host) for the upload and unpacked on the device; the alpha rows known before the last '
                            'chunk of beliefs is scored are read back beside that kernel'},
