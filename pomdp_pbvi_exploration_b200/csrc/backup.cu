@@ -1093,7 +1093,14 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const size_t slice = ((bytes / T) + 63) & ~size_t(63);
     for (int t = 0; t < T; t++) {
         const size_t lo = std::min(bytes, (size_t)t * slice), hi = std::min(bytes, lo + slice);
-        if (hi > lo) th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+        if (hi <= lo) continue;
+        bool spawned = false;
+        try {                                                       // no C++ exception may cross the C ABI
+            th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+            spawned = true;
+        } catch (...) {
+        }
+        if (!spawned) std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
     }
     for (auto& x : th) x.join();
 }
@@ -1163,10 +1170,18 @@ static int host_select_packed(pbvi_model* m, const double* h_beliefs, int nB, co
     const unsigned hw = std::thread::hardware_concurrency();
     const int T = std::max(1, std::min({32, (int)(hw > 1 ? hw - 1 : 1), n_slabs}));     // one core stays with this thread
     std::vector<std::thread> packers;
-    packers.reserve(T);
-    for (int t = 0; t < T; t++)
-        packers.emplace_back([=] { pbvi_pack_slabs_host(h_beliefs, nB, S, SL, t, T, h_bm, h_rs, h_pk, (int64_t)region, h_tot); });
+    int started = 0;
+    try {                                                           // no C++ exception may cross the C ABI
+        packers.reserve(T);
+        for (; started < T; started++) {
+            const int t = started;
+            packers.emplace_back([=] { pbvi_pack_slabs_host(h_beliefs, nB, S, SL, t, T, h_bm, h_rs, h_pk, (int64_t)region, h_tot); });
+        }
+    } catch (...) {
+    }
     auto join_all = [&] { for (auto& th : packers) if (th.joinable()) th.join(); };
+    for (int t = started; t < T; t++)                               // threads the system refused: their slabs are packed here, now
+        pbvi_pack_slabs_host(h_beliefs, nB, S, SL, t, T, h_bm, h_rs, h_pk, (int64_t)region, h_tot);
 
     const int unit = SL * std::min(T, 16);                          // one round of the packers: ready after ONE slab time
     const pbvi::Arena::Mark mark = m->arena.mark();
