@@ -211,6 +211,41 @@ def gen_tiger_extras():
     save('tiger_extras', **out)
 
 
+GRID_FLAVOURS = ['ra', 'ssra', 'ssga', 'fsvi', 'fsvi_eg', 'perseus', 'hsvi']     # SSEA / GER crash on grids in the reference (NaN successors)
+
+
+def gen_grid_extras():
+    """Expansion flavours and whole solves on the 4x4 no-loop grid (R = 1, end state, impossible (a, o) pairs): everything the
+    reference can run there -- its SSEA / GER assert on the NaN successors of impossible observations."""
+    print('[grid extras]')
+    with quiet():
+        m, s0 = ref.load_POMDP_file(os.path.join(EXAMPLES, '4x4.95-no_loop.POMDP'))
+    gamma = s0.gamma
+    with quiet():
+        mdp_vf, _ = ref.VI_Solver(gamma=gamma, eps=1e-6).solve(m, print_progress=False)
+    out = dict(mdp_alpha=mdp_vf.alpha_vector_array, mdp_action=np.array(mdp_vf.actions), gamma=np.float64(gamma))
+    solver, vf, hist = solve_snapshots(m, gamma, 'perseus', 4, 6, 1)
+    B = hist.belief_sets[-1].belief_array.copy()
+    V = hist.value_functions[-1]
+    out.update(beliefs=B, alphas=V.alpha_vector_array, alpha_actions=np.array(V.actions))
+    for flavour in GRID_FLAVOURS:
+        kw = {'mdp_policy': mdp_vf} if flavour in ('fsvi', 'fsvi_eg', 'hsvi') else {}
+        sv = ref.PBVI_Solver(gamma=gamma, eps=1e-6, expand_function=flavour, **kw)
+        seed_all(7)
+        with quiet(), np.errstate(all='ignore'):
+            nb = sv.expand(m, ref.BeliefSet(m, B.copy()), max_generation=5, value_function=V, **sv.expand_function_params)
+        out[f'ref_expand_{flavour}'] = nb.belief_array.copy()
+    for flavour in GRID_FLAVOURS:
+        with np.errstate(all='ignore'):
+            solver, vf, hist = solve_snapshots(m, gamma, flavour, 5, 8, 3)
+        out[f'ref_solve_{flavour}_alpha'] = vf.alpha_vector_array.copy()
+        out[f'ref_solve_{flavour}_action'] = np.array(vf.actions).copy()
+        out[f'ref_solve_{flavour}_beliefs'] = hist.belief_sets[-1].belief_array.copy()
+        out[f'ref_solve_{flavour}_vcounts'] = np.array(hist.alpha_vector_counts)
+        out[f'ref_solve_{flavour}_bcounts'] = np.array(hist.beliefs_counts)
+    save('grid_extras', **out)
+
+
 def gen_olfactory():
     print('[olfactory]')
     m, ground, nose = olfactory_reference_model(wrap=True)
@@ -411,6 +446,8 @@ if __name__ == '__main__':
     if on('4x4'):
         gen_small_model('4x4.95.POMDP', 'grid4x4', flavour='fsvi', expansions=6, growth=8)
         gen_small_model('4x4.95-no_loop.POMDP', 'grid4x4_noloop', flavour='perseus', expansions=6, growth=8)
+    if on('grid_extras'):
+        gen_grid_extras()
     if on('tigergrid'):
         gen_small_model('tiger-grid.POMDP', 'tigergrid', flavour='fsvi', expansions=6, growth=10)
     if on('hallway'):
