@@ -448,6 +448,19 @@ if __name__ == '__main__':
         gen_small_model('4x4.95-no_loop.POMDP', 'grid4x4_noloop', flavour='perseus', expansions=6, growth=8)
     if on('grid_extras'):
         gen_grid_extras()
+    # the other example models the reference's reader accepts (its parser rejects parr95, saci-s12-a6-z5 and shuttle; cit is 284 states)
+    if on('cheese'):
+        gen_small_model('cheese.95.POMDP', 'cheese', flavour='fsvi', expansions=6, growth=8)
+    if on('network'):
+        gen_small_model('network.95.POMDP', 'network', flavour='perseus', expansions=6, growth=8)
+    if on('hanks'):
+        gen_small_model('hanks.95.POMDP', 'hanks', flavour='ssra', expansions=6, growth=8)
+    if on('grid4x3'):
+        gen_small_model('4x3.95.POMDP', 'grid4x3', flavour='fsvi', expansions=6, growth=8)
+    if on('maze4x5x2'):
+        gen_small_model('4x5x2.95.POMDP', 'maze4x5x2', flavour='perseus', expansions=6, growth=8)
+    if on('cit'):
+        gen_small_model('cit.POMDP', 'cit', flavour='fsvi', expansions=4, growth=10)
     if on('tigergrid'):
         gen_small_model('tiger-grid.POMDP', 'tigergrid', flavour='fsvi', expansions=6, growth=10)
     if on('hallway'):

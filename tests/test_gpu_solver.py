@@ -14,7 +14,7 @@ from oracle import pbvi_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid', 'hallway', 'synth300', 'olfactory_wrap']
+MODELS = ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid', 'hallway', 'cheese', 'grid4x3', 'cit', 'synth300', 'olfactory_wrap']
 
 
 def seed_all(seed):

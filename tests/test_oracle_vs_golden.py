@@ -11,7 +11,7 @@ import pytest
 from oracle import pbvi_oracle as orc
 from conftest import load_golden
 
-MODELS = ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid', 'hallway', 'synth300', 'olfactory_wrap']
+MODELS = ['tiger', 'grid4x4', 'grid4x4_noloop', 'tigergrid', 'hallway', 'cheese', 'grid4x3', 'cit', 'synth300', 'olfactory_wrap']
 GAP_TOL = 1e-9
 
 
